@@ -1,0 +1,159 @@
+/*
+ * libeotpatch -- C ABI of the B200-native EOT patch-attack hot path.
+ *
+ * The reference exposes this path as Python/Keras layers, not as an FFI; each
+ * entry point below names the reference interface it stands in for.  All pointers are DEVICE
+ * pointers unless stated otherwise; every call is asynchronous on the caller's stream, never
+ * allocates or frees device memory, never synchronises, keeps no pointer after it returns and
+ * has no mutable global state (reentrant across host threads / streams).
+ *
+ * Return value: EOT_OK (0) or an EotStatus code; the message of the last failure on the calling
+ * thread is available through eot_last_error().
+ *
+ * Tensors are float32, NHWC, contiguous.  Ragged per-image boxes are CSR: boxes[N,4] with
+ * box_offsets[B+1].
+ */
+#ifndef EOTPATCH_H_
+#define EOTPATCH_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum EotStatus {
+  EOT_OK = 0,
+  EOT_ERR_NULL_POINTER = 1,
+  EOT_ERR_BAD_SHAPE = 2,
+  EOT_ERR_WORKSPACE_TOO_SMALL = 3,
+  EOT_ERR_CUDA = 4,
+  EOT_ERR_MISALIGNED = 5,
+  EOT_ERR_GEOMETRY = 6 /* eot_check_workspace: a patch window did not fit the image */
+} EotStatus;
+
+/* Transform seeds of one person box: everything `Patcher.create` / `add_patch_to_image` draw from
+ * TF's RNG (attacker.py:426-427,436,473-474; Masker: attack_detection.py:411,421,453).  48 bytes. */
+typedef struct EotBoxParams {
+  float uy, ux;        /* unit uniforms of the centre jitter U(-tol*h/2, tol*h/2), (.. w ..)        */
+  float delta;         /* tf.image.random_brightness delta, U[-.3,.3)                                */
+  float cos_t, sin_t;  /* rotation angle U[-20deg,20deg) as (cos, sin), evaluated by the caller      */
+  float pa, pb;        /* projective row of the 8-parameter transform (0,0 = the reference rotation) */
+  float scale;         /* >= 0: per-box patch scale (Masker training U(.3,.5)); < 0: shared *scale   */
+  uint32_t key0, key1; /* Philox4x32-10 key of the per-texel noise tf.random.uniform(+-noise_amp)    */
+  uint32_t rsv0, rsv1;
+} EotBoxParams;
+
+#define EOT_FLAG_MASK_OUTPUT 1u /* Masker: also write mask = original - pasted (attack_detection.py:429-430) */
+
+typedef struct EotShape {
+  int32_t batch;          /* B images held by this rank                                            */
+  int32_t height, width;  /* H, W                                                                  */
+  int32_t patch_size;     /* P: patch texture is [P,P,3]                                           */
+  int32_t num_patches;    /* 1: one shared patch (Patcher); B: one texture per image (Masker train) */
+  int32_t total_boxes;    /* N = box_offsets[B]                                                    */
+  uint32_t flags;         /* EOT_FLAG_*                                                            */
+  float tolerance;        /* centre jitter fraction: .2 Patcher (attacker.py:465), .5/0 Masker     */
+  float noise_amp;        /* .01 Patcher (attacker.py:426), .1 Masker (attack_detection.py:411)    */
+  float min_patch_area;   /* 4 (attacker.py:347,392)                                               */
+  float max_scale;        /* upper bound of scale used to size the workspace (<=0: 1.0)            */
+  /* element strides of the patch view (channel stride is 1); 0 = contiguous [num_patches,P,P,3].
+   * Negative strides express the Masker's flips of `images[:, :240, :240]` without a copy.       */
+  int64_t patch_stride_n, patch_stride_y, patch_stride_x;
+} EotShape;
+
+/* Integer placement of a patch as the reference computes it (attacker.py:418-420,431-434). */
+typedef struct EotBoxGeometry {
+  int32_t y0, x0, ps, d, pad_lo, pad_hi, valid, span;
+} EotBoxGeometry;
+
+const char* eot_last_error(void);
+int eot_version(void);
+
+/* Bytes of the saved-state workspace eot_apply_fwd fills and eot_apply_bwd reads. */
+int eot_workspace_bytes(const EotShape* shape, size_t* bytes);
+
+/* `Patcher.create` + area filter + int cast for every box (attacker.py:392-394,418,448-488),
+ * by the same device code eot_apply_fwd uses.  geometry_out: [N] EotBoxGeometry. */
+int eot_box_geometry(const EotShape* shape, const float* boxes, const int32_t* box_offsets,
+                     const EotBoxParams* params, const float* scale, EotBoxGeometry* geometry_out,
+                     void* stream);
+
+/* `Patcher.call` (attacker.py:490-498) / `Masker.call` (attack_detection.py:478-498):
+ * out_images[B,H,W,3] = images with every valid box patched in order; out_masks (optional,
+ * needs EOT_FLAG_MASK_OUTPUT) as the Masker's second output.  `patch` points at element
+ * [0,0,0,0] of the (possibly strided) patch view; `scale` is a device scalar (the trainable
+ * scale_regressor); print_wb is [B,6] = (w0,w1,w2,b0,b1,b2) of random_print_adjust.
+ * out_images may alias images (in-place). */
+int eot_apply_fwd(const EotShape* shape, const float* patch, const float* scale, const float* images,
+                  const float* boxes, const int32_t* box_offsets, const EotBoxParams* params,
+                  const float* print_wb, float* out_images, float* out_masks, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
+/* `tape.gradient(loss, patch)` through the patcher (attacker.py:217; chain of SURVEY.md 3.2):
+ * grad_images = dL/d(out_images) [B,H,W,3]; grad_patch [P,P,3] (shared patch only).
+ * accumulate != 0 adds into grad_patch, otherwise it is overwritten.  Needs the workspace of the
+ * matching eot_apply_fwd call, unmodified. */
+int eot_apply_bwd(const EotShape* shape, const float* patch, const float* print_wb,
+                  const float* grad_images, void* workspace, size_t workspace_bytes,
+                  float* grad_patch, int accumulate, void* stream);
+
+/* Synchronises `stream` and reports whether any box failed the reference's implicit shape
+ * requirements during the last eot_apply_fwd on this workspace (debug / tests only). */
+int eot_check_workspace(const EotShape* shape, const void* workspace, void* stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Person-score objective: pre_nms (max-reduce branch) + person filter + valid-box filter +
+ * per-image max (attacker.py:118-141,190; tf2/postprocess.py:67-79,104-116,136-156;
+ * tf2/anchors.py:30-58).
+ * ------------------------------------------------------------------------------------------ */
+#define SCORE_MAX_LEVELS 8
+
+typedef struct ScoreShape {
+  int32_t batch;
+  int32_t num_levels;                       /* 5 for min_level 3 .. max_level 7              */
+  int32_t num_classes;                      /* 90                                            */
+  int32_t anchors_per_loc;                  /* 9                                             */
+  int32_t level_locs[SCORE_MAX_LEVELS];     /* H_l * W_l                                     */
+  int32_t total_anchors;                    /* A = 9 * sum(level_locs)                       */
+  float image_height, image_width;          /* for the valid-box filter (attacker.py:79-83)  */
+  float min_area;                           /* 100 (attacker.py:88)                          */
+} ScoreShape;
+
+int score_workspace_bytes(const ScoreShape* shape, size_t* bytes);
+
+/* cls_levels / box_levels: HOST arrays of num_levels device pointers, level l is
+ * [B, H_l, W_l, 9*num_classes] / [B, H_l, W_l, 9*4].  anchors: [A,4].
+ * Outputs: max_scores[B] = maximum(reduce_max(candidate scores), 0); argmax_anchor[B] = lowest
+ * anchor index attaining it (-1: no candidate); num_candidates[B]. */
+int score_max_fwd(const ScoreShape* shape, const float* const* cls_levels,
+                  const float* const* box_levels, const float* anchors, float* max_scores,
+                  int32_t* argmax_anchor, int32_t* num_candidates, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
+/* Dense, zero-filled dL/dcls per level (what the framework's conv backward consumes) for
+ * loss = sum_b(M_b^2 + (M_b - scale)^2) (attacker.py:191,193): one non-zero per image, ties split
+ * equally as TF's Max / UnsortedSegmentMax gradients do.  dscale_out: device scalar,
+ * sum_b -2 (M_b - scale).  loss_out (optional): device scalar with the data term of the loss. */
+int score_max_bwd(const ScoreShape* shape, const float* const* cls_levels, const float* max_scores,
+                  const float* scale, float* const* dcls_levels, float* dscale_out,
+                  float* loss_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Patch update (attacker.py:191-193,307-316,51-54): total-variation term and Adam + constraint.
+ * ------------------------------------------------------------------------------------------ */
+/* grad_patch += weight * d TV(patch)/d patch ; tv_out (optional device scalar) = TV(patch). */
+int patch_tv_grad(const float* patch, int32_t patch_size, float weight, float* grad_patch,
+                  float* tv_out, void* stream);
+
+/* Keras Adam step on `n` floats followed by clip to [lo,hi] (the tf.Variable constraint).
+ * step is the 1-based iteration. */
+int adam_clip_update(float* var, float* m, float* v, const float* grad, int64_t n, float lr,
+                     float beta1, float beta2, float eps, int64_t step, float lo, float hi,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EOTPATCH_H_ */

@@ -1,0 +1,84 @@
+"""ctypes binding of libeotpatch.so (C ABI declared in include/eotpatch.h).
+
+There is NO fallback: if the shared library is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libeotpatch.so")
+
+EOT_FLAG_MASK_OUTPUT = 1
+SCORE_MAX_LEVELS = 8
+
+# every symbol include/eotpatch.h declares (tests check the export list against the header)
+SYMBOLS = ["eot_last_error", "eot_version", "eot_workspace_bytes", "eot_box_geometry", "eot_apply_fwd",
+           "eot_apply_bwd", "eot_check_workspace", "score_workspace_bytes", "score_max_fwd", "score_max_bwd",
+           "patch_tv_grad", "adam_clip_update"]
+
+
+class EotShape(ctypes.Structure):
+    _fields_ = [("batch", ctypes.c_int32), ("height", ctypes.c_int32), ("width", ctypes.c_int32),
+                ("patch_size", ctypes.c_int32), ("num_patches", ctypes.c_int32), ("total_boxes", ctypes.c_int32),
+                ("flags", ctypes.c_uint32), ("tolerance", ctypes.c_float), ("noise_amp", ctypes.c_float),
+                ("min_patch_area", ctypes.c_float), ("max_scale", ctypes.c_float),
+                ("patch_stride_n", ctypes.c_int64), ("patch_stride_y", ctypes.c_int64),
+                ("patch_stride_x", ctypes.c_int64)]
+
+
+class ScoreShape(ctypes.Structure):
+    _fields_ = [("batch", ctypes.c_int32), ("num_levels", ctypes.c_int32), ("num_classes", ctypes.c_int32),
+                ("anchors_per_loc", ctypes.c_int32), ("level_locs", ctypes.c_int32 * SCORE_MAX_LEVELS),
+                ("total_anchors", ctypes.c_int32), ("image_height", ctypes.c_float),
+                ("image_width", ctypes.c_float), ("min_area", ctypes.c_float)]
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+def _declare(lib):
+    vp, i32, i64, f32, sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
+    lib.eot_last_error.restype = ctypes.c_char_p
+    lib.eot_last_error.argtypes = []
+    lib.eot_version.restype = ctypes.c_int
+    lib.eot_workspace_bytes.argtypes = [ctypes.POINTER(EotShape), ctypes.POINTER(sz)]
+    lib.eot_box_geometry.argtypes = [ctypes.POINTER(EotShape), vp, vp, vp, vp, vp, vp]
+    lib.eot_apply_fwd.argtypes = [ctypes.POINTER(EotShape), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.eot_apply_bwd.argtypes = [ctypes.POINTER(EotShape), vp, vp, vp, vp, sz, vp, ctypes.c_int, vp]
+    lib.eot_check_workspace.argtypes = [ctypes.POINTER(EotShape), vp, vp]
+    lib.score_workspace_bytes.argtypes = [ctypes.POINTER(ScoreShape), ctypes.POINTER(sz)]
+    lib.score_max_fwd.argtypes = [ctypes.POINTER(ScoreShape), ctypes.POINTER(vp), ctypes.POINTER(vp), vp, vp, vp,
+                                  vp, vp, sz, vp]
+    lib.score_max_bwd.argtypes = [ctypes.POINTER(ScoreShape), ctypes.POINTER(vp), vp, vp, ctypes.POINTER(vp), vp,
+                                  vp, vp, sz, vp]
+    lib.patch_tv_grad.argtypes = [vp, i32, f32, vp, vp, vp]
+    lib.adam_clip_update.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i64, f32, f32, vp]
+    for name in SYMBOLS:
+        if name != "eot_last_error":
+            getattr(lib, name).restype = ctypes.c_int
+
+
+def load() -> ctypes.CDLL:
+    """The CUDA library, loaded once.  Raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU fallback for the EOT patch path)")
+                lib = ctypes.CDLL(LIB_PATH)
+                _declare(lib)
+                _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().eot_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed with status {rc}: {msg}")

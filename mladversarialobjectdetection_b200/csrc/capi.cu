@@ -1,0 +1,33 @@
+// Error plumbing and small host utilities of libeotpatch (see include/eotpatch.h).
+#include "eot_common.cuh"
+
+#include <stdarg.h>
+#include <stdio.h>
+
+namespace eot {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return EOT_ERR_CUDA;
+}
+
+int sm_count() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+  return n;
+}
+
+}  // namespace eot
+
+extern "C" const char* eot_last_error(void) { return eot::g_err; }
+extern "C" int eot_version(void) { return 100; }

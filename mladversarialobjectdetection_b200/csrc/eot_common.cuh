@@ -1,0 +1,213 @@
+// Shared device/host definitions for libeotpatch (sm_100a).
+//
+// Parity note: this translation-unit family is compiled with -fmad=false.  The reference runs every
+// arithmetic op as its own float32 TF kernel (one rounding per op), and the `< -1` mask decision of
+// attacker.py:440 depends on the last bit, so no multiply-add may be contracted.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/eotpatch.h"
+
+namespace eot {
+
+// ---- constants of the restated TF ops (tensorflow/python/ops/image_ops_impl.py) -------------------
+#define EOT_K00 0.299f
+#define EOT_K10 0.587f
+#define EOT_K20 0.114f
+#define EOT_K01 (-0.14714119f)
+#define EOT_K11 (-0.28886916f)
+#define EOT_K21 0.43601035f
+#define EOT_K02 0.61497538f
+#define EOT_K12 (-0.51496512f)
+#define EOT_K22 (-0.10001026f)
+// yuv_to_rgb kernel rows: Y -> (1,1,1); U -> (0, -0.394642334, 2.03206185); V -> (1.13988303, -0.58062185, 0)
+#define EOT_I10 0.0f
+#define EOT_I11 (-0.394642334f)
+#define EOT_I12 2.03206185f
+#define EOT_I20 1.13988303f
+#define EOT_I21 (-0.58062185f)
+#define EOT_I22 0.0f
+#define EOT_C127_255 ((float)(127.0 / 255.0))   // brightness_matcher.py:32
+#define EOT_C255_127 ((float)(255.0 / 127.0))   // brightness_matcher.py:41
+#define EOT_SQRT2 1.41421354f                   // float32(2. ** .5), attacker.py:470
+
+constexpr int kResizeRows = 4;        // output rows per resize work item
+constexpr int kCompChunk = 2048;      // window elements per composite work item
+constexpr int kThreads = 256;
+
+// Per-box plan written by the geometry kernel; 128 bytes.
+struct __align__(16) BoxPlan {
+  int32_t y0, x0, ps, d;
+  int32_t pad_lo, pad_hi, valid, span;
+  float T[8];     // output->input transform of tfa.image.rotate (+ projective row)
+  float Ti[8];    // its inverse, normalised (gradient warp)
+  float delta;
+  uint32_t key0, key1;
+  int32_t image;
+  int64_t u_off;  // float offset of this box's transformed-patch buffer
+  int32_t first_box, last_box;   // CSR range of the owning image
+};
+static_assert(sizeof(BoxPlan) == 128, "BoxPlan must stay 128 bytes");
+
+// Workspace layout (byte offsets); identical on host and device.
+struct Layout {
+  size_t off_ysum_img;     // double[B]
+  size_t off_ysum_patch;   // double[B]
+  size_t off_gy_sum;       // double[B]   (backward: sum of dL/dY per image)
+  size_t off_counters;     // int32[8]: 0 resize items, 1 composite items, 2 error flag, 3 bwd items
+  size_t off_plans;        // BoxPlan[N]
+  size_t off_starts;       // int32[N][Lmin]
+  size_t off_weights;      // float[N][wcap]
+  size_t off_match;        // float[B][P*P*3]
+  size_t off_u;            // float[N][slot]
+  size_t off_items_resize; // int2[N*ceil(Lmin/kResizeRows)]
+  size_t off_items_comp;   // int2[N*ceil(3*Lmin*Lmin/kCompChunk)]
+  size_t off_gm;           // float[B][P*P*3] backward: dL/d(matched patch) per image
+  size_t off_gu;           // float[N][slot]  backward: dL/d(u) per box
+  size_t total;
+  int64_t slot;            // floats per u slot
+  int32_t wcap;            // floats per weight table
+  int32_t lmin;            // max patch side
+};
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+__host__ __device__ inline Layout make_layout(const EotShape& s) {
+  Layout L;
+  const size_t B = (size_t)s.batch, N = (size_t)(s.total_boxes > 0 ? s.total_boxes : 0);
+  const int lfull = s.height < s.width ? s.height : s.width;
+  float ms = (s.max_scale > 0.f && s.max_scale < 1.f) ? s.max_scale : 1.f;
+  int lmin = (int)((float)(s.height > s.width ? s.height : s.width) * ms) + 1;
+  if (lmin > lfull) lmin = lfull;
+  L.lmin = lmin;
+  L.wcap = 2 * s.patch_size + 3 * lmin + 8;
+  L.slot = (int64_t)align_up((size_t)lmin * lmin * 3, 32);
+  const size_t PP3 = (size_t)s.patch_size * s.patch_size * 3;
+  size_t o = 0;
+  L.off_ysum_img = o;     o = align_up(o + B * sizeof(double), 256);
+  L.off_ysum_patch = o;   o = align_up(o + B * sizeof(double), 256);
+  L.off_gy_sum = o;       o = align_up(o + B * sizeof(double), 256);
+  L.off_counters = o;     o = align_up(o + 8 * sizeof(int32_t), 256);
+  L.off_plans = o;        o = align_up(o + N * sizeof(BoxPlan), 256);
+  L.off_starts = o;       o = align_up(o + N * (size_t)lmin * sizeof(int32_t), 256);
+  L.off_weights = o;      o = align_up(o + N * (size_t)L.wcap * sizeof(float), 256);
+  L.off_match = o;        o = align_up(o + B * PP3 * sizeof(float), 256);
+  L.off_u = o;            o = align_up(o + N * (size_t)L.slot * sizeof(float), 256);
+  L.off_items_resize = o; o = align_up(o + N * (size_t)((lmin + kResizeRows - 1) / kResizeRows) * 8, 256);
+  L.off_items_comp = o;   o = align_up(o + N * (((size_t)3 * lmin * lmin + kCompChunk - 1) / kCompChunk + 1) * 8, 256);
+  L.off_gm = o;           o = align_up(o + B * PP3 * sizeof(float), 256);
+  L.off_gu = o;           o = align_up(o + N * (size_t)L.slot * sizeof(float), 256);
+  L.total = o;
+  return L;
+}
+
+// ---- error plumbing (host) -------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+int sm_count();
+
+#define EOT_CHECK_CUDA(expr)                                   \
+  do {                                                         \
+    cudaError_t _e = (expr);                                   \
+    if (_e != cudaSuccess) return ::eot::cuda_fail(_e, #expr); \
+  } while (0)
+
+#ifdef __CUDACC__
+// ---- small device helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum (blockDim.x multiple of 32, <= 1024); result valid in thread 0.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* smem /* >= 32 entries */) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) smem[wid] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? smem[threadIdx.x] : T(0);
+  if (wid == 0) v = warp_sum(v);
+  __syncthreads();
+  return v;
+}
+
+// Philox4x32-10, counter (c0,0,0,0), key (k0,k1).
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t k0, uint32_t k1) {
+  uint32_t c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    if (r > 0) { k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// TF Uint32ToFloat + random_uniform range map: u*(hi-lo)+lo with lo=-amp, hi=amp.
+__device__ __forceinline__ float noise_from_word(uint32_t w, float amp) {
+  const float u = __uint_as_float((w & 0x7FFFFFu) | 0x3F800000u) - 1.0f;
+  const float lo = -amp;
+  const float rng = amp - lo;
+  return u * rng + lo;
+}
+
+// print adjust + rescale + Y of one patch texel (attacker.py:372, brightness_matcher.py:32,58).
+struct TexelYuv { float y, u, v, q0, q1, q2; };
+__device__ __forceinline__ TexelYuv texel_yuv(float p0, float p1, float p2, const float* __restrict__ wb) {
+  TexelYuv t;
+  t.q0 = wb[0] * p0 + wb[3];
+  t.q1 = wb[1] * p1 + wb[4];
+  t.q2 = wb[2] * p2 + wb[5];
+  const float s0 = (clampf(t.q0, -1.f, 1.f) + 1.0f) * EOT_C127_255;
+  const float s1 = (clampf(t.q1, -1.f, 1.f) + 1.0f) * EOT_C127_255;
+  const float s2 = (clampf(t.q2, -1.f, 1.f) + 1.0f) * EOT_C127_255;
+  t.y = (s0 * EOT_K00 + s1 * EOT_K10) + s2 * EOT_K20;
+  t.u = (s0 * EOT_K01 + s1 * EOT_K11) + s2 * EOT_K21;
+  t.v = (s0 * EOT_K02 + s1 * EOT_K12) + s2 * EOT_K22;
+  return t;
+}
+
+// ImageProjectiveTransformV3 BILINEAR / CONSTANT sampling of the (virtually) padded transformed
+// patch of one box, channel c, at window pixel (xo, yo).  u holds the PRE-clip values
+// (resize + noise) + delta; the clip of attacker.py:428 is applied on read; everything outside the
+// ps x ps core -- the -2 pad ring of attacker.py:435 and the -2 fill of :437 -- reads as -2.
+__device__ __forceinline__ float warp_sample(const BoxPlan& pl, const float* __restrict__ u, int xo, int yo, int c) {
+  const float xf = (float)xo, yf = (float)yo;
+  const float proj = (pl.T[6] * xf + pl.T[7] * yf) + 1.0f;
+  if (proj == 0.0f) return -2.0f;
+  const float ix = ((pl.T[0] * xf + pl.T[1] * yf) + pl.T[2]) / proj;
+  const float iy = ((pl.T[3] * xf + pl.T[4] * yf) + pl.T[5]) / proj;
+  const float x0f = floorf(ix), y0f = floorf(iy);
+  const float x1f = x0f + 1.0f, y1f = y0f + 1.0f;
+  const float lo = (float)pl.pad_lo, hi = (float)(pl.pad_lo + pl.ps);
+  const bool bx0 = (x0f >= lo) && (x0f < hi), bx1 = (x1f >= lo) && (x1f < hi);
+  const bool by0 = (y0f >= lo) && (y0f < hi), by1 = (y1f >= lo) && (y1f < hi);
+  const int xi0 = (int)x0f - pl.pad_lo, yi0 = (int)y0f - pl.pad_lo;
+  const int rs = pl.ps * 3;
+  float v00 = -2.0f, v01 = -2.0f, v10 = -2.0f, v11 = -2.0f;
+  if (by0 && bx0) v00 = clampf(__ldg(u + (int64_t)yi0 * rs + xi0 * 3 + c), -1.f, 1.f);
+  if (by0 && bx1) v01 = clampf(__ldg(u + (int64_t)yi0 * rs + (xi0 + 1) * 3 + c), -1.f, 1.f);
+  if (by1 && bx0) v10 = clampf(__ldg(u + (int64_t)(yi0 + 1) * rs + xi0 * 3 + c), -1.f, 1.f);
+  if (by1 && bx1) v11 = clampf(__ldg(u + (int64_t)(yi0 + 1) * rs + (xi0 + 1) * 3 + c), -1.f, 1.f);
+  const float wx1 = x1f - ix, wx0 = ix - x0f, wy1 = y1f - iy, wy0 = iy - y0f;
+  const float a = wx1 * v00 + wx0 * v01;
+  const float b = wx1 * v10 + wx0 * v11;
+  return wy1 * a + wy0 * b;
+}
+#endif  // __CUDACC__
+
+}  // namespace eot

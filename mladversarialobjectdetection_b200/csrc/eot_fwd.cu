@@ -1,0 +1,529 @@
+// Forward of the EOT patch application: Patcher.call / Masker.call
+// (reference: attacker.py:344-498, attack_detection.py:321-498, brightness_matcher.py:25-73).
+//
+// Kernels (all on the caller's stream, no host sync; ragged counts come in as CSR):
+//   k_patch_stats     mean Y of the print-adjusted patch, per image          (B x P^2, tiny)
+//   k_geometry        Patcher.create + area filter + int cast, span tables, work lists
+//   k_image_pass      ONE streaming pass over the batch: copy image -> out (128-bit I/O) while
+//                     accumulating mean Y of the target image               (the HBM-bound part)
+//   k_match           print adjust + brightness match -> matched patch per image
+//   k_resize          antialiased triangle resize (rows then columns, sequential float32
+//                     accumulation as ScaleAndTranslate) + noise + brightness delta -> u_j
+//   k_composite       per window element: projective bilinear sample of the padded u_j, `< -1`
+//                     mask, background select, clip, store (gather form of the sequential paste)
+#include "eot_common.cuh"
+
+#include <math.h>
+
+namespace eot {
+
+// ------------------------------------------------------------------------------------------------
+// geometry
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float centre_clamp(float c, float extent, float limit) {
+  float lo = fmaxf(c - extent / 2.0f, 0.0f);
+  if (lo + extent > limit) lo = limit - extent;
+  return lo;
+}
+
+// Patcher.create (attacker.py:448-488), area filter (:392-394), int cast (:418), pad split (:431-433),
+// rotation transform (tfa angles_to_projective_transforms) and its inverse.
+__device__ inline BoxPlan make_plan(const float* __restrict__ box, float shared_scale, const EotBoxParams& p,
+                                    const EotShape& s, int image, int first, int last, int64_t u_off,
+                                    int* err_flag) {
+  BoxPlan pl;
+  const float H = (float)s.height, W = (float)s.width;
+  const float ymin = box[0], xmin = box[1], ymax = box[2], xmax = box[3];
+  const float scale = p.scale >= 0.0f ? p.scale : shared_scale;
+  const float tol = s.tolerance;
+  const float h = ymax - ymin, w = xmax - xmin;
+  const float longer = fmaxf(h, w);
+  const float psf = floorf(longer * scale);
+  const float diag = fminf(EOT_SQRT2 * psf, W);
+  const float lo_y = (-tol * h) / 2.0f, hi_y = (tol * h) / 2.0f;
+  const float jy = p.uy * (hi_y - lo_y) + lo_y;
+  const float lo_x = (-tol * w) / 2.0f, hi_x = (tol * w) / 2.0f;
+  const float jx = p.ux * (hi_x - lo_x) + lo_x;
+  const float cy = (ymin + h / 2.0f) + jy;
+  const float cx = (xmin + w / 2.0f) + jx;
+  const float y0f = centre_clamp(cy, diag, H);
+  const float x0f = centre_clamp(cx, diag, W);
+  pl.valid = (psf * psf > s.min_patch_area) ? 1 : 0;
+  pl.y0 = (int)y0f;
+  pl.x0 = (int)x0f;
+  pl.ps = (int)psf;
+  pl.d = (int)diag;
+  const int off2 = pl.d - pl.ps;
+  pl.pad_lo = off2 >= 0 ? off2 / 2 : -((-off2 + 1) / 2);   // floor((d-ps)/2)
+  pl.pad_hi = off2 - pl.pad_lo;                            // ceil((d-ps)/2)
+  pl.span = 0;
+  pl.image = image;
+  pl.first_box = first;
+  pl.last_box = last;
+  pl.u_off = u_off;
+  pl.delta = p.delta;
+  pl.key0 = p.key0;
+  pl.key1 = p.key1;
+  if (pl.valid) {
+    const Layout L = make_layout(s);
+    const bool bad = !(psf == psf) || pl.y0 < 0 || pl.x0 < 0 || pl.y0 + pl.d > s.height || pl.x0 + pl.d > s.width ||
+                     pl.d < pl.ps || pl.ps > L.lmin;
+    if (bad) {   // TF would fail in tf.pad / tensor_scatter_nd_update; we skip the box and flag it
+      pl.valid = 0;
+      if (err_flag) atomicExch(err_flag, 1);
+    }
+  }
+  const float c = p.cos_t, sn = p.sin_t;
+  const float wm1 = (float)(pl.d - 1), hm1 = (float)(pl.d - 1);
+  pl.T[0] = c;
+  pl.T[1] = -sn;
+  pl.T[2] = (wm1 - (c * wm1 - sn * hm1)) / 2.0f;
+  pl.T[3] = sn;
+  pl.T[4] = c;
+  pl.T[5] = (hm1 - (sn * wm1 + c * hm1)) / 2.0f;
+  pl.T[6] = p.pa;
+  pl.T[7] = p.pb;
+  {  // inverse by the adjugate in float64, rounded once (image_ops.py: _image_projective_transform_v3_grad)
+    const double a = pl.T[0], b = pl.T[1], cc = pl.T[2], d = pl.T[3], e = pl.T[4], f = pl.T[5], g = pl.T[6], hh = pl.T[7];
+    const double A = e - f * hh, Bm = -(d - f * g), C = d * hh - e * g;
+    const double Dm = -(b - cc * hh), E = a - cc * g, Fm = -(a * hh - b * g);
+    const double G = b * f - cc * e, Hm = -(a * f - cc * d), I = a * e - b * d;
+    pl.Ti[0] = (float)(A / I);  pl.Ti[1] = (float)(Dm / I); pl.Ti[2] = (float)(G / I);
+    pl.Ti[3] = (float)(Bm / I); pl.Ti[4] = (float)(E / I);  pl.Ti[5] = (float)(Hm / I);
+    pl.Ti[6] = (float)(C / I);  pl.Ti[7] = (float)(Fm / I);
+  }
+  return pl;
+}
+
+// ScaleAndTranslate ComputeSpansCore (triangle kernel, antialias) for one output index.
+struct SpanCfg { float inv_scale, ks, one_over; int span; };
+__device__ __forceinline__ SpanCfg span_cfg(int out_size, int in_size) {
+  SpanCfg c;
+  const float scale = (float)out_size / (float)in_size;
+  c.inv_scale = (float)(1.0 / (double)scale);
+  c.ks = fmaxf(c.inv_scale, 1.0f);
+  int span = 2 * (int)ceilf(1.0f * c.ks) + 1;
+  c.span = span < in_size ? span : in_size;
+  c.one_over = 1.0f / c.ks;
+  return c;
+}
+__device__ __forceinline__ float tri_weight(int src, float sample_f, float one_over) {
+  const float kernel_pos = ((float)src + 0.5f) - sample_f;
+  const float a = fabsf(kernel_pos * one_over);
+  return a < 1.0f ? 1.0f - a : 0.0f;
+}
+__device__ inline void span_row(int o, const SpanCfg& c, int in_size, int* start_out, float* __restrict__ w_out) {
+  const float col_f = (float)o + 0.5f;
+  const float sample_f = col_f * c.inv_scale + (-c.inv_scale * 0.0f);
+  if (sample_f < 0.0f || sample_f > (float)in_size) {
+    *start_out = 0;
+    for (int k = 0; k < c.span; ++k) w_out[k] = 0.0f;
+    return;
+  }
+  long long s0 = (long long)ceilf((sample_f - c.ks) - 0.5f);
+  long long s1 = (long long)floorf((sample_f + c.ks) - 0.5f);
+  s0 = s0 < 0 ? 0 : (s0 > in_size - 1 ? in_size - 1 : s0);
+  s1 = (s1 < 0 ? 0 : (s1 > in_size - 1 ? in_size - 1 : s1)) + 1;
+  int n = (int)(s1 - s0);
+  if (n > c.span) n = c.span;
+  float total = 0.0f;
+  for (int k = 0; k < n; ++k) total = total + tri_weight((int)s0 + k, sample_f, c.one_over);
+  const bool ok = fabsf(total) >= 1000.0f * 1.17549435e-38f;
+  const float inv_total = ok ? 1.0f / total : 0.0f;
+  for (int k = 0; k < c.span; ++k)
+    w_out[k] = (k < n && ok) ? tri_weight((int)s0 + k, sample_f, c.one_over) * inv_total : 0.0f;
+  *start_out = (int)s0;
+}
+
+__global__ void __launch_bounds__(128) k_geometry(EotShape s, Layout L, const float* __restrict__ boxes,
+                                                   const int32_t* __restrict__ offsets,
+                                                   const EotBoxParams* __restrict__ params,
+                                                   const float* __restrict__ scale, char* ws,
+                                                   EotBoxGeometry* geom_out) {
+  const int b = blockIdx.x;
+  const int first = offsets[b], last = offsets[b + 1];
+  BoxPlan* plans = ws ? reinterpret_cast<BoxPlan*>(ws + L.off_plans) : nullptr;
+  int* counters = ws ? reinterpret_cast<int*>(ws + L.off_counters) : nullptr;
+  const float sc = *scale;
+  for (int j = first + threadIdx.x; j < last; j += blockDim.x) {
+    BoxPlan pl = make_plan(boxes + (size_t)j * 4, sc, params[j], s, b, first, last, (int64_t)j * L.slot,
+                           counters ? counters + 2 : nullptr);
+    if (pl.valid) pl.span = span_cfg(pl.ps, s.patch_size).span;
+    if (plans) plans[j] = pl;
+    if (geom_out) {
+      EotBoxGeometry g = {pl.y0, pl.x0, pl.ps, pl.d, pl.pad_lo, pl.pad_hi, pl.valid, pl.span};
+      geom_out[j] = g;
+    }
+  }
+  if (!ws) return;
+  __syncthreads();
+  int* starts = reinterpret_cast<int*>(ws + L.off_starts);
+  float* weights = reinterpret_cast<float*>(ws + L.off_weights);
+  int2* items_r = reinterpret_cast<int2*>(ws + L.off_items_resize);
+  int2* items_c = reinterpret_cast<int2*>(ws + L.off_items_comp);
+  __shared__ int base_r, base_c;
+  for (int j = first; j < last; ++j) {
+    const BoxPlan& pl = plans[j];
+    if (!pl.valid) continue;
+    const SpanCfg cfg = span_cfg(pl.ps, s.patch_size);
+    for (int o = threadIdx.x; o < pl.ps; o += blockDim.x)
+      span_row(o, cfg, s.patch_size, starts + (size_t)j * L.lmin + o, weights + (size_t)j * L.wcap + (size_t)o * cfg.span);
+    const int nres = (pl.ps + kResizeRows - 1) / kResizeRows;
+    const int ncomp = (pl.d * pl.d * 3 + kCompChunk - 1) / kCompChunk;
+    if (threadIdx.x == 0) {
+      base_r = atomicAdd(counters + 0, nres);
+      base_c = atomicAdd(counters + 1, ncomp);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nres; i += blockDim.x) items_r[base_r + i] = make_int2(j, i);
+    for (int i = threadIdx.x; i < ncomp; i += blockDim.x) items_c[base_c + i] = make_int2(j, i);
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// patch luma statistics: mean Y of rescale(print_adjust(patch)) per image
+// (attacker.py:372 -> brightness_matcher.py:54,58,62-63)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_patch_stats(EotShape s, const float* __restrict__ patch,
+                                                          const float* __restrict__ print_wb, double* ysum_patch) {
+  __shared__ double red[32];
+  const int b = blockIdx.y;
+  const int P = s.patch_size;
+  const float* wb = print_wb + (size_t)b * 6;
+  const float* base = patch + (s.num_patches > 1 ? (int64_t)b * s.patch_stride_n : 0);
+  double acc = 0.0;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < P * P; t += gridDim.x * blockDim.x) {
+    const int py = t / P, px = t - py * P;
+    const float* p = base + (int64_t)py * s.patch_stride_y + (int64_t)px * s.patch_stride_x;
+    acc += (double)texel_yuv(__ldg(p), __ldg(p + 1), __ldg(p + 2), wb).y;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(ysum_patch + b, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// image pass: out = image (128-bit loads/stores, 4 pixels = 3 x float4 per thread per step) and
+// sum of Y over the image (brightness_matcher.py:55,59,62,64) in float64.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPassPixPerThread = 16;   // 4 steps of 4 pixels
+constexpr int kPassPixPerBlock = kThreads * kPassPixPerThread;
+
+__device__ __forceinline__ float luma_of(float r, float g, float b) {
+  const float t0 = (r + 1.0f) * EOT_C127_255, t1 = (g + 1.0f) * EOT_C127_255, t2 = (b + 1.0f) * EOT_C127_255;
+  return (t0 * EOT_K00 + t1 * EOT_K10) + t2 * EOT_K20;
+}
+
+template <bool kVec>
+__global__ void __launch_bounds__(kThreads) k_image_pass(int HW, const float* __restrict__ images, float* out,
+                                                         float* mask, double* ysum_img) {
+  __shared__ double red[32];
+  const int b = blockIdx.y;
+  const size_t img_off = (size_t)b * HW * 3;
+  const float* in = images + img_off;
+  float* o = (out && out != images) ? out + img_off : nullptr;
+  float* mk = mask ? mask + img_off : nullptr;
+  double acc = 0.0;
+  const int pix0 = blockIdx.x * kPassPixPerBlock;
+  if (kVec) {
+    const float4* in4 = reinterpret_cast<const float4*>(in);
+    float4* o4 = reinterpret_cast<float4*>(o);
+    float4* m4 = reinterpret_cast<float4*>(mk);
+    float4 v[kPassPixPerThread / 4][3];
+#pragma unroll
+    for (int st = 0; st < kPassPixPerThread / 4; ++st) {
+      const int pix = pix0 + (st * kThreads + threadIdx.x) * 4;
+      if (pix < HW) {
+        const int q = (pix >> 2) * 3;
+        v[st][0] = __ldg(in4 + q);
+        v[st][1] = __ldg(in4 + q + 1);
+        v[st][2] = __ldg(in4 + q + 2);
+      }
+    }
+#pragma unroll
+    for (int st = 0; st < kPassPixPerThread / 4; ++st) {
+      const int pix = pix0 + (st * kThreads + threadIdx.x) * 4;
+      if (pix < HW) {
+        const int q = (pix >> 2) * 3;
+        const float4 a = v[st][0], bb = v[st][1], c = v[st][2];
+        if (o) { o4[q] = a; o4[q + 1] = bb; o4[q + 2] = c; }
+        if (mk) { const float4 z = make_float4(0.f, 0.f, 0.f, 0.f); m4[q] = z; m4[q + 1] = z; m4[q + 2] = z; }
+        acc += (double)luma_of(a.x, a.y, a.z);
+        acc += (double)luma_of(a.w, bb.x, bb.y);
+        acc += (double)luma_of(bb.z, bb.w, c.x);
+        acc += (double)luma_of(c.y, c.z, c.w);
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < kPassPixPerBlock; i += kThreads) {
+      const int pix = pix0 + i;
+      if (pix < HW) {
+        const float r = in[(size_t)pix * 3], g = in[(size_t)pix * 3 + 1], bl = in[(size_t)pix * 3 + 2];
+        if (o) { o[(size_t)pix * 3] = r; o[(size_t)pix * 3 + 1] = g; o[(size_t)pix * 3 + 2] = bl; }
+        if (mk) { mk[(size_t)pix * 3] = 0.f; mk[(size_t)pix * 3 + 1] = 0.f; mk[(size_t)pix * 3 + 2] = 0.f; }
+        acc += (double)luma_of(r, g, bl);
+      }
+    }
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(ysum_img + b, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// print adjust + brightness match of the patch for image b (attacker.py:372; brightness_matcher.py:43-73)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_match(EotShape s, Layout L, const float* __restrict__ patch,
+                                                    const float* __restrict__ print_wb, char* ws) {
+  const int b = blockIdx.y;
+  const int P = s.patch_size;
+  const double* ysum_img = reinterpret_cast<const double*>(ws + L.off_ysum_img);
+  const double* ysum_patch = reinterpret_cast<const double*>(ws + L.off_ysum_patch);
+  const float mu_t = (float)(ysum_img[b] / (double)((size_t)s.height * s.width));
+  const float mu_s = (float)(ysum_patch[b] / (double)((size_t)P * P));
+  const float* wb = print_wb + (size_t)b * 6;
+  const float* base = patch + (s.num_patches > 1 ? (int64_t)b * s.patch_stride_n : 0);
+  float* m = reinterpret_cast<float*>(ws + L.off_match) + (size_t)b * P * P * 3;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < P * P; t += gridDim.x * blockDim.x) {
+    const int py = t / P, px = t - py * P;
+    const float* p = base + (int64_t)py * s.patch_stride_y + (int64_t)px * s.patch_stride_x;
+    const TexelYuv y = texel_yuv(__ldg(p), __ldg(p + 1), __ldg(p + 2), wb);
+    const float yp = clampf((y.y - mu_s) + mu_t, 0.0f, 1.0f);
+    // rgb = [Y',U,V] . K'  as ((Y'*K'0c + U*K'1c) + V*K'2c)
+    const float r = (yp * 1.0f + y.u * EOT_I10) + y.v * EOT_I20;
+    const float g = (yp * 1.0f + y.u * EOT_I11) + y.v * EOT_I21;
+    const float bl = (yp * 1.0f + y.u * EOT_I12) + y.v * EOT_I22;
+    m[(size_t)t * 3 + 0] = clampf(r, 0.0f, 1.0f) * EOT_C255_127 - 1.0f;
+    m[(size_t)t * 3 + 1] = clampf(g, 0.0f, 1.0f) * EOT_C255_127 - 1.0f;
+    m[(size_t)t * 3 + 2] = clampf(bl, 0.0f, 1.0f) * EOT_C255_127 - 1.0f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// resize + noise + delta for one strip of kResizeRows output rows of one box
+// (attacker.py:425-427; ScaleAndTranslate GatherRows then GatherColumns)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_resize(EotShape s, Layout L, char* ws) {
+  extern __shared__ float inter[];   // [kResizeRows][P*3]
+  const int P = s.patch_size, P3 = P * 3;
+  const BoxPlan* plans = reinterpret_cast<const BoxPlan*>(ws + L.off_plans);
+  const int2* items = reinterpret_cast<const int2*>(ws + L.off_items_resize);
+  const int n_items = reinterpret_cast<const int*>(ws + L.off_counters)[0];
+  const float* match = reinterpret_cast<const float*>(ws + L.off_match);
+  float* ubuf = reinterpret_cast<float*>(ws + L.off_u);
+  for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    const int2 item = items[it];
+    const int j = item.x;
+    const BoxPlan* pl = plans + j;
+    const int ps = pl->ps, span = pl->span;
+    const float delta = pl->delta;
+    const uint32_t key0 = pl->key0, key1 = pl->key1;
+    const int oy0 = item.y * kResizeRows;
+    const int rows = min(kResizeRows, ps - oy0);
+    const float* m = match + (size_t)pl->image * P * P3;
+    const int* starts = reinterpret_cast<const int*>(ws + L.off_starts) + (size_t)j * L.lmin;
+    const float* wts = reinterpret_cast<const float*>(ws + L.off_weights) + (size_t)j * L.wcap;
+    float* u = ubuf + pl->u_off;
+    for (int idx = threadIdx.x; idx < rows * P3; idx += blockDim.x) {
+      const int r = idx / P3, f = idx - r * P3;
+      const int oy = oy0 + r;
+      const int st = starts[oy];
+      const float* w = wts + (size_t)oy * span;
+      const int nk = min(span, P - st);
+      float acc = 0.0f;
+      for (int k = 0; k < nk; ++k) acc = acc + w[k] * __ldg(m + (size_t)(st + k) * P3 + f);
+      inter[idx] = acc;
+    }
+    __syncthreads();
+    const int e_begin = oy0 * ps * 3, e_end = (oy0 + rows) * ps * 3;
+    for (int g = e_begin / 4 + threadIdx.x; g < (e_end + 3) / 4; g += blockDim.x) {
+      const uint4 rnd = philox4x32_10((uint32_t)g, key0, key1);
+      const uint32_t words[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int e = g * 4 + q;
+        if (e < e_begin || e >= e_end) continue;
+        const int pix = e / 3, c = e - pix * 3;
+        const int oy = pix / ps, ox = pix - oy * ps;
+        const int r = oy - oy0;
+        const int st = starts[ox];
+        const float* w = wts + (size_t)ox * span;
+        const int nk = min(span, P - st);
+        float acc = 0.0f;
+        for (int k = 0; k < nk; ++k) acc = acc + w[k] * inter[r * P3 + (st + k) * 3 + c];
+        u[e] = (acc + noise_from_word(words[q], s.noise_amp)) + delta;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// composite (attacker.py:436-444 in gather form).  Sequential-paste semantics: an element's final
+// value is clip(R_j) of the LAST box j (in paste order) covering it with R_j >= -1, else
+// clip(original); elements outside every window are untouched by this kernel.  An element covered by
+// several windows is written only by the items of the last covering box.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxSmemPlans = 48;
+
+__global__ void __launch_bounds__(kThreads) k_composite(EotShape s, Layout L, char* ws,
+                                                        const float* __restrict__ images, float* out, float* mask) {
+  __shared__ BoxPlan sp[kMaxSmemPlans];
+  const BoxPlan* plans = reinterpret_cast<const BoxPlan*>(ws + L.off_plans);
+  const int2* items = reinterpret_cast<const int2*>(ws + L.off_items_comp);
+  const int n_items = reinterpret_cast<const int*>(ws + L.off_counters)[1];
+  const float* ubuf = reinterpret_cast<const float*>(ws + L.off_u);
+  const int H = s.height, W = s.width;
+  for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    const int2 item = items[it];
+    const int j = item.x;
+    const int first = plans[j].first_box, last = plans[j].last_box;
+    const int nb = last - first;
+    const BoxPlan* pp;
+    if (nb <= kMaxSmemPlans) {
+      const int4* src = reinterpret_cast<const int4*>(plans + first);
+      int4* dst = reinterpret_cast<int4*>(sp);
+      for (int i = threadIdx.x; i < nb * (int)(sizeof(BoxPlan) / 16); i += blockDim.x) dst[i] = src[i];
+      __syncthreads();
+      pp = sp;
+    } else {
+      pp = plans + first;
+    }
+    const int jl = j - first;
+    const BoxPlan& me = pp[jl];
+    const int D = me.d, D3 = D * 3;
+    const int total = D * D3;
+    const int i_end = min(total, (item.y + 1) * kCompChunk);
+    for (int i = item.y * kCompChunk + threadIdx.x; i < i_end; i += blockDim.x) {
+      const int y = i / D3, rem = i - y * D3;
+      const int x = rem / 3, c = rem - x * 3;
+      const int gy = me.y0 + y, gx = me.x0 + x;
+      bool owned = true;
+      for (int q = jl + 1; q < nb; ++q) {
+        const BoxPlan& o = pp[q];
+        if (o.valid && gy >= o.y0 && gy < o.y0 + o.d && gx >= o.x0 && gx < o.x0 + o.d) { owned = false; break; }
+      }
+      if (!owned) continue;
+      const size_t gidx = (((size_t)me.image * H + gy) * W + gx) * 3 + c;
+      const float orig = __ldg(images + gidx);
+      float v = orig;
+      for (int q = jl; q >= 0; --q) {
+        const BoxPlan& o = pp[q];
+        if (!o.valid) continue;
+        const int ly = gy - o.y0, lx = gx - o.x0;
+        if (ly < 0 || ly >= o.d || lx < 0 || lx >= o.d) continue;
+        const float R = warp_sample(o, ubuf + o.u_off, lx, ly, c);
+        if (!(R < -1.0f)) { v = R; break; }
+      }
+      v = clampf(v, -1.0f, 1.0f);
+      out[gidx] = v;
+      if (mask) mask[gidx] = orig - v;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host entry points
+// ------------------------------------------------------------------------------------------------
+static int check_shape(const EotShape* s) {
+  if (!s) { set_error("shape is NULL"); return EOT_ERR_NULL_POINTER; }
+  if (s->batch <= 0 || s->height <= 0 || s->width <= 0 || s->patch_size <= 0 || s->total_boxes < 0 ||
+      (s->num_patches != 1 && s->num_patches != s->batch)) {
+    set_error("bad shape: batch=%d H=%d W=%d P=%d num_patches=%d N=%d", s->batch, s->height, s->width,
+              s->patch_size, s->num_patches, s->total_boxes);
+    return EOT_ERR_BAD_SHAPE;
+  }
+  if ((int64_t)s->height * s->width * 3 >= (int64_t)1 << 31) { set_error("image too large for int32 indexing"); return EOT_ERR_BAD_SHAPE; }
+  return EOT_OK;
+}
+
+static EotShape normalised(const EotShape& in) {
+  EotShape s = in;
+  if (s.patch_stride_x == 0) s.patch_stride_x = 3;
+  if (s.patch_stride_y == 0) s.patch_stride_y = (int64_t)s.patch_size * 3;
+  if (s.patch_stride_n == 0) s.patch_stride_n = (int64_t)s.patch_size * s.patch_size * 3;
+  return s;
+}
+
+}  // namespace eot
+
+using namespace eot;
+
+extern "C" int eot_workspace_bytes(const EotShape* shape, size_t* bytes) {
+  if (int rc = check_shape(shape)) return rc;
+  if (!bytes) { set_error("bytes is NULL"); return EOT_ERR_NULL_POINTER; }
+  *bytes = make_layout(*shape).total;
+  return EOT_OK;
+}
+
+extern "C" int eot_box_geometry(const EotShape* shape, const float* boxes, const int32_t* box_offsets,
+                                const EotBoxParams* params, const float* scale, EotBoxGeometry* geometry_out,
+                                void* stream) {
+  if (int rc = check_shape(shape)) return rc;
+  if (!box_offsets || !scale || !geometry_out || (shape->total_boxes > 0 && (!boxes || !params))) {
+    set_error("eot_box_geometry: NULL pointer");
+    return EOT_ERR_NULL_POINTER;
+  }
+  const EotShape s = normalised(*shape);
+  k_geometry<<<s.batch, 128, 0, (cudaStream_t)stream>>>(s, make_layout(s), boxes, box_offsets, params, scale, nullptr, geometry_out);
+  EOT_CHECK_CUDA(cudaPeekAtLastError());
+  return EOT_OK;
+}
+
+extern "C" int eot_apply_fwd(const EotShape* shape, const float* patch, const float* scale, const float* images,
+                             const float* boxes, const int32_t* box_offsets, const EotBoxParams* params,
+                             const float* print_wb, float* out_images, float* out_masks, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  if (int rc = check_shape(shape)) return rc;
+  if (!patch || !scale || !images || !box_offsets || !print_wb || !out_images || !workspace ||
+      (shape->total_boxes > 0 && (!boxes || !params))) {
+    set_error("eot_apply_fwd: NULL pointer");
+    return EOT_ERR_NULL_POINTER;
+  }
+  const bool want_mask = (shape->flags & EOT_FLAG_MASK_OUTPUT) != 0;
+  if (want_mask && !out_masks) { set_error("EOT_FLAG_MASK_OUTPUT set but out_masks is NULL"); return EOT_ERR_NULL_POINTER; }
+  const EotShape s = normalised(*shape);
+  const Layout L = make_layout(s);
+  if (workspace_bytes < L.total) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes, L.total);
+    return EOT_ERR_WORKSPACE_TOO_SMALL;
+  }
+  if (((uintptr_t)workspace & 255) != 0) { set_error("workspace must be 256-byte aligned"); return EOT_ERR_MISALIGNED; }
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = static_cast<char*>(workspace);
+  float* mask = want_mask ? out_masks : nullptr;
+  const int B = s.batch, P = s.patch_size, HW = s.height * s.width;
+
+  EOT_CHECK_CUDA(cudaMemsetAsync(ws + L.off_ysum_img, 0, L.off_plans - L.off_ysum_img, st));
+  const int pchunks = max(1, min((P * P + kThreads * 4 - 1) / (kThreads * 4), 64));
+  k_patch_stats<<<dim3(pchunks, B), kThreads, 0, st>>>(s, patch, print_wb, reinterpret_cast<double*>(ws + L.off_ysum_patch));
+  k_geometry<<<B, 128, 0, st>>>(s, L, boxes, box_offsets, params, scale, ws, nullptr);
+  const dim3 pgrid((HW + kPassPixPerBlock - 1) / kPassPixPerBlock, B);
+  const bool vec = (HW % 4 == 0) && (((uintptr_t)images | (uintptr_t)out_images | (uintptr_t)(mask ? mask : out_images)) & 15) == 0;
+  if (vec)
+    k_image_pass<true><<<pgrid, kThreads, 0, st>>>(HW, images, out_images, mask, reinterpret_cast<double*>(ws + L.off_ysum_img));
+  else
+    k_image_pass<false><<<pgrid, kThreads, 0, st>>>(HW, images, out_images, mask, reinterpret_cast<double*>(ws + L.off_ysum_img));
+  if (s.total_boxes > 0) {
+    k_match<<<dim3(pchunks, B), kThreads, 0, st>>>(s, L, patch, print_wb, ws);
+    const int nsm = sm_count();
+    const size_t smem = (size_t)kResizeRows * P * 3 * sizeof(float);
+    if (smem > 48 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_resize<<<nsm * 4, kThreads, smem, st>>>(s, L, ws);
+    k_composite<<<nsm * 8, kThreads, 0, st>>>(s, L, ws, images, out_images, mask);
+  }
+  EOT_CHECK_CUDA(cudaPeekAtLastError());
+  return EOT_OK;
+}
+
+extern "C" int eot_check_workspace(const EotShape* shape, const void* workspace, void* stream) {
+  if (int rc = check_shape(shape)) return rc;
+  if (!workspace) { set_error("workspace is NULL"); return EOT_ERR_NULL_POINTER; }
+  const Layout L = make_layout(normalised(*shape));
+  int flag = 0;
+  EOT_CHECK_CUDA(cudaMemcpyAsync(&flag, static_cast<const char*>(workspace) + L.off_counters + 2 * sizeof(int), sizeof(int),
+                                 cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  EOT_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  if (flag) { set_error("a patch window did not fit the image (the reference would fail in tf.pad / scatter)"); return EOT_ERR_GEOMETRY; }
+  return EOT_OK;
+}

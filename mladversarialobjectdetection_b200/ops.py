@@ -1,0 +1,264 @@
+"""Functional layer over the C ABI: torch tensors in, torch tensors out, zero-copy (data_ptr + the
+current CUDA stream).  PyTorch only provides device memory and streams here; all arithmetic of the
+hot path runs in libeotpatch.so.  Everything raises if the input is not on a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import EotShape, ScoreShape
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("the EOT patch path runs on CUDA only (no CPU fallback); got a CPU tensor")
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def params_to_tensor(params: np.ndarray, device) -> torch.Tensor:
+    """[N] EotBoxParams records (numpy structured, 48 B each) -> uint8 device tensor [N,48]."""
+    raw = np.ascontiguousarray(params).view(np.uint8).reshape(-1, 48)
+    return torch.from_numpy(raw.copy()).to(device, non_blocking=True)
+
+
+@dataclass
+class PatchGeometry:
+    """Shapes / hyper-parameters of one Patcher or Masker call."""
+    tolerance: float = 0.2          # attacker.py:465
+    noise_amp: float = 0.01         # attacker.py:426
+    min_patch_area: float = 4.0     # attacker.py:347
+    max_scale: float = 1.0
+
+
+def _shape(images: torch.Tensor, patch: torch.Tensor, n_boxes: int, g: PatchGeometry, want_mask: bool) -> EotShape:
+    B, H, W, C = images.shape
+    if C != 3:
+        raise ValueError("images must be [B,H,W,3]")
+    s = EotShape()
+    s.batch, s.height, s.width = B, H, W
+    if patch.dim() == 3:
+        P, P2, c = patch.shape
+        s.num_patches = 1
+        sn, sy, sx, sc = 0, patch.stride(0), patch.stride(1), patch.stride(2)
+    elif patch.dim() == 4:
+        n, P, P2, c = patch.shape
+        if n != B:
+            raise ValueError("per-image patches must be [B,P,P,3]")
+        s.num_patches = B
+        sn, sy, sx, sc = patch.stride()
+    else:
+        raise ValueError("patch must be [P,P,3] or [B,P,P,3]")
+    if P != P2 or c != 3 or sc != 1:
+        raise ValueError("patch must be square, 3-channel, with unit channel stride")
+    s.patch_size = P
+    s.total_boxes = n_boxes
+    s.flags = _lib.EOT_FLAG_MASK_OUTPUT if want_mask else 0
+    s.tolerance, s.noise_amp, s.min_patch_area, s.max_scale = g.tolerance, g.noise_amp, g.min_patch_area, g.max_scale
+    s.patch_stride_n, s.patch_stride_y, s.patch_stride_x = sn, sy, sx
+    return s
+
+
+def workspace_bytes(shape: EotShape) -> int:
+    n = ctypes.c_size_t(0)
+    _lib.check(_lib.load().eot_workspace_bytes(ctypes.byref(shape), ctypes.byref(n)), "eot_workspace_bytes")
+    return int(n.value)
+
+
+def box_geometry(images_shape: Tuple[int, int, int, int], patch_size: int, boxes: torch.Tensor,
+                 offsets: torch.Tensor, params: torch.Tensor, scale: torch.Tensor,
+                 g: PatchGeometry = PatchGeometry()) -> torch.Tensor:
+    """`Patcher.create` + area filter + int cast for all boxes -> int32 [N,8]
+    (y0,x0,ps,d,pad_lo,pad_hi,valid,span).  Reference: attacker.py:392-394,418,448-488."""
+    _need_cuda(boxes, offsets, params, scale)
+    B, H, W, _ = images_shape
+    s = EotShape()
+    s.batch, s.height, s.width, s.patch_size, s.num_patches = B, H, W, patch_size, 1
+    s.total_boxes = int(boxes.shape[0])
+    s.tolerance, s.noise_amp, s.min_patch_area, s.max_scale = g.tolerance, g.noise_amp, g.min_patch_area, g.max_scale
+    out = torch.zeros((s.total_boxes, 8), dtype=torch.int32, device=boxes.device)
+    _lib.check(_lib.load().eot_box_geometry(ctypes.byref(s), _ptr(_f32c(boxes, "boxes")), _ptr(offsets), _ptr(params),
+                                            _ptr(scale), _ptr(out), _stream()), "eot_box_geometry")
+    return out
+
+
+@dataclass
+class ApplyContext:
+    """What eot_apply_bwd needs from the forward call (the 'saved tensors')."""
+    shape: EotShape
+    workspace: torch.Tensor
+    patch: torch.Tensor
+    print_wb: torch.Tensor
+
+
+def apply_forward(patch: torch.Tensor, scale: torch.Tensor, images: torch.Tensor, boxes: torch.Tensor,
+                  offsets: torch.Tensor, params: torch.Tensor, print_wb: torch.Tensor,
+                  g: PatchGeometry = PatchGeometry(), *, want_mask: bool = False,
+                  out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None):
+    """`Patcher.call` / `Masker.call` on the GPU (attacker.py:490-498, attack_detection.py:478-498).
+
+    boxes [N,4] + offsets [B+1] int32 are the CSR form of the reference's ragged boxes; params is the
+    uint8 [N,48] EotBoxParams tensor; print_wb [B,6]; scale a 0-d/1-element float32 device tensor.
+    Returns (out_images, out_masks|None, ApplyContext)."""
+    _need_cuda(patch, scale, images, boxes, offsets, params, print_wb)
+    images = _f32c(images, "images")
+    print_wb = _f32c(print_wb, "print_wb")
+    boxes = _f32c(boxes, "boxes")
+    if patch.dtype != torch.float32:
+        raise TypeError("patch must be float32")
+    if offsets.dtype != torch.int32 or offsets.numel() != images.shape[0] + 1:
+        raise ValueError("offsets must be int32 [B+1]")
+    n_boxes = int(boxes.shape[0])
+    shape = _shape(images, patch, n_boxes, g, want_mask)
+    need = workspace_bytes(shape)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=images.device)
+    if out is None:
+        out = torch.empty_like(images)
+    mask = torch.empty_like(images) if want_mask else None
+    _lib.check(_lib.load().eot_apply_fwd(ctypes.byref(shape), _ptr(patch), _ptr(scale), _ptr(images), _ptr(boxes),
+                                         _ptr(offsets), _ptr(params), _ptr(print_wb), _ptr(out), _ptr(mask),
+                                         _ptr(workspace), ctypes.c_size_t(workspace.numel()), _stream()),
+               "eot_apply_fwd")
+    return out, mask, ApplyContext(shape, workspace, patch, print_wb)
+
+
+def apply_backward(ctx: ApplyContext, grad_images: torch.Tensor, *, grad_patch: Optional[torch.Tensor] = None,
+                   accumulate: bool = False) -> torch.Tensor:
+    """dL/dpatch [P,P,3] from dL/d(out_images) (attacker.py:217)."""
+    _need_cuda(grad_images)
+    if ctx.shape.num_patches != 1:
+        raise ValueError("the backward exists for the shared adversarial patch only (Masker carries no gradient)")
+    grad_images = _f32c(grad_images, "grad_images")
+    P = ctx.shape.patch_size
+    if grad_patch is None:
+        grad_patch = torch.empty((P, P, 3), dtype=torch.float32, device=grad_images.device)
+        accumulate = False
+    patch = ctx.patch if ctx.patch.is_contiguous() else ctx.patch.contiguous()
+    _lib.check(_lib.load().eot_apply_bwd(ctypes.byref(ctx.shape), _ptr(patch), _ptr(ctx.print_wb), _ptr(grad_images),
+                                         _ptr(ctx.workspace), ctypes.c_size_t(ctx.workspace.numel()),
+                                         _ptr(grad_patch), int(bool(accumulate)), _stream()), "eot_apply_bwd")
+    return grad_patch
+
+
+def check_workspace(ctx: ApplyContext) -> None:
+    """Synchronising check that every valid box fitted the image (tests / debugging)."""
+    _lib.check(_lib.load().eot_check_workspace(ctypes.byref(ctx.shape), _ptr(ctx.workspace), _stream()),
+               "eot_check_workspace")
+
+
+# --------------------------------------------------------------------------------------------------
+# person-score objective
+# --------------------------------------------------------------------------------------------------
+def _score_shape(cls_levels: Sequence[torch.Tensor], num_classes: int, H: int, W: int, min_area: float) -> ScoreShape:
+    s = ScoreShape()
+    s.batch = cls_levels[0].shape[0]
+    s.num_levels = len(cls_levels)
+    s.num_classes = num_classes
+    per_loc = cls_levels[0].shape[-1] // num_classes
+    s.anchors_per_loc = per_loc
+    tot = 0
+    for i, c in enumerate(cls_levels):
+        if c.dim() != 4 or c.shape[-1] != per_loc * num_classes or c.shape[0] != s.batch:
+            raise ValueError("cls level tensors must be [B,h,w,anchors*classes]")
+        s.level_locs[i] = c.shape[1] * c.shape[2]
+        tot += c.shape[1] * c.shape[2]
+    s.total_anchors = tot * per_loc
+    s.image_height, s.image_width, s.min_area = float(H), float(W), float(min_area)
+    return s
+
+
+def _ptr_array(tensors: Sequence[torch.Tensor]):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+@dataclass
+class ScoreContext:
+    shape: ScoreShape
+    workspace: torch.Tensor
+    cls_levels: Sequence[torch.Tensor]
+    max_scores: torch.Tensor
+
+
+def score_max_forward(cls_levels: Sequence[torch.Tensor], box_levels: Sequence[torch.Tensor], anchors: torch.Tensor,
+                      image_hw: Tuple[int, int], *, num_classes: int = 90, min_area: float = 100.0):
+    """pre_nms (max-reduce) + person filter + valid filter + per-image max
+    (attacker.py:118-141,190; tf2/postprocess.py:104-156).  Levels are NHWC [B,h,w,9*C] / [B,h,w,36]."""
+    _need_cuda(anchors, *cls_levels, *box_levels)
+    cls_levels = [_f32c(c, "cls level") for c in cls_levels]
+    box_levels = [_f32c(b, "box level") for b in box_levels]
+    shape = _score_shape(cls_levels, num_classes, image_hw[0], image_hw[1], min_area)
+    if anchors.shape != (shape.total_anchors, 4):
+        raise ValueError(f"anchors must be [{shape.total_anchors},4], got {tuple(anchors.shape)}")
+    n = ctypes.c_size_t(0)
+    lib = _lib.load()
+    _lib.check(lib.score_workspace_bytes(ctypes.byref(shape), ctypes.byref(n)), "score_workspace_bytes")
+    dev = anchors.device
+    ws = torch.empty(int(n.value), dtype=torch.uint8, device=dev)
+    B = shape.batch
+    max_scores = torch.empty(B, dtype=torch.float32, device=dev)
+    argmax = torch.empty(B, dtype=torch.int32, device=dev)
+    ncand = torch.empty(B, dtype=torch.int32, device=dev)
+    _lib.check(lib.score_max_fwd(ctypes.byref(shape), _ptr_array(cls_levels), _ptr_array(box_levels),
+                                 _ptr(_f32c(anchors, "anchors")), _ptr(max_scores), _ptr(argmax), _ptr(ncand),
+                                 _ptr(ws), ctypes.c_size_t(ws.numel()), _stream()), "score_max_fwd")
+    return max_scores, argmax, ncand, ScoreContext(shape, ws, cls_levels, max_scores)
+
+
+def score_max_backward(ctx: ScoreContext, scale: torch.Tensor, *, want_loss: bool = True):
+    """Dense zero-filled dL/dcls per level + dL/dscale (+ data loss) for
+    loss = sum(M^2 + (M-scale)^2) (attacker.py:191,193)."""
+    dev = ctx.max_scores.device
+    dcls = [torch.empty_like(c) for c in ctx.cls_levels]
+    dscale = torch.empty((), dtype=torch.float32, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev) if want_loss else None
+    _lib.check(_lib.load().score_max_bwd(ctypes.byref(ctx.shape), _ptr_array(ctx.cls_levels), _ptr(ctx.max_scores),
+                                         _ptr(scale), _ptr_array(dcls), _ptr(dscale), _ptr(loss),
+                                         _ptr(ctx.workspace), ctypes.c_size_t(ctx.workspace.numel()), _stream()),
+               "score_max_bwd")
+    return dcls, dscale, loss
+
+
+# --------------------------------------------------------------------------------------------------
+# patch update
+# --------------------------------------------------------------------------------------------------
+def tv_grad_(patch: torch.Tensor, grad_patch: torch.Tensor, weight: float = 1e-5, want_tv: bool = True):
+    """grad_patch += weight * dTV/dpatch (attacker.py:192-193); returns TV(patch) as a device scalar."""
+    _need_cuda(patch, grad_patch)
+    tv = torch.empty((), dtype=torch.float32, device=patch.device) if want_tv else None
+    _lib.check(_lib.load().patch_tv_grad(_ptr(_f32c(patch, "patch")), patch.shape[0], ctypes.c_float(weight),
+                                         _ptr(grad_patch), _ptr(tv), _stream()), "patch_tv_grad")
+    return tv
+
+
+def adam_clip_(var: torch.Tensor, m: torch.Tensor, v: torch.Tensor, grad: torch.Tensor, step: int, *, lr: float,
+               lo: float, hi: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-7) -> None:
+    """Keras Adam update + clip constraint in one kernel (attacker_train.py:38, attacker.py:51-54,315)."""
+    _need_cuda(var, m, v, grad)
+    for t in (var, m, v, grad):
+        if not t.is_contiguous() or t.dtype != torch.float32:
+            raise ValueError("adam_clip_ needs contiguous float32 tensors")
+    _lib.check(_lib.load().adam_clip_update(_ptr(var), _ptr(m), _ptr(v), _ptr(grad), var.numel(), lr, beta1, beta2,
+                                            eps, step, lo, hi, _stream()), "adam_clip_update")
