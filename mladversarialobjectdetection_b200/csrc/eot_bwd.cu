@@ -1,5 +1,275 @@
+// Backward of the EOT patch application: dL/d(out_images) -> dL/dpatch
+// (reference: tape.gradient at attacker.py:217; chain of SURVEY.md section 3.2 / App. D).
+//
+//   k_bwd_window   per transformed-patch texel: TF's registered gradient of
+//                  ImageProjectiveTransformV3 (the SAME bilinear warp applied to the gradient with
+//                  the inverted transform, fill 0), reading dL/d(window) on the fly with the
+//                  TensorScatterUpdate / clip / SelectV2 routing evaluated per tap; then the inner
+//                  clip mask of attacker.py:428.  -> g_u[box]
+//   k_bwd_resize   exact transpose of the antialiased resize (ScaleAndTranslateGrad), one CTA per
+//                  (image, strip of patch rows) looping over the image's boxes, accumulating in a
+//                  shared-memory patch-gradient tile (no global atomics); then the first half of the
+//                  BrightnessMatcher backward (clip mask, K'^T) and the per-image sum of dL/dY
+//                  (warp-shuffle tree + one atomic per CTA).
+//   k_bwd_texel    second half: subtract the per-image mean of dL/dY, K^T, rescale, print-adjust
+//                  clip mask and weights; partial sums over image groups.
+//   k_bwd_reduce   deterministic sum of the partials (+ optional accumulate).
 #include "eot_common.cuh"
+
+namespace eot {
+
+constexpr int kMaxSmemPlansBwd = 48;
+constexpr int kBwdRows = 4;      // patch rows per k_bwd_resize CTA
+constexpr int kBwdGroups = 16;   // image groups of k_bwd_texel
+
+// gradient that reaches R_j at window element (xi, yi, c) of box jl (local index in pp[0..nb))
+__device__ __forceinline__ float routed_grad(const BoxPlan* pp, int nb, int jl, const float* __restrict__ ubuf,
+                                             const float* __restrict__ G, int H, int W, int xi, int yi, int c) {
+  const BoxPlan& me = pp[jl];
+  const float R = warp_sample(me, ubuf + me.u_off, xi, yi, c);
+  if (!(R >= -1.0f && R <= 1.0f)) return 0.0f;            // SelectV2 took the background, or outer clip
+  const int gy = me.y0 + yi, gx = me.x0 + xi;
+  for (int q = jl + 1; q < nb; ++q) {                      // a later paste that covered this element?
+    const BoxPlan& o = pp[q];
+    if (!o.valid) continue;
+    const int ly = gy - o.y0, lx = gx - o.x0;
+    if (ly < 0 || ly >= o.d || lx < 0 || lx >= o.d) continue;
+    const float Rq = warp_sample(o, ubuf + o.u_off, lx, ly, c);
+    if (!(Rq < -1.0f)) return 0.0f;                        // overwritten: TensorScatterUpdate grad is 0 here
+  }
+  return __ldg(G + (((size_t)me.image * H + gy) * W + gx) * 3 + c);
+}
+
+__global__ void __launch_bounds__(kThreads) k_bwd_window(EotShape s, Layout L, char* ws, const float* __restrict__ G) {
+  __shared__ BoxPlan sp[kMaxSmemPlansBwd];
+  const BoxPlan* plans = reinterpret_cast<const BoxPlan*>(ws + L.off_plans);
+  const int2* items = reinterpret_cast<const int2*>(ws + L.off_items_resize);
+  const int n_items = reinterpret_cast<const int*>(ws + L.off_counters)[0];
+  const float* ubuf = reinterpret_cast<const float*>(ws + L.off_u);
+  float* gubuf = reinterpret_cast<float*>(ws + L.off_gu);
+  const int H = s.height, W = s.width;
+  for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    const int2 item = items[it];
+    const int j = item.x;
+    const int first = plans[j].first_box, last = plans[j].last_box;
+    const int nb = last - first;
+    const BoxPlan* pp;
+    if (nb <= kMaxSmemPlansBwd) {
+      const int4* src = reinterpret_cast<const int4*>(plans + first);
+      int4* dst = reinterpret_cast<int4*>(sp);
+      for (int i = threadIdx.x; i < nb * (int)(sizeof(BoxPlan) / 16); i += blockDim.x) dst[i] = src[i];
+      __syncthreads();
+      pp = sp;
+    } else {
+      pp = plans + first;
+    }
+    const int jl = j - first;
+    const BoxPlan& me = pp[jl];
+    const int ps = me.ps, D = me.d;
+    const float* u = ubuf + me.u_off;
+    float* gu = gubuf + me.u_off;
+    const int oy0 = item.y * kResizeRows;
+    const int rows = min(kResizeRows, ps - oy0);
+    const int e_begin = oy0 * ps * 3, e_end = (oy0 + rows) * ps * 3;
+    for (int e = e_begin + threadIdx.x; e < e_end; e += blockDim.x) {
+      const int pix = e / 3, c = e - pix * 3;
+      const int ty = pix / ps, tx = pix - ty * ps;
+      const float xf = (float)(tx + me.pad_lo), yf = (float)(ty + me.pad_lo);
+      float g = 0.0f;
+      const float proj = (me.Ti[6] * xf + me.Ti[7] * yf) + 1.0f;
+      if (proj != 0.0f) {
+        const float ix = ((me.Ti[0] * xf + me.Ti[1] * yf) + me.Ti[2]) / proj;
+        const float iy = ((me.Ti[3] * xf + me.Ti[4] * yf) + me.Ti[5]) / proj;
+        const float x0f = floorf(ix), y0f = floorf(iy);
+        const float x1f = x0f + 1.0f, y1f = y0f + 1.0f;
+        const float Df = (float)D;
+        const bool bx0 = x0f >= 0.0f && x0f < Df, bx1 = x1f >= 0.0f && x1f < Df;
+        const bool by0 = y0f >= 0.0f && y0f < Df, by1 = y1f >= 0.0f && y1f < Df;
+        const int xi0 = (int)x0f, yi0 = (int)y0f;
+        const float v00 = (by0 && bx0) ? routed_grad(pp, nb, jl, ubuf, G, H, W, xi0, yi0, c) : 0.0f;
+        const float v01 = (by0 && bx1) ? routed_grad(pp, nb, jl, ubuf, G, H, W, xi0 + 1, yi0, c) : 0.0f;
+        const float v10 = (by1 && bx0) ? routed_grad(pp, nb, jl, ubuf, G, H, W, xi0, yi0 + 1, c) : 0.0f;
+        const float v11 = (by1 && bx1) ? routed_grad(pp, nb, jl, ubuf, G, H, W, xi0 + 1, yi0 + 1, c) : 0.0f;
+        const float wx1 = x1f - ix, wx0 = ix - x0f, wy1 = y1f - iy, wy0 = iy - y0f;
+        g = wy1 * (wx1 * v00 + wx0 * v01) + wy0 * (wx1 * v10 + wx0 * v11);
+      }
+      const float up = u[e];
+      gu[e] = (up >= -1.0f && up <= 1.0f) ? g : 0.0f;        // inner clip (attacker.py:428)
+    }
+    __syncthreads();
+  }
+}
+
+// first output index o whose span [start[o], start[o]+span) can contain input index i, and the last.
+__device__ __forceinline__ void inverse_span(const int* __restrict__ starts, int n_out, int span, int i, int* lo, int* hi) {
+  int a = 0, b = n_out;                       // lower_bound: first o with starts[o] >= i - span + 1
+  const int key = i - span + 1;
+  while (a < b) { const int m = (a + b) >> 1; if (starts[m] < key) a = m + 1; else b = m; }
+  *lo = a;
+  a = 0; b = n_out;                           // upper_bound: first o with starts[o] > i
+  while (a < b) { const int m = (a + b) >> 1; if (starts[m] <= i) a = m + 1; else b = m; }
+  *hi = a - 1;
+}
+
+__global__ void __launch_bounds__(kThreads) k_bwd_resize(EotShape s, Layout L, char* ws, const float* __restrict__ patch,
+                                                         const float* __restrict__ print_wb,
+                                                         const int32_t* __restrict__ offsets) {
+  extern __shared__ float smem[];
+  __shared__ double red[32];
+  const int P = s.patch_size, P3 = P * 3;
+  float* acc_tile = smem;                              // [kBwdRows][P3]   patch-gradient accumulator
+  float* tmp = smem + kBwdRows * P3;                   // [kBwdRows][lmin*3]
+  const int b = blockIdx.y;
+  const int py0 = blockIdx.x * kBwdRows;
+  const int rows = min(kBwdRows, P - py0);
+  const BoxPlan* plans = reinterpret_cast<const BoxPlan*>(ws + L.off_plans);
+  const float* gubuf = reinterpret_cast<const float*>(ws + L.off_gu);
+  for (int i = threadIdx.x; i < kBwdRows * P3; i += blockDim.x) acc_tile[i] = 0.0f;
+  __syncthreads();
+  for (int j = offsets[b]; j < offsets[b + 1]; ++j) {
+    const BoxPlan* pl = plans + j;
+    if (!pl->valid) continue;
+    const int ps = pl->ps, ps3 = ps * 3, span = pl->span;
+    const int* starts = reinterpret_cast<const int*>(ws + L.off_starts) + (size_t)j * L.lmin;
+    const float* wts = reinterpret_cast<const float*>(ws + L.off_weights) + (size_t)j * L.wcap;
+    const float* gu = gubuf + pl->u_off;
+    // rows: tmp[r][f] = sum_oy w[oy][py - start[oy]] * gu[oy][f]
+    for (int idx = threadIdx.x; idx < rows * ps3; idx += blockDim.x) {
+      const int r = idx / ps3, f = idx - r * ps3;
+      const int py = py0 + r;
+      int lo, hi;
+      inverse_span(starts, ps, span, py, &lo, &hi);
+      float a = 0.0f;
+      for (int oy = lo; oy <= hi; ++oy) {
+        const int k = py - starts[oy];
+        if (k >= 0 && k < span) a += wts[(size_t)oy * span + k] * __ldg(gu + (size_t)oy * ps3 + f);
+      }
+      tmp[r * (L.lmin * 3) + f] = a;
+    }
+    __syncthreads();
+    // columns: acc[r][px][c] += sum_ox w[ox][px - start[ox]] * tmp[r][ox][c]
+    for (int idx = threadIdx.x; idx < rows * P3; idx += blockDim.x) {
+      const int r = idx / P3, f = idx - r * P3;
+      const int px = f / 3, c = f - px * 3;
+      int lo, hi;
+      inverse_span(starts, ps, span, px, &lo, &hi);
+      float a = 0.0f;
+      for (int ox = lo; ox <= hi; ++ox) {
+        const int k = px - starts[ox];
+        if (k >= 0 && k < span) a += wts[(size_t)ox * span + k] * tmp[r * (L.lmin * 3) + ox * 3 + c];
+      }
+      acc_tile[idx] += a;
+    }
+    __syncthreads();
+  }
+  // BrightnessMatcher backward, first half (brightness_matcher.py:65-72 reversed)
+  const double* ysum_img = reinterpret_cast<const double*>(ws + L.off_ysum_img);
+  const double* ysum_patch = reinterpret_cast<const double*>(ws + L.off_ysum_patch);
+  const float mu_t = (float)(ysum_img[b] / (double)((size_t)s.height * s.width));
+  const float mu_s = (float)(ysum_patch[b] / (double)((size_t)P * P));
+  const float* wb = print_wb + (size_t)b * 6;
+  float* gm = reinterpret_cast<float*>(ws + L.off_gm) + (size_t)b * P * P3;
+  double gy_acc = 0.0;
+  for (int idx = threadIdx.x; idx < rows * P; idx += blockDim.x) {
+    const int r = idx / P, px = idx - r * P;
+    const int py = py0 + r;
+    const float* p = patch + ((size_t)py * P + px) * 3;
+    const TexelYuv y = texel_yuv(__ldg(p), __ldg(p + 1), __ldg(p + 2), wb);
+    const float y_pre = (y.y - mu_s) + mu_t;
+    const float yp = clampf(y_pre, 0.0f, 1.0f);
+    const float rr = (yp * 1.0f + y.u * EOT_I10) + y.v * EOT_I20;
+    const float gg = (yp * 1.0f + y.u * EOT_I11) + y.v * EOT_I21;
+    const float bb = (yp * 1.0f + y.u * EOT_I12) + y.v * EOT_I22;
+    const float* a = acc_tile + r * P3 + px * 3;
+    const float g0 = (rr >= 0.0f && rr <= 1.0f) ? a[0] * EOT_C255_127 : 0.0f;
+    const float g1 = (gg >= 0.0f && gg <= 1.0f) ? a[1] * EOT_C255_127 : 0.0f;
+    const float g2 = (bb >= 0.0f && bb <= 1.0f) ? a[2] * EOT_C255_127 : 0.0f;
+    float gY = g0 + g1 + g2;                                       // K' row Y = (1,1,1)
+    const float gU = g0 * EOT_I10 + g1 * EOT_I11 + g2 * EOT_I12;
+    const float gV = g0 * EOT_I20 + g1 * EOT_I21 + g2 * EOT_I22;
+    if (!(y_pre >= 0.0f && y_pre <= 1.0f)) gY = 0.0f;
+    gy_acc += (double)gY;
+    float* o = gm + ((size_t)py * P + px) * 3;
+    o[0] = gY; o[1] = gU; o[2] = gV;
+  }
+  gy_acc = block_sum(gy_acc, red);
+  if (threadIdx.x == 0) atomicAdd(reinterpret_cast<double*>(ws + L.off_gy_sum) + b, gy_acc);
+}
+
+__global__ void __launch_bounds__(kThreads) k_bwd_texel(EotShape s, Layout L, char* ws, const float* __restrict__ patch,
+                                                        const float* __restrict__ print_wb, int groups) {
+  const int P = s.patch_size, PP = P * P;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= PP) return;
+  const int g = blockIdx.y;
+  const float p0 = __ldg(patch + (size_t)t * 3), p1 = __ldg(patch + (size_t)t * 3 + 1), p2 = __ldg(patch + (size_t)t * 3 + 2);
+  const float* gmb = reinterpret_cast<const float*>(ws + L.off_gm);
+  const double* gy_sum = reinterpret_cast<const double*>(ws + L.off_gy_sum);
+  float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+  for (int b = g; b < s.batch; b += groups) {
+    const float* wb = print_wb + (size_t)b * 6;
+    const float* gm = gmb + ((size_t)b * PP + t) * 3;
+    const float mean_gy = (float)(gy_sum[b] / (double)PP);
+    const float gYs = gm[0] - mean_gy;                              // d(-mean(Ys)) term
+    const float gU = gm[1], gV = gm[2];
+    // g_s = g_yuv . K^T ; g_q = g_s * 127/255 ; print adjust: clip mask and weight
+    const float s0 = (gYs * EOT_K00 + gU * EOT_K01 + gV * EOT_K02) * EOT_C127_255;
+    const float s1 = (gYs * EOT_K10 + gU * EOT_K11 + gV * EOT_K12) * EOT_C127_255;
+    const float s2 = (gYs * EOT_K20 + gU * EOT_K21 + gV * EOT_K22) * EOT_C127_255;
+    const float q0 = wb[0] * p0 + wb[3], q1 = wb[1] * p1 + wb[4], q2 = wb[2] * p2 + wb[5];
+    if (q0 >= -1.0f && q0 <= 1.0f) a0 += s0 * wb[0];
+    if (q1 >= -1.0f && q1 <= 1.0f) a1 += s1 * wb[1];
+    if (q2 >= -1.0f && q2 <= 1.0f) a2 += s2 * wb[2];
+  }
+  float* part = reinterpret_cast<float*>(ws + L.off_gp_part) + ((size_t)g * PP + t) * 3;
+  part[0] = a0; part[1] = a1; part[2] = a2;
+}
+
+__global__ void __launch_bounds__(kThreads) k_bwd_reduce(const float* __restrict__ part, int n, int groups,
+                                                         float* grad_patch, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a = accumulate ? grad_patch[i] : 0.0f;
+  for (int g = 0; g < groups; ++g) a += part[(size_t)g * n + i];
+  grad_patch[i] = a;
+}
+
+}  // namespace eot
+
 using namespace eot;
-extern "C" int eot_apply_bwd(const EotShape*, const float*, const float*, const float*, void*, size_t, float*, int, void*) {
-  set_error("eot_apply_bwd: not built yet"); return EOT_ERR_BAD_SHAPE;
+
+extern "C" int eot_apply_bwd(const EotShape* shape, const float* patch, const float* print_wb, const float* grad_images,
+                             void* workspace, size_t workspace_bytes, float* grad_patch, int accumulate, void* stream) {
+  if (!shape) { set_error("shape is NULL"); return EOT_ERR_NULL_POINTER; }
+  if (!patch || !print_wb || !grad_images || !workspace || !grad_patch) {
+    set_error("eot_apply_bwd: NULL pointer");
+    return EOT_ERR_NULL_POINTER;
+  }
+  if (shape->batch <= 0 || shape->patch_size <= 0 || shape->num_patches != 1) {
+    set_error("eot_apply_bwd: needs the shared-patch shape of the forward call (num_patches == 1)");
+    return EOT_ERR_BAD_SHAPE;
+  }
+  EotShape s = *shape;
+  const Layout L = make_layout(s);
+  if (workspace_bytes < L.total) { set_error("workspace too small: %zu < %zu", workspace_bytes, L.total); return EOT_ERR_WORKSPACE_TOO_SMALL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = static_cast<char*>(workspace);
+  const int B = s.batch, P = s.patch_size, PP = P * P, n = PP * 3;
+  if (s.total_boxes == 0) {
+    if (!accumulate) EOT_CHECK_CUDA(cudaMemsetAsync(grad_patch, 0, (size_t)n * sizeof(float), st));
+    return EOT_OK;
+  }
+  const int32_t* offsets = reinterpret_cast<const int32_t*>(ws + L.off_offsets);
+  EOT_CHECK_CUDA(cudaMemsetAsync(ws + L.off_gy_sum, 0, (size_t)B * sizeof(double), st));
+  const int nsm = sm_count();
+  k_bwd_window<<<nsm * 8, kThreads, 0, st>>>(s, L, ws, grad_images);
+  const size_t smem = ((size_t)kBwdRows * P * 3 + (size_t)kBwdRows * L.lmin * 3) * sizeof(float);
+  if (smem > 48 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_bwd_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_bwd_resize<<<dim3((P + kBwdRows - 1) / kBwdRows, B), kThreads, smem, st>>>(s, L, ws, patch, print_wb, offsets);
+  const int groups = B < kBwdGroups ? B : kBwdGroups;
+  k_bwd_texel<<<dim3((PP + kThreads - 1) / kThreads, groups), kThreads, 0, st>>>(s, L, ws, patch, print_wb, groups);
+  k_bwd_reduce<<<(n + kThreads - 1) / kThreads, kThreads, 0, st>>>(reinterpret_cast<const float*>(ws + L.off_gp_part), n, groups,
+                                                                    grad_patch, accumulate);
+  EOT_CHECK_CUDA(cudaPeekAtLastError());
+  return EOT_OK;
 }

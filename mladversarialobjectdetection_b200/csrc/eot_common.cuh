@@ -66,6 +66,8 @@ struct Layout {
   size_t off_items_comp;   // int2[N*ceil(3*Lmin*Lmin/kCompChunk)]
   size_t off_gm;           // float[B][P*P*3] backward: dL/d(matched patch) per image
   size_t off_gu;           // float[N][slot]  backward: dL/d(u) per box
+  size_t off_gp_part;      // float[16][P*P*3] backward: partial dL/dpatch per image group
+  size_t off_offsets;      // int32[B+1] copy of the CSR row splits (the backward has no other source)
   size_t total;
   int64_t slot;            // floats per u slot
   int32_t wcap;            // floats per weight table
@@ -99,6 +101,8 @@ __host__ __device__ inline Layout make_layout(const EotShape& s) {
   L.off_items_comp = o;   o = align_up(o + N * (((size_t)3 * lmin * lmin + kCompChunk - 1) / kCompChunk + 1) * 8, 256);
   L.off_gm = o;           o = align_up(o + B * PP3 * sizeof(float), 256);
   L.off_gu = o;           o = align_up(o + N * (size_t)L.slot * sizeof(float), 256);
+  L.off_gp_part = o;      o = align_up(o + 16 * PP3 * sizeof(float), 256);
+  L.off_offsets = o;      o = align_up(o + (B + 1) * sizeof(int32_t), 256);
   L.total = o;
   return L;
 }

@@ -145,6 +145,11 @@ __global__ void __launch_bounds__(128) k_geometry(EotShape s, Layout L, const fl
   BoxPlan* plans = ws ? reinterpret_cast<BoxPlan*>(ws + L.off_plans) : nullptr;
   int* counters = ws ? reinterpret_cast<int*>(ws + L.off_counters) : nullptr;
   const float sc = *scale;
+  if (ws && threadIdx.x == 0) {
+    int32_t* off_copy = reinterpret_cast<int32_t*>(ws + L.off_offsets);
+    off_copy[b] = first;
+    if (b == gridDim.x - 1) off_copy[b + 1] = last;
+  }
   for (int j = first + threadIdx.x; j < last; j += blockDim.x) {
     BoxPlan pl = make_plan(boxes + (size_t)j * 4, sc, params[j], s, b, first, last, (int64_t)j * L.slot,
                            counters ? counters + 2 : nullptr);
