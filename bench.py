@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""Benchmark of the EOT patch-attack step (BASELINE.json metric: patched images/s per attack step, fwd+bwd,
+and apply-kernel HBM GB/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one `PatchAttacker.train_step` on one batch of synthetic COCO-shaped input (config 2 of
+BASELINE.json: EfficientDet-D0-shaped victim, 64 images of 512x512 per GPU, 100x100 patch, 1..8 person boxes
+per image): clean victim pass + score kernel, patch application, victim forward on the patched batch, score
+objective, victim backward, patch backward, (NCCL all-reduce of the packed gradient when N > 1), TV gradient,
+fused Adam + clip.  Weak scaling: the per-GPU batch is fixed.  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "patched images/sec per attack step (fwd+bwd)"
+UNIT = "images/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU (config 2: 64)")
+    ap.add_argument("--image", type=int, default=512)
+    ap.add_argument("--patch", type=int, default=100)
+    ap.add_argument("--victim", default="efficientdet-d0")
+    ap.add_argument("--max-boxes", type=int, default=8)
+    ap.add_argument("--perspective", type=float, default=0.0)
+    ap.add_argument("--kernel-iters", type=int, default=20)
+    ap.add_argument("--cpu-sample-batch", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-first-pass", action="store_true", help="skip the clean victim pass (NOT the headline)")
+    return ap.parse_args()
+
+
+def workload_config(args, n_gpus):
+    return {"workload": f"{args.victim} attack step, {args.batch} img/GPU of {args.image}x{args.image}, "
+                        f"{args.patch}x{args.patch} patch, 1-{args.max_boxes} boxes/img, affine EOT"
+                        + (" + projective row" if args.perspective > 0 else ""),
+            "global_batch": args.batch * n_gpus, "per_gpu_batch": args.batch, "image": args.image, "patch": args.patch,
+            "victim": args.victim + " (random init, torch/cuDNN stand-in for the Keras model)",
+            "parallelism": f"dp{n_gpus}", "first_pass_included": not args.no_first_pass,
+            "l2": "inputs larger than L2 (images %.0f MB/GPU > 126 MB)" % (args.batch * args.image ** 2 * 12 / 1e6)}
+
+
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def mark(self):
+        return len(self.rows)
+
+    def stop(self, start=0):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()          # the exact process we started
+        rows = [r for r in self.rows[start:] if len(r) >= 7] or [r for r in self.rows if len(r) >= 7]
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": float(rows[0][1]) if rows else None,
+                "power_w_max": max((float(r[2]) for r in rows if r[2].replace(".", "").isdigit()), default=None),
+                "samples": len(rows), "reasons": reasons}
+
+
+def event_time_ms(fn, iters, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_step_factory(args, batch):
+    """Oracle port of the same step on the host cores (the reference's TF path cannot run: no TensorFlow)."""
+    from mladversarialobjectdetection_b200 import synth, victim
+    from oracle import objective, step as ostep
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = victim.get_victim_model(args.victim, device="cpu", image_size=args.image)
+    bt = synth.make_batch(batch, args.image, args.image, max_boxes=args.max_boxes, perspective=args.perspective)
+    bx, pr = bt.ragged()
+    anchors = objective.anchor_boxes(args.image)
+    state = dict(patch=synth.make_patch(args.patch), scale=0.4)
+    adam_p, adam_s = ostep.AdamState(state["patch"].shape), ostep.AdamState((1,))
+
+    def run():
+        out = ostep.attack_step(model, state["patch"], state["scale"], bt.images, bx, pr, bt.print_wb, anchors,
+                                adam_p, adam_s, first_pass=not args.no_first_pass)
+        state["patch"], state["scale"] = out["new_patch"], out["new_scale"]
+        return out
+    return run
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = args.cpu_sample_batch
+    run = cpu_reference_step_factory(args, B)
+    for _ in range(args.warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run()
+    dt = time.perf_counter() - t0
+    val = B * args.steps / dt
+    cores = os.cpu_count() or 1
+    sample = f"{args.steps} attack steps on {B} images of the same workload (oracle port: NumPy patcher/objective + torch-CPU victim)"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, args.gpus),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "reference = op-for-op CPU restatement (oracle/) of the TF path; TensorFlow is not installed"}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+def run_ours(args):
+    from mladversarialobjectdetection_b200 import _lib, anchors as anchors_mod, ops, synth, victim
+    from mladversarialobjectdetection_b200.attacker import PatchAttacker
+    from mladversarialobjectdetection_b200.ragged import RaggedBoxes
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.benchmark = True
+    lib = _lib.load()
+
+    B, H, P = args.batch, args.image, args.patch
+    model = victim.get_victim_model(args.victim, device=dev, image_size=H)
+    attacker = PatchAttacker(model, patch_size=P, device=dev, seed=7, perspective=args.perspective)
+    attacker.compile(learning_rate=1e-2)
+    attacker.always_first_pass = not args.no_first_pass
+    attacker._patcher.first_image = rank * B
+    bt = synth.make_batch(B, H, H, first_image=rank * B, max_boxes=args.max_boxes, perspective=args.perspective)
+    images = torch.from_numpy(bt.images).to(dev)
+    boxes = RaggedBoxes(torch.from_numpy(bt.boxes).to(dev), torch.from_numpy(bt.offsets).to(dev))
+
+    def step():
+        return attacker.train_step(images, boxes=boxes, global_batch=B * world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    time.sleep(0.3)
+    mark = clocks.mark() if clocks else 0
+    l0 = lib.eot_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = int(lib.eot_launch_count() - l0)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- end to end through the public API with HOST buffers (H2D of the step's inputs + D2H of the loss) ----
+    pinned = torch.from_numpy(bt.images).pin_memory()
+    pinned_boxes = torch.from_numpy(bt.boxes).pin_memory()
+    pinned_off = torch.from_numpy(bt.offsets).pin_memory()
+    dimg = torch.empty_like(images)
+    dbox = torch.empty_like(boxes.values)
+    doff = torch.empty_like(boxes.row_splits)
+
+    def e2e_step():
+        dimg.copy_(pinned, non_blocking=True)
+        dbox.copy_(pinned_boxes, non_blocking=True)
+        doff.copy_(pinned_off, non_blocking=True)
+        m = attacker.train_step(dimg, boxes=RaggedBoxes(dbox, doff), global_batch=B * world)
+        return float(m["loss"].item())                                    # D2H read of the step's result
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss_val = e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e = {"value": world * B * args.steps / (e2e_ms / 1e3), "unit": UNIT,
+           "h2d_bytes_per_step": int(pinned.numel() * 4 + pinned_boxes.numel() * 4 + pinned_off.numel() * 4),
+           "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps, "loss": loss_val}
+    clock_info = clocks.stop(mark) if clocks else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel roofline, measured live with CUDA events on the launch stream (rank 0) ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    it = args.kernel_iters
+    sc = attacker._scale_regressor
+    params = attacker._patcher.sampler.box_params(0, rank * B, boxes.row_splits, boxes.values.shape[0])
+    wb = attacker._patcher.sampler.print_wb(0, rank * B, B, dev)
+    out = torch.empty_like(images)
+    _, _, ctx = ops.apply_forward(attacker._patch, sc, images, boxes.values, boxes.row_splits, params, wb, out=out)
+    ws = ctx.workspace
+    t_fwd = event_time_ms(lambda: ops.apply_forward(attacker._patch, sc, images, boxes.values, boxes.row_splits, params,
+                                                    wb, out=out, workspace=ws), it)
+    geo = ops.box_geometry(tuple(images.shape), P, boxes.values, boxes.row_splits, params, sc).cpu().numpy()
+    win_bytes = float((geo[geo[:, 6] == 1][:, 3].astype(np.float64) ** 2).sum() * 12)
+    G = torch.randn_like(images)
+    gp = torch.empty_like(attacker._patch)
+    t_bwd = event_time_ms(lambda: ops.apply_backward(ctx, G, grad_patch=gp), it)
+    with torch.no_grad():
+        cls, box = model(images)
+    anc = torch.from_numpy(anchors_mod.anchor_table((H, H))).to(dev)
+    A = anc.shape[0]
+    holder = {}
+
+    def score_f():
+        holder["r"] = ops.score_max_forward(cls, box, anc, (H, H))
+    t_sf = event_time_ms(score_f, it)
+    sctx = holder["r"][3]
+    t_sb = event_time_ms(lambda: ops.score_max_backward(sctx, sc), it)
+
+    def entry(name, bytes_per_launch, ms_, bound_note=None):
+        ach = bytes_per_launch / (ms_ * 1e-3) / 1e9
+        d = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+             "ms": ms_, "algorithmic_bytes": bytes_per_launch, "traffic": None}
+        if bound_note:
+            d["note"] = bound_note
+        return d
+    kernels = [
+        entry("eot_apply_fwd (k_image_pass + k_resize + k_composite ...)", 24.0 * H * H * B + 12.0 * P * P, t_fwd),
+        entry("eot_apply_bwd (k_bwd_window + k_bwd_resize + ...)", win_bytes + 12.0 * P * P, t_bwd,
+              "expected latency/shared-memory bound: touches only the patch windows"),
+        entry("score_max_fwd (k_score_fwd)", 376.0 * A * B + 16.0 * A, t_sf),
+        entry("score_max_bwd (k_score_zero + scatter)", 360.0 * A * B, t_sb),
+    ]
+    # the step runs the score forward twice (clean pass + attacked pass)
+    share = {k["kernel"]: k["ms"] * (2 if k["kernel"].startswith("score_max_fwd") and not args.no_first_pass else 1)
+             for k in kernels}
+    dominant = max(kernels, key=lambda k: share[k["kernel"]])
+    roofline = dict(dominant)
+    roofline["peak_source"] = peak_src
+    roofline["share_of_step"] = share[dominant["kernel"]] / (ms / args.steps)
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):       # dram__bytes_read+write per launch from the committed ncu --set full capture
+        tr = json.load(open(traffic_file))
+        for k in kernels + [roofline]:
+            for key, v in tr.items():
+                if k["kernel"].startswith(key):
+                    k["traffic"] = v
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        run = cpu_reference_step_factory(args, args.cpu_sample_batch)
+        t0 = time.perf_counter()
+        run()
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": args.cpu_sample_batch / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                        "sample": f"1 attack step on {args.cpu_sample_batch} images of the same workload (oracle port: "
+                                  f"NumPy patcher/objective + torch-CPU victim), {dt:.1f} s"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world), "clocks": clock_info, "e2e": e2e,
+            "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
+            "apply_kernel_hbm_gbs": {"fwd": kernels[0]["achieved"], "bwd": kernels[1]["achieved"]}}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

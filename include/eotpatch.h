@@ -70,6 +70,8 @@ typedef struct EotBoxGeometry {
 
 const char* eot_last_error(void);
 int eot_version(void);
+/* Number of CUDA kernels this library has launched since it was loaded (all threads). */
+uint64_t eot_launch_count(void);
 
 /* Bytes of the saved-state workspace eot_apply_fwd fills and eot_apply_bwd reads. */
 int eot_workspace_bytes(const EotShape* shape, size_t* bytes);
@@ -98,6 +100,11 @@ int eot_apply_fwd(const EotShape* shape, const float* patch, const float* scale,
 int eot_apply_bwd(const EotShape* shape, const float* patch, const float* print_wb,
                   const float* grad_images, void* workspace, size_t workspace_bytes,
                   float* grad_patch, int accumulate, void* stream);
+
+/* `BrightnessMatcher()((src, tgt))` on its own (brightness_matcher.py:43-73): src [src_pixels,3],
+ * tgt [tgt_pixels,3] -> out [src_pixels,3].  workspace: 16 bytes, 8-byte aligned. */
+int eot_brightness_match(const float* src, int64_t src_pixels, const float* tgt, int64_t tgt_pixels,
+                         float* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Synchronises `stream` and reports whether any box failed the reference's implicit shape
  * requirements during the last eot_apply_fwd on this workspace (debug / tests only). */

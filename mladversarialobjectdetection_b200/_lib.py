@@ -15,8 +15,8 @@ EOT_FLAG_MASK_OUTPUT = 1
 SCORE_MAX_LEVELS = 8
 
 # every symbol include/eotpatch.h declares (tests check the export list against the header)
-SYMBOLS = ["eot_last_error", "eot_version", "eot_workspace_bytes", "eot_box_geometry", "eot_apply_fwd",
-           "eot_apply_bwd", "eot_check_workspace", "score_workspace_bytes", "score_max_fwd", "score_max_bwd",
+SYMBOLS = ["eot_last_error", "eot_version", "eot_launch_count", "eot_workspace_bytes", "eot_box_geometry", "eot_apply_fwd",
+           "eot_apply_bwd", "eot_brightness_match", "eot_check_workspace", "score_workspace_bytes", "score_max_fwd", "score_max_bwd",
            "patch_tv_grad", "adam_clip_update"]
 
 
@@ -45,10 +45,13 @@ def _declare(lib):
     lib.eot_last_error.restype = ctypes.c_char_p
     lib.eot_last_error.argtypes = []
     lib.eot_version.restype = ctypes.c_int
+    lib.eot_launch_count.restype = ctypes.c_uint64
+    lib.eot_launch_count.argtypes = []
     lib.eot_workspace_bytes.argtypes = [ctypes.POINTER(EotShape), ctypes.POINTER(sz)]
     lib.eot_box_geometry.argtypes = [ctypes.POINTER(EotShape), vp, vp, vp, vp, vp, vp]
     lib.eot_apply_fwd.argtypes = [ctypes.POINTER(EotShape), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.eot_apply_bwd.argtypes = [ctypes.POINTER(EotShape), vp, vp, vp, vp, sz, vp, ctypes.c_int, vp]
+    lib.eot_brightness_match.argtypes = [vp, i64, vp, i64, vp, vp, sz, vp]
     lib.eot_check_workspace.argtypes = [ctypes.POINTER(EotShape), vp, vp]
     lib.score_workspace_bytes.argtypes = [ctypes.POINTER(ScoreShape), ctypes.POINTER(sz)]
     lib.score_max_fwd.argtypes = [ctypes.POINTER(ScoreShape), ctypes.POINTER(vp), ctypes.POINTER(vp), vp, vp, vp,
@@ -58,7 +61,7 @@ def _declare(lib):
     lib.patch_tv_grad.argtypes = [vp, i32, f32, vp, vp, vp]
     lib.adam_clip_update.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i64, f32, f32, vp]
     for name in SYMBOLS:
-        if name != "eot_last_error":
+        if name not in ("eot_last_error", "eot_launch_count"):
             getattr(lib, name).restype = ctypes.c_int
 
 

@@ -1,0 +1,228 @@
+"""Host-side mirror of the reference's `attacker.py` for the hot path: `Patcher` (attacker.py:344-498) and
+`PatchAttacker` call / train_step / test_step / save_weights (attacker.py:24-342).
+
+Same class names, constructor arguments and call signatures as the reference, so a script written against
+`attacker.PatchAttacker` keeps working; tensors are torch CUDA tensors (device memory + streams are the only
+thing torch provides here) and every per-pixel / per-anchor operation runs in libeotpatch.so:
+
+    images' = Patcher([boxes, images])          -> eot_apply_fwd
+    second_pass + max_scores + loss             -> victim forward (framework convs) + score_max_fwd
+    tape.gradient(loss, [scale, patch])         -> score_max_bwd -> victim backward -> eot_apply_bwd (+ patch_tv_grad)
+    optimizer.apply_gradients + constraints     -> adam_clip_update (after an NCCL all-reduce when sharded)
+"""
+from __future__ import annotations
+
+import ast
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import anchors as _anchors
+from . import ops, patch_io
+from .ragged import RaggedBoxes
+from .sampler import TransformSampler
+
+
+class Patcher:
+    """apply patch to persons in an image (reference: attacker.py:344)."""
+
+    def __init__(self, patch: torch.Tensor, scale_regressor: torch.Tensor, *args, min_patch_area=4, name=None,
+                 seed: int = 0, perspective: float = 0.0, **kwargs):
+        self._patch = patch
+        self._scale = scale_regressor
+        self.min_patch_area = min_patch_area
+        self.name = name
+        self.geometry = ops.PatchGeometry(tolerance=0.2, noise_amp=0.01, min_patch_area=float(min_patch_area))
+        self.sampler = TransformSampler(seed, perspective=perspective)
+        self.first_image = 0          # global index of this rank's first image (data-parallel sharding)
+        self._step = 0
+        self._workspace = None
+        self.last_context: Optional[ops.ApplyContext] = None
+
+    def __call__(self, inputs, transforms=None, out=None):
+        return self.call(inputs, transforms=transforms, out=out)
+
+    def call(self, inputs, transforms=None, out=None):
+        """called during training by the attacker for each batch (attacker.py:490-498).
+
+        inputs = [boxes (RaggedBoxes), images [B,H,W,3]].  `transforms=(params_u8 [N,48], print_wb [B,6])`
+        replaces the internally drawn transform seeds (parity tests, replay)."""
+        boxes, images = inputs
+        if not isinstance(boxes, RaggedBoxes):
+            boxes = RaggedBoxes.from_rows(boxes, images.device)
+        n = int(boxes.values.shape[0])
+        if transforms is None:
+            params = self.sampler.box_params(self._step, self.first_image, boxes.row_splits, n)
+            print_wb = self.sampler.print_wb(self._step, self.first_image, images.shape[0], images.device)
+            self._step += 1
+        else:
+            params, print_wb = transforms
+        out_images, _, ctx = ops.apply_forward(self._patch, self._scale, images, boxes.values, boxes.row_splits,
+                                               params, print_wb, self.geometry, out=out, workspace=self._workspace)
+        self._workspace = ctx.workspace
+        self.last_context = ctx
+        return out_images
+
+    def backward(self, grad_images: torch.Tensor, grad_patch: Optional[torch.Tensor] = None, accumulate=False):
+        """dL/dpatch for the last call (the part of tape.gradient at attacker.py:217 that crosses this layer)."""
+        if self.last_context is None:
+            raise RuntimeError("Patcher.backward called before Patcher.__call__")
+        return ops.apply_backward(self.last_context, grad_images, grad_patch=grad_patch, accumulate=accumulate)
+
+
+class PatchAttacker:
+    """attack with malicious patches (reference: attacker.py:24)."""
+
+    def __init__(self, model, initial_patch=None, config_override=None, visualize_freq=200, *,
+                 patch_size: int = 640, device=None, seed: int = 0, process_group=None, perspective: float = 0.0):
+        self.model = model
+        self.config = model.config
+        if config_override:
+            self.config.override(config_override)
+        self.device = torch.device(device) if device is not None else next(model.parameters()).device
+        if initial_patch is None:
+            # np.random.uniform(-1., 1., size=(640, 640, 3)), scale .4 (attacker.py:43-44)
+            patch_img = np.random.default_rng(seed).uniform(-1.0, 1.0, size=(patch_size, patch_size, 3))
+            scale = 0.4
+        else:
+            patch_img, scale = patch_io.load_weights(initial_patch)
+        # the only two variables updated during training (attacker.py:50-54); constraints = clip
+        self._patch = torch.tensor(np.asarray(patch_img), dtype=torch.float32, device=self.device).contiguous()
+        self._scale_regressor = torch.tensor(float(scale), dtype=torch.float32, device=self.device)
+        self.visualize_freq = visualize_freq
+        self._patcher = Patcher(self._patch, self._scale_regressor, name="Patcher", seed=seed, perspective=perspective)
+        self._trainable_variables = [self._scale_regressor, self._patch]
+        self.bins = np.arange(self.config.nms_configs["score_thresh"], .805, .01, dtype="float32")
+        self.process_group = process_group
+        self.learning_rate = 1e-2
+        self._opt_step = 0
+        n = self._patch.numel() + 1
+        self._flat_var = None
+        self._adam_m = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self._adam_v = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self._anchors = None
+        self.metrics = {}
+
+    # -- Keras-like surface ------------------------------------------------------------------------
+    def compile(self, optimizer=None, learning_rate: Optional[float] = None, run_eagerly=False):
+        """attacker_train.py:38 compiles with Adam(1e-2); only the learning rate is configurable here."""
+        if learning_rate is not None:
+            self.learning_rate = float(learning_rate)
+        elif optimizer is not None and hasattr(optimizer, "learning_rate"):
+            self.learning_rate = float(optimizer.learning_rate)
+
+    @property
+    def trainable_variables(self):
+        return self._trainable_variables
+
+    def _anchor_table(self, images: torch.Tensor) -> torch.Tensor:
+        hw = (int(images.shape[1]), int(images.shape[2]))
+        if self._anchors is None or self._anchors[0] != hw:
+            c = self.config
+            tab = _anchors.anchor_table(hw, c.min_level, c.max_level, c.num_scales, tuple(c.aspect_ratios), c.anchor_scale)
+            self._anchors = (hw, torch.from_numpy(tab).to(self.device))
+        return self._anchors[1]
+
+    # -- passes ------------------------------------------------------------------------------------
+    def _score(self, images: torch.Tensor):
+        cls_outputs, box_outputs = self.model(images, pre_mode=None, post_mode=None)
+        M, argmax, ncand, ctx = ops.score_max_forward(cls_outputs, box_outputs, self._anchor_table(images),
+                                                      (images.shape[1], images.shape[2]),
+                                                      num_classes=self.config.num_classes)
+        return cls_outputs, box_outputs, M, argmax, ncand, ctx
+
+    def first_pass(self, images: torch.Tensor):
+        """clean pass through the victim (attacker.py:91-116).  Returns (boxes RaggedBoxes, scores list)."""
+        from . import postprocess
+        with torch.no_grad():
+            cls_outputs, box_outputs, _, _, _, ctx = self._score(images)
+            return postprocess.person_boxes_after_nms(self.config, ctx, box_outputs, self._anchor_table(images),
+                                                      images.shape[1:3], thresh=True)
+
+    def second_pass(self, images: torch.Tensor):
+        """pass after addition of patches (attacker.py:118-141): per-image max candidate score + context."""
+        cls_outputs, box_outputs, M, argmax, ncand, ctx = self._score(images)
+        return cls_outputs, M, argmax, ncand, ctx
+
+    def call(self, images: torch.Tensor, *, training=True, boxes: Optional[RaggedBoxes] = None, transforms=None):
+        """called on each batch (attacker.py:172-219).  Returns [dL/dscale, dL/dpatch] when training, else
+        (max_scores, argmax_anchor).  `boxes` overrides the first pass' detections (synthetic benchmarks)."""
+        det_boxes, _ = self.first_pass(images) if boxes is None or self.always_first_pass else (None, None)
+        if boxes is None:
+            boxes = det_boxes
+        patched = self._patcher([boxes, images], transforms=transforms)
+        if not training:
+            with torch.no_grad():
+                _, M, argmax, _, _ = self.second_pass(patched)
+            self._record_metrics(M, None, None)
+            return M, argmax
+        patched.requires_grad_(True)
+        cls_outputs, M, argmax, ncand, sctx = self.second_pass(patched)
+        dcls, dscale, data_loss = ops.score_max_backward(sctx, self._scale_regressor)
+        torch.autograd.backward(cls_outputs, dcls)                       # victim backward on the framework path
+        grad_patch = self._patcher.backward(patched.grad)
+        self._last = dict(max_scores=M, data_loss=data_loss, dscale=dscale, ncand=ncand)
+        return [dscale, grad_patch]
+
+    always_first_pass = True
+
+    # -- steps -------------------------------------------------------------------------------------
+    def _pack(self, dscale, grad_patch, M):
+        n = grad_patch.numel()
+        buf = torch.empty(n + 4, dtype=torch.float32, device=self.device)
+        buf[:n] = grad_patch.reshape(-1)
+        buf[n] = dscale
+        buf[n + 1] = self._last["data_loss"]
+        buf[n + 2] = M.sum()
+        buf[n + 3] = (M * M).sum()
+        return buf
+
+    def train_step(self, inputs, boxes: Optional[RaggedBoxes] = None, transforms=None, global_batch: Optional[int] = None):
+        """called for each batch during training (attacker.py:307-316)."""
+        dscale, grad_patch = self.call(inputs, training=True, boxes=boxes, transforms=transforms)
+        M = self._last["max_scores"]
+        buf = self._pack(dscale, grad_patch, M)
+        B = inputs.shape[0]
+        if self.process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                              and torch.distributed.get_world_size() > 1):
+            # loss is a SUM over images (attacker.py:193): a sum all-reduce reproduces the single-GPU step
+            torch.distributed.all_reduce(buf, group=self.process_group)
+            B = global_batch if global_batch is not None else B * torch.distributed.get_world_size(self.process_group)
+        n = self._patch.numel()
+        g_patch = buf[:n].view_as(self._patch)
+        tv = ops.tv_grad_(self._patch, g_patch, 1e-5)                   # + 1e-5 * d TV/d patch, once (attacker.py:192-193)
+        self._apply_gradients(buf[n:n + 1], g_patch)
+        self._record_metrics(None, buf, tv, B)
+        return self.metrics
+
+    def _apply_gradients(self, g_scale: torch.Tensor, g_patch: torch.Tensor):
+        """optimizer.apply_gradients + variable constraints (attacker.py:315, 51-54): one fused Adam+clip per variable."""
+        self._opt_step += 1
+        n = self._patch.numel()
+        ops.adam_clip_(self._patch.view(-1), self._adam_m[:n], self._adam_v[:n], g_patch.reshape(-1), self._opt_step,
+                       lr=self.learning_rate, lo=-1.0, hi=1.0)
+        ops.adam_clip_(self._scale_regressor.view(1), self._adam_m[n:], self._adam_v[n:], g_scale, self._opt_step,
+                       lr=self.learning_rate, lo=0.0, hi=1.0)
+
+    def test_step(self, inputs, boxes: Optional[RaggedBoxes] = None, transforms=None):
+        """called for each batch during validation (attacker.py:318-326)."""
+        self.call(inputs, training=False, boxes=boxes, transforms=transforms)
+        return self.metrics
+
+    def _record_metrics(self, M, buf, tv, B=None):
+        """add_metric calls of attacker.py:196-201 (device scalars; nothing is synchronised here)."""
+        if buf is not None:
+            n = self._patch.numel()
+            data_loss, s1, s2 = buf[n + 1], buf[n + 2], buf[n + 3]
+            mean = s1 / B
+            self.metrics = dict(loss=data_loss + 1e-5 * tv, scale=self._scale_regressor, tv_loss=tv,
+                                mean_max_score=mean, std_max_score=torch.sqrt(torch.clamp(s2 / B - mean * mean, min=0.0)))
+        elif M is not None:
+            self.metrics = dict(mean_max_score=M.mean(), std_max_score=M.std(unbiased=False), scale=self._scale_regressor)
+
+    def save_weights(self, dirpath, **kwargs):
+        """save patch and current scale to disk (attacker.py:328-341): scale.txt, patch.png, patch.tiff."""
+        patch_io.save_weights(dirpath, self._patch.detach().cpu().numpy(), float(self._scale_regressor),
+                              self.config.mean_rgb, self.config.stddev_rgb)

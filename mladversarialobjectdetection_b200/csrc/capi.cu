@@ -1,6 +1,7 @@
 // Error plumbing and small host utilities of libeotpatch (see include/eotpatch.h).
 #include "eot_common.cuh"
 
+#include <atomic>
 #include <stdarg.h>
 #include <stdio.h>
 
@@ -20,6 +21,9 @@ int cuda_fail(cudaError_t e, const char* what) {
   return EOT_ERR_CUDA;
 }
 
+static std::atomic<unsigned long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
 int sm_count() {
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;
@@ -31,3 +35,4 @@ int sm_count() {
 
 extern "C" const char* eot_last_error(void) { return eot::g_err; }
 extern "C" int eot_version(void) { return 100; }
+extern "C" uint64_t eot_launch_count(void) { return eot::g_launches.load(std::memory_order_relaxed); }

@@ -270,6 +270,7 @@ extern "C" int eot_apply_bwd(const EotShape* shape, const float* patch, const fl
   k_bwd_texel<<<dim3((PP + kThreads - 1) / kThreads, groups), kThreads, 0, st>>>(s, L, ws, patch, print_wb, groups);
   k_bwd_reduce<<<(n + kThreads - 1) / kThreads, kThreads, 0, st>>>(reinterpret_cast<const float*>(ws + L.off_gp_part), n, groups,
                                                                     grad_patch, accumulate);
+  count_launches(4);
   EOT_CHECK_CUDA(cudaPeekAtLastError());
   return EOT_OK;
 }

@@ -111,6 +111,7 @@ __host__ __device__ inline Layout make_layout(const EotShape& s) {
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 int sm_count();
+void count_launches(int n);   // kernels launched by this library since load (bench.py reports the delta)
 
 #define EOT_CHECK_CUDA(expr)                                   \
   do {                                                         \

@@ -304,6 +304,38 @@ __global__ void __launch_bounds__(kThreads) k_match(EotShape s, Layout L, const 
 }
 
 // ------------------------------------------------------------------------------------------------
+// stand-alone BrightnessMatcher()((src, tgt)) (brightness_matcher.py:43-73): no print adjust, no clip
+// of the source before the rescale.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_bm_ysum(const float* __restrict__ x, long long n_pix, double* sum) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pix; i += (long long)gridDim.x * blockDim.x)
+    acc += (double)luma_of(__ldg(x + i * 3), __ldg(x + i * 3 + 1), __ldg(x + i * 3 + 2));
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(sum, acc);
+}
+
+__global__ void __launch_bounds__(kThreads) k_bm_apply(const float* __restrict__ src, long long n_src, long long n_tgt,
+                                                       const double* __restrict__ sums, float* out) {
+  const float mu_s = (float)(sums[0] / (double)n_src), mu_t = (float)(sums[1] / (double)n_tgt);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_src; i += (long long)gridDim.x * blockDim.x) {
+    const float s0 = (src[i * 3] + 1.0f) * EOT_C127_255, s1 = (src[i * 3 + 1] + 1.0f) * EOT_C127_255,
+                s2 = (src[i * 3 + 2] + 1.0f) * EOT_C127_255;
+    const float y = (s0 * EOT_K00 + s1 * EOT_K10) + s2 * EOT_K20;
+    const float u = (s0 * EOT_K01 + s1 * EOT_K11) + s2 * EOT_K21;
+    const float v = (s0 * EOT_K02 + s1 * EOT_K12) + s2 * EOT_K22;
+    const float yp = clampf((y - mu_s) + mu_t, 0.0f, 1.0f);
+    const float r = (yp * 1.0f + u * EOT_I10) + v * EOT_I20;
+    const float g = (yp * 1.0f + u * EOT_I11) + v * EOT_I21;
+    const float b = (yp * 1.0f + u * EOT_I12) + v * EOT_I22;
+    out[i * 3] = clampf(r, 0.0f, 1.0f) * EOT_C255_127 - 1.0f;
+    out[i * 3 + 1] = clampf(g, 0.0f, 1.0f) * EOT_C255_127 - 1.0f;
+    out[i * 3 + 2] = clampf(b, 0.0f, 1.0f) * EOT_C255_127 - 1.0f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // resize + noise + delta for one strip of kResizeRows output rows of one box
 // (attacker.py:425-427; ScaleAndTranslate GatherRows then GatherColumns)
 // ------------------------------------------------------------------------------------------------
@@ -471,6 +503,7 @@ extern "C" int eot_box_geometry(const EotShape* shape, const float* boxes, const
   }
   const EotShape s = normalised(*shape);
   k_geometry<<<s.batch, 128, 0, (cudaStream_t)stream>>>(s, make_layout(s), boxes, box_offsets, params, scale, nullptr, geometry_out);
+  count_launches(1);
   EOT_CHECK_CUDA(cudaPeekAtLastError());
   return EOT_OK;
 }
@@ -516,7 +549,9 @@ extern "C" int eot_apply_fwd(const EotShape* shape, const float* patch, const fl
     if (smem > 48 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_resize<<<nsm * 4, kThreads, smem, st>>>(s, L, ws);
     k_composite<<<nsm * 8, kThreads, 0, st>>>(s, L, ws, images, out_images, mask);
+    count_launches(3);
   }
+  count_launches(3);
   EOT_CHECK_CUDA(cudaPeekAtLastError());
   return EOT_OK;
 }
@@ -530,5 +565,24 @@ extern "C" int eot_check_workspace(const EotShape* shape, const void* workspace,
                                  cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   EOT_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   if (flag) { set_error("a patch window did not fit the image (the reference would fail in tf.pad / scatter)"); return EOT_ERR_GEOMETRY; }
+  return EOT_OK;
+}
+
+extern "C" int eot_brightness_match(const float* src, int64_t src_pixels, const float* tgt, int64_t tgt_pixels,
+                                    float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!src || !tgt || !out || !workspace) { set_error("eot_brightness_match: NULL pointer"); return EOT_ERR_NULL_POINTER; }
+  if (src_pixels <= 0 || tgt_pixels <= 0) { set_error("eot_brightness_match: empty image"); return EOT_ERR_BAD_SHAPE; }
+  if (workspace_bytes < 16 || ((uintptr_t)workspace & 7)) { set_error("eot_brightness_match: workspace needs 16 aligned bytes"); return EOT_ERR_WORKSPACE_TOO_SMALL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  double* sums = static_cast<double*>(workspace);
+  EOT_CHECK_CUDA(cudaMemsetAsync(sums, 0, 16, st));
+  const int cap = sm_count() * 8;
+  const int gs = (int)((src_pixels + kThreads - 1) / kThreads < cap ? (src_pixels + kThreads - 1) / kThreads : cap);
+  const int gt = (int)((tgt_pixels + kThreads - 1) / kThreads < cap ? (tgt_pixels + kThreads - 1) / kThreads : cap);
+  k_bm_ysum<<<gs, kThreads, 0, st>>>(src, src_pixels, sums);
+  k_bm_ysum<<<gt, kThreads, 0, st>>>(tgt, tgt_pixels, sums + 1);
+  k_bm_apply<<<gs, kThreads, 0, st>>>(src, src_pixels, tgt_pixels, sums, out);
+  count_launches(3);
+  EOT_CHECK_CUDA(cudaPeekAtLastError());
   return EOT_OK;
 }

@@ -58,6 +58,7 @@ extern "C" int patch_tv_grad(const float* patch, int32_t patch_size, float weigh
   const int n = patch_size * patch_size * 3;
   const int blocks = min((n + kThreads - 1) / kThreads, sm_count() * 8);
   k_tv_grad<<<blocks, kThreads, 0, st>>>(patch, patch_size, weight, grad_patch, tv_out);
+  count_launches(1);
   EOT_CHECK_CUDA(cudaPeekAtLastError());
   return EOT_OK;
 }
@@ -73,6 +74,7 @@ extern "C" int adam_clip_update(float* var, float* m, float* v, const float* gra
   if (nb > cap) nb = cap;
   const int blocks = (int)nb;
   k_adam_clip<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(var, m, v, grad, n, alpha, 1.0f - beta1, 1.0f - beta2, eps, lo, hi);
+  count_launches(1);
   EOT_CHECK_CUDA(cudaPeekAtLastError());
   return EOT_OK;
 }

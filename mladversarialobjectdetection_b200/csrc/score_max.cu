@@ -292,6 +292,7 @@ extern "C" int score_max_fwd(const ScoreShape* shape, const float* const* cls_le
   k_score_finalize<<<(s.batch + 127) / 128, 128, 0, st>>>(s.batch, keys, ncand, max_scores, argmax_anchor, num_candidates);
   const int tgrid = (s.total_anchors + kThreads * 8 - 1) / (kThreads * 8);
   k_score_ties<<<dim3(tgrid, s.batch), kThreads, 0, st>>>(s.total_anchors, keys, cand, nties, reinterpret_cast<int*>(ws + L.off_ties));
+  count_launches(3);
   EOT_CHECK_CUDA(cudaPeekAtLastError());
   return EOT_OK;
 }
@@ -330,6 +331,7 @@ extern "C" int score_max_bwd(const ScoreShape* shape, const float* const* cls_le
   const int* nties = reinterpret_cast<const int*>(ws + L.off_counts) + s.batch;
   k_score_scatter<<<s.batch, 128, 0, st>>>(s, lv, max_scores, scale, keys, nties, reinterpret_cast<const int*>(ws + L.off_ties));
   if (dscale_out || loss_out) k_score_scalars<<<1, kThreads, 0, st>>>(s.batch, max_scores, scale, dscale_out, loss_out);
+  count_launches((dscale_out || loss_out) ? 3 : 2);
   EOT_CHECK_CUDA(cudaPeekAtLastError());
   return EOT_OK;
 }

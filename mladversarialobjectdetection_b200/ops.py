@@ -160,6 +160,19 @@ def apply_backward(ctx: ApplyContext, grad_images: torch.Tensor, *, grad_patch: 
     return grad_patch
 
 
+def brightness_match(src: torch.Tensor, tgt: torch.Tensor) -> torch.Tensor:
+    """`BrightnessMatcher()((src, tgt))` (brightness_matcher.py:43-73): src [h,w,3], tgt [H,W,3] in [-1,1]."""
+    _need_cuda(src, tgt)
+    src, tgt = _f32c(src, "src"), _f32c(tgt, "tgt")
+    if src.shape[-1] != 3 or tgt.shape[-1] != 3:
+        raise ValueError("src and tgt must be [...,3]")
+    out = torch.empty_like(src)
+    ws = torch.empty(2, dtype=torch.float64, device=src.device)
+    _lib.check(_lib.load().eot_brightness_match(_ptr(src), src.numel() // 3, _ptr(tgt), tgt.numel() // 3, _ptr(out),
+                                                _ptr(ws), ctypes.c_size_t(16), _stream()), "eot_brightness_match")
+    return out
+
+
 def check_workspace(ctx: ApplyContext) -> None:
     """Synchronising check that every valid box fitted the image (tests / debugging)."""
     _lib.check(_lib.load().eot_check_workspace(ctypes.byref(ctx.shape), _ptr(ctx.workspace), _stream()),
@@ -225,6 +238,19 @@ def score_max_forward(cls_levels: Sequence[torch.Tensor], box_levels: Sequence[t
                                  _ptr(_f32c(anchors, "anchors")), _ptr(max_scores), _ptr(argmax), _ptr(ncand),
                                  _ptr(ws), ctypes.c_size_t(ws.numel()), _stream()), "score_max_fwd")
     return max_scores, argmax, ncand, ScoreContext(shape, ws, cls_levels, max_scores)
+
+
+def _align(x: int, a: int = 256) -> int:
+    return (x + a - 1) // a * a
+
+
+def score_candidate_view(ctx: ScoreContext) -> torch.Tensor:
+    """[B,A] float32 view of the candidate scores score_max_fwd left in its workspace (score, or -1 where the
+    anchor is not a person / not a valid box): the reference's ragged `scores` of attacker.py:134-139 in dense
+    form.  Layout mirrors `score_layout` in csrc/score_max.cu."""
+    B, A = ctx.shape.batch, ctx.shape.total_anchors
+    off = _align(_align(B * 8) + 2 * B * 4)
+    return ctx.workspace[off: off + B * A * 4].view(torch.float32).view(B, A)
 
 
 def score_max_backward(ctx: ScoreContext, scale: torch.Tensor, *, want_loss: bool = True):

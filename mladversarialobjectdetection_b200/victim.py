@@ -1,0 +1,256 @@
+"""Random-init EfficientDet-shaped victim on the framework's own GPU path (cuDNN through torch).
+
+The reference's victim is the vendored Keras EfficientDet (automl/efficientdet/tf2/efficientdet_keras.py:778-994,
+called with pre_mode=None, post_mode=None at attacker.py:98,125); TensorFlow is not available in this image and
+the north star keeps the detector's convolutions on the framework path, so this module is a stand-in with the
+same interface and cost shape: NHWC float32 images in, five class / box level tensors out in NHWC
+([B,h_l,w_l,9*90], [B,h_l,w_l,9*4], levels 3..7).  It exists so the attack step can be timed end to end;
+nothing in the parity suite depends on its weights.  Architecture tables: hparams_config.py:302-346.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as Fn
+
+
+@dataclass
+class VictimConfig:
+    name: str = "efficientdet-d0"
+    image_size: int = 512
+    width_mult: float = 1.0           # EfficientNet width / depth coefficients
+    depth_mult: float = 1.0
+    fpn_channels: int = 64
+    fpn_layers: int = 3
+    head_layers: int = 3
+    num_classes: int = 90
+    min_level: int = 3
+    max_level: int = 7
+    num_scales: int = 3
+    aspect_ratios: Tuple[float, ...] = (1.0, 2.0, 0.5)
+    anchor_scale: float = 4.0
+    mean_rgb: float = 127.0           # only used for on-disk de-normalisation (attacker.py:338)
+    stddev_rgb: float = 128.0
+    nms_configs: dict = field(default_factory=lambda: dict(method="gaussian", iou_thresh=None, score_thresh=0.0,
+                                                           sigma=None, max_nms_inputs=0, max_output_size=100))
+
+    def override(self, d: dict) -> None:
+        """Config.override subset used by PatchAttacker(config_override=...) (hparams_config.py:85-115)."""
+        for k, v in d.items():
+            if isinstance(v, dict) and isinstance(getattr(self, k, None), dict):
+                getattr(self, k).update(v)
+            elif hasattr(self, k):
+                setattr(self, k, v)
+            else:
+                raise KeyError(f"unknown config key {k}")
+
+
+CONFIGS = {
+    "efficientdet-d0": dict(image_size=512, width_mult=1.0, depth_mult=1.0, fpn_channels=64, fpn_layers=3, head_layers=3),
+    "efficientdet-d1": dict(image_size=640, width_mult=1.0, depth_mult=1.1, fpn_channels=88, fpn_layers=4, head_layers=3),
+    "efficientdet-d2": dict(image_size=768, width_mult=1.1, depth_mult=1.2, fpn_channels=112, fpn_layers=5, head_layers=3),
+    "efficientdet-d3": dict(image_size=896, width_mult=1.2, depth_mult=1.4, fpn_channels=160, fpn_layers=6, head_layers=4),
+    "efficientdet-d4": dict(image_size=1024, width_mult=1.4, depth_mult=1.8, fpn_channels=224, fpn_layers=7, head_layers=4),
+    "efficientdet-lite4": dict(image_size=640, width_mult=1.4, depth_mult=1.8, fpn_channels=224, fpn_layers=7, head_layers=4),
+}
+
+
+def get_config(name: str) -> VictimConfig:
+    return VictimConfig(name=name, **CONFIGS[name])
+
+
+def _round_filters(c: int, mult: float, divisor: int = 8) -> int:
+    c *= mult
+    new = max(divisor, int(c + divisor / 2) // divisor * divisor)
+    if new < 0.9 * c:
+        new += divisor
+    return int(new)
+
+
+class ConvBN(nn.Sequential):
+    def __init__(self, cin, cout, k=1, stride=1, groups=1, act=True):
+        layers = [nn.Conv2d(cin, cout, k, stride, k // 2, groups=groups, bias=False), nn.BatchNorm2d(cout, eps=1e-3)]
+        if act:
+            layers.append(nn.SiLU(inplace=True))
+        super().__init__(*layers)
+
+
+class MBConv(nn.Module):
+    def __init__(self, cin, cout, expand, k, stride, se_ratio=0.25):
+        super().__init__()
+        mid = cin * expand
+        self.expand = ConvBN(cin, mid, 1) if expand != 1 else nn.Identity()
+        self.dw = ConvBN(mid, mid, k, stride, groups=mid)
+        se = max(1, int(cin * se_ratio))
+        self.se_reduce = nn.Conv2d(mid, se, 1)
+        self.se_expand = nn.Conv2d(se, mid, 1)
+        self.project = ConvBN(mid, cout, 1, act=False)
+        self.skip = stride == 1 and cin == cout
+
+    def forward(self, x):
+        y = self.dw(self.expand(x))
+        s = y.mean((2, 3), keepdim=True)
+        y = y * torch.sigmoid(self.se_expand(Fn.silu(self.se_reduce(s))))
+        y = self.project(y)
+        return x + y if self.skip else y
+
+
+class Backbone(nn.Module):
+    """EfficientNet-B* trunk returning the stride 8/16/32 features."""
+    BLOCKS = [(1, 3, 1, 16, 1), (6, 3, 2, 24, 2), (6, 5, 2, 40, 2), (6, 3, 2, 80, 3), (6, 5, 1, 112, 3),
+              (6, 5, 2, 192, 4), (6, 3, 1, 320, 1)]
+
+    def __init__(self, width, depth):
+        super().__init__()
+        c = _round_filters(32, width)
+        self.stem = ConvBN(3, c, 3, 2)
+        stages, self.out_channels, self.taps = [], [], []
+        for i, (e, k, s, co, r) in enumerate(self.BLOCKS):
+            co = _round_filters(co, width)
+            blocks = []
+            for j in range(int(math.ceil(r * depth))):
+                blocks.append(MBConv(c, co, e, k, s if j == 0 else 1))
+                c = co
+            stages.append(nn.Sequential(*blocks))
+            if i in (2, 4, 6):
+                self.out_channels.append(c)
+        self.stages = nn.ModuleList(stages)
+
+    def forward(self, x):
+        x = self.stem(x)
+        feats = []
+        for i, st in enumerate(self.stages):
+            x = st(x)
+            if i in (2, 4, 6):
+                feats.append(x)
+        return feats
+
+
+class SepConvBN(nn.Sequential):
+    def __init__(self, c, act=False):
+        super().__init__(nn.Conv2d(c, c, 3, 1, 1, groups=c, bias=False), nn.Conv2d(c, c, 1, bias=True),
+                         nn.BatchNorm2d(c, eps=1e-3))
+
+
+class Fuse(nn.Module):
+    """Fast normalised fusion (weights relu'd and normalised) + swish + separable conv + BN."""
+
+    def __init__(self, n, c):
+        super().__init__()
+        self.w = nn.Parameter(torch.ones(n))
+        self.conv = SepConvBN(c)
+
+    def forward(self, xs: Sequence[torch.Tensor]):
+        w = Fn.relu(self.w)
+        w = w / (w.sum() + 1e-4)
+        y = xs[0] * w[0]
+        for i in range(1, len(xs)):
+            y = y + xs[i] * w[i]
+        return self.conv(Fn.silu(y))
+
+
+def _down(x):
+    return Fn.max_pool2d(x, 3, 2, 1)
+
+
+def _up(x, ref):
+    return Fn.interpolate(x, size=ref.shape[-2:], mode="nearest")
+
+
+class BiFPNLayer(nn.Module):
+    def __init__(self, c, in_channels=None):
+        super().__init__()
+        self.lateral = None
+        if in_channels is not None:      # first layer: project backbone features (two copies for P4/P5 like upstream)
+            self.lateral = nn.ModuleList([ConvBN(ci, c, 1, act=False) for ci in in_channels])
+            self.lateral2 = nn.ModuleList([ConvBN(ci, c, 1, act=False) for ci in in_channels[1:]])
+            self.p6 = ConvBN(in_channels[-1], c, 1, act=False)
+        self.td = nn.ModuleList([Fuse(2, c) for _ in range(4)])       # P6', P5', P4', P3 out
+        self.bu = nn.ModuleList([Fuse(3, c) for _ in range(3)] + [Fuse(2, c)])   # P4, P5, P6, P7 out
+
+    def forward(self, feats: List[torch.Tensor]):
+        if self.lateral is not None:
+            c3, c4, c5 = feats
+            p6 = _down(self.p6(c5))
+            p7 = _down(p6)
+            p3, p4, p5 = self.lateral[0](c3), self.lateral[1](c4), self.lateral[2](c5)
+            p4b, p5b = self.lateral2[0](c4), self.lateral2[1](c5)
+        else:
+            p3, p4, p5, p6, p7 = feats
+            p4b, p5b = p4, p5
+        t6 = self.td[0]([p6, _up(p7, p6)])
+        t5 = self.td[1]([p5, _up(t6, p5)])
+        t4 = self.td[2]([p4, _up(t5, p4)])
+        o3 = self.td[3]([p3, _up(t4, p3)])
+        o4 = self.bu[0]([p4b, t4, _down(o3)])
+        o5 = self.bu[1]([p5b, t5, _down(o4)])
+        o6 = self.bu[2]([p6, t6, _down(o5)])
+        o7 = self.bu[3]([p7, _down(o6)])
+        return [o3, o4, o5, o6, o7]
+
+
+class Head(nn.Module):
+    """Class / box net: shared separable convs, per-level BN, swish, then the prediction conv."""
+
+    def __init__(self, c, layers, out, levels=5, bias_init=0.0):
+        super().__init__()
+        self.dw = nn.ModuleList([nn.Conv2d(c, c, 3, 1, 1, groups=c, bias=False) for _ in range(layers)])
+        self.pw = nn.ModuleList([nn.Conv2d(c, c, 1) for _ in range(layers)])
+        self.bn = nn.ModuleList([nn.ModuleList([nn.BatchNorm2d(c, eps=1e-3) for _ in range(levels)]) for _ in range(layers)])
+        self.out_dw = nn.Conv2d(c, c, 3, 1, 1, groups=c, bias=False)
+        self.out_pw = nn.Conv2d(c, out, 1)
+        nn.init.constant_(self.out_pw.bias, bias_init)
+
+    def forward(self, feats):
+        outs = []
+        for lvl, x in enumerate(feats):
+            for i in range(len(self.dw)):
+                x = Fn.silu(self.bn[i][lvl](self.pw[i](self.dw[i](x))))
+            outs.append(self.out_pw(self.out_dw(x)))
+        return outs
+
+
+class EfficientDetVictim(nn.Module):
+    """`model(images, pre_mode=None, post_mode=None) -> (cls_outputs, box_outputs)` (attacker.py:98)."""
+
+    def __init__(self, config: VictimConfig):
+        super().__init__()
+        self.config = config
+        self.backbone = Backbone(config.width_mult, config.depth_mult)
+        c = config.fpn_channels
+        self.fpn = nn.ModuleList([BiFPNLayer(c, self.backbone.out_channels if i == 0 else None)
+                                  for i in range(config.fpn_layers)])
+        na = config.num_scales * len(config.aspect_ratios)
+        self.class_net = Head(c, config.head_layers, na * config.num_classes,
+                              bias_init=-math.log((1 - 0.01) / 0.01))      # efficientdet_keras.py:469
+        self.box_net = Head(c, config.head_layers, na * 4)
+        self.eval()                                                          # is_training_bn=False (infer_lib.py:171)
+        for p in self.parameters():
+            p.requires_grad_(False)                                          # only [scale, patch] train (attacker.py:63)
+
+    def forward(self, images: torch.Tensor, pre_mode=None, post_mode=None):
+        if pre_mode is not None or post_mode is not None:
+            raise NotImplementedError("the attack path calls the victim with pre_mode=None, post_mode=None")
+        x = images.permute(0, 3, 1, 2)                                       # NHWC memory == channels_last view
+        feats = self.backbone(x)
+        for layer in self.fpn:
+            feats = layer(feats)
+        cls = [o.permute(0, 2, 3, 1) for o in self.class_net(feats)]         # NHWC views, no copy
+        box = [o.permute(0, 2, 3, 1) for o in self.box_net(feats)]
+        return cls, box
+
+
+def get_victim_model(name: str = "efficientdet-d0", device="cuda", seed: int = 0, image_size: int = None) -> EfficientDetVictim:
+    """Counterpart of util.get_victim_model (util.py:177-189) with random-init weights."""
+    cfg = get_config(name)
+    if image_size is not None:
+        cfg.image_size = image_size
+    g = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    model = EfficientDetVictim(cfg)
+    torch.random.set_rng_state(g)
+    return model.to(device=device, memory_format=torch.channels_last)

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_symbols():
     src = open(os.path.join(ROOT, "include", "eotpatch.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(?:int|const char\*)\s+(\w+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(?:int|uint64_t|const char\*)\s+(\w+)\s*\(", src)))
 
 
 def test_header_symbols_match_binding_list():

@@ -1,0 +1,155 @@
+"""GPU: the whole attack step through the reference-shaped Python API (PatchAttacker.train_step) vs the
+oracle port of the same step, with the SAME victim weights (GPU vs CPU convolutions differ in the last bits,
+so the step-level bars are looser than the kernel-level ones in test_gpu_forward/backward/score)."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from mladversarialobjectdetection_b200 import ops, synth, victim
+from mladversarialobjectdetection_b200.attack_detection import Masker
+from mladversarialobjectdetection_b200.attacker import PatchAttacker, Patcher
+from mladversarialobjectdetection_b200.brightness_matcher import BrightnessMatcher
+from mladversarialobjectdetection_b200.ragged import RaggedBoxes
+from oracle import objective, patcher, step as ostep
+
+pytestmark = pytest.mark.gpu
+F = np.float32
+
+
+@pytest.fixture(scope="module")
+def no_tf32():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def test_train_step_matches_oracle_step(no_tf32):
+    H, P, B = 128, 32, 3
+    model = victim.get_victim_model("efficientdet-d0", device="cuda", image_size=H, seed=5)
+    # make the person class competitive so that every image has candidates
+    model.class_net.out_pw.bias.data.view(9, 90)[:, 0] += 6.0
+    cpu_model = victim.get_victim_model("efficientdet-d0", device="cpu", image_size=H, seed=5)
+    cpu_model.load_state_dict({k: v.cpu() for k, v in model.state_dict().items()})
+    bt = synth.make_batch(B, H, H, seed=77, max_boxes=3, min_boxes=1)
+    att = PatchAttacker(model, patch_size=P, device="cuda", seed=3)
+    att.compile(learning_rate=1e-2)
+    patch0 = att._patch.cpu().numpy().copy()
+    images = torch.from_numpy(bt.images).cuda()
+    boxes = RaggedBoxes(torch.from_numpy(bt.boxes).cuda(), torch.from_numpy(bt.offsets).cuda())
+    tr = (ops.params_to_tensor(bt.params, "cuda"), torch.from_numpy(bt.print_wb).cuda())
+    dscale, gpatch = att.call(images, training=True, boxes=boxes, transforms=tr)
+    torch.cuda.synchronize()
+    bx, pr = bt.ragged()
+    ref = ostep.attack_step(cpu_model, patch0, 0.4, bt.images, bx, pr, bt.print_wb, objective.anchor_boxes(H),
+                            first_pass=False)
+    M = att._last["max_scores"].cpu().numpy()
+    assert (ref["max_scores"] > 0).all()
+    np.testing.assert_allclose(M, ref["max_scores"], atol=2e-4)
+    assert abs(float(dscale) - float(ref["dscale"])) < 2e-3
+    g = gpatch.cpu().numpy()
+    gref = ref["grad_patch"] - F(1e-5) * __import__("oracle.tfops", fromlist=["x"]).total_variation(patch0)[1]
+    rel = np.linalg.norm(g - gref) / np.linalg.norm(gref)
+    assert rel < 2e-2, rel
+    # full train_step: metrics + Adam + constraints
+    att2 = PatchAttacker(model, patch_size=P, device="cuda", seed=3)
+    m = att2.train_step(images, boxes=boxes, transforms=tr)
+    torch.cuda.synchronize()
+    assert abs(float(m["loss"]) - float(ref["loss"])) < 5e-3 * max(1.0, float(ref["loss"]))
+    assert abs(float(m["tv_loss"]) - float(ref["tv"])) / float(ref["tv"]) < 1e-5
+    newp = att2._patch.cpu().numpy()
+    assert np.abs(newp).max() <= 1.0
+    moved = np.abs(newp - patch0)
+    assert 0.009 < np.median(moved[moved > 0]) <= 0.0101          # Adam's first step is lr * sign-like
+    assert 0.0 <= float(att2._scale_regressor) <= 1.0 and float(att2._scale_regressor) != 0.4
+
+
+def test_patcher_layer_signature_and_internal_sampler():
+    H, P = 160, 40
+    bt = synth.make_batch(2, H, H, seed=78, max_boxes=3)
+    patch = torch.from_numpy(synth.make_patch(P)).cuda()
+    scale = torch.tensor(0.4, device="cuda")
+    layer = Patcher(patch, scale, min_patch_area=4, name="Patcher", seed=11)
+    images = torch.from_numpy(bt.images).cuda()
+    rows = [bt.boxes_of(b) for b in range(2)]
+    out1 = layer([rows, images])                     # ragged python rows accepted, transforms drawn on device
+    out2 = layer([rows, images])
+    torch.cuda.synchronize()
+    assert out1.shape == images.shape and not torch.equal(out1, out2)        # fresh transforms per call
+    assert not torch.equal(out1, images)
+    layer2 = Patcher(patch, scale, seed=11)
+    assert torch.equal(layer2([rows, images]), out1)                         # same seed -> same draw
+    # replay through the oracle with the sampler's draw
+    s = layer2.sampler
+    boxes = RaggedBoxes.from_rows(rows, "cuda")
+    prm = s.box_params(0, 0, boxes.row_splits, boxes.values.shape[0]).cpu().numpy().view(synth.BOX_PARAMS).reshape(-1)
+    wb = s.print_wb(0, 0, 2, "cuda").cpu().numpy()
+    off = bt.offsets
+    ref, _, _ = patcher.patcher_forward(patch.cpu().numpy(), bt.images, rows, [prm[off[b]:off[b + 1]] for b in range(2)], wb, 0.4)
+    np.testing.assert_array_equal(out1.cpu().numpy(), ref)
+
+
+def test_sharded_draw_equals_single_rank_draw():
+    H, P, B = 128, 24, 4
+    bt = synth.make_batch(B, H, H, seed=79, max_boxes=3)
+    patch = torch.from_numpy(synth.make_patch(P)).cuda()
+    scale = torch.tensor(0.4, device="cuda")
+    images = torch.from_numpy(bt.images).cuda()
+    full = RaggedBoxes(torch.from_numpy(bt.boxes).cuda(), torch.from_numpy(bt.offsets).cuda())
+    whole = Patcher(patch, scale, seed=5)([full, images])
+    parts = []
+    for r in range(2):
+        lay = Patcher(patch, scale, seed=5)
+        lay.first_image = r * 2
+        parts.append(lay([full.slice_rows(r * 2, r * 2 + 2), images[r * 2:r * 2 + 2]]))
+    assert torch.equal(torch.cat(parts), whole)
+
+
+def test_brightness_matcher_layer():
+    rng = np.random.default_rng(80)
+    src = rng.uniform(-1.3, 1.3, (37, 53, 3)).astype(F)      # not square, slightly out of range: no clip before rescale
+    tgt = rng.uniform(-1, 1, (90, 70, 3)).astype(F)
+    out = BrightnessMatcher(name="Brightness_Matcher")((torch.from_numpy(src).cuda(), torch.from_numpy(tgt).cuda()))
+    ms = patcher.MatchState  # noqa
+    from oracle import tfops
+    s = (src + F(1)) * tfops.C_127_255
+    yuv = tfops.dot3(s, tfops.RGB2YUV)
+    mu_s, mu_t = tfops.mean_f64(yuv[..., 0]), patcher.image_mean_y(tgt)
+    yp = np.clip((yuv[..., 0] - mu_s) + mu_t, 0, 1)
+    rgb = tfops.dot3(np.stack([yp, yuv[..., 1], yuv[..., 2]], -1), tfops.YUV2RGB)
+    ref = np.clip(rgb, 0, 1) * tfops.C_255_127 - F(1)
+    np.testing.assert_array_equal(out.cpu().numpy(), ref.astype(F))
+
+
+def test_masker_layer_outputs_and_eval_branch():
+    H = 320
+    bt = synth.make_batch(3, H, H, seed=81, max_boxes=3)
+    images = torch.from_numpy(bt.images).cuda()
+    boxes = RaggedBoxes(torch.from_numpy(bt.boxes).cuda(), torch.from_numpy(bt.offsets).cuda())
+    patch = torch.from_numpy(synth.make_patch(64)).cuda()
+    scale = torch.tensor(0.4, device="cuda")
+    mk = Masker(patch, scale, seed=2)
+    out, mask = mk([boxes, images], training=True)
+    torch.cuda.synchronize()
+    assert out.shape == images.shape == mask.shape
+    changed = (out != images).any(-1)
+    assert changed.any() and torch.equal(mask[changed], (images - out)[changed])
+    assert float(mask[~changed].abs().max()) == 0.0
+    out_e, mask_e = mk([boxes, images], training=False)        # learned patch, tolerance 0, shared scale
+    assert not torch.equal(out_e, out)
+
+
+def test_save_and_resume_weights_roundtrip():
+    model = victim.get_victim_model("efficientdet-d0", device="cuda", image_size=128, seed=1)
+    att = PatchAttacker(model, patch_size=24, device="cuda", seed=9)
+    d = os.path.join(tempfile.mkdtemp(), "ckpt")
+    att.save_weights(d)
+    assert sorted(os.listdir(d)) == ["patch.png", "patch.tiff", "scale.txt"]
+    att2 = PatchAttacker(model, initial_patch=d, device="cuda")
+    assert torch.equal(att2._patch, att._patch) and abs(float(att2._scale_regressor) - 0.4) < 1e-7
+    with pytest.raises(FileExistsError):
+        att.save_weights(d)                                     # os.makedirs without exist_ok (attacker.py:334)
