@@ -22,22 +22,33 @@ constexpr int kMaxSmemPlansBwd = 48;
 constexpr int kBwdRows = 4;      // patch rows per k_bwd_resize CTA
 constexpr int kBwdGroups = 16;   // image groups of k_bwd_texel
 
-// gradient that reaches R_j at window element (xi, yi, c) of box jl (local index in pp[0..nb))
-__device__ __forceinline__ float routed_grad(const BoxPlan* pp, int nb, int jl, const float* __restrict__ ubuf,
-                                             const float* __restrict__ G, int H, int W, int xi, int yi, int c) {
+// gradient that reaches R_j at window pixel (xi, yi) of box jl (local index in pp[0..nb)), 3 channels
+__device__ __forceinline__ void routed_grad3(const BoxPlan* pp, int nb, int jl, const float* __restrict__ ubuf,
+                                             const float* __restrict__ G, int H, int W, int xi, int yi, float g[3]) {
   const BoxPlan& me = pp[jl];
-  const float R = warp_sample(me, ubuf + me.u_off, xi, yi, c);
-  if (!(R >= -1.0f && R <= 1.0f)) return 0.0f;            // SelectV2 took the background, or outer clip
+  float R[3];
+  warp_sample3(me, ubuf + me.u_off, xi, yi, R);
+  bool pass[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) pass[c] = (R[c] >= -1.0f && R[c] <= 1.0f);   // SelectV2 took R, outer clip open
+  g[0] = g[1] = g[2] = 0.0f;
+  if (!(pass[0] || pass[1] || pass[2])) return;
   const int gy = me.y0 + yi, gx = me.x0 + xi;
-  for (int q = jl + 1; q < nb; ++q) {                      // a later paste that covered this element?
+  for (int q = jl + 1; q < nb; ++q) {                      // a later paste that covered this pixel?
     const BoxPlan& o = pp[q];
     if (!o.valid) continue;
     const int ly = gy - o.y0, lx = gx - o.x0;
     if (ly < 0 || ly >= o.d || lx < 0 || lx >= o.d) continue;
-    const float Rq = warp_sample(o, ubuf + o.u_off, lx, ly, c);
-    if (!(Rq < -1.0f)) return 0.0f;                        // overwritten: TensorScatterUpdate grad is 0 here
+    float Rq[3];
+    warp_sample3(o, ubuf + o.u_off, lx, ly, Rq);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) pass[c] = pass[c] && (Rq[c] < -1.0f);   // else overwritten: scatter grad is 0
+    if (!(pass[0] || pass[1] || pass[2])) return;
   }
-  return __ldg(G + (((size_t)me.image * H + gy) * W + gx) * 3 + c);
+  const float* gp = G + (((size_t)me.image * H + gy) * W + gx) * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    if (pass[c]) g[c] = __ldg(gp + c);
 }
 
 __global__ void __launch_bounds__(kThreads) k_bwd_window(EotShape s, Layout L, char* ws, const float* __restrict__ G) {
@@ -48,6 +59,7 @@ __global__ void __launch_bounds__(kThreads) k_bwd_window(EotShape s, Layout L, c
   const float* ubuf = reinterpret_cast<const float*>(ws + L.off_u);
   float* gubuf = reinterpret_cast<float*>(ws + L.off_gu);
   const int H = s.height, W = s.width;
+  const int RR = L.resize_rows;
   for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
     const int2 item = items[it];
     const int j = item.x;
@@ -68,47 +80,47 @@ __global__ void __launch_bounds__(kThreads) k_bwd_window(EotShape s, Layout L, c
     const int ps = me.ps, D = me.d;
     const float* u = ubuf + me.u_off;
     float* gu = gubuf + me.u_off;
-    const int oy0 = item.y * kResizeRows;
-    const int rows = min(kResizeRows, ps - oy0);
-    const int e_begin = oy0 * ps * 3, e_end = (oy0 + rows) * ps * 3;
-    for (int e = e_begin + threadIdx.x; e < e_end; e += blockDim.x) {
-      const int pix = e / 3, c = e - pix * 3;
-      const int ty = pix / ps, tx = pix - ty * ps;
+    const int oy0 = item.y * RR;
+    const int rows = min(RR, ps - oy0);
+    const bool affine = (me.Ti[6] == 0.0f && me.Ti[7] == 0.0f);
+    for (int t = threadIdx.x; t < rows * ps; t += blockDim.x) {
+      const int r = t / ps, tx = t - r * ps;
+      const int ty = oy0 + r;
       const float xf = (float)(tx + me.pad_lo), yf = (float)(ty + me.pad_lo);
-      float g = 0.0f;
-      const float proj = (me.Ti[6] * xf + me.Ti[7] * yf) + 1.0f;
-      if (proj != 0.0f) {
-        const float ix = ((me.Ti[0] * xf + me.Ti[1] * yf) + me.Ti[2]) / proj;
-        const float iy = ((me.Ti[3] * xf + me.Ti[4] * yf) + me.Ti[5]) / proj;
+      float g[3] = {0.0f, 0.0f, 0.0f};
+      float ix = (me.Ti[0] * xf + me.Ti[1] * yf) + me.Ti[2];
+      float iy = (me.Ti[3] * xf + me.Ti[4] * yf) + me.Ti[5];
+      bool ok = true;
+      if (!affine) {
+        const float proj = (me.Ti[6] * xf + me.Ti[7] * yf) + 1.0f;
+        ok = proj != 0.0f;
+        if (ok) { ix = ix / proj; iy = iy / proj; }
+      }
+      if (ok) {
         const float x0f = floorf(ix), y0f = floorf(iy);
         const float x1f = x0f + 1.0f, y1f = y0f + 1.0f;
         const float Df = (float)D;
         const bool bx0 = x0f >= 0.0f && x0f < Df, bx1 = x1f >= 0.0f && x1f < Df;
         const bool by0 = y0f >= 0.0f && y0f < Df, by1 = y1f >= 0.0f && y1f < Df;
         const int xi0 = (int)x0f, yi0 = (int)y0f;
-        const float v00 = (by0 && bx0) ? routed_grad(pp, nb, jl, ubuf, G, H, W, xi0, yi0, c) : 0.0f;
-        const float v01 = (by0 && bx1) ? routed_grad(pp, nb, jl, ubuf, G, H, W, xi0 + 1, yi0, c) : 0.0f;
-        const float v10 = (by1 && bx0) ? routed_grad(pp, nb, jl, ubuf, G, H, W, xi0, yi0 + 1, c) : 0.0f;
-        const float v11 = (by1 && bx1) ? routed_grad(pp, nb, jl, ubuf, G, H, W, xi0 + 1, yi0 + 1, c) : 0.0f;
+        float v00[3] = {0.f, 0.f, 0.f}, v01[3] = {0.f, 0.f, 0.f}, v10[3] = {0.f, 0.f, 0.f}, v11[3] = {0.f, 0.f, 0.f};
+        if (by0 && bx0) routed_grad3(pp, nb, jl, ubuf, G, H, W, xi0, yi0, v00);
+        if (by0 && bx1) routed_grad3(pp, nb, jl, ubuf, G, H, W, xi0 + 1, yi0, v01);
+        if (by1 && bx0) routed_grad3(pp, nb, jl, ubuf, G, H, W, xi0, yi0 + 1, v10);
+        if (by1 && bx1) routed_grad3(pp, nb, jl, ubuf, G, H, W, xi0 + 1, yi0 + 1, v11);
         const float wx1 = x1f - ix, wx0 = ix - x0f, wy1 = y1f - iy, wy0 = iy - y0f;
-        g = wy1 * (wx1 * v00 + wx0 * v01) + wy0 * (wx1 * v10 + wx0 * v11);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) g[c] = wy1 * (wx1 * v00[c] + wx0 * v01[c]) + wy0 * (wx1 * v10[c] + wx0 * v11[c]);
       }
-      const float up = u[e];
-      gu[e] = (up >= -1.0f && up <= 1.0f) ? g : 0.0f;        // inner clip (attacker.py:428)
+      const size_t e = ((size_t)ty * ps + tx) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float up = u[e + c];
+        gu[e + c] = (up >= -1.0f && up <= 1.0f) ? g[c] : 0.0f;        // inner clip (attacker.py:428)
+      }
     }
     __syncthreads();
   }
-}
-
-// first output index o whose span [start[o], start[o]+span) can contain input index i, and the last.
-__device__ __forceinline__ void inverse_span(const int* __restrict__ starts, int n_out, int span, int i, int* lo, int* hi) {
-  int a = 0, b = n_out;                       // lower_bound: first o with starts[o] >= i - span + 1
-  const int key = i - span + 1;
-  while (a < b) { const int m = (a + b) >> 1; if (starts[m] < key) a = m + 1; else b = m; }
-  *lo = a;
-  a = 0; b = n_out;                           // upper_bound: first o with starts[o] > i
-  while (a < b) { const int m = (a + b) >> 1; if (starts[m] <= i) a = m + 1; else b = m; }
-  *hi = a - 1;
 }
 
 __global__ void __launch_bounds__(kThreads) k_bwd_resize(EotShape s, Layout L, char* ws, const float* __restrict__ patch,
@@ -132,17 +144,17 @@ __global__ void __launch_bounds__(kThreads) k_bwd_resize(EotShape s, Layout L, c
     const int ps = pl->ps, ps3 = ps * 3, span = pl->span;
     const int* starts = reinterpret_cast<const int*>(ws + L.off_starts) + (size_t)j * L.lmin;
     const float* wts = reinterpret_cast<const float*>(ws + L.off_weights) + (size_t)j * L.wcap;
+    const int2* inv = reinterpret_cast<const int2*>(ws + L.off_inv) + (size_t)j * P;
     const float* gu = gubuf + pl->u_off;
     // rows: tmp[r][f] = sum_oy w[oy][py - start[oy]] * gu[oy][f]
     for (int idx = threadIdx.x; idx < rows * ps3; idx += blockDim.x) {
       const int r = idx / ps3, f = idx - r * ps3;
       const int py = py0 + r;
-      int lo, hi;
-      inverse_span(starts, ps, span, py, &lo, &hi);
+      const int2 rng = __ldg(inv + py);
       float a = 0.0f;
-      for (int oy = lo; oy <= hi; ++oy) {
-        const int k = py - starts[oy];
-        if (k >= 0 && k < span) a += wts[(size_t)oy * span + k] * __ldg(gu + (size_t)oy * ps3 + f);
+      for (int oy = rng.x; oy <= rng.y; ++oy) {
+        const int k = py - __ldg(starts + oy);
+        if (k >= 0 && k < span) a += __ldg(wts + (size_t)oy * span + k) * __ldg(gu + (size_t)oy * ps3 + f);
       }
       tmp[r * (L.lmin * 3) + f] = a;
     }
@@ -151,12 +163,11 @@ __global__ void __launch_bounds__(kThreads) k_bwd_resize(EotShape s, Layout L, c
     for (int idx = threadIdx.x; idx < rows * P3; idx += blockDim.x) {
       const int r = idx / P3, f = idx - r * P3;
       const int px = f / 3, c = f - px * 3;
-      int lo, hi;
-      inverse_span(starts, ps, span, px, &lo, &hi);
+      const int2 rng = __ldg(inv + px);
       float a = 0.0f;
-      for (int ox = lo; ox <= hi; ++ox) {
-        const int k = px - starts[ox];
-        if (k >= 0 && k < span) a += wts[(size_t)ox * span + k] * tmp[r * (L.lmin * 3) + ox * 3 + c];
+      for (int ox = rng.x; ox <= rng.y; ++ox) {
+        const int k = px - __ldg(starts + ox);
+        if (k >= 0 && k < span) a += __ldg(wts + (size_t)ox * span + k) * tmp[r * (L.lmin * 3) + ox * 3 + c];
       }
       acc_tile[idx] += a;
     }

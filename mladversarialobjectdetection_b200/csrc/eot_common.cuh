@@ -33,8 +33,7 @@ namespace eot {
 #define EOT_C255_127 ((float)(255.0 / 127.0))   // brightness_matcher.py:41
 #define EOT_SQRT2 1.41421354f                   // float32(2. ** .5), attacker.py:470
 
-constexpr int kResizeRows = 4;        // output rows per resize work item
-constexpr int kCompChunk = 2048;      // window elements per composite work item
+constexpr int kCompRows = 16;         // window rows per composite work item (one warp per row)
 constexpr int kThreads = 256;
 
 // Per-box plan written by the geometry kernel; 128 bytes.
@@ -62,8 +61,9 @@ struct Layout {
   size_t off_weights;      // float[N][wcap]
   size_t off_match;        // float[B][P*P*3]
   size_t off_u;            // float[N][slot]
-  size_t off_items_resize; // int2[N*ceil(Lmin/kResizeRows)]
-  size_t off_items_comp;   // int2[N*ceil(3*Lmin*Lmin/kCompChunk)]
+  size_t off_items_resize; // int2[N*ceil(Lmin/resize_rows)]
+  size_t off_items_comp;   // int2[N*ceil(Lmin/kCompRows)]
+  size_t off_inv;          // int2[N][P]  for patch index i: first/last output index whose span holds i
   size_t off_gm;           // float[B][P*P*3] backward: dL/d(matched patch) per image
   size_t off_gu;           // float[N][slot]  backward: dL/d(u) per box
   size_t off_gp_part;      // float[16][P*P*3] backward: partial dL/dpatch per image group
@@ -72,6 +72,7 @@ struct Layout {
   int64_t slot;            // floats per u slot
   int32_t wcap;            // floats per weight table
   int32_t lmin;            // max patch side
+  int32_t resize_rows;     // output rows per resize work item (bounded by shared memory: rows * P * 12 B)
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -86,6 +87,8 @@ __host__ __device__ inline Layout make_layout(const EotShape& s) {
   L.lmin = lmin;
   L.wcap = 2 * s.patch_size + 3 * lmin + 8;
   L.slot = (int64_t)align_up((size_t)lmin * lmin * 3, 32);
+  int rr = 12288 / (s.patch_size * 3);       // <= 48 KB of float32 intermediate rows
+  L.resize_rows = rr > 16 ? 16 : (rr < 1 ? 1 : rr);
   const size_t PP3 = (size_t)s.patch_size * s.patch_size * 3;
   size_t o = 0;
   L.off_ysum_img = o;     o = align_up(o + B * sizeof(double), 256);
@@ -97,8 +100,9 @@ __host__ __device__ inline Layout make_layout(const EotShape& s) {
   L.off_weights = o;      o = align_up(o + N * (size_t)L.wcap * sizeof(float), 256);
   L.off_match = o;        o = align_up(o + B * PP3 * sizeof(float), 256);
   L.off_u = o;            o = align_up(o + N * (size_t)L.slot * sizeof(float), 256);
-  L.off_items_resize = o; o = align_up(o + N * (size_t)((lmin + kResizeRows - 1) / kResizeRows) * 8, 256);
-  L.off_items_comp = o;   o = align_up(o + N * (((size_t)3 * lmin * lmin + kCompChunk - 1) / kCompChunk + 1) * 8, 256);
+  L.off_items_resize = o; o = align_up(o + N * (size_t)((lmin + L.resize_rows - 1) / L.resize_rows) * 8, 256);
+  L.off_items_comp = o;   o = align_up(o + N * (size_t)((lmin + kCompRows - 1) / kCompRows) * 8, 256);
+  L.off_inv = o;          o = align_up(o + N * (size_t)s.patch_size * 8, 256);
   L.off_gm = o;           o = align_up(o + B * PP3 * sizeof(float), 256);
   L.off_gu = o;           o = align_up(o + N * (size_t)L.slot * sizeof(float), 256);
   L.off_gp_part = o;      o = align_up(o + 16 * PP3 * sizeof(float), 256);
@@ -212,6 +216,47 @@ __device__ __forceinline__ float warp_sample(const BoxPlan& pl, const float* __r
   const float a = wx1 * v00 + wx0 * v01;
   const float b = wx1 * v10 + wx0 * v11;
   return wy1 * a + wy0 * b;
+}
+
+// Same sampling for the three channels of one window pixel (coordinates computed once).  For the
+// reference's pure rotation the projective row is zero, proj == 1 exactly and x / 1 == x, so the two
+// divisions are skipped without changing a bit.
+__device__ __forceinline__ void warp_sample3(const BoxPlan& pl, const float* __restrict__ u, int xo, int yo, float R[3]) {
+  const float xf = (float)xo, yf = (float)yo;
+  float ix = (pl.T[0] * xf + pl.T[1] * yf) + pl.T[2];
+  float iy = (pl.T[3] * xf + pl.T[4] * yf) + pl.T[5];
+  if (pl.T[6] != 0.0f || pl.T[7] != 0.0f) {
+    const float proj = (pl.T[6] * xf + pl.T[7] * yf) + 1.0f;
+    if (proj == 0.0f) { R[0] = R[1] = R[2] = -2.0f; return; }
+    ix = ix / proj;
+    iy = iy / proj;
+  }
+  const float x0f = floorf(ix), y0f = floorf(iy);
+  const float x1f = x0f + 1.0f, y1f = y0f + 1.0f;
+  const float lo = (float)pl.pad_lo, hi = (float)(pl.pad_lo + pl.ps);
+  const bool bx0 = (x0f >= lo) && (x0f < hi), bx1 = (x1f >= lo) && (x1f < hi);
+  const bool by0 = (y0f >= lo) && (y0f < hi), by1 = (y1f >= lo) && (y1f < hi);
+  const float wx1 = x1f - ix, wx0 = ix - x0f, wy1 = y1f - iy, wy0 = iy - y0f;
+  if (!((bx0 || bx1) && (by0 || by1))) {      // all four taps are pad / fill: same arithmetic on -2
+    const float a = wx1 * -2.0f + wx0 * -2.0f;
+    const float r = wy1 * a + wy0 * a;
+    R[0] = R[1] = R[2] = r;
+    return;
+  }
+  const int xi0 = (int)x0f - pl.pad_lo, yi0 = (int)y0f - pl.pad_lo;
+  const int rs = pl.ps * 3;
+  const float* p00 = u + (int64_t)yi0 * rs + xi0 * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v00 = -2.0f, v01 = -2.0f, v10 = -2.0f, v11 = -2.0f;
+    if (by0 && bx0) v00 = clampf(__ldg(p00 + c), -1.f, 1.f);
+    if (by0 && bx1) v01 = clampf(__ldg(p00 + 3 + c), -1.f, 1.f);
+    if (by1 && bx0) v10 = clampf(__ldg(p00 + rs + c), -1.f, 1.f);
+    if (by1 && bx1) v11 = clampf(__ldg(p00 + rs + 3 + c), -1.f, 1.f);
+    const float a = wx1 * v00 + wx0 * v01;
+    const float b = wx1 * v10 + wx0 * v11;
+    R[c] = wy1 * a + wy0 * b;
+  }
 }
 #endif  // __CUDACC__
 

@@ -135,70 +135,77 @@ __device__ inline void span_row(int o, const SpanCfg& c, int in_size, int* start
   *start_out = (int)s0;
 }
 
-__global__ void __launch_bounds__(128) k_geometry(EotShape s, Layout L, const float* __restrict__ boxes,
-                                                   const int32_t* __restrict__ offsets,
-                                                   const EotBoxParams* __restrict__ params,
-                                                   const float* __restrict__ scale, char* ws,
-                                                   EotBoxGeometry* geom_out) {
-  const int b = blockIdx.x;
-  const int first = offsets[b], last = offsets[b + 1];
-  BoxPlan* plans = ws ? reinterpret_cast<BoxPlan*>(ws + L.off_plans) : nullptr;
+// first output index whose span [start, start+span) can hold input index i, and the last one
+// (starts[] is non-decreasing).  Used by the resize adjoint of the backward.
+__device__ __forceinline__ int2 inverse_span_search(const int* starts, int n_out, int span, int i) {
+  int a = 0, b = n_out;
+  const int key = i - span + 1;
+  while (a < b) { const int m = (a + b) >> 1; if (starts[m] < key) a = m + 1; else b = m; }
+  const int lo = a;
+  a = 0; b = n_out;
+  while (a < b) { const int m = (a + b) >> 1; if (starts[m] <= i) a = m + 1; else b = m; }
+  return make_int2(lo, a - 1);
+}
+
+// One CTA per box: plan, span table, inverse-span table, work items.
+__device__ void geometry_block(const EotShape& s, const Layout& L, int j, const float* __restrict__ boxes,
+                               const int32_t* __restrict__ offsets, const EotBoxParams* __restrict__ params,
+                               const float* __restrict__ scale, char* ws, EotBoxGeometry* geom_out) {
+  __shared__ BoxPlan spl;
+  __shared__ int base_r, base_c;
   int* counters = ws ? reinterpret_cast<int*>(ws + L.off_counters) : nullptr;
-  const float sc = *scale;
-  if (ws && threadIdx.x == 0) {
-    int32_t* off_copy = reinterpret_cast<int32_t*>(ws + L.off_offsets);
-    off_copy[b] = first;
-    if (b == gridDim.x - 1) off_copy[b + 1] = last;
-  }
-  for (int j = first + threadIdx.x; j < last; j += blockDim.x) {
-    BoxPlan pl = make_plan(boxes + (size_t)j * 4, sc, params[j], s, b, first, last, (int64_t)j * L.slot,
-                           counters ? counters + 2 : nullptr);
+  if (threadIdx.x == 0) {
+    int a = 0, b = s.batch;                       // image of box j: last b with offsets[b] <= j
+    while (a < b) { const int m = (a + b) >> 1; if (offsets[m + 1] <= j) a = m + 1; else b = m; }
+    BoxPlan pl = make_plan(boxes + (size_t)j * 4, *scale, params[j], s, a, offsets[a], offsets[a + 1],
+                           (int64_t)j * L.slot, counters ? counters + 2 : nullptr);
     if (pl.valid) pl.span = span_cfg(pl.ps, s.patch_size).span;
-    if (plans) plans[j] = pl;
+    spl = pl;
+    if (ws) reinterpret_cast<BoxPlan*>(ws + L.off_plans)[j] = pl;
     if (geom_out) {
       EotBoxGeometry g = {pl.y0, pl.x0, pl.ps, pl.d, pl.pad_lo, pl.pad_hi, pl.valid, pl.span};
       geom_out[j] = g;
     }
+    if (ws && pl.valid) {
+      base_r = atomicAdd(counters + 0, (pl.ps + L.resize_rows - 1) / L.resize_rows);
+      base_c = atomicAdd(counters + 1, (pl.d + kCompRows - 1) / kCompRows);
+    }
   }
-  if (!ws) return;
   __syncthreads();
-  int* starts = reinterpret_cast<int*>(ws + L.off_starts);
-  float* weights = reinterpret_cast<float*>(ws + L.off_weights);
+  if (!ws || !spl.valid) return;
+  const int ps = spl.ps, P = s.patch_size;
+  int* starts = reinterpret_cast<int*>(ws + L.off_starts) + (size_t)j * L.lmin;
+  float* weights = reinterpret_cast<float*>(ws + L.off_weights) + (size_t)j * L.wcap;
+  const SpanCfg cfg = span_cfg(ps, P);
+  for (int o = threadIdx.x; o < ps; o += blockDim.x) span_row(o, cfg, P, starts + o, weights + (size_t)o * cfg.span);
+  const int nres = (ps + L.resize_rows - 1) / L.resize_rows, ncomp = (spl.d + kCompRows - 1) / kCompRows;
   int2* items_r = reinterpret_cast<int2*>(ws + L.off_items_resize);
   int2* items_c = reinterpret_cast<int2*>(ws + L.off_items_comp);
-  __shared__ int base_r, base_c;
-  for (int j = first; j < last; ++j) {
-    const BoxPlan& pl = plans[j];
-    if (!pl.valid) continue;
-    const SpanCfg cfg = span_cfg(pl.ps, s.patch_size);
-    for (int o = threadIdx.x; o < pl.ps; o += blockDim.x)
-      span_row(o, cfg, s.patch_size, starts + (size_t)j * L.lmin + o, weights + (size_t)j * L.wcap + (size_t)o * cfg.span);
-    const int nres = (pl.ps + kResizeRows - 1) / kResizeRows;
-    const int ncomp = (pl.d * pl.d * 3 + kCompChunk - 1) / kCompChunk;
-    if (threadIdx.x == 0) {
-      base_r = atomicAdd(counters + 0, nres);
-      base_c = atomicAdd(counters + 1, ncomp);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < nres; i += blockDim.x) items_r[base_r + i] = make_int2(j, i);
-    for (int i = threadIdx.x; i < ncomp; i += blockDim.x) items_c[base_c + i] = make_int2(j, i);
-    __syncthreads();
-  }
+  for (int i = threadIdx.x; i < nres; i += blockDim.x) items_r[base_r + i] = make_int2(j, i);
+  for (int i = threadIdx.x; i < ncomp; i += blockDim.x) items_c[base_c + i] = make_int2(j, i);
+  __syncthreads();                                  // starts[] of this box are complete
+  int2* inv = reinterpret_cast<int2*>(ws + L.off_inv) + (size_t)j * P;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) inv[i] = inverse_span_search(starts, ps, cfg.span, i);
+}
+
+__global__ void __launch_bounds__(kThreads) k_geometry_only(EotShape s, Layout L, const float* __restrict__ boxes,
+                                                            const int32_t* __restrict__ offsets,
+                                                            const EotBoxParams* __restrict__ params,
+                                                            const float* __restrict__ scale, EotBoxGeometry* geom_out) {
+  geometry_block(s, L, blockIdx.x, boxes, offsets, params, scale, nullptr, geom_out);
 }
 
 // ------------------------------------------------------------------------------------------------
 // patch luma statistics: mean Y of rescale(print_adjust(patch)) per image
 // (attacker.py:372 -> brightness_matcher.py:54,58,62-63)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_patch_stats(EotShape s, const float* __restrict__ patch,
-                                                          const float* __restrict__ print_wb, double* ysum_patch) {
-  __shared__ double red[32];
-  const int b = blockIdx.y;
+__device__ void patch_stats_block(const EotShape& s, int b, int chunk, int nchunks, const float* __restrict__ patch,
+                                  const float* __restrict__ print_wb, double* ysum_patch, double* red) {
   const int P = s.patch_size;
   const float* wb = print_wb + (size_t)b * 6;
   const float* base = patch + (s.num_patches > 1 ? (int64_t)b * s.patch_stride_n : 0);
   double acc = 0.0;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < P * P; t += gridDim.x * blockDim.x) {
+  for (int t = chunk * blockDim.x + threadIdx.x; t < P * P; t += nchunks * blockDim.x) {
     const int py = t / P, px = t - py * P;
     const float* p = base + (int64_t)py * s.patch_stride_y + (int64_t)px * s.patch_stride_x;
     acc += (double)texel_yuv(__ldg(p), __ldg(p + 1), __ldg(p + 2), wb).y;
@@ -220,16 +227,14 @@ __device__ __forceinline__ float luma_of(float r, float g, float b) {
 }
 
 template <bool kVec>
-__global__ void __launch_bounds__(kThreads) k_image_pass(int HW, const float* __restrict__ images, float* out,
-                                                         float* mask, double* ysum_img) {
-  __shared__ double red[32];
-  const int b = blockIdx.y;
+__device__ __forceinline__ void image_pass_block(int HW, int b, int chunk, const float* __restrict__ images, float* out,
+                                                 float* mask, double* ysum_img, double* red) {
   const size_t img_off = (size_t)b * HW * 3;
   const float* in = images + img_off;
   float* o = (out && out != images) ? out + img_off : nullptr;
   float* mk = mask ? mask + img_off : nullptr;
   double acc = 0.0;
-  const int pix0 = blockIdx.x * kPassPixPerBlock;
+  const int pix0 = chunk * kPassPixPerBlock;
   if (kVec) {
     const float4* in4 = reinterpret_cast<const float4*>(in);
     float4* o4 = reinterpret_cast<float4*>(o);
@@ -272,6 +277,40 @@ __global__ void __launch_bounds__(kThreads) k_image_pass(int HW, const float* __
   }
   acc = block_sum(acc, red);
   if (threadIdx.x == 0) atomicAdd(ysum_img + b, acc);
+}
+
+// One launch, three independent roles selected by the block index (they only meet at k_match):
+//   [0, N)                         geometry of box j
+//   [N, N + B*pchunks)             patch luma statistics
+//   [N + B*pchunks, ... + B*cpi)   image pass (copy + luma sum), the HBM-bound bulk
+template <bool kVec>
+__global__ void __launch_bounds__(kThreads) k_prepass(EotShape s, Layout L, const float* __restrict__ patch,
+                                                      const float* __restrict__ print_wb, const float* __restrict__ boxes,
+                                                      const int32_t* __restrict__ offsets,
+                                                      const EotBoxParams* __restrict__ params,
+                                                      const float* __restrict__ scale, const float* __restrict__ images,
+                                                      float* out, float* mask, char* ws, int pchunks, int cpi) {
+  __shared__ double red[32];
+  int blk = blockIdx.x;
+  const int N = s.total_boxes;
+  if (blk < N) {
+    geometry_block(s, L, blk, boxes, offsets, params, scale, ws, nullptr);
+    return;
+  }
+  blk -= N;
+  if (blk < s.batch * pchunks) {
+    const int b = blk / pchunks;
+    patch_stats_block(s, b, blk - b * pchunks, pchunks, patch, print_wb, reinterpret_cast<double*>(ws + L.off_ysum_patch), red);
+    return;
+  }
+  blk -= s.batch * pchunks;
+  const int b = blk / cpi, chunk = blk - b * cpi;
+  if (chunk == 0 && threadIdx.x == 0) {                 // CSR copy for the backward
+    int32_t* off_copy = reinterpret_cast<int32_t*>(ws + L.off_offsets);
+    off_copy[b] = offsets[b];
+    if (b == s.batch - 1) off_copy[b + 1] = offsets[b + 1];
+  }
+  image_pass_block<kVec>(s.height * s.width, b, chunk, images, out, mask, reinterpret_cast<double*>(ws + L.off_ysum_img), red);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -336,17 +375,18 @@ __global__ void __launch_bounds__(kThreads) k_bm_apply(const float* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-// resize + noise + delta for one strip of kResizeRows output rows of one box
+// resize + noise + delta for one strip of L.resize_rows output rows of one box
 // (attacker.py:425-427; ScaleAndTranslate GatherRows then GatherColumns)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_resize(EotShape s, Layout L, char* ws) {
-  extern __shared__ float inter[];   // [kResizeRows][P*3]
+__global__ void __launch_bounds__(kThreads, 4) k_resize(EotShape s, Layout L, char* ws) {
+  extern __shared__ float inter[];   // [resize_rows][P*3]
   const int P = s.patch_size, P3 = P * 3;
   const BoxPlan* plans = reinterpret_cast<const BoxPlan*>(ws + L.off_plans);
   const int2* items = reinterpret_cast<const int2*>(ws + L.off_items_resize);
   const int n_items = reinterpret_cast<const int*>(ws + L.off_counters)[0];
   const float* match = reinterpret_cast<const float*>(ws + L.off_match);
   float* ubuf = reinterpret_cast<float*>(ws + L.off_u);
+  const int RR = L.resize_rows;
   for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
     const int2 item = items[it];
     const int j = item.x;
@@ -354,8 +394,8 @@ __global__ void __launch_bounds__(kThreads) k_resize(EotShape s, Layout L, char*
     const int ps = pl->ps, span = pl->span;
     const float delta = pl->delta;
     const uint32_t key0 = pl->key0, key1 = pl->key1;
-    const int oy0 = item.y * kResizeRows;
-    const int rows = min(kResizeRows, ps - oy0);
+    const int oy0 = item.y * RR;
+    const int rows = min(RR, ps - oy0);
     const float* m = match + (size_t)pl->image * P * P3;
     const int* starts = reinterpret_cast<const int*>(ws + L.off_starts) + (size_t)j * L.lmin;
     const float* wts = reinterpret_cast<const float*>(ws + L.off_weights) + (size_t)j * L.wcap;
@@ -363,11 +403,11 @@ __global__ void __launch_bounds__(kThreads) k_resize(EotShape s, Layout L, char*
     for (int idx = threadIdx.x; idx < rows * P3; idx += blockDim.x) {
       const int r = idx / P3, f = idx - r * P3;
       const int oy = oy0 + r;
-      const int st = starts[oy];
+      const int st = __ldg(starts + oy);
       const float* w = wts + (size_t)oy * span;
       const int nk = min(span, P - st);
       float acc = 0.0f;
-      for (int k = 0; k < nk; ++k) acc = acc + w[k] * __ldg(m + (size_t)(st + k) * P3 + f);
+      for (int k = 0; k < nk; ++k) acc = acc + __ldg(w + k) * __ldg(m + (size_t)(st + k) * P3 + f);
       inter[idx] = acc;
     }
     __syncthreads();
@@ -382,11 +422,11 @@ __global__ void __launch_bounds__(kThreads) k_resize(EotShape s, Layout L, char*
         const int pix = e / 3, c = e - pix * 3;
         const int oy = pix / ps, ox = pix - oy * ps;
         const int r = oy - oy0;
-        const int st = starts[ox];
+        const int st = __ldg(starts + ox);
         const float* w = wts + (size_t)ox * span;
         const int nk = min(span, P - st);
         float acc = 0.0f;
-        for (int k = 0; k < nk; ++k) acc = acc + w[k] * inter[r * P3 + (st + k) * 3 + c];
+        for (int k = 0; k < nk; ++k) acc = acc + __ldg(w + k) * inter[r * P3 + (st + k) * 3 + c];
         u[e] = (acc + noise_from_word(words[q], s.noise_amp)) + delta;
       }
     }
@@ -397,19 +437,27 @@ __global__ void __launch_bounds__(kThreads) k_resize(EotShape s, Layout L, char*
 // ------------------------------------------------------------------------------------------------
 // composite (attacker.py:436-444 in gather form).  Sequential-paste semantics: an element's final
 // value is clip(R_j) of the LAST box j (in paste order) covering it with R_j >= -1, else
-// clip(original); elements outside every window are untouched by this kernel.  An element covered by
+// clip(original); elements outside every window are untouched by this kernel.  A pixel covered by
 // several windows is written only by the items of the last covering box.
+//
+// One work item = kCompRows window rows of one box; one warp per row, one lane per pixel (the
+// sampling coordinates are shared by the three channels); the row segment is transposed through
+// shared memory so that global loads and stores are contiguous 128-byte warp accesses.
 // ------------------------------------------------------------------------------------------------
-constexpr int kMaxSmemPlans = 48;
+constexpr int kMaxSmemPlans = 32;
 
 __global__ void __launch_bounds__(kThreads) k_composite(EotShape s, Layout L, char* ws,
                                                         const float* __restrict__ images, float* out, float* mask) {
   __shared__ BoxPlan sp[kMaxSmemPlans];
+  __shared__ float stage[kThreads / 32][2][96];
   const BoxPlan* plans = reinterpret_cast<const BoxPlan*>(ws + L.off_plans);
   const int2* items = reinterpret_cast<const int2*>(ws + L.off_items_comp);
   const int n_items = reinterpret_cast<const int*>(ws + L.off_counters)[1];
   const float* ubuf = reinterpret_cast<const float*>(ws + L.off_u);
   const int H = s.height, W = s.width;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* sv = stage[warp][0];   // values to store
+  float* so = stage[warp][1];   // original pixels of the segment
   for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
     const int2 item = items[it];
     const int j = item.x;
@@ -427,33 +475,55 @@ __global__ void __launch_bounds__(kThreads) k_composite(EotShape s, Layout L, ch
     }
     const int jl = j - first;
     const BoxPlan& me = pp[jl];
-    const int D = me.d, D3 = D * 3;
-    const int total = D * D3;
-    const int i_end = min(total, (item.y + 1) * kCompChunk);
-    for (int i = item.y * kCompChunk + threadIdx.x; i < i_end; i += blockDim.x) {
-      const int y = i / D3, rem = i - y * D3;
-      const int x = rem / 3, c = rem - x * 3;
-      const int gy = me.y0 + y, gx = me.x0 + x;
-      bool owned = true;
-      for (int q = jl + 1; q < nb; ++q) {
-        const BoxPlan& o = pp[q];
-        if (o.valid && gy >= o.y0 && gy < o.y0 + o.d && gx >= o.x0 && gx < o.x0 + o.d) { owned = false; break; }
+    const int D = me.d;
+    const int y_end = min(D, (item.y + 1) * kCompRows);
+    for (int y = item.y * kCompRows + warp; y < y_end; y += kThreads / 32) {
+      const int gy = me.y0 + y;
+      const size_t row_base = (((size_t)me.image * H + gy) * W + me.x0) * 3;
+      for (int xb = 0; xb < D; xb += 32) {
+        const int nseg = min(32, D - xb) * 3;              // floats in this segment
+        const size_t seg = row_base + (size_t)xb * 3;
+        for (int i = lane; i < nseg; i += 32) so[i] = __ldg(images + seg + i);
+        __syncwarp();
+        const int x = xb + lane;
+        bool write = false;
+        if (x < D) {
+          const int gx = me.x0 + x;
+          write = true;
+          for (int q = jl + 1; q < nb; ++q) {
+            const BoxPlan& o = pp[q];
+            if (o.valid && gy >= o.y0 && gy < o.y0 + o.d && gx >= o.x0 && gx < o.x0 + o.d) { write = false; break; }
+          }
+          if (write) {
+            float v[3] = {so[lane * 3], so[lane * 3 + 1], so[lane * 3 + 2]};
+            bool found[3] = {false, false, false};
+            for (int q = jl; q >= 0; --q) {
+              const BoxPlan& o = pp[q];
+              if (!o.valid) continue;
+              const int ly = gy - o.y0, lx = gx - o.x0;
+              if (ly < 0 || ly >= o.d || lx < 0 || lx >= o.d) continue;
+              float R[3];
+              warp_sample3(o, ubuf + o.u_off, lx, ly, R);
+#pragma unroll
+              for (int c = 0; c < 3; ++c)
+                if (!found[c] && !(R[c] < -1.0f)) { v[c] = R[c]; found[c] = true; }
+              if (found[0] && found[1] && found[2]) break;
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) sv[lane * 3 + c] = clampf(v[c], -1.0f, 1.0f);
+          }
+        }
+        const unsigned wmask = __ballot_sync(0xffffffffu, write);
+        __syncwarp();
+        for (int i = lane; i < nseg; i += 32) {
+          if ((wmask >> (i / 3)) & 1u) {
+            const float v = sv[i];
+            out[seg + i] = v;
+            if (mask) mask[seg + i] = so[i] - v;
+          }
+        }
+        __syncwarp();
       }
-      if (!owned) continue;
-      const size_t gidx = (((size_t)me.image * H + gy) * W + gx) * 3 + c;
-      const float orig = __ldg(images + gidx);
-      float v = orig;
-      for (int q = jl; q >= 0; --q) {
-        const BoxPlan& o = pp[q];
-        if (!o.valid) continue;
-        const int ly = gy - o.y0, lx = gx - o.x0;
-        if (ly < 0 || ly >= o.d || lx < 0 || lx >= o.d) continue;
-        const float R = warp_sample(o, ubuf + o.u_off, lx, ly, c);
-        if (!(R < -1.0f)) { v = R; break; }
-      }
-      v = clampf(v, -1.0f, 1.0f);
-      out[gidx] = v;
-      if (mask) mask[gidx] = orig - v;
     }
     __syncthreads();
   }
@@ -502,8 +572,10 @@ extern "C" int eot_box_geometry(const EotShape* shape, const float* boxes, const
     return EOT_ERR_NULL_POINTER;
   }
   const EotShape s = normalised(*shape);
-  k_geometry<<<s.batch, 128, 0, (cudaStream_t)stream>>>(s, make_layout(s), boxes, box_offsets, params, scale, nullptr, geometry_out);
-  count_launches(1);
+  if (s.total_boxes > 0) {
+    k_geometry_only<<<s.total_boxes, kThreads, 0, (cudaStream_t)stream>>>(s, make_layout(s), boxes, box_offsets, params, scale, geometry_out);
+    count_launches(1);
+  }
   EOT_CHECK_CUDA(cudaPeekAtLastError());
   return EOT_OK;
 }
@@ -534,24 +606,26 @@ extern "C" int eot_apply_fwd(const EotShape* shape, const float* patch, const fl
 
   EOT_CHECK_CUDA(cudaMemsetAsync(ws + L.off_ysum_img, 0, L.off_plans - L.off_ysum_img, st));
   const int pchunks = max(1, min((P * P + kThreads * 4 - 1) / (kThreads * 4), 64));
-  k_patch_stats<<<dim3(pchunks, B), kThreads, 0, st>>>(s, patch, print_wb, reinterpret_cast<double*>(ws + L.off_ysum_patch));
-  k_geometry<<<B, 128, 0, st>>>(s, L, boxes, box_offsets, params, scale, ws, nullptr);
-  const dim3 pgrid((HW + kPassPixPerBlock - 1) / kPassPixPerBlock, B);
+  const int cpi = (HW + kPassPixPerBlock - 1) / kPassPixPerBlock;
+  const long long nblocks = (long long)s.total_boxes + (long long)B * pchunks + (long long)B * cpi;
+  if (nblocks >= (1ll << 31)) { set_error("eot_apply_fwd: grid too large"); return EOT_ERR_BAD_SHAPE; }
   const bool vec = (HW % 4 == 0) && (((uintptr_t)images | (uintptr_t)out_images | (uintptr_t)(mask ? mask : out_images)) & 15) == 0;
   if (vec)
-    k_image_pass<true><<<pgrid, kThreads, 0, st>>>(HW, images, out_images, mask, reinterpret_cast<double*>(ws + L.off_ysum_img));
+    k_prepass<true><<<(unsigned)nblocks, kThreads, 0, st>>>(s, L, patch, print_wb, boxes, box_offsets, params, scale, images,
+                                                            out_images, mask, ws, pchunks, cpi);
   else
-    k_image_pass<false><<<pgrid, kThreads, 0, st>>>(HW, images, out_images, mask, reinterpret_cast<double*>(ws + L.off_ysum_img));
+    k_prepass<false><<<(unsigned)nblocks, kThreads, 0, st>>>(s, L, patch, print_wb, boxes, box_offsets, params, scale, images,
+                                                             out_images, mask, ws, pchunks, cpi);
+  count_launches(1);
   if (s.total_boxes > 0) {
     k_match<<<dim3(pchunks, B), kThreads, 0, st>>>(s, L, patch, print_wb, ws);
     const int nsm = sm_count();
-    const size_t smem = (size_t)kResizeRows * P * 3 * sizeof(float);
+    const size_t smem = (size_t)L.resize_rows * P * 3 * sizeof(float);
     if (smem > 48 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_resize<<<nsm * 4, kThreads, smem, st>>>(s, L, ws);
     k_composite<<<nsm * 8, kThreads, 0, st>>>(s, L, ws, images, out_images, mask);
     count_launches(3);
   }
-  count_launches(3);
   EOT_CHECK_CUDA(cudaPeekAtLastError());
   return EOT_OK;
 }

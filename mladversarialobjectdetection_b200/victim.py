@@ -252,5 +252,30 @@ def get_victim_model(name: str = "efficientdet-d0", device="cuda", seed: int = 0
     g = torch.random.get_rng_state()
     torch.manual_seed(seed)
     model = EfficientDetVictim(cfg)
+    _calibrate_batchnorm(model)
     torch.random.set_rng_state(g)
     return model.to(device=device, memory_format=torch.channels_last)
+
+
+def _calibrate_batchnorm(model: EfficientDetVictim, size: int = 128) -> None:
+    """Data-dependent init: one pass of random images (on the CPU, so every rank gets bit-identical weights)
+    sets each BatchNorm's running statistics to the statistics it actually sees.  Without it a random-init
+    network of this depth has vanishing activations (logits == bias, dL/dimage ~ 1e-15) and would be a
+    degenerate victim for step-level tests, although its cost would be the same."""
+    bns = [m for m in model.modules() if isinstance(m, nn.BatchNorm2d)]
+    for bn in bns:
+        bn.reset_running_stats()
+        bn.momentum = None            # cumulative average
+    model.train()
+    with torch.no_grad():
+        model(torch.rand(2, size, size, 3) * 2 - 1)
+    model.eval()
+    for bn in bns:
+        bn.momentum = 0.1
+    # the prediction convs have no BN behind them: scale them so logits / box regressions are O(1)
+    with torch.no_grad():
+        cls, box = model(torch.rand(2, size, size, 3) * 2 - 1)
+        for head, outs, target in ((model.class_net, cls, 1.5), (model.box_net, box, 0.3)):
+            bias = head.out_pw.bias.view(1, 1, 1, -1)
+            std = torch.cat([(o - bias).reshape(-1) for o in outs]).std()
+            head.out_pw.weight.mul_(target / float(std))

@@ -1,0 +1,77 @@
+"""Runs only this repo's kernels on config-2 shapes (no victim): used for ncu captures and quick timing.
+
+    python scripts/kernel_loop.py [--batch 64] [--image 512] [--patch 100] [--iters 3] [--what fwd,bwd,score]
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from mladversarialobjectdetection_b200 import anchors as anchors_mod, ops, synth
+from mladversarialobjectdetection_b200.anchors import feature_sizes
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=64)
+ap.add_argument("--image", type=int, default=512)
+ap.add_argument("--patch", type=int, default=100)
+ap.add_argument("--iters", type=int, default=3)
+ap.add_argument("--warmup", type=int, default=2)
+ap.add_argument("--what", default="fwd,bwd,score")
+ap.add_argument("--max-boxes", type=int, default=8)
+ap.add_argument("--time", action="store_true")
+args = ap.parse_args()
+B, H, P = args.batch, args.image, args.patch
+dev = "cuda"
+bt = synth.make_batch(B, H, H, max_boxes=args.max_boxes)
+images = torch.from_numpy(bt.images).to(dev)
+boxes, offsets = torch.from_numpy(bt.boxes).to(dev), torch.from_numpy(bt.offsets).to(dev)
+params, wb = ops.params_to_tensor(bt.params, dev), torch.from_numpy(bt.print_wb).to(dev)
+patch = torch.from_numpy(synth.make_patch(P)).to(dev)
+scale = torch.tensor(0.4, device=dev)
+out = torch.empty_like(images)
+_, _, ctx = ops.apply_forward(patch, scale, images, boxes, offsets, params, wb, out=out)
+G = torch.randn_like(images)
+gp = torch.empty_like(patch)
+what = args.what.split(",")
+if "score" in what:
+    fs = feature_sizes((H, H), 7)[3:]
+    cls = [torch.randn(B, h, w, 810, device=dev) - 3 for h, w in fs]
+    box = [torch.randn(B, h, w, 36, device=dev) * 0.3 for h, w in fs]
+    for c in cls:
+        c.view(B, -1, 90)[..., 0] += 2
+    anc = torch.from_numpy(anchors_mod.anchor_table((H, H))).to(dev)
+
+
+def one():
+    res = {}
+    if "fwd" in what:
+        ops.apply_forward(patch, scale, images, boxes, offsets, params, wb, out=out, workspace=ctx.workspace)
+    if "bwd" in what:
+        ops.apply_backward(ctx, G, grad_patch=gp)
+    if "score" in what:
+        r = ops.score_max_forward(cls, box, anc, (H, H))
+        ops.score_max_backward(r[3], scale)
+
+
+for _ in range(args.warmup):
+    one()
+torch.cuda.synchronize()
+if args.time:
+    for name in what:
+        what_saved, what = what, [name]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        one(); torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.iters):
+            one()
+        e1.record(); torch.cuda.synchronize()
+        print(f"{name}: {e0.elapsed_time(e1) / args.iters * 1e3:.1f} us per call")
+        what = what_saved
+else:
+    for _ in range(args.iters):
+        one()
+    torch.cuda.synchronize()
+print("done")
