@@ -1,13 +1,13 @@
 // Backward of the EOT patch application: dL/d(out_images) -> dL/dpatch
 // (reference: tape.gradient at attacker.py:217; chain of SURVEY.md section 3.2 / App. D).
 //
-//   k_bwd_window   per transformed-patch texel: TF's registered gradient of
-//                  ImageProjectiveTransformV3 (the SAME bilinear warp applied to the gradient with
-//                  the inverted transform, fill 0), reading dL/d(window) on the fly with the
-//                  TensorScatterUpdate / clip / SelectV2 routing evaluated per tap; then the inner
-//                  clip mask of attacker.py:428.  -> g_u[box]
+//   k_bwd_window   per transformed-patch texel (3 channels): TF's registered gradient of
+//                  ImageProjectiveTransformV3 -- the SAME bilinear warp applied to the gradient with
+//                  the inverted transform, fill 0 -- reading dL/d(window) through the route bytes the
+//                  forward composite left (TensorScatterUpdate / SelectV2 / outer clip routing), then
+//                  the inner clip mask of attacker.py:428.  -> g_u[box]
 //   k_bwd_resize   exact transpose of the antialiased resize (ScaleAndTranslateGrad), one CTA per
-//                  (image, strip of patch rows) looping over the image's boxes, accumulating in a
+//                  (image, block of patch rows) looping over the image's boxes, accumulating in a
 //                  shared-memory patch-gradient tile (no global atomics); then the first half of the
 //                  BrightnessMatcher backward (clip mask, K'^T) and the per-image sum of dL/dY
 //                  (warp-shuffle tree + one atomic per CTA).
@@ -18,125 +18,108 @@
 
 namespace eot {
 
-constexpr int kMaxSmemPlansBwd = 48;
-constexpr int kBwdRows = 4;      // patch rows per k_bwd_resize CTA
 constexpr int kBwdGroups = 16;   // image groups of k_bwd_texel
+constexpr int kBwdChunk = 8;     // patch rows per tap fetch in k_bwd_resize
+constexpr int kBwdMaxTaps = 16;
 
-// gradient that reaches R_j at window pixel (xi, yi) of box jl (local index in pp[0..nb)), 3 channels
-__device__ __forceinline__ void routed_grad3(const BoxPlan* pp, int nb, int jl, const float* __restrict__ ubuf,
-                                             const float* __restrict__ G, int H, int W, int xi, int yi, float g[3]) {
-  const BoxPlan& me = pp[jl];
-  float R[3];
-  warp_sample3(me, ubuf + me.u_off, xi, yi, R);
-  bool pass[3];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) pass[c] = (R[c] >= -1.0f && R[c] <= 1.0f);   // SelectV2 took R, outer clip open
+// gradient that reaches R_j at window pixel (xi, yi) of a box, 3 channels: the route byte says which
+// channels of the pasted pixel came from this box (SelectV2), passed the outer clip and were not
+// overwritten by a later paste (TensorScatterUpdate grad).
+__device__ __forceinline__ void routed_grad3(const uint8_t* __restrict__ route, const float* __restrict__ Gwin, int D, int W,
+                                             int xi, int yi, float g[3]) {
+  const unsigned bits = route[yi * D + xi];
   g[0] = g[1] = g[2] = 0.0f;
-  if (!(pass[0] || pass[1] || pass[2])) return;
-  const int gy = me.y0 + yi, gx = me.x0 + xi;
-  for (int q = jl + 1; q < nb; ++q) {                      // a later paste that covered this pixel?
-    const BoxPlan& o = pp[q];
-    if (!o.valid) continue;
-    const int ly = gy - o.y0, lx = gx - o.x0;
-    if (ly < 0 || ly >= o.d || lx < 0 || lx >= o.d) continue;
-    float Rq[3];
-    warp_sample3(o, ubuf + o.u_off, lx, ly, Rq);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) pass[c] = pass[c] && (Rq[c] < -1.0f);   // else overwritten: scatter grad is 0
-    if (!(pass[0] || pass[1] || pass[2])) return;
-  }
-  const float* gp = G + (((size_t)me.image * H + gy) * W + gx) * 3;
+  if (!bits) return;
+  const float* gp = Gwin + ((size_t)yi * W + xi) * 3;
 #pragma unroll
   for (int c = 0; c < 3; ++c)
-    if (pass[c]) g[c] = __ldg(gp + c);
+    if ((bits >> c) & 1u) g[c] = __ldg(gp + c);
 }
 
 __global__ void __launch_bounds__(kThreads) k_bwd_window(EotShape s, Layout L, char* ws, const float* __restrict__ G) {
-  __shared__ BoxPlan sp[kMaxSmemPlansBwd];
   const BoxPlan* plans = reinterpret_cast<const BoxPlan*>(ws + L.off_plans);
   const int2* items = reinterpret_cast<const int2*>(ws + L.off_items_resize);
   const int n_items = reinterpret_cast<const int*>(ws + L.off_counters)[0];
   const float* ubuf = reinterpret_cast<const float*>(ws + L.off_u);
   float* gubuf = reinterpret_cast<float*>(ws + L.off_gu);
+  const uint8_t* routes = reinterpret_cast<const uint8_t*>(ws + L.off_route);
   const int H = s.height, W = s.width;
   const int RR = L.resize_rows;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
     const int2 item = items[it];
     const int j = item.x;
-    const int first = plans[j].first_box, last = plans[j].last_box;
-    const int nb = last - first;
-    const BoxPlan* pp;
-    if (nb <= kMaxSmemPlansBwd) {
-      const int4* src = reinterpret_cast<const int4*>(plans + first);
-      int4* dst = reinterpret_cast<int4*>(sp);
-      for (int i = threadIdx.x; i < nb * (int)(sizeof(BoxPlan) / 16); i += blockDim.x) dst[i] = src[i];
-      __syncthreads();
-      pp = sp;
-    } else {
-      pp = plans + first;
-    }
-    const int jl = j - first;
-    const BoxPlan& me = pp[jl];
+    const BoxPlan me = plans[j];
     const int ps = me.ps, D = me.d;
     const float* u = ubuf + me.u_off;
     float* gu = gubuf + me.u_off;
+    const uint8_t* route = routes + (size_t)j * L.rslot;
+    const float* Gwin = G + (((size_t)me.image * H + me.y0) * W + me.x0) * 3;
     const int oy0 = item.y * RR;
     const int rows = min(RR, ps - oy0);
     const bool affine = (me.Ti[6] == 0.0f && me.Ti[7] == 0.0f);
-    for (int t = threadIdx.x; t < rows * ps; t += blockDim.x) {
-      const int r = t / ps, tx = t - r * ps;
+    const float Df = (float)D;
+    for (int r = warp; r < rows; r += kThreads / 32) {
       const int ty = oy0 + r;
-      const float xf = (float)(tx + me.pad_lo), yf = (float)(ty + me.pad_lo);
-      float g[3] = {0.0f, 0.0f, 0.0f};
-      float ix = (me.Ti[0] * xf + me.Ti[1] * yf) + me.Ti[2];
-      float iy = (me.Ti[3] * xf + me.Ti[4] * yf) + me.Ti[5];
-      bool ok = true;
-      if (!affine) {
-        const float proj = (me.Ti[6] * xf + me.Ti[7] * yf) + 1.0f;
-        ok = proj != 0.0f;
-        if (ok) { ix = ix / proj; iy = iy / proj; }
-      }
-      if (ok) {
-        const float x0f = floorf(ix), y0f = floorf(iy);
-        const float x1f = x0f + 1.0f, y1f = y0f + 1.0f;
-        const float Df = (float)D;
-        const bool bx0 = x0f >= 0.0f && x0f < Df, bx1 = x1f >= 0.0f && x1f < Df;
-        const bool by0 = y0f >= 0.0f && y0f < Df, by1 = y1f >= 0.0f && y1f < Df;
-        const int xi0 = (int)x0f, yi0 = (int)y0f;
-        float v00[3] = {0.f, 0.f, 0.f}, v01[3] = {0.f, 0.f, 0.f}, v10[3] = {0.f, 0.f, 0.f}, v11[3] = {0.f, 0.f, 0.f};
-        if (by0 && bx0) routed_grad3(pp, nb, jl, ubuf, G, H, W, xi0, yi0, v00);
-        if (by0 && bx1) routed_grad3(pp, nb, jl, ubuf, G, H, W, xi0 + 1, yi0, v01);
-        if (by1 && bx0) routed_grad3(pp, nb, jl, ubuf, G, H, W, xi0, yi0 + 1, v10);
-        if (by1 && bx1) routed_grad3(pp, nb, jl, ubuf, G, H, W, xi0 + 1, yi0 + 1, v11);
-        const float wx1 = x1f - ix, wx0 = ix - x0f, wy1 = y1f - iy, wy0 = iy - y0f;
+      const float yf = (float)(ty + me.pad_lo);
+      for (int tx = lane; tx < ps; tx += 32) {
+        const float xf = (float)(tx + me.pad_lo);
+        float g[3] = {0.0f, 0.0f, 0.0f};
+        float ix = (me.Ti[0] * xf + me.Ti[1] * yf) + me.Ti[2];
+        float iy = (me.Ti[3] * xf + me.Ti[4] * yf) + me.Ti[5];
+        bool ok = true;
+        if (!affine) {
+          const float proj = (me.Ti[6] * xf + me.Ti[7] * yf) + 1.0f;
+          ok = proj != 0.0f;
+          if (ok) { ix = ix / proj; iy = iy / proj; }
+        }
+        if (ok) {
+          const float x0f = floorf(ix), y0f = floorf(iy);
+          const float x1f = x0f + 1.0f, y1f = y0f + 1.0f;
+          const bool bx0 = x0f >= 0.0f && x0f < Df, bx1 = x1f >= 0.0f && x1f < Df;
+          const bool by0 = y0f >= 0.0f && y0f < Df, by1 = y1f >= 0.0f && y1f < Df;
+          const int xi0 = (int)x0f, yi0 = (int)y0f;
+          float v00[3] = {0.f, 0.f, 0.f}, v01[3] = {0.f, 0.f, 0.f}, v10[3] = {0.f, 0.f, 0.f}, v11[3] = {0.f, 0.f, 0.f};
+          if (by0 && bx0) routed_grad3(route, Gwin, D, W, xi0, yi0, v00);
+          if (by0 && bx1) routed_grad3(route, Gwin, D, W, xi0 + 1, yi0, v01);
+          if (by1 && bx0) routed_grad3(route, Gwin, D, W, xi0, yi0 + 1, v10);
+          if (by1 && bx1) routed_grad3(route, Gwin, D, W, xi0 + 1, yi0 + 1, v11);
+          const float wx1 = x1f - ix, wx0 = ix - x0f, wy1 = y1f - iy, wy0 = iy - y0f;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) g[c] = wy1 * (wx1 * v00[c] + wx0 * v01[c]) + wy0 * (wx1 * v10[c] + wx0 * v11[c]);
-      }
-      const size_t e = ((size_t)ty * ps + tx) * 3;
+          for (int c = 0; c < 3; ++c) g[c] = wy1 * (wx1 * v00[c] + wx0 * v01[c]) + wy0 * (wx1 * v10[c] + wx0 * v11[c]);
+        }
+        const int e = (ty * ps + tx) * 3;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float up = u[e + c];
-        gu[e + c] = (up >= -1.0f && up <= 1.0f) ? g[c] : 0.0f;        // inner clip (attacker.py:428)
+        for (int c = 0; c < 3; ++c) {
+          const float up = u[e + c];
+          gu[e + c] = (up >= -1.0f && up <= 1.0f) ? g[c] : 0.0f;        // inner clip (attacker.py:428)
+        }
       }
     }
-    __syncthreads();
   }
 }
 
+// Exact transpose of the antialiased resize for the boxes of one image, restricted to a block of patch rows:
+//   rows:    tmp[r][f]      = sum_oy w[oy][py - start[oy]] * gu[oy][f]          (tap list hoisted per row)
+//   columns: acc[r][px][c] += sum_ox w[ox][px - start[ox]] * tmp[r][ox][c]      (kBwdChunk rows per tap fetch)
 __global__ void __launch_bounds__(kThreads) k_bwd_resize(EotShape s, Layout L, char* ws, const float* __restrict__ patch,
                                                          const float* __restrict__ print_wb,
-                                                         const int32_t* __restrict__ offsets) {
+                                                         const int32_t* __restrict__ offsets, int rows_per_cta) {
   extern __shared__ float smem[];
   __shared__ double red[32];
+  __shared__ int tap_off[kBwdChunk][kBwdMaxTaps];
+  __shared__ float tap_w[kBwdChunk][kBwdMaxTaps];
+  __shared__ int2 tap_rng[kBwdChunk];
   const int P = s.patch_size, P3 = P * 3;
-  float* acc_tile = smem;                              // [kBwdRows][P3]   patch-gradient accumulator
-  float* tmp = smem + kBwdRows * P3;                   // [kBwdRows][lmin*3]
+  const int tstride = L.lmin * 3;
+  float* acc_tile = smem;                              // [rows_per_cta][P3]   patch-gradient accumulator
+  float* tmp = smem + (size_t)rows_per_cta * P3;       // [kBwdChunk][lmin*3]
   const int b = blockIdx.y;
-  const int py0 = blockIdx.x * kBwdRows;
-  const int rows = min(kBwdRows, P - py0);
+  const int py0 = blockIdx.x * rows_per_cta;
+  const int rows = min(rows_per_cta, P - py0);
   const BoxPlan* plans = reinterpret_cast<const BoxPlan*>(ws + L.off_plans);
   const float* gubuf = reinterpret_cast<const float*>(ws + L.off_gu);
-  for (int i = threadIdx.x; i < kBwdRows * P3; i += blockDim.x) acc_tile[i] = 0.0f;
+  for (int i = threadIdx.x; i < rows_per_cta * P3; i += blockDim.x) acc_tile[i] = 0.0f;
   __syncthreads();
   for (int j = offsets[b]; j < offsets[b + 1]; ++j) {
     const BoxPlan* pl = plans + j;
@@ -146,32 +129,63 @@ __global__ void __launch_bounds__(kThreads) k_bwd_resize(EotShape s, Layout L, c
     const float* wts = reinterpret_cast<const float*>(ws + L.off_weights) + (size_t)j * L.wcap;
     const int2* inv = reinterpret_cast<const int2*>(ws + L.off_inv) + (size_t)j * P;
     const float* gu = gubuf + pl->u_off;
-    // rows: tmp[r][f] = sum_oy w[oy][py - start[oy]] * gu[oy][f]
-    for (int idx = threadIdx.x; idx < rows * ps3; idx += blockDim.x) {
-      const int r = idx / ps3, f = idx - r * ps3;
-      const int py = py0 + r;
-      const int2 rng = __ldg(inv + py);
-      float a = 0.0f;
-      for (int oy = rng.x; oy <= rng.y; ++oy) {
-        const int k = py - __ldg(starts + oy);
-        if (k >= 0 && k < span) a += __ldg(wts + (size_t)oy * span + k) * __ldg(gu + (size_t)oy * ps3 + f);
+    for (int c0 = 0; c0 < rows; c0 += kBwdChunk) {
+      const int crow = min(kBwdChunk, rows - c0);
+      if (threadIdx.x < kBwdChunk * kBwdMaxTaps) {       // hoist the tap list of each patch row of the chunk
+        const int r = threadIdx.x / kBwdMaxTaps, k = threadIdx.x - r * kBwdMaxTaps;
+        if (r < crow) {
+          const int py = py0 + c0 + r;
+          const int2 rng = inv[py];
+          if (k == 0) tap_rng[r] = rng;
+          const int oy = rng.x + k;
+          float w = 0.0f;
+          if (oy <= rng.y) {
+            const int kk = py - starts[oy];
+            if (kk >= 0 && kk < span) w = wts[oy * span + kk];
+          }
+          tap_off[r][k] = oy * ps3;
+          tap_w[r][k] = w;
+        }
       }
-      tmp[r * (L.lmin * 3) + f] = a;
-    }
-    __syncthreads();
-    // columns: acc[r][px][c] += sum_ox w[ox][px - start[ox]] * tmp[r][ox][c]
-    for (int idx = threadIdx.x; idx < rows * P3; idx += blockDim.x) {
-      const int r = idx / P3, f = idx - r * P3;
-      const int px = f / 3, c = f - px * 3;
-      const int2 rng = __ldg(inv + px);
-      float a = 0.0f;
-      for (int ox = rng.x; ox <= rng.y; ++ox) {
-        const int k = px - __ldg(starts + ox);
-        if (k >= 0 && k < span) a += __ldg(wts + (size_t)ox * span + k) * tmp[r * (L.lmin * 3) + ox * 3 + c];
+      __syncthreads();
+      for (int f = threadIdx.x; f < ps3; f += blockDim.x) {
+        for (int r = 0; r < crow; ++r) {
+          const int2 rng = tap_rng[r];
+          const int cnt = rng.y - rng.x + 1;
+          float a = 0.0f;
+          if (cnt <= kBwdMaxTaps) {
+            for (int k = 0; k < cnt; ++k) a += tap_w[r][k] * gu[tap_off[r][k] + f];
+          } else {                                       // very strong up-sampling: walk the span tables directly
+            const int py = py0 + c0 + r;
+            for (int oy = rng.x; oy <= rng.y; ++oy) {
+              const int kk = py - starts[oy];
+              if (kk >= 0 && kk < span) a += wts[oy * span + kk] * gu[oy * ps3 + f];
+            }
+          }
+          tmp[r * tstride + f] = a;
+        }
       }
-      acc_tile[idx] += a;
+      __syncthreads();
+      for (int f = threadIdx.x; f < P3; f += blockDim.x) {
+        const int px = f / 3, c = f - px * 3;
+        const int2 rng = inv[px];
+        float a[kBwdChunk];
+#pragma unroll
+        for (int r = 0; r < kBwdChunk; ++r) a[r] = 0.0f;
+        for (int ox = rng.x; ox <= rng.y; ++ox) {
+          const int kk = px - starts[ox];
+          if (kk < 0 || kk >= span) continue;
+          const float w = wts[ox * span + kk];
+          const float* tp = tmp + ox * 3 + c;
+#pragma unroll
+          for (int r = 0; r < kBwdChunk; ++r) a[r] += w * tp[r * tstride];
+        }
+#pragma unroll
+        for (int r = 0; r < kBwdChunk; ++r)
+          if (r < crow) acc_tile[(c0 + r) * P3 + f] += a[r];
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
   // BrightnessMatcher backward, first half (brightness_matcher.py:65-72 reversed)
   const double* ysum_img = reinterpret_cast<const double*>(ws + L.off_ysum_img);
@@ -274,9 +288,20 @@ extern "C" int eot_apply_bwd(const EotShape* shape, const float* patch, const fl
   EOT_CHECK_CUDA(cudaMemsetAsync(ws + L.off_gy_sum, 0, (size_t)B * sizeof(double), st));
   const int nsm = sm_count();
   k_bwd_window<<<nsm * 8, kThreads, 0, st>>>(s, L, ws, grad_images);
-  const size_t smem = ((size_t)kBwdRows * P * 3 + (size_t)kBwdRows * L.lmin * 3) * sizeof(float);
+  // patch rows per CTA: enough CTAs to fill the GPU about twice, a multiple of the chunk
+  const int pmax = ((P + kBwdChunk - 1) / kBwdChunk) * kBwdChunk;
+  int rpc = (int)(((long long)B * P) / (2ll * nsm));
+  rpc = rpc < kBwdChunk ? kBwdChunk : (rpc / kBwdChunk) * kBwdChunk;
+  if (rpc > 64) rpc = 64;
+  if (rpc > pmax) rpc = pmax;
+  size_t smem = ((size_t)rpc * P * 3 + (size_t)kBwdChunk * L.lmin * 3) * sizeof(float);
+  while (smem > 160 * 1024 && rpc > kBwdChunk) {
+    rpc -= kBwdChunk;
+    smem = ((size_t)rpc * P * 3 + (size_t)kBwdChunk * L.lmin * 3) * sizeof(float);
+  }
+  if (smem > 200 * 1024) { set_error("eot_apply_bwd: shared-memory tile too large (P=%d, L=%d)", P, L.lmin); return EOT_ERR_BAD_SHAPE; }
   if (smem > 48 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_bwd_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_bwd_resize<<<dim3((P + kBwdRows - 1) / kBwdRows, B), kThreads, smem, st>>>(s, L, ws, patch, print_wb, offsets);
+  k_bwd_resize<<<dim3((P + rpc - 1) / rpc, B), kThreads, smem, st>>>(s, L, ws, patch, print_wb, offsets, rpc);
   const int groups = B < kBwdGroups ? B : kBwdGroups;
   k_bwd_texel<<<dim3((PP + kThreads - 1) / kThreads, groups), kThreads, 0, st>>>(s, L, ws, patch, print_wb, groups);
   k_bwd_reduce<<<(n + kThreads - 1) / kThreads, kThreads, 0, st>>>(reinterpret_cast<const float*>(ws + L.off_gp_part), n, groups,

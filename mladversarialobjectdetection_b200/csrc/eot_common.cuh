@@ -64,6 +64,7 @@ struct Layout {
   size_t off_items_resize; // int2[N*ceil(Lmin/resize_rows)]
   size_t off_items_comp;   // int2[N*ceil(Lmin/kCompRows)]
   size_t off_inv;          // int2[N][P]  for patch index i: first/last output index whose span holds i
+  size_t off_route;        // uint8[N][rslot] per window pixel: bit c = channel c of the output came from this box (and passes the clip)
   size_t off_gm;           // float[B][P*P*3] backward: dL/d(matched patch) per image
   size_t off_gu;           // float[N][slot]  backward: dL/d(u) per box
   size_t off_gp_part;      // float[16][P*P*3] backward: partial dL/dpatch per image group
@@ -73,6 +74,7 @@ struct Layout {
   int32_t wcap;            // floats per weight table
   int32_t lmin;            // max patch side
   int32_t resize_rows;     // output rows per resize work item (bounded by shared memory: rows * P * 12 B)
+  int64_t rslot;           // bytes per route map
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -103,6 +105,8 @@ __host__ __device__ inline Layout make_layout(const EotShape& s) {
   L.off_items_resize = o; o = align_up(o + N * (size_t)((lmin + L.resize_rows - 1) / L.resize_rows) * 8, 256);
   L.off_items_comp = o;   o = align_up(o + N * (size_t)((lmin + kCompRows - 1) / kCompRows) * 8, 256);
   L.off_inv = o;          o = align_up(o + N * (size_t)s.patch_size * 8, 256);
+  L.rslot = (int64_t)align_up((size_t)lfull * lfull, 32);
+  L.off_route = o;        o = align_up(o + N * (size_t)L.rslot, 256);
   L.off_gm = o;           o = align_up(o + B * PP3 * sizeof(float), 256);
   L.off_gu = o;           o = align_up(o + N * (size_t)L.slot * sizeof(float), 256);
   L.off_gp_part = o;      o = align_up(o + 16 * PP3 * sizeof(float), 256);
@@ -191,51 +195,45 @@ __device__ __forceinline__ TexelYuv texel_yuv(float p0, float p1, float p2, cons
 }
 
 // ImageProjectiveTransformV3 BILINEAR / CONSTANT sampling of the (virtually) padded transformed
-// patch of one box, channel c, at window pixel (xo, yo).  u holds the PRE-clip values
+// patch of one box at a window pixel, three channels at once.  u holds the PRE-clip values
 // (resize + noise) + delta; the clip of attacker.py:428 is applied on read; everything outside the
 // ps x ps core -- the -2 pad ring of attacker.py:435 and the -2 fill of :437 -- reads as -2.
-__device__ __forceinline__ float warp_sample(const BoxPlan& pl, const float* __restrict__ u, int xo, int yo, int c) {
-  const float xf = (float)xo, yf = (float)yo;
-  const float proj = (pl.T[6] * xf + pl.T[7] * yf) + 1.0f;
-  if (proj == 0.0f) return -2.0f;
-  const float ix = ((pl.T[0] * xf + pl.T[1] * yf) + pl.T[2]) / proj;
-  const float iy = ((pl.T[3] * xf + pl.T[4] * yf) + pl.T[5]) / proj;
-  const float x0f = floorf(ix), y0f = floorf(iy);
-  const float x1f = x0f + 1.0f, y1f = y0f + 1.0f;
-  const float lo = (float)pl.pad_lo, hi = (float)(pl.pad_lo + pl.ps);
-  const bool bx0 = (x0f >= lo) && (x0f < hi), bx1 = (x1f >= lo) && (x1f < hi);
-  const bool by0 = (y0f >= lo) && (y0f < hi), by1 = (y1f >= lo) && (y1f < hi);
-  const int xi0 = (int)x0f - pl.pad_lo, yi0 = (int)y0f - pl.pad_lo;
-  const int rs = pl.ps * 3;
-  float v00 = -2.0f, v01 = -2.0f, v10 = -2.0f, v11 = -2.0f;
-  if (by0 && bx0) v00 = clampf(__ldg(u + (int64_t)yi0 * rs + xi0 * 3 + c), -1.f, 1.f);
-  if (by0 && bx1) v01 = clampf(__ldg(u + (int64_t)yi0 * rs + (xi0 + 1) * 3 + c), -1.f, 1.f);
-  if (by1 && bx0) v10 = clampf(__ldg(u + (int64_t)(yi0 + 1) * rs + xi0 * 3 + c), -1.f, 1.f);
-  if (by1 && bx1) v11 = clampf(__ldg(u + (int64_t)(yi0 + 1) * rs + (xi0 + 1) * 3 + c), -1.f, 1.f);
-  const float wx1 = x1f - ix, wx0 = ix - x0f, wy1 = y1f - iy, wy0 = iy - y0f;
-  const float a = wx1 * v00 + wx0 * v01;
-  const float b = wx1 * v10 + wx0 * v11;
-  return wy1 * a + wy0 * b;
+// For the reference's pure rotation the projective row is zero, proj == 1 exactly and x / 1 == x, so
+// the two divisions are skipped without changing a bit.
+struct Sampler {
+  float t0, t1, t2, t3, t4, t5, t6, t7;
+  float lo, hi;          // core bounds in padded coordinates
+  int pad_lo, rs;        // rs = ps * 3
+  const float* u;
+  bool affine;
+};
+
+__device__ __forceinline__ Sampler make_sampler(const BoxPlan& pl, const float* ubuf) {
+  Sampler S;
+  S.t0 = pl.T[0]; S.t1 = pl.T[1]; S.t2 = pl.T[2]; S.t3 = pl.T[3];
+  S.t4 = pl.T[4]; S.t5 = pl.T[5]; S.t6 = pl.T[6]; S.t7 = pl.T[7];
+  S.lo = (float)pl.pad_lo;
+  S.hi = (float)(pl.pad_lo + pl.ps);
+  S.pad_lo = pl.pad_lo;
+  S.rs = pl.ps * 3;
+  S.u = ubuf + pl.u_off;
+  S.affine = (pl.T[6] == 0.0f && pl.T[7] == 0.0f);
+  return S;
 }
 
-// Same sampling for the three channels of one window pixel (coordinates computed once).  For the
-// reference's pure rotation the projective row is zero, proj == 1 exactly and x / 1 == x, so the two
-// divisions are skipped without changing a bit.
-__device__ __forceinline__ void warp_sample3(const BoxPlan& pl, const float* __restrict__ u, int xo, int yo, float R[3]) {
-  const float xf = (float)xo, yf = (float)yo;
-  float ix = (pl.T[0] * xf + pl.T[1] * yf) + pl.T[2];
-  float iy = (pl.T[3] * xf + pl.T[4] * yf) + pl.T[5];
-  if (pl.T[6] != 0.0f || pl.T[7] != 0.0f) {
-    const float proj = (pl.T[6] * xf + pl.T[7] * yf) + 1.0f;
+__device__ __forceinline__ void sample3(const Sampler& S, float xf, float yf, float R[3]) {
+  float ix = (S.t0 * xf + S.t1 * yf) + S.t2;
+  float iy = (S.t3 * xf + S.t4 * yf) + S.t5;
+  if (!S.affine) {
+    const float proj = (S.t6 * xf + S.t7 * yf) + 1.0f;
     if (proj == 0.0f) { R[0] = R[1] = R[2] = -2.0f; return; }
     ix = ix / proj;
     iy = iy / proj;
   }
   const float x0f = floorf(ix), y0f = floorf(iy);
   const float x1f = x0f + 1.0f, y1f = y0f + 1.0f;
-  const float lo = (float)pl.pad_lo, hi = (float)(pl.pad_lo + pl.ps);
-  const bool bx0 = (x0f >= lo) && (x0f < hi), bx1 = (x1f >= lo) && (x1f < hi);
-  const bool by0 = (y0f >= lo) && (y0f < hi), by1 = (y1f >= lo) && (y1f < hi);
+  const bool bx0 = (x0f >= S.lo) && (x0f < S.hi), bx1 = (x1f >= S.lo) && (x1f < S.hi);
+  const bool by0 = (y0f >= S.lo) && (y0f < S.hi), by1 = (y1f >= S.lo) && (y1f < S.hi);
   const float wx1 = x1f - ix, wx0 = ix - x0f, wy1 = y1f - iy, wy0 = iy - y0f;
   if (!((bx0 || bx1) && (by0 || by1))) {      // all four taps are pad / fill: same arithmetic on -2
     const float a = wx1 * -2.0f + wx0 * -2.0f;
@@ -243,16 +241,27 @@ __device__ __forceinline__ void warp_sample3(const BoxPlan& pl, const float* __r
     R[0] = R[1] = R[2] = r;
     return;
   }
-  const int xi0 = (int)x0f - pl.pad_lo, yi0 = (int)y0f - pl.pad_lo;
-  const int rs = pl.ps * 3;
-  const float* p00 = u + (int64_t)yi0 * rs + xi0 * 3;
+  const int off = ((int)y0f - S.pad_lo) * S.rs + ((int)x0f - S.pad_lo) * 3;
+  const float* p00 = S.u + off;
+  if (bx0 && bx1 && by0 && by1) {             // interior: 12 unconditional loads
+    const float* p10 = p00 + S.rs;
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
+    for (int c = 0; c < 3; ++c) {
+      const float v00 = clampf(p00[c], -1.f, 1.f), v01 = clampf(p00[3 + c], -1.f, 1.f);
+      const float v10 = clampf(p10[c], -1.f, 1.f), v11 = clampf(p10[3 + c], -1.f, 1.f);
+      const float a = wx1 * v00 + wx0 * v01;
+      const float b = wx1 * v10 + wx0 * v11;
+      R[c] = wy1 * a + wy0 * b;
+    }
+    return;
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {               // edge of the core: per-tap validity
     float v00 = -2.0f, v01 = -2.0f, v10 = -2.0f, v11 = -2.0f;
-    if (by0 && bx0) v00 = clampf(__ldg(p00 + c), -1.f, 1.f);
-    if (by0 && bx1) v01 = clampf(__ldg(p00 + 3 + c), -1.f, 1.f);
-    if (by1 && bx0) v10 = clampf(__ldg(p00 + rs + c), -1.f, 1.f);
-    if (by1 && bx1) v11 = clampf(__ldg(p00 + rs + 3 + c), -1.f, 1.f);
+    if (by0 && bx0) v00 = clampf(p00[c], -1.f, 1.f);
+    if (by0 && bx1) v01 = clampf(p00[3 + c], -1.f, 1.f);
+    if (by1 && bx0) v10 = clampf(p00[S.rs + c], -1.f, 1.f);
+    if (by1 && bx1) v11 = clampf(p00[S.rs + 3 + c], -1.f, 1.f);
     const float a = wx1 * v00 + wx0 * v01;
     const float b = wx1 * v10 + wx0 * v11;
     R[c] = wy1 * a + wy0 * b;

@@ -376,60 +376,68 @@ __global__ void __launch_bounds__(kThreads) k_bm_apply(const float* __restrict__
 
 // ------------------------------------------------------------------------------------------------
 // resize + noise + delta for one strip of L.resize_rows output rows of one box
-// (attacker.py:425-427; ScaleAndTranslate GatherRows then GatherColumns)
+// (attacker.py:425-427; ScaleAndTranslate GatherRows then GatherColumns).
+// Rows pass: a thread owns a column of the [P,3] row and walks the strip's rows; columns pass: a warp
+// owns a row, lanes own Philox groups of 4 consecutive elements.  Accumulation order == the oracle's.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 4) k_resize(EotShape s, Layout L, char* ws) {
-  extern __shared__ float inter[];   // [resize_rows][P*3]
+__device__ __forceinline__ void resize_item(const EotShape& s, const Layout& L, char* ws, int2 item, float* inter) {
   const int P = s.patch_size, P3 = P * 3;
-  const BoxPlan* plans = reinterpret_cast<const BoxPlan*>(ws + L.off_plans);
-  const int2* items = reinterpret_cast<const int2*>(ws + L.off_items_resize);
-  const int n_items = reinterpret_cast<const int*>(ws + L.off_counters)[0];
-  const float* match = reinterpret_cast<const float*>(ws + L.off_match);
-  float* ubuf = reinterpret_cast<float*>(ws + L.off_u);
+  const BoxPlan* pl = reinterpret_cast<const BoxPlan*>(ws + L.off_plans) + item.x;
+  const int j = item.x;
+  const int ps = pl->ps, span = pl->span, ps3 = ps * 3;
+  const float delta = pl->delta;
+  const uint32_t key0 = pl->key0, key1 = pl->key1;
   const int RR = L.resize_rows;
-  for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-    const int2 item = items[it];
-    const int j = item.x;
-    const BoxPlan* pl = plans + j;
-    const int ps = pl->ps, span = pl->span;
-    const float delta = pl->delta;
-    const uint32_t key0 = pl->key0, key1 = pl->key1;
-    const int oy0 = item.y * RR;
-    const int rows = min(RR, ps - oy0);
-    const float* m = match + (size_t)pl->image * P * P3;
-    const int* starts = reinterpret_cast<const int*>(ws + L.off_starts) + (size_t)j * L.lmin;
-    const float* wts = reinterpret_cast<const float*>(ws + L.off_weights) + (size_t)j * L.wcap;
-    float* u = ubuf + pl->u_off;
-    for (int idx = threadIdx.x; idx < rows * P3; idx += blockDim.x) {
-      const int r = idx / P3, f = idx - r * P3;
+  const int oy0 = item.y * RR;
+  const int rows = min(RR, ps - oy0);
+  const float* m = reinterpret_cast<const float*>(ws + L.off_match) + (size_t)pl->image * P * P3;
+  const int* starts = reinterpret_cast<const int*>(ws + L.off_starts) + (size_t)j * L.lmin;
+  const float* wts = reinterpret_cast<const float*>(ws + L.off_weights) + (size_t)j * L.wcap;
+  float* u = reinterpret_cast<float*>(ws + L.off_u) + pl->u_off;
+  for (int f = threadIdx.x; f < P3; f += blockDim.x) {
+    for (int r = 0; r < rows; ++r) {
       const int oy = oy0 + r;
-      const int st = __ldg(starts + oy);
-      const float* w = wts + (size_t)oy * span;
+      const int st = starts[oy];
+      const float* w = wts + oy * span;
       const int nk = min(span, P - st);
+      const float* mp = m + st * P3 + f;
       float acc = 0.0f;
-      for (int k = 0; k < nk; ++k) acc = acc + __ldg(w + k) * __ldg(m + (size_t)(st + k) * P3 + f);
-      inter[idx] = acc;
+      for (int k = 0; k < nk; ++k) acc = acc + w[k] * mp[k * P3];
+      inter[r * P3 + f] = acc;
     }
-    __syncthreads();
-    const int e_begin = oy0 * ps * 3, e_end = (oy0 + rows) * ps * 3;
-    for (int g = e_begin / 4 + threadIdx.x; g < (e_end + 3) / 4; g += blockDim.x) {
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int r = warp; r < rows; r += nwarps) {
+    const int e_begin = (oy0 + r) * ps3, e_end = e_begin + ps3;
+    const float* irow = inter + r * P3;
+    for (int g = (e_begin >> 2) + lane; g <= ((e_end - 1) >> 2); g += 32) {
       const uint4 rnd = philox4x32_10((uint32_t)g, key0, key1);
       const uint32_t words[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int e = g * 4 + q;
         if (e < e_begin || e >= e_end) continue;
-        const int pix = e / 3, c = e - pix * 3;
-        const int oy = pix / ps, ox = pix - oy * ps;
-        const int r = oy - oy0;
-        const int st = __ldg(starts + ox);
-        const float* w = wts + (size_t)ox * span;
+        const int er = e - e_begin;
+        const int ox = er / 3, c = er - ox * 3;
+        const int st = starts[ox];
+        const float* w = wts + ox * span;
         const int nk = min(span, P - st);
+        const float* ip = irow + st * 3 + c;
         float acc = 0.0f;
-        for (int k = 0; k < nk; ++k) acc = acc + __ldg(w + k) * inter[r * P3 + (st + k) * 3 + c];
+        for (int k = 0; k < nk; ++k) acc = acc + w[k] * ip[k * 3];
         u[e] = (acc + noise_from_word(words[q], s.noise_amp)) + delta;
       }
     }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 4) k_resize(EotShape s, Layout L, char* ws) {
+  extern __shared__ float inter[];   // [resize_rows][P*3]
+  const int2* items = reinterpret_cast<const int2*>(ws + L.off_items_resize);
+  const int n_items = reinterpret_cast<const int*>(ws + L.off_counters)[0];
+  for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    resize_item(s, L, ws, items[it], inter);
     __syncthreads();
   }
 }
@@ -440,91 +448,139 @@ __global__ void __launch_bounds__(kThreads, 4) k_resize(EotShape s, Layout L, ch
 // clip(original); elements outside every window are untouched by this kernel.  A pixel covered by
 // several windows is written only by the items of the last covering box.
 //
-// One work item = kCompRows window rows of one box; one warp per row, one lane per pixel (the
-// sampling coordinates are shared by the three channels); the row segment is transposed through
-// shared memory so that global loads and stores are contiguous 128-byte warp accesses.
+// One work item = kCompRows window rows of one box; one warp per row, one lane per pixel (sampling
+// coordinates shared by the three channels); the row segment is transposed through shared memory so
+// that global loads and stores are contiguous 128-byte warp accesses.  Each pixel also leaves a
+// route byte per covering box (bit c: channel c of the output came from this box and passes the
+// outer clip) -- the backward's TensorScatterUpdate / SelectV2 / clip routing without re-sampling.
 // ------------------------------------------------------------------------------------------------
-constexpr int kMaxSmemPlans = 32;
+constexpr int kMaxWin = 256;   // person boxes per image held in shared memory (the reference's NMS keeps <= 100)
+
+struct CompositeSmem {
+  int4 win[kMaxWin];                 // y0, x0, d, valid of every box of the image
+  unsigned ovmask[kMaxWin / 32];     // boxes whose window intersects this item's rows
+  float stage[kThreads / 32][2][96];
+};
+
+__device__ __forceinline__ bool covers(const int4 w, int gy, int gx) {
+  return gy >= w.x && gy < w.x + w.z && gx >= w.y && gx < w.y + w.z;
+}
+
+__device__ __forceinline__ void composite_item(const EotShape& s, const Layout& L, char* ws,
+                                               const float* __restrict__ images, float* out, float* mask, int2 item,
+                                               CompositeSmem& sm) {
+  const BoxPlan* plans = reinterpret_cast<const BoxPlan*>(ws + L.off_plans);
+  const float* ubuf = reinterpret_cast<const float*>(ws + L.off_u);
+  uint8_t* routes = reinterpret_cast<uint8_t*>(ws + L.off_route);
+  const int H = s.height, W = s.width;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = item.x;
+  const BoxPlan me = plans[j];
+  const int first = me.first_box;
+  int nb = me.last_box - first;
+  if (nb > kMaxWin) {                                  // unsupported: flag and treat the first kMaxWin only
+    if (threadIdx.x == 0) atomicExch(reinterpret_cast<int*>(ws + L.off_counters) + 2, 2);
+    nb = kMaxWin;
+  }
+  const int jl = j - first;
+  const int D = me.d;
+  const int ya = me.y0 + item.y * kCompRows, yb = min(me.y0 + D, ya + kCompRows);
+  for (int q = threadIdx.x; q < ((nb + 31) & ~31); q += blockDim.x) {
+    int4 w = make_int4(0, 0, 0, 0);
+    if (q < nb) {
+      const BoxPlan* o = plans + first + q;
+      w = make_int4(o->y0, o->x0, o->d, o->valid);
+      sm.win[q] = w;
+    }
+    const bool ov = q < nb && q != jl && w.w && w.x < yb && w.x + w.z > ya && w.y < me.x0 + D && w.y + w.z > me.x0;
+    const unsigned bits = __ballot_sync(0xffffffffu, ov);
+    if ((q & 31) == 0) sm.ovmask[q >> 5] = bits;
+  }
+  __syncthreads();
+  const int nwords = (nb + 31) >> 5;
+  const Sampler S = make_sampler(me, ubuf);
+  uint8_t* my_route = routes + (size_t)j * L.rslot;
+  float* sv = sm.stage[warp][0];
+  float* so = sm.stage[warp][1];
+  for (int gy = ya + warp; gy < yb; gy += kThreads / 32) {
+    const int y = gy - me.y0;
+    const float yf = (float)y;
+    const size_t row_base = (((size_t)me.image * H + gy) * W + me.x0) * 3;
+    for (int xb = 0; xb < D; xb += 32) {
+      const int nseg = min(32, D - xb) * 3;              // floats in this segment
+      const size_t seg = row_base + (size_t)xb * 3;
+      for (int i = lane; i < nseg; i += 32) so[i] = __ldg(images + seg + i);
+      __syncwarp();
+      const int x = xb + lane;
+      bool write = x < D;
+      const int gx = me.x0 + x;
+      if (write) {
+        for (int w = jl >> 5; w < nwords && write; ++w) {        // a later box covering this pixel owns it
+          unsigned m = sm.ovmask[w];
+          if (w == (jl >> 5)) m &= ~((2u << (jl & 31)) - 1u);
+          while (m) {
+            const int q = (w << 5) + __ffs(m) - 1;
+            m &= m - 1;
+            if (covers(sm.win[q], gy, gx)) { write = false; break; }
+          }
+        }
+      }
+      if (write) {
+        float v[3] = {so[lane * 3], so[lane * 3 + 1], so[lane * 3 + 2]};
+        float R[3];
+        sample3(S, (float)x, yf, R);
+        unsigned found = 0, bits = 0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          if (!(R[c] < -1.0f)) { v[c] = R[c]; found |= 1u << c; if (R[c] <= 1.0f) bits |= 1u << c; }
+        my_route[y * D + x] = (uint8_t)bits;
+        for (int w = jl >> 5; w >= 0; --w) {                       // earlier pastes underneath, newest first
+          unsigned m = sm.ovmask[w];
+          if (w == (jl >> 5)) m &= (1u << (jl & 31)) - 1u;
+          while (m) {
+            const int q = (w << 5) + 31 - __clz(m);
+            m &= ~(1u << (q & 31));
+            const int4 wq = sm.win[q];
+            if (!covers(wq, gy, gx)) continue;
+            unsigned qbits = 0;
+            if (found != 7u) {
+              const BoxPlan& o = plans[first + q];
+              const Sampler Sq = make_sampler(o, ubuf);
+              float Rq[3];
+              sample3(Sq, (float)(gx - wq.y), (float)(gy - wq.x), Rq);
+#pragma unroll
+              for (int c = 0; c < 3; ++c)
+                if (!((found >> c) & 1u) && !(Rq[c] < -1.0f)) {
+                  v[c] = Rq[c]; found |= 1u << c; if (Rq[c] <= 1.0f) qbits |= 1u << c;
+                }
+            }
+            routes[(size_t)(first + q) * L.rslot + (size_t)(gy - wq.x) * wq.z + (gx - wq.y)] = (uint8_t)qbits;
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sv[lane * 3 + c] = clampf(v[c], -1.0f, 1.0f);
+      }
+      const unsigned wmask = __ballot_sync(0xffffffffu, write);
+      __syncwarp();
+      for (int i = lane; i < nseg; i += 32) {
+        if ((wmask >> (i / 3)) & 1u) {
+          const float v = sv[i];
+          out[seg + i] = v;
+          if (mask) mask[seg + i] = so[i] - v;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
 
 __global__ void __launch_bounds__(kThreads) k_composite(EotShape s, Layout L, char* ws,
                                                         const float* __restrict__ images, float* out, float* mask) {
-  __shared__ BoxPlan sp[kMaxSmemPlans];
-  __shared__ float stage[kThreads / 32][2][96];
-  const BoxPlan* plans = reinterpret_cast<const BoxPlan*>(ws + L.off_plans);
+  __shared__ CompositeSmem sm;
   const int2* items = reinterpret_cast<const int2*>(ws + L.off_items_comp);
   const int n_items = reinterpret_cast<const int*>(ws + L.off_counters)[1];
-  const float* ubuf = reinterpret_cast<const float*>(ws + L.off_u);
-  const int H = s.height, W = s.width;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* sv = stage[warp][0];   // values to store
-  float* so = stage[warp][1];   // original pixels of the segment
   for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-    const int2 item = items[it];
-    const int j = item.x;
-    const int first = plans[j].first_box, last = plans[j].last_box;
-    const int nb = last - first;
-    const BoxPlan* pp;
-    if (nb <= kMaxSmemPlans) {
-      const int4* src = reinterpret_cast<const int4*>(plans + first);
-      int4* dst = reinterpret_cast<int4*>(sp);
-      for (int i = threadIdx.x; i < nb * (int)(sizeof(BoxPlan) / 16); i += blockDim.x) dst[i] = src[i];
-      __syncthreads();
-      pp = sp;
-    } else {
-      pp = plans + first;
-    }
-    const int jl = j - first;
-    const BoxPlan& me = pp[jl];
-    const int D = me.d;
-    const int y_end = min(D, (item.y + 1) * kCompRows);
-    for (int y = item.y * kCompRows + warp; y < y_end; y += kThreads / 32) {
-      const int gy = me.y0 + y;
-      const size_t row_base = (((size_t)me.image * H + gy) * W + me.x0) * 3;
-      for (int xb = 0; xb < D; xb += 32) {
-        const int nseg = min(32, D - xb) * 3;              // floats in this segment
-        const size_t seg = row_base + (size_t)xb * 3;
-        for (int i = lane; i < nseg; i += 32) so[i] = __ldg(images + seg + i);
-        __syncwarp();
-        const int x = xb + lane;
-        bool write = false;
-        if (x < D) {
-          const int gx = me.x0 + x;
-          write = true;
-          for (int q = jl + 1; q < nb; ++q) {
-            const BoxPlan& o = pp[q];
-            if (o.valid && gy >= o.y0 && gy < o.y0 + o.d && gx >= o.x0 && gx < o.x0 + o.d) { write = false; break; }
-          }
-          if (write) {
-            float v[3] = {so[lane * 3], so[lane * 3 + 1], so[lane * 3 + 2]};
-            bool found[3] = {false, false, false};
-            for (int q = jl; q >= 0; --q) {
-              const BoxPlan& o = pp[q];
-              if (!o.valid) continue;
-              const int ly = gy - o.y0, lx = gx - o.x0;
-              if (ly < 0 || ly >= o.d || lx < 0 || lx >= o.d) continue;
-              float R[3];
-              warp_sample3(o, ubuf + o.u_off, lx, ly, R);
-#pragma unroll
-              for (int c = 0; c < 3; ++c)
-                if (!found[c] && !(R[c] < -1.0f)) { v[c] = R[c]; found[c] = true; }
-              if (found[0] && found[1] && found[2]) break;
-            }
-#pragma unroll
-            for (int c = 0; c < 3; ++c) sv[lane * 3 + c] = clampf(v[c], -1.0f, 1.0f);
-          }
-        }
-        const unsigned wmask = __ballot_sync(0xffffffffu, write);
-        __syncwarp();
-        for (int i = lane; i < nseg; i += 32) {
-          if ((wmask >> (i / 3)) & 1u) {
-            const float v = sv[i];
-            out[seg + i] = v;
-            if (mask) mask[seg + i] = so[i] - v;
-          }
-        }
-        __syncwarp();
-      }
-    }
+    composite_item(s, L, ws, images, out, mask, items[it], sm);
     __syncthreads();
   }
 }
