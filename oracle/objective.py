@@ -90,13 +90,14 @@ def second_pass_post(cls_all: np.ndarray, box_all: np.ndarray, anchors: np.ndarr
     Returns dict with per-anchor `cls`, `logit`, `score`, `boxes`, `cand` (bool [B,A])."""
     cls = np.argmax(cls_all, axis=-1).astype(np.int32)          # first max index wins ties
     logit = np.max(cls_all, axis=-1)
-    boxes = decode(box_all, anchors[None])
-    score = sigmoid(logit)
-    bh = boxes[..., 2] - boxes[..., 0]
-    bw = boxes[..., 3] - boxes[..., 1]
-    area = bh * bw
-    cond1 = (bw / F(W) <= F(1.0)) & (bh / F(H) <= F(1.0))
-    cond2 = area > F(100.0)
+    with np.errstate(over="ignore", invalid="ignore"):           # exp() of a wild regression -> inf, as in TF
+        boxes = decode(box_all, anchors[None])
+        score = sigmoid(logit)
+        bh = boxes[..., 2] - boxes[..., 0]
+        bw = boxes[..., 3] - boxes[..., 1]
+        area = bh * bw
+        cond1 = (bw / F(W) <= F(1.0)) & (bh / F(H) <= F(1.0))
+        cond2 = area > F(100.0)
     cand = (cls == 0) & cond1 & cond2
     return dict(cls=cls, logit=logit, score=score, boxes=boxes, cand=cand, area=area, bh=bh, bw=bw)
 
