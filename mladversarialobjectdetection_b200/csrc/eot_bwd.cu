@@ -51,8 +51,8 @@ __global__ void __launch_bounds__(kThreads) k_bwd_window(EotShape s, Layout L, c
     const int j = item.x;
     const BoxPlan me = plans[j];
     const int ps = me.ps, D = me.d;
-    const float* u = ubuf + me.u_off;
-    float* gu = gubuf + me.u_off;
+    const float4* u4 = reinterpret_cast<const float4*>(ubuf + me.u_off);
+    float* gu = gubuf + (size_t)j * L.gslot;
     const uint8_t* route = routes + (size_t)j * L.rslot;
     const float* Gwin = G + (((size_t)me.image * H + me.y0) * W + me.x0) * 3;
     const int oy0 = item.y * RR;
@@ -88,12 +88,10 @@ __global__ void __launch_bounds__(kThreads) k_bwd_window(EotShape s, Layout L, c
 #pragma unroll
           for (int c = 0; c < 3; ++c) g[c] = wy1 * (wx1 * v00[c] + wx0 * v01[c]) + wy0 * (wx1 * v10[c] + wx0 * v11[c]);
         }
-        const int e = (ty * ps + tx) * 3;
+        const int t = ty * ps + tx;
+        const unsigned bits = __float_as_uint(u4[t].w);                  // inner clip pass bits (attacker.py:428)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float up = u[e + c];
-          gu[e + c] = (up >= -1.0f && up <= 1.0f) ? g[c] : 0.0f;        // inner clip (attacker.py:428)
-        }
+        for (int c = 0; c < 3; ++c) gu[t * 3 + c] = ((bits >> c) & 1u) ? g[c] : 0.0f;
       }
     }
   }
@@ -128,7 +126,7 @@ __global__ void __launch_bounds__(kThreads) k_bwd_resize(EotShape s, Layout L, c
     const int* starts = reinterpret_cast<const int*>(ws + L.off_starts) + (size_t)j * L.lmin;
     const float* wts = reinterpret_cast<const float*>(ws + L.off_weights) + (size_t)j * L.wcap;
     const int2* inv = reinterpret_cast<const int2*>(ws + L.off_inv) + (size_t)j * P;
-    const float* gu = gubuf + pl->u_off;
+    const float* gu = gubuf + (size_t)j * L.gslot;
     for (int c0 = 0; c0 < rows; c0 += kBwdChunk) {
       const int crow = min(kBwdChunk, rows - c0);
       if (threadIdx.x < kBwdChunk * kBwdMaxTaps) {       // hoist the tap list of each patch row of the chunk

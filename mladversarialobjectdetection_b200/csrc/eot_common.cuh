@@ -55,22 +55,24 @@ struct Layout {
   size_t off_ysum_img;     // double[B]
   size_t off_ysum_patch;   // double[B]
   size_t off_gy_sum;       // double[B]   (backward: sum of dL/dY per image)
+  size_t off_oor;          // int32[B]    image b holds a value outside [-1,1] (then clip(background) is not the identity)
   size_t off_counters;     // int32[8]: 0 resize items, 1 composite items, 2 error flag, 3 bwd items
   size_t off_plans;        // BoxPlan[N]
   size_t off_starts;       // int32[N][Lmin]
   size_t off_weights;      // float[N][wcap]
   size_t off_match;        // float[B][P*P*3]
-  size_t off_u;            // float[N][slot]
+  size_t off_u;            // float4[N][slot/4]: clipped (r,g,b) of the transformed patch + inner-clip pass bits
   size_t off_items_resize; // int2[N*ceil(Lmin/resize_rows)]
   size_t off_items_comp;   // int2[N*ceil(Lmin/kCompRows)]
   size_t off_inv;          // int2[N][P]  for patch index i: first/last output index whose span holds i
   size_t off_route;        // uint8[N][rslot] per window pixel: bit c = channel c of the output came from this box (and passes the clip)
   size_t off_gm;           // float[B][P*P*3] backward: dL/d(matched patch) per image
-  size_t off_gu;           // float[N][slot]  backward: dL/d(u) per box
+  size_t off_gu;           // float[N][gslot]  backward: dL/d(u) per box
   size_t off_gp_part;      // float[16][P*P*3] backward: partial dL/dpatch per image group
   size_t off_offsets;      // int32[B+1] copy of the CSR row splits (the backward has no other source)
   size_t total;
-  int64_t slot;            // floats per u slot
+  int64_t slot;            // floats per u slot (4 per texel)
+  int64_t gslot;           // floats per g_u slot (3 per texel)
   int32_t wcap;            // floats per weight table
   int32_t lmin;            // max patch side
   int32_t resize_rows;     // output rows per resize work item (bounded by shared memory: rows * P * 12 B)
@@ -88,7 +90,8 @@ __host__ __device__ inline Layout make_layout(const EotShape& s) {
   if (lmin > lfull) lmin = lfull;
   L.lmin = lmin;
   L.wcap = 2 * s.patch_size + 3 * lmin + 8;
-  L.slot = (int64_t)align_up((size_t)lmin * lmin * 3, 32);
+  L.slot = (int64_t)align_up((size_t)lmin * lmin * 4, 32);
+  L.gslot = (int64_t)align_up((size_t)lmin * lmin * 3, 32);
   int rr = 12288 / (s.patch_size * 3);       // <= 48 KB of float32 intermediate rows
   L.resize_rows = rr > 16 ? 16 : (rr < 1 ? 1 : rr);
   const size_t PP3 = (size_t)s.patch_size * s.patch_size * 3;
@@ -96,6 +99,7 @@ __host__ __device__ inline Layout make_layout(const EotShape& s) {
   L.off_ysum_img = o;     o = align_up(o + B * sizeof(double), 256);
   L.off_ysum_patch = o;   o = align_up(o + B * sizeof(double), 256);
   L.off_gy_sum = o;       o = align_up(o + B * sizeof(double), 256);
+  L.off_oor = o;          o = align_up(o + B * sizeof(int32_t), 256);
   L.off_counters = o;     o = align_up(o + 8 * sizeof(int32_t), 256);
   L.off_plans = o;        o = align_up(o + N * sizeof(BoxPlan), 256);
   L.off_starts = o;       o = align_up(o + N * (size_t)lmin * sizeof(int32_t), 256);
@@ -108,7 +112,7 @@ __host__ __device__ inline Layout make_layout(const EotShape& s) {
   L.rslot = (int64_t)align_up((size_t)lfull * lfull, 32);
   L.off_route = o;        o = align_up(o + N * (size_t)L.rslot, 256);
   L.off_gm = o;           o = align_up(o + B * PP3 * sizeof(float), 256);
-  L.off_gu = o;           o = align_up(o + N * (size_t)L.slot * sizeof(float), 256);
+  L.off_gu = o;           o = align_up(o + N * (size_t)L.gslot * sizeof(float), 256);
   L.off_gp_part = o;      o = align_up(o + 16 * PP3 * sizeof(float), 256);
   L.off_offsets = o;      o = align_up(o + (B + 1) * sizeof(int32_t), 256);
   L.total = o;
@@ -195,16 +199,16 @@ __device__ __forceinline__ TexelYuv texel_yuv(float p0, float p1, float p2, cons
 }
 
 // ImageProjectiveTransformV3 BILINEAR / CONSTANT sampling of the (virtually) padded transformed
-// patch of one box at a window pixel, three channels at once.  u holds the PRE-clip values
-// (resize + noise) + delta; the clip of attacker.py:428 is applied on read; everything outside the
+// patch of one box at a window pixel, three channels at once.  u holds clip((resize + noise) + delta)
+// (attacker.py:425-428) as RGBX texels; everything outside the
 // ps x ps core -- the -2 pad ring of attacker.py:435 and the -2 fill of :437 -- reads as -2.
 // For the reference's pure rotation the projective row is zero, proj == 1 exactly and x / 1 == x, so
 // the two divisions are skipped without changing a bit.
 struct Sampler {
   float t0, t1, t2, t3, t4, t5, t6, t7;
   float lo, hi;          // core bounds in padded coordinates
-  int pad_lo, rs;        // rs = ps * 3
-  const float* u;
+  int pad_lo, ps;
+  const float4* u;       // [ps*ps] texels: (r,g,b) already clipped to [-1,1]; .w = inner-clip pass bits
   bool affine;
 };
 
@@ -215,10 +219,17 @@ __device__ __forceinline__ Sampler make_sampler(const BoxPlan& pl, const float* 
   S.lo = (float)pl.pad_lo;
   S.hi = (float)(pl.pad_lo + pl.ps);
   S.pad_lo = pl.pad_lo;
-  S.rs = pl.ps * 3;
-  S.u = ubuf + pl.u_off;
+  S.ps = pl.ps;
+  S.u = reinterpret_cast<const float4*>(ubuf + pl.u_off);
   S.affine = (pl.T[6] == 0.0f && pl.T[7] == 0.0f);
   return S;
+}
+
+__device__ __forceinline__ void blend3(const float4 v00, const float4 v01, const float4 v10, const float4 v11, float wx1,
+                                       float wx0, float wy1, float wy0, float R[3]) {
+  R[0] = wy1 * (wx1 * v00.x + wx0 * v01.x) + wy0 * (wx1 * v10.x + wx0 * v11.x);
+  R[1] = wy1 * (wx1 * v00.y + wx0 * v01.y) + wy0 * (wx1 * v10.y + wx0 * v11.y);
+  R[2] = wy1 * (wx1 * v00.z + wx0 * v01.z) + wy0 * (wx1 * v10.z + wx0 * v11.z);
 }
 
 __device__ __forceinline__ void sample3(const Sampler& S, float xf, float yf, float R[3]) {
@@ -235,37 +246,21 @@ __device__ __forceinline__ void sample3(const Sampler& S, float xf, float yf, fl
   const bool bx0 = (x0f >= S.lo) && (x0f < S.hi), bx1 = (x1f >= S.lo) && (x1f < S.hi);
   const bool by0 = (y0f >= S.lo) && (y0f < S.hi), by1 = (y1f >= S.lo) && (y1f < S.hi);
   const float wx1 = x1f - ix, wx0 = ix - x0f, wy1 = y1f - iy, wy0 = iy - y0f;
-  if (!((bx0 || bx1) && (by0 || by1))) {      // all four taps are pad / fill: same arithmetic on -2
-    const float a = wx1 * -2.0f + wx0 * -2.0f;
-    const float r = wy1 * a + wy0 * a;
-    R[0] = R[1] = R[2] = r;
+  const float4 fill = make_float4(-2.0f, -2.0f, -2.0f, 0.0f);
+  if (!((bx0 || bx1) && (by0 || by1))) {      // all four taps are pad / fill
+    blend3(fill, fill, fill, fill, wx1, wx0, wy1, wy0, R);
     return;
   }
-  const int off = ((int)y0f - S.pad_lo) * S.rs + ((int)x0f - S.pad_lo) * 3;
-  const float* p00 = S.u + off;
-  if (bx0 && bx1 && by0 && by1) {             // interior: 12 unconditional loads
-    const float* p10 = p00 + S.rs;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float v00 = clampf(p00[c], -1.f, 1.f), v01 = clampf(p00[3 + c], -1.f, 1.f);
-      const float v10 = clampf(p10[c], -1.f, 1.f), v11 = clampf(p10[3 + c], -1.f, 1.f);
-      const float a = wx1 * v00 + wx0 * v01;
-      const float b = wx1 * v10 + wx0 * v11;
-      R[c] = wy1 * a + wy0 * b;
-    }
+  const float4* p00 = S.u + (((int)y0f - S.pad_lo) * S.ps + ((int)x0f - S.pad_lo));
+  if (bx0 && bx1 && by0 && by1) {             // interior: 4 unconditional 128-bit loads
+    blend3(p00[0], p00[1], p00[S.ps], p00[S.ps + 1], wx1, wx0, wy1, wy0, R);
     return;
   }
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {               // edge of the core: per-tap validity
-    float v00 = -2.0f, v01 = -2.0f, v10 = -2.0f, v11 = -2.0f;
-    if (by0 && bx0) v00 = clampf(p00[c], -1.f, 1.f);
-    if (by0 && bx1) v01 = clampf(p00[3 + c], -1.f, 1.f);
-    if (by1 && bx0) v10 = clampf(p00[S.rs + c], -1.f, 1.f);
-    if (by1 && bx1) v11 = clampf(p00[S.rs + 3 + c], -1.f, 1.f);
-    const float a = wx1 * v00 + wx0 * v01;
-    const float b = wx1 * v10 + wx0 * v11;
-    R[c] = wy1 * a + wy0 * b;
-  }
+  const float4 v00 = (by0 && bx0) ? p00[0] : fill;
+  const float4 v01 = (by0 && bx1) ? p00[1] : fill;
+  const float4 v10 = (by1 && bx0) ? p00[S.ps] : fill;
+  const float4 v11 = (by1 && bx1) ? p00[S.ps + 1] : fill;
+  blend3(v00, v01, v10, v11, wx1, wx0, wy1, wy0, R);
 }
 #endif  // __CUDACC__
 

@@ -228,8 +228,9 @@ __device__ __forceinline__ float luma_of(float r, float g, float b) {
 
 template <bool kVec>
 __device__ __forceinline__ void image_pass_block(int HW, int b, int chunk, const float* __restrict__ images, float* out,
-                                                 float* mask, double* ysum_img, double* red) {
+                                                 float* mask, double* ysum_img, int* oor_flags, double* red) {
   const size_t img_off = (size_t)b * HW * 3;
+  bool oor = false;                                     // any value outside [-1,1] (or NaN)
   const float* in = images + img_off;
   float* o = (out && out != images) ? out + img_off : nullptr;
   float* mk = mask ? mask + img_off : nullptr;
@@ -262,6 +263,11 @@ __device__ __forceinline__ void image_pass_block(int HW, int b, int chunk, const
         acc += (double)luma_of(a.w, bb.x, bb.y);
         acc += (double)luma_of(bb.z, bb.w, c.x);
         acc += (double)luma_of(c.y, c.z, c.w);
+        const float m0 = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w)));
+        const float m1 = fmaxf(fmaxf(fabsf(bb.x), fabsf(bb.y)), fmaxf(fabsf(bb.z), fabsf(bb.w)));
+        const float m2 = fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fmaxf(fabsf(c.z), fabsf(c.w)));
+        const float sum = (a.x + a.y + a.z + a.w) + (bb.x + bb.y + bb.z + bb.w) + (c.x + c.y + c.z + c.w);
+        oor = oor || !(fmaxf(fmaxf(m0, m1), m2) <= 1.0f) || (sum != sum);      // fmaxf drops NaN: test the sum too
       }
     }
   } else {
@@ -272,11 +278,16 @@ __device__ __forceinline__ void image_pass_block(int HW, int b, int chunk, const
         if (o) { o[(size_t)pix * 3] = r; o[(size_t)pix * 3 + 1] = g; o[(size_t)pix * 3 + 2] = bl; }
         if (mk) { mk[(size_t)pix * 3] = 0.f; mk[(size_t)pix * 3 + 1] = 0.f; mk[(size_t)pix * 3 + 2] = 0.f; }
         acc += (double)luma_of(r, g, bl);
+        oor = oor || !(fabsf(r) <= 1.0f) || !(fabsf(g) <= 1.0f) || !(fabsf(bl) <= 1.0f);
       }
     }
   }
+  const int any_oor = __syncthreads_or(oor ? 1 : 0);
   acc = block_sum(acc, red);
-  if (threadIdx.x == 0) atomicAdd(ysum_img + b, acc);
+  if (threadIdx.x == 0) {
+    atomicAdd(ysum_img + b, acc);
+    if (any_oor) atomicOr(oor_flags + b, 1);
+  }
 }
 
 // One launch, three independent roles selected by the block index (they only meet at k_match):
@@ -310,7 +321,8 @@ __global__ void __launch_bounds__(kThreads) k_prepass(EotShape s, Layout L, cons
     off_copy[b] = offsets[b];
     if (b == s.batch - 1) off_copy[b + 1] = offsets[b + 1];
   }
-  image_pass_block<kVec>(s.height * s.width, b, chunk, images, out, mask, reinterpret_cast<double*>(ws + L.off_ysum_img), red);
+  image_pass_block<kVec>(s.height * s.width, b, chunk, images, out, mask, reinterpret_cast<double*>(ws + L.off_ysum_img),
+                         reinterpret_cast<int*>(ws + L.off_oor), red);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -375,16 +387,25 @@ __global__ void __launch_bounds__(kThreads) k_bm_apply(const float* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-// resize + noise + delta for one strip of L.resize_rows output rows of one box
-// (attacker.py:425-427; ScaleAndTranslate GatherRows then GatherColumns).
-// Rows pass: a thread owns a column of the [P,3] row and walks the strip's rows; columns pass: a warp
-// owns a row, lanes own Philox groups of 4 consecutive elements.  Accumulation order == the oracle's.
+// resize + noise + delta + clip for one strip of L.resize_rows output rows of one box
+// (attacker.py:425-428; ScaleAndTranslate GatherRows then GatherColumns).
+// The box's span table is staged in shared memory first (no dependent global loads in the loops).
+// Rows pass: a thread owns a column of the [P,3] row and walks the strip's rows.  Columns pass: a lane
+// owns a quad of 4 consecutive texels = 12 elements = exactly 3 Philox groups.  Accumulation order ==
+// the oracle's.  Output texel: (clip r, clip g, clip b, inner-clip pass bits).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void resize_item(const EotShape& s, const Layout& L, char* ws, int2 item, float* inter) {
+__host__ __device__ inline size_t resize_smem_bytes(const EotShape& s, const Layout& L) {
+  return ((size_t)L.resize_rows * s.patch_size * 3 + (size_t)L.wcap + (size_t)L.lmin) * sizeof(float);
+}
+
+__device__ __forceinline__ void resize_item(const EotShape& s, const Layout& L, char* ws, int2 item, float* smem) {
   const int P = s.patch_size, P3 = P * 3;
+  float* inter = smem;                                       // [resize_rows][P3]
+  float* s_w = smem + L.resize_rows * P3;                    // [ps][span]
+  int* s_st = reinterpret_cast<int*>(s_w + L.wcap);          // [ps]
   const BoxPlan* pl = reinterpret_cast<const BoxPlan*>(ws + L.off_plans) + item.x;
   const int j = item.x;
-  const int ps = pl->ps, span = pl->span, ps3 = ps * 3;
+  const int ps = pl->ps, span = pl->span;
   const float delta = pl->delta;
   const uint32_t key0 = pl->key0, key1 = pl->key1;
   const int RR = L.resize_rows;
@@ -393,51 +414,100 @@ __device__ __forceinline__ void resize_item(const EotShape& s, const Layout& L, 
   const float* m = reinterpret_cast<const float*>(ws + L.off_match) + (size_t)pl->image * P * P3;
   const int* starts = reinterpret_cast<const int*>(ws + L.off_starts) + (size_t)j * L.lmin;
   const float* wts = reinterpret_cast<const float*>(ws + L.off_weights) + (size_t)j * L.wcap;
-  float* u = reinterpret_cast<float*>(ws + L.off_u) + pl->u_off;
-  for (int f = threadIdx.x; f < P3; f += blockDim.x) {
-    for (int r = 0; r < rows; ++r) {
+  float4* u4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(ws + L.off_u) + pl->u_off);
+  for (int i = threadIdx.x; i < ps; i += blockDim.x) s_st[i] = starts[i];
+  for (int i = threadIdx.x; i < ps * span; i += blockDim.x) s_w[i] = wts[i];
+  __syncthreads();
+  // rows pass over the flattened (row, column) index so that every warp is full
+  if (span == 3) {                                       // up-sampling / near unit scale: plain bilinear, 3 taps
+    int r = 0, f = threadIdx.x;
+    while (f >= P3) { f -= P3; ++r; }
+    while (r < rows) {
       const int oy = oy0 + r;
-      const int st = starts[oy];
-      const float* w = wts + oy * span;
+      const int st = s_st[oy];
+      const float* w = s_w + oy * 3;
+      // weights past the true span are stored as 0 and the clamped row is finite, so the extra taps add +0
+      const float* m0 = m + st * P3 + f;
+      const float* m1 = m + min(st + 1, P - 1) * P3 + f;
+      const float* m2 = m + min(st + 2, P - 1) * P3 + f;
+      float acc = 0.0f + w[0] * m0[0];
+      acc = acc + w[1] * m1[0];
+      acc = acc + w[2] * m2[0];
+      inter[r * P3 + f] = acc;
+      f += blockDim.x;
+      while (f >= P3) { f -= P3; ++r; }
+    }
+  } else {
+    int r = 0, f = threadIdx.x;
+    while (f >= P3) { f -= P3; ++r; }
+    while (r < rows) {
+      const int oy = oy0 + r;
+      const int st = s_st[oy];
+      const float* w = s_w + oy * span;
       const int nk = min(span, P - st);
       const float* mp = m + st * P3 + f;
       float acc = 0.0f;
       for (int k = 0; k < nk; ++k) acc = acc + w[k] * mp[k * P3];
       inter[r * P3 + f] = acc;
+      f += blockDim.x;
+      while (f >= P3) { f -= P3; ++r; }
     }
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int r = warp; r < rows; r += nwarps) {
-    const int e_begin = (oy0 + r) * ps3, e_end = e_begin + ps3;
-    const float* irow = inter + r * P3;
-    for (int g = (e_begin >> 2) + lane; g <= ((e_end - 1) >> 2); g += 32) {
-      const uint4 rnd = philox4x32_10((uint32_t)g, key0, key1);
-      const uint32_t words[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+  const int p_begin = oy0 * ps, p_end = (oy0 + rows) * ps;   // flat texel range of the strip
+  for (int q = (p_begin >> 2) + threadIdx.x; q <= ((p_end - 1) >> 2); q += blockDim.x) {
+    uint32_t words[12];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int e = g * 4 + q;
-        if (e < e_begin || e >= e_end) continue;
-        const int er = e - e_begin;
-        const int ox = er / 3, c = er - ox * 3;
-        const int st = starts[ox];
-        const float* w = wts + ox * span;
-        const int nk = min(span, P - st);
-        const float* ip = irow + st * 3 + c;
-        float acc = 0.0f;
-        for (int k = 0; k < nk; ++k) acc = acc + w[k] * ip[k * 3];
-        u[e] = (acc + noise_from_word(words[q], s.noise_amp)) + delta;
+    for (int g = 0; g < 3; ++g) {
+      const uint4 rnd = philox4x32_10((uint32_t)(3 * q + g), key0, key1);
+      words[4 * g] = rnd.x; words[4 * g + 1] = rnd.y; words[4 * g + 2] = rnd.z; words[4 * g + 3] = rnd.w;
+    }
+    int p = 4 * q;
+    int oy = p / ps, ox = p - oy * ps;
+#pragma unroll
+    for (int t = 0; t < 4; ++t, ++p) {
+      if (p >= p_begin && p < p_end) {
+        const int st = s_st[ox];
+        const float* w = s_w + ox * span;
+        const float* irow = inter + (oy - oy0) * P3;
+        float a0, a1, a2;
+        if (span == 3) {
+          const float* i0 = irow + st * 3;
+          const float* i1 = irow + min(st + 1, P - 1) * 3;
+          const float* i2 = irow + min(st + 2, P - 1) * 3;
+          const float w0 = w[0], w1 = w[1], w2 = w[2];
+          a0 = 0.0f + w0 * i0[0]; a1 = 0.0f + w0 * i0[1]; a2 = 0.0f + w0 * i0[2];
+          a0 = a0 + w1 * i1[0];   a1 = a1 + w1 * i1[1];   a2 = a2 + w1 * i1[2];
+          a0 = a0 + w2 * i2[0];   a1 = a1 + w2 * i2[1];   a2 = a2 + w2 * i2[2];
+        } else {
+          const int nk = min(span, P - st);
+          const float* ip = irow + st * 3;
+          a0 = a1 = a2 = 0.0f;
+          for (int k = 0; k < nk; ++k) {
+            const float wk = w[k];
+            a0 = a0 + wk * ip[k * 3];
+            a1 = a1 + wk * ip[k * 3 + 1];
+            a2 = a2 + wk * ip[k * 3 + 2];
+          }
+        }
+        const float v0 = (a0 + noise_from_word(words[3 * t], s.noise_amp)) + delta;
+        const float v1 = (a1 + noise_from_word(words[3 * t + 1], s.noise_amp)) + delta;
+        const float v2 = (a2 + noise_from_word(words[3 * t + 2], s.noise_amp)) + delta;
+        const unsigned bits = (unsigned)(v0 >= -1.0f && v0 <= 1.0f) | ((unsigned)(v1 >= -1.0f && v1 <= 1.0f) << 1) |
+                              ((unsigned)(v2 >= -1.0f && v2 <= 1.0f) << 2);
+        u4[p] = make_float4(clampf(v0, -1.0f, 1.0f), clampf(v1, -1.0f, 1.0f), clampf(v2, -1.0f, 1.0f), __uint_as_float(bits));
       }
+      if (++ox == ps) { ox = 0; ++oy; }
     }
   }
 }
 
 __global__ void __launch_bounds__(kThreads, 4) k_resize(EotShape s, Layout L, char* ws) {
-  extern __shared__ float inter[];   // [resize_rows][P*3]
+  extern __shared__ float resize_smem[];
   const int2* items = reinterpret_cast<const int2*>(ws + L.off_items_resize);
   const int n_items = reinterpret_cast<const int*>(ws + L.off_counters)[0];
   for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-    resize_item(s, L, ws, items[it], inter);
+    resize_item(s, L, ws, items[it], resize_smem);
     __syncthreads();
   }
 }
@@ -459,11 +529,32 @@ constexpr int kMaxWin = 256;   // person boxes per image held in shared memory (
 struct CompositeSmem {
   int4 win[kMaxWin];                 // y0, x0, d, valid of every box of the image
   unsigned ovmask[kMaxWin / 32];     // boxes whose window intersects this item's rows
-  float stage[kThreads / 32][2][96];
+  float stage[kThreads / 32][96];    // one 32-pixel row segment per warp, for coalesced stores
 };
 
 __device__ __forceinline__ bool covers(const int4 w, int gy, int gx) {
   return gy >= w.x && gy < w.x + w.z && gx >= w.y && gx < w.y + w.z;
+}
+
+// Conservative range of window columns x in row y whose sample can touch the ps x ps core (affine T):
+// outside it all four taps are pad/fill, R == -2 and the pixel keeps its background.
+__device__ __forceinline__ void core_range(const Sampler& S, float yf, int D, int* xa, int* xb) {
+  float lo = 0.0f, hi = (float)(D - 1);
+  const float a[2] = {S.t0, S.t3};
+  const float c[2] = {S.t1 * yf + S.t2, S.t4 * yf + S.t5};
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float l = S.lo - 1.5f - c[i], h = S.hi + 0.5f - c[i];      // need l < a*x < h (half-pixel safety margin)
+    if (fabsf(a[i]) < 1e-6f) {
+      if (!(0.0f > l - 1.0f && 0.0f < h + 1.0f)) { lo = 1.0f; hi = 0.0f; }
+    } else {
+      const float x1 = l / a[i], x2 = h / a[i];
+      lo = fmaxf(lo, fminf(x1, x2) - 1.0f);
+      hi = fminf(hi, fmaxf(x1, x2) + 1.0f);
+    }
+  }
+  *xa = (int)floorf(lo);
+  *xb = (int)ceilf(hi);
 }
 
 __device__ __forceinline__ void composite_item(const EotShape& s, const Layout& L, char* ws,
@@ -485,96 +576,158 @@ __device__ __forceinline__ void composite_item(const EotShape& s, const Layout& 
   const int jl = j - first;
   const int D = me.d;
   const int ya = me.y0 + item.y * kCompRows, yb = min(me.y0 + D, ya + kCompRows);
-  for (int q = threadIdx.x; q < ((nb + 31) & ~31); q += blockDim.x) {
-    int4 w = make_int4(0, 0, 0, 0);
-    if (q < nb) {
-      const BoxPlan* o = plans + first + q;
-      w = make_int4(o->y0, o->x0, o->d, o->valid);
-      sm.win[q] = w;
-    }
-    const bool ov = q < nb && q != jl && w.w && w.x < yb && w.x + w.z > ya && w.y < me.x0 + D && w.y + w.z > me.x0;
-    const unsigned bits = __ballot_sync(0xffffffffu, ov);
-    if ((q & 31) == 0) sm.ovmask[q >> 5] = bits;
-  }
-  __syncthreads();
   const int nwords = (nb + 31) >> 5;
+  bool any_later = false, any_earlier = false;
+  if (nb > 1) {
+    for (int q = threadIdx.x; q < nwords * 32; q += blockDim.x) {
+      int4 w = make_int4(0, 0, 0, 0);
+      if (q < nb) {
+        const BoxPlan* o = plans + first + q;
+        w = make_int4(o->y0, o->x0, o->d, o->valid);
+        sm.win[q] = w;
+      }
+      const bool ov = q < nb && q != jl && w.w && w.x < yb && w.x + w.z > ya && w.y < me.x0 + D && w.y + w.z > me.x0;
+      const unsigned bits = __ballot_sync(0xffffffffu, ov);
+      if ((q & 31) == 0) sm.ovmask[q >> 5] = bits;
+    }
+    __syncthreads();
+    for (int w = 0; w < nwords; ++w) {
+      const unsigned m = sm.ovmask[w];
+      const unsigned below = w < (jl >> 5) ? 0xffffffffu : (w > (jl >> 5) ? 0u : ((1u << (jl & 31)) - 1u));
+      any_earlier = any_earlier || (m & below);
+      any_later = any_later || (m & ~below);
+    }
+  }
   const Sampler S = make_sampler(me, ubuf);
   uint8_t* my_route = routes + (size_t)j * L.rslot;
-  float* sv = sm.stage[warp][0];
-  float* so = sm.stage[warp][1];
+  const bool oor = reinterpret_cast<const int*>(ws + L.off_oor)[me.image] != 0;
+  // every pixel of the window has to be visited when the background clip is not the identity, when the
+  // Masker's mask needs the original, when an earlier paste may show through, or for a projective T
+  const bool full = oor || mask != nullptr || !S.affine;
+  const float* img_win = images + (((size_t)me.image * H + me.y0) * W + me.x0) * 3;     // window origin
+  float* out_win = out + (((size_t)me.image * H + me.y0) * W + me.x0) * 3;
+  float* mask_win = mask ? mask + (((size_t)me.image * H + me.y0) * W + me.x0) * 3 : nullptr;
+  float* sv = sm.stage[warp];
+  const int p0 = lane / 3, p1 = (lane + 32) / 3, p2 = (lane + 64) / 3;   // pixel of the element a lane stores
   for (int gy = ya + warp; gy < yb; gy += kThreads / 32) {
     const int y = gy - me.y0;
     const float yf = (float)y;
-    const size_t row_base = (((size_t)me.image * H + gy) * W + me.x0) * 3;
-    for (int xb = 0; xb < D; xb += 32) {
-      const int nseg = min(32, D - xb) * 3;              // floats in this segment
-      const size_t seg = row_base + (size_t)xb * 3;
-      for (int i = lane; i < nseg; i += 32) so[i] = __ldg(images + seg + i);
-      __syncwarp();
-      const int x = xb + lane;
-      bool write = x < D;
-      const int gx = me.x0 + x;
-      if (write) {
-        for (int w = jl >> 5; w < nwords && write; ++w) {        // a later box covering this pixel owns it
+    int xa = 0, xb = D - 1;
+    bool row_earlier = false;
+    if (!full) {
+      core_range(S, yf, D, &xa, &xb);
+      if (any_earlier) {                                   // widen to the earlier windows crossing this row
+        for (int w = jl >> 5; w >= 0; --w) {
           unsigned m = sm.ovmask[w];
-          if (w == (jl >> 5)) m &= ~((2u << (jl & 31)) - 1u);
+          if (w == (jl >> 5)) m &= (1u << (jl & 31)) - 1u;
           while (m) {
             const int q = (w << 5) + __ffs(m) - 1;
             m &= m - 1;
-            if (covers(sm.win[q], gy, gx)) { write = false; break; }
+            const int4 wq = sm.win[q];
+            if (gy >= wq.x && gy < wq.x + wq.z) {
+              row_earlier = true;
+              xa = min(xa, max(0, wq.y - me.x0));
+              xb = max(xb, min(D - 1, wq.y + wq.z - 1 - me.x0));
+            }
           }
         }
       }
+    } else {
+      row_earlier = any_earlier;
+    }
+    const int row_off = y * W * 3;                          // offset of this window row from the window origin
+    uint8_t* rrow = my_route + y * D;
+    for (int xs = 0; xs < D; xs += 32) {
+      const int x = xs + lane;
+      if (xs + 31 < xa || xs > xb) {                         // whole segment is background of this box
+        if (x < D && !any_later) rrow[x] = 0;
+        else if (x < D) {
+          bool mine = true;
+          for (int w = jl >> 5; w < nwords && mine; ++w) {
+            unsigned m = sm.ovmask[w];
+            if (w == (jl >> 5)) m &= ~((2u << (jl & 31)) - 1u);
+            while (m) { const int q = (w << 5) + __ffs(m) - 1; m &= m - 1; if (covers(sm.win[q], gy, me.x0 + x)) { mine = false; break; } }
+          }
+          if (mine) rrow[x] = 0;
+        }
+        continue;
+      }
+      const int gx = me.x0 + x;
+      bool write = x < D;
+      if (write && any_later) {                               // a later box covering this pixel owns it
+        for (int w = jl >> 5; w < nwords && write; ++w) {
+          unsigned m = sm.ovmask[w];
+          if (w == (jl >> 5)) m &= ~((2u << (jl & 31)) - 1u);
+          while (m) { const int q = (w << 5) + __ffs(m) - 1; m &= m - 1; if (covers(sm.win[q], gy, gx)) { write = false; break; } }
+        }
+      }
+      bool store = false;
+      float orig[3] = {0.0f, 0.0f, 0.0f};
       if (write) {
-        float v[3] = {so[lane * 3], so[lane * 3 + 1], so[lane * 3 + 2]};
-        float R[3];
+        float v[3], R[3];
         sample3(S, (float)x, yf, R);
         unsigned found = 0, bits = 0;
 #pragma unroll
         for (int c = 0; c < 3; ++c)
           if (!(R[c] < -1.0f)) { v[c] = R[c]; found |= 1u << c; if (R[c] <= 1.0f) bits |= 1u << c; }
-        my_route[y * D + x] = (uint8_t)bits;
-        for (int w = jl >> 5; w >= 0; --w) {                       // earlier pastes underneath, newest first
-          unsigned m = sm.ovmask[w];
-          if (w == (jl >> 5)) m &= (1u << (jl & 31)) - 1u;
-          while (m) {
-            const int q = (w << 5) + 31 - __clz(m);
-            m &= ~(1u << (q & 31));
-            const int4 wq = sm.win[q];
-            if (!covers(wq, gy, gx)) continue;
-            unsigned qbits = 0;
-            if (found != 7u) {
-              const BoxPlan& o = plans[first + q];
-              const Sampler Sq = make_sampler(o, ubuf);
-              float Rq[3];
-              sample3(Sq, (float)(gx - wq.y), (float)(gy - wq.x), Rq);
+        rrow[x] = (uint8_t)bits;
+        if (found != 7u || mask) {
+          const float* op = img_win + row_off + x * 3;
+          orig[0] = __ldg(op); orig[1] = __ldg(op + 1); orig[2] = __ldg(op + 2);
 #pragma unroll
-              for (int c = 0; c < 3; ++c)
-                if (!((found >> c) & 1u) && !(Rq[c] < -1.0f)) {
-                  v[c] = Rq[c]; found |= 1u << c; if (Rq[c] <= 1.0f) qbits |= 1u << c;
-                }
+          for (int c = 0; c < 3; ++c) if (!((found >> c) & 1u)) v[c] = orig[c];
+        }
+        if (row_earlier) {                                     // earlier pastes underneath, newest first
+          for (int w = jl >> 5; w >= 0; --w) {
+            unsigned m = sm.ovmask[w];
+            if (w == (jl >> 5)) m &= (1u << (jl & 31)) - 1u;
+            while (m) {
+              const int q = (w << 5) + 31 - __clz(m);
+              m &= ~(1u << (q & 31));
+              const int4 wq = sm.win[q];
+              if (!covers(wq, gy, gx)) continue;
+              unsigned qbits = 0;
+              if (found != 7u) {
+                const Sampler Sq = make_sampler(plans[first + q], ubuf);
+                float Rq[3];
+                sample3(Sq, (float)(gx - wq.y), (float)(gy - wq.x), Rq);
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                  if (!((found >> c) & 1u) && !(Rq[c] < -1.0f)) {
+                    v[c] = Rq[c]; found |= 1u << c; if (Rq[c] <= 1.0f) qbits |= 1u << c;
+                  }
+              }
+              routes[(size_t)(first + q) * L.rslot + (size_t)(gy - wq.x) * wq.z + (gx - wq.y)] = (uint8_t)qbits;
             }
-            routes[(size_t)(first + q) * L.rslot + (size_t)(gy - wq.x) * wq.z + (gx - wq.y)] = (uint8_t)qbits;
           }
         }
+        store = found != 0u || oor || mask != nullptr;          // untouched in-range background stays as copied
+        if (store) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) sv[lane * 3 + c] = clampf(v[c], -1.0f, 1.0f);
-      }
-      const unsigned wmask = __ballot_sync(0xffffffffu, write);
-      __syncwarp();
-      for (int i = lane; i < nseg; i += 32) {
-        if ((wmask >> (i / 3)) & 1u) {
-          const float v = sv[i];
-          out[seg + i] = v;
-          if (mask) mask[seg + i] = so[i] - v;
+          for (int c = 0; c < 3; ++c) sv[lane * 3 + c] = clampf(v[c], -1.0f, 1.0f);
         }
       }
-      __syncwarp();
+      const unsigned smask = __ballot_sync(0xffffffffu, store);
+      if (smask) {
+        const int seg = row_off + xs * 3;
+        if (mask_win) {                                        // Masker: mask = original - pasted (per pixel, 3 scalars)
+          if (store) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) mask_win[seg + lane * 3 + c] = orig[c] - sv[lane * 3 + c];
+          }
+        }
+        __syncwarp();
+        float* op = out_win + seg + lane;
+        if ((smask >> p0) & 1u) op[0] = sv[lane];
+        if ((smask >> p1) & 1u) op[32] = sv[lane + 32];
+        if ((smask >> p2) & 1u) op[64] = sv[lane + 64];
+        __syncwarp();
+      }
     }
   }
 }
 
-__global__ void __launch_bounds__(kThreads) k_composite(EotShape s, Layout L, char* ws,
+__global__ void __launch_bounds__(kThreads, 3) k_composite(EotShape s, Layout L, char* ws,
                                                         const float* __restrict__ images, float* out, float* mask) {
   __shared__ CompositeSmem sm;
   const int2* items = reinterpret_cast<const int2*>(ws + L.off_items_comp);
@@ -676,7 +829,7 @@ extern "C" int eot_apply_fwd(const EotShape* shape, const float* patch, const fl
   if (s.total_boxes > 0) {
     k_match<<<dim3(pchunks, B), kThreads, 0, st>>>(s, L, patch, print_wb, ws);
     const int nsm = sm_count();
-    const size_t smem = (size_t)L.resize_rows * P * 3 * sizeof(float);
+    const size_t smem = resize_smem_bytes(s, L);
     if (smem > 48 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_resize<<<nsm * 4, kThreads, smem, st>>>(s, L, ws);
     k_composite<<<nsm * 8, kThreads, 0, st>>>(s, L, ws, images, out_images, mask);
