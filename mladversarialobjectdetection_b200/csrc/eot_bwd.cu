@@ -20,7 +20,6 @@ namespace eot {
 
 constexpr int kBwdGroups = 16;   // image groups of k_bwd_texel
 constexpr int kBwdChunk = 8;     // patch rows per tap fetch in k_bwd_resize
-constexpr int kBwdMaxTaps = 16;
 
 // gradient that reaches R_j at window pixel (xi, yi) of a box, 3 channels: the route byte says which
 // channels of the pasted pixel came from this box (SelectV2), passed the outer clip and were not
@@ -97,28 +96,33 @@ __global__ void __launch_bounds__(kThreads) k_bwd_window(EotShape s, Layout L, c
   }
 }
 
-// Exact transpose of the antialiased resize for the boxes of one image, restricted to a block of patch rows:
-//   rows:    tmp[r][f]      = sum_oy w[oy][py - start[oy]] * gu[oy][f]          (tap list hoisted per row)
+// Exact transpose of the antialiased resize for the boxes of one image, restricted to a block of patch rows.
+// Per box the span / inverse-span tables are staged in shared memory once; then, per chunk of patch rows,
+//   rows:    tmp[r][f]      = sum_oy w[oy][py - start[oy]] * gu[oy][f]
 //   columns: acc[r][px][c] += sum_ox w[ox][px - start[ox]] * tmp[r][ox][c]      (kBwdChunk rows per tap fetch)
+__host__ __device__ inline size_t bwd_resize_smem_bytes(const EotShape& s, const Layout& L, int rows_per_cta) {
+  return ((size_t)rows_per_cta * s.patch_size * 3 + (size_t)kBwdChunk * L.lmin * 3 + (size_t)L.wcap + (size_t)L.lmin +
+          2 * (size_t)s.patch_size) * sizeof(float);
+}
+
 __global__ void __launch_bounds__(kThreads) k_bwd_resize(EotShape s, Layout L, char* ws, const float* __restrict__ patch,
                                                          const float* __restrict__ print_wb,
                                                          const int32_t* __restrict__ offsets, int rows_per_cta) {
   extern __shared__ float smem[];
   __shared__ double red[32];
-  __shared__ int tap_off[kBwdChunk][kBwdMaxTaps];
-  __shared__ float tap_w[kBwdChunk][kBwdMaxTaps];
-  __shared__ int2 tap_rng[kBwdChunk];
   const int P = s.patch_size, P3 = P * 3;
   const int tstride = L.lmin * 3;
-  float* acc_tile = smem;                              // [rows_per_cta][P3]   patch-gradient accumulator
-  float* tmp = smem + (size_t)rows_per_cta * P3;       // [kBwdChunk][lmin*3]
+  float* acc_tile = smem;                                          // [rows_per_cta][P3]   patch-gradient accumulator
+  float* tmp = acc_tile + (size_t)rows_per_cta * P3;               // [kBwdChunk][lmin*3]
+  float* s_w = tmp + (size_t)kBwdChunk * tstride;                  // [ps][span]
+  int* s_st = reinterpret_cast<int*>(s_w + L.wcap);                // [ps]
+  int2* s_inv = reinterpret_cast<int2*>(s_st + L.lmin);            // [P]
   const int b = blockIdx.y;
   const int py0 = blockIdx.x * rows_per_cta;
   const int rows = min(rows_per_cta, P - py0);
   const BoxPlan* plans = reinterpret_cast<const BoxPlan*>(ws + L.off_plans);
   const float* gubuf = reinterpret_cast<const float*>(ws + L.off_gu);
   for (int i = threadIdx.x; i < rows_per_cta * P3; i += blockDim.x) acc_tile[i] = 0.0f;
-  __syncthreads();
   for (int j = offsets[b]; j < offsets[b + 1]; ++j) {
     const BoxPlan* pl = plans + j;
     if (!pl->valid) continue;
@@ -127,38 +131,21 @@ __global__ void __launch_bounds__(kThreads) k_bwd_resize(EotShape s, Layout L, c
     const float* wts = reinterpret_cast<const float*>(ws + L.off_weights) + (size_t)j * L.wcap;
     const int2* inv = reinterpret_cast<const int2*>(ws + L.off_inv) + (size_t)j * P;
     const float* gu = gubuf + (size_t)j * L.gslot;
+    __syncthreads();                                               // previous box done with the tables
+    for (int i = threadIdx.x; i < ps; i += blockDim.x) s_st[i] = starts[i];
+    for (int i = threadIdx.x; i < ps * span; i += blockDim.x) s_w[i] = wts[i];
+    for (int i = threadIdx.x; i < P; i += blockDim.x) s_inv[i] = inv[i];
+    __syncthreads();
     for (int c0 = 0; c0 < rows; c0 += kBwdChunk) {
       const int crow = min(kBwdChunk, rows - c0);
-      if (threadIdx.x < kBwdChunk * kBwdMaxTaps) {       // hoist the tap list of each patch row of the chunk
-        const int r = threadIdx.x / kBwdMaxTaps, k = threadIdx.x - r * kBwdMaxTaps;
-        if (r < crow) {
-          const int py = py0 + c0 + r;
-          const int2 rng = inv[py];
-          if (k == 0) tap_rng[r] = rng;
-          const int oy = rng.x + k;
-          float w = 0.0f;
-          if (oy <= rng.y) {
-            const int kk = py - starts[oy];
-            if (kk >= 0 && kk < span) w = wts[oy * span + kk];
-          }
-          tap_off[r][k] = oy * ps3;
-          tap_w[r][k] = w;
-        }
-      }
-      __syncthreads();
       for (int f = threadIdx.x; f < ps3; f += blockDim.x) {
         for (int r = 0; r < crow; ++r) {
-          const int2 rng = tap_rng[r];
-          const int cnt = rng.y - rng.x + 1;
+          const int py = py0 + c0 + r;
+          const int2 rng = s_inv[py];
           float a = 0.0f;
-          if (cnt <= kBwdMaxTaps) {
-            for (int k = 0; k < cnt; ++k) a += tap_w[r][k] * gu[tap_off[r][k] + f];
-          } else {                                       // very strong up-sampling: walk the span tables directly
-            const int py = py0 + c0 + r;
-            for (int oy = rng.x; oy <= rng.y; ++oy) {
-              const int kk = py - starts[oy];
-              if (kk >= 0 && kk < span) a += wts[oy * span + kk] * gu[oy * ps3 + f];
-            }
+          for (int oy = rng.x; oy <= rng.y; ++oy) {
+            const int kk = py - s_st[oy];
+            if (kk >= 0 && kk < span) a += s_w[oy * span + kk] * gu[oy * ps3 + f];
           }
           tmp[r * tstride + f] = a;
         }
@@ -166,14 +153,14 @@ __global__ void __launch_bounds__(kThreads) k_bwd_resize(EotShape s, Layout L, c
       __syncthreads();
       for (int f = threadIdx.x; f < P3; f += blockDim.x) {
         const int px = f / 3, c = f - px * 3;
-        const int2 rng = inv[px];
+        const int2 rng = s_inv[px];
         float a[kBwdChunk];
 #pragma unroll
         for (int r = 0; r < kBwdChunk; ++r) a[r] = 0.0f;
         for (int ox = rng.x; ox <= rng.y; ++ox) {
-          const int kk = px - starts[ox];
+          const int kk = px - s_st[ox];
           if (kk < 0 || kk >= span) continue;
-          const float w = wts[ox * span + kk];
+          const float w = s_w[ox * span + kk];
           const float* tp = tmp + ox * 3 + c;
 #pragma unroll
           for (int r = 0; r < kBwdChunk; ++r) a[r] += w * tp[r * tstride];
@@ -185,6 +172,7 @@ __global__ void __launch_bounds__(kThreads) k_bwd_resize(EotShape s, Layout L, c
       __syncthreads();
     }
   }
+  __syncthreads();
   // BrightnessMatcher backward, first half (brightness_matcher.py:65-72 reversed)
   const double* ysum_img = reinterpret_cast<const double*>(ws + L.off_ysum_img);
   const double* ysum_patch = reinterpret_cast<const double*>(ws + L.off_ysum_patch);
@@ -213,6 +201,141 @@ __global__ void __launch_bounds__(kThreads) k_bwd_resize(EotShape s, Layout L, c
     if (!(y_pre >= 0.0f && y_pre <= 1.0f)) gY = 0.0f;
     gy_acc += (double)gY;
     float* o = gm + ((size_t)py * P + px) * 3;
+    o[0] = gY; o[1] = gU; o[2] = gV;
+  }
+  gy_acc = block_sum(gy_acc, red);
+  if (threadIdx.x == 0) atomicAdd(reinterpret_cast<double*>(ws + L.off_gy_sum) + b, gy_acc);
+}
+
+// Fully parallel variant: one CTA per (box, chunk of kBwdChunk patch rows) writes that box's share of
+// dL/d(matched patch) to its own slot; k_bwd_match then sums an image's boxes in a fixed order (no atomics,
+// deterministic) and applies the first half of the BrightnessMatcher backward.
+constexpr int kBwdMaxTaps = 24;
+
+__host__ __device__ inline size_t bwd_resize2_smem_bytes(const EotShape& s, const Layout& L) {
+  return ((size_t)kBwdChunk * L.lmin * 3 + (size_t)L.wcap + (size_t)L.lmin + 2 * (size_t)s.patch_size) * sizeof(float);
+}
+
+__global__ void __launch_bounds__(kThreads) k_bwd_resize2(EotShape s, Layout L, char* ws) {
+  extern __shared__ float smem[];
+  __shared__ int tap_off[kBwdChunk][kBwdMaxTaps];
+  __shared__ float tap_w[kBwdChunk][kBwdMaxTaps];
+  __shared__ int tap_cnt[kBwdChunk];
+  const int P = s.patch_size, P3 = P * 3;
+  const int tstride = L.lmin * 3;
+  float* tmp = smem;                                               // [kBwdChunk][lmin*3]
+  float* s_w = tmp + (size_t)kBwdChunk * tstride;                  // [ps][span]
+  int* s_st = reinterpret_cast<int*>(s_w + L.wcap);                // [ps]
+  int2* s_inv = reinterpret_cast<int2*>(s_st + L.lmin);            // [P]
+  const int j = blockIdx.y;
+  const BoxPlan* pl = reinterpret_cast<const BoxPlan*>(ws + L.off_plans) + j;
+  if (!pl->valid) return;
+  const int py0 = blockIdx.x * kBwdChunk;
+  const int crow = min(kBwdChunk, P - py0);
+  const int ps = pl->ps, ps3 = ps * 3, span = pl->span;
+  const int* starts = reinterpret_cast<const int*>(ws + L.off_starts) + (size_t)j * L.lmin;
+  const float* wts = reinterpret_cast<const float*>(ws + L.off_weights) + (size_t)j * L.wcap;
+  const int2* inv = reinterpret_cast<const int2*>(ws + L.off_inv) + (size_t)j * P;
+  const float* gu = reinterpret_cast<const float*>(ws + L.off_gu) + (size_t)j * L.gslot;
+  float* gbox = reinterpret_cast<float*>(ws + L.off_gbox) + (size_t)j * P * P3;
+  for (int i = threadIdx.x; i < ps; i += blockDim.x) s_st[i] = starts[i];
+  for (int i = threadIdx.x; i < ps * span; i += blockDim.x) s_w[i] = wts[i];
+  for (int i = threadIdx.x; i < P; i += blockDim.x) s_inv[i] = inv[i];
+  __syncthreads();
+  if (threadIdx.x < kBwdChunk * kBwdMaxTaps) {                     // tap list of each patch row of the chunk
+    const int r = threadIdx.x / kBwdMaxTaps, k = threadIdx.x - r * kBwdMaxTaps;
+    if (r < crow) {
+      const int py = py0 + r;
+      const int2 rng = s_inv[py];
+      if (k == 0) tap_cnt[r] = rng.y - rng.x + 1;
+      const int oy = rng.x + k;
+      float w = 0.0f;
+      if (oy <= rng.y) {
+        const int kk = py - s_st[oy];
+        if (kk >= 0 && kk < span) w = s_w[oy * span + kk];
+      }
+      tap_off[r][k] = oy * ps3;
+      tap_w[r][k] = w;
+    }
+  }
+  __syncthreads();
+  for (int f = threadIdx.x; f < ps3; f += blockDim.x) {
+    for (int r = 0; r < crow; ++r) {
+      const int cnt = tap_cnt[r];
+      float a = 0.0f;
+      if (cnt <= kBwdMaxTaps) {
+        for (int k = 0; k < cnt; ++k) a += tap_w[r][k] * gu[tap_off[r][k] + f];
+      } else {                                                     // very strong up-sampling: walk the tables
+        const int py = py0 + r;
+        const int2 rng = s_inv[py];
+        for (int oy = rng.x; oy <= rng.y; ++oy) {
+          const int kk = py - s_st[oy];
+          if (kk >= 0 && kk < span) a += s_w[oy * span + kk] * gu[oy * ps3 + f];
+        }
+      }
+      tmp[r * tstride + f] = a;
+    }
+  }
+  __syncthreads();
+  for (int f = threadIdx.x; f < P3; f += blockDim.x) {
+    const int px = f / 3, c = f - px * 3;
+    const int2 rng = s_inv[px];
+    float a[kBwdChunk];
+#pragma unroll
+    for (int r = 0; r < kBwdChunk; ++r) a[r] = 0.0f;
+    for (int ox = rng.x; ox <= rng.y; ++ox) {
+      const int kk = px - s_st[ox];
+      if (kk < 0 || kk >= span) continue;
+      const float w = s_w[ox * span + kk];
+      const float* tp = tmp + ox * 3 + c;
+#pragma unroll
+      for (int r = 0; r < kBwdChunk; ++r) a[r] += w * tp[r * tstride];
+    }
+#pragma unroll
+    for (int r = 0; r < kBwdChunk; ++r)
+      if (r < crow) gbox[(size_t)(py0 + r) * P3 + f] = a[r];
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_bwd_match(EotShape s, Layout L, char* ws, const float* __restrict__ patch,
+                                                        const float* __restrict__ print_wb,
+                                                        const int32_t* __restrict__ offsets) {
+  __shared__ double red[32];
+  const int P = s.patch_size, PP = P * P;
+  const int b = blockIdx.y;
+  const BoxPlan* plans = reinterpret_cast<const BoxPlan*>(ws + L.off_plans);
+  const float* gbox = reinterpret_cast<const float*>(ws + L.off_gbox);
+  const double* ysum_img = reinterpret_cast<const double*>(ws + L.off_ysum_img);
+  const double* ysum_patch = reinterpret_cast<const double*>(ws + L.off_ysum_patch);
+  const float mu_t = (float)(ysum_img[b] / (double)((size_t)s.height * s.width));
+  const float mu_s = (float)(ysum_patch[b] / (double)PP);
+  const float* wb = print_wb + (size_t)b * 6;
+  float* gm = reinterpret_cast<float*>(ws + L.off_gm) + (size_t)b * PP * 3;
+  const int j0 = offsets[b], j1 = offsets[b + 1];
+  double gy_acc = 0.0;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < PP; t += gridDim.x * blockDim.x) {
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+    for (int j = j0; j < j1; ++j) {
+      if (!plans[j].valid) continue;
+      const float* g = gbox + ((size_t)j * PP + t) * 3;
+      a0 += g[0]; a1 += g[1]; a2 += g[2];
+    }
+    const float* p = patch + (size_t)t * 3;
+    const TexelYuv y = texel_yuv(__ldg(p), __ldg(p + 1), __ldg(p + 2), wb);
+    const float y_pre = (y.y - mu_s) + mu_t;
+    const float yp = clampf(y_pre, 0.0f, 1.0f);
+    const float rr = (yp * 1.0f + y.u * EOT_I10) + y.v * EOT_I20;
+    const float gg = (yp * 1.0f + y.u * EOT_I11) + y.v * EOT_I21;
+    const float bb = (yp * 1.0f + y.u * EOT_I12) + y.v * EOT_I22;
+    const float g0 = (rr >= 0.0f && rr <= 1.0f) ? a0 * EOT_C255_127 : 0.0f;
+    const float g1 = (gg >= 0.0f && gg <= 1.0f) ? a1 * EOT_C255_127 : 0.0f;
+    const float g2 = (bb >= 0.0f && bb <= 1.0f) ? a2 * EOT_C255_127 : 0.0f;
+    float gY = g0 + g1 + g2;                                       // K' row Y = (1,1,1)
+    const float gU = g0 * EOT_I10 + g1 * EOT_I11 + g2 * EOT_I12;
+    const float gV = g0 * EOT_I20 + g1 * EOT_I21 + g2 * EOT_I22;
+    if (!(y_pre >= 0.0f && y_pre <= 1.0f)) gY = 0.0f;
+    gy_acc += (double)gY;
+    float* o = gm + (size_t)t * 3;
     o[0] = gY; o[1] = gU; o[2] = gV;
   }
   gy_acc = block_sum(gy_acc, red);
@@ -286,20 +409,30 @@ extern "C" int eot_apply_bwd(const EotShape* shape, const float* patch, const fl
   EOT_CHECK_CUDA(cudaMemsetAsync(ws + L.off_gy_sum, 0, (size_t)B * sizeof(double), st));
   const int nsm = sm_count();
   k_bwd_window<<<nsm * 8, kThreads, 0, st>>>(s, L, ws, grad_images);
-  // patch rows per CTA: enough CTAs to fill the GPU about twice, a multiple of the chunk
-  const int pmax = ((P + kBwdChunk - 1) / kBwdChunk) * kBwdChunk;
-  int rpc = (int)(((long long)B * P) / (2ll * nsm));
-  rpc = rpc < kBwdChunk ? kBwdChunk : (rpc / kBwdChunk) * kBwdChunk;
-  if (rpc > 64) rpc = 64;
-  if (rpc > pmax) rpc = pmax;
-  size_t smem = ((size_t)rpc * P * 3 + (size_t)kBwdChunk * L.lmin * 3) * sizeof(float);
-  while (smem > 160 * 1024 && rpc > kBwdChunk) {
-    rpc -= kBwdChunk;
-    smem = ((size_t)rpc * P * 3 + (size_t)kBwdChunk * L.lmin * 3) * sizeof(float);
+  if (L.use_gbox) {
+    const size_t smem2 = bwd_resize2_smem_bytes(s, L);
+    if (smem2 > 200 * 1024) { set_error("eot_apply_bwd: shared-memory tile too large (L=%d)", L.lmin); return EOT_ERR_BAD_SHAPE; }
+    if (smem2 > 48 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_bwd_resize2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    k_bwd_resize2<<<dim3((P + kBwdChunk - 1) / kBwdChunk, s.total_boxes), kThreads, smem2, st>>>(s, L, ws);
+    const int mchunks = max(1, min((PP + kThreads - 1) / kThreads, 64));
+    k_bwd_match<<<dim3(mchunks, B), kThreads, 0, st>>>(s, L, ws, patch, print_wb, offsets);
+    count_launches(1);
+  } else {
+    // patch rows per CTA: enough CTAs to fill the GPU about twice, a multiple of the chunk
+    const int pmax = ((P + kBwdChunk - 1) / kBwdChunk) * kBwdChunk;
+    int rpc = (int)(((long long)B * P) / (2ll * nsm));
+    rpc = rpc < kBwdChunk ? kBwdChunk : (rpc / kBwdChunk) * kBwdChunk;
+    if (rpc > 64) rpc = 64;
+    if (rpc > pmax) rpc = pmax;
+    size_t smem = bwd_resize_smem_bytes(s, L, rpc);
+    while (smem > 100 * 1024 && rpc > kBwdChunk) {
+      rpc -= kBwdChunk;
+      smem = bwd_resize_smem_bytes(s, L, rpc);
+    }
+    if (smem > 200 * 1024) { set_error("eot_apply_bwd: shared-memory tile too large (P=%d, L=%d)", P, L.lmin); return EOT_ERR_BAD_SHAPE; }
+    if (smem > 48 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_bwd_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_bwd_resize<<<dim3((P + rpc - 1) / rpc, B), kThreads, smem, st>>>(s, L, ws, patch, print_wb, offsets, rpc);
   }
-  if (smem > 200 * 1024) { set_error("eot_apply_bwd: shared-memory tile too large (P=%d, L=%d)", P, L.lmin); return EOT_ERR_BAD_SHAPE; }
-  if (smem > 48 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_bwd_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_bwd_resize<<<dim3((P + rpc - 1) / rpc, B), kThreads, smem, st>>>(s, L, ws, patch, print_wb, offsets, rpc);
   const int groups = B < kBwdGroups ? B : kBwdGroups;
   k_bwd_texel<<<dim3((PP + kThreads - 1) / kThreads, groups), kThreads, 0, st>>>(s, L, ws, patch, print_wb, groups);
   k_bwd_reduce<<<(n + kThreads - 1) / kThreads, kThreads, 0, st>>>(reinterpret_cast<const float*>(ws + L.off_gp_part), n, groups,

@@ -69,6 +69,7 @@ struct Layout {
   size_t off_gm;           // float[B][P*P*3] backward: dL/d(matched patch) per image
   size_t off_gu;           // float[N][gslot]  backward: dL/d(u) per box
   size_t off_gp_part;      // float[16][P*P*3] backward: partial dL/dpatch per image group
+  size_t off_gbox;         // float[N][P*P*3]  backward: dL/d(matched patch) per box (0 bytes when it would exceed gbox_cap)
   size_t off_offsets;      // int32[B+1] copy of the CSR row splits (the backward has no other source)
   size_t total;
   int64_t slot;            // floats per u slot (4 per texel)
@@ -77,6 +78,7 @@ struct Layout {
   int32_t lmin;            // max patch side
   int32_t resize_rows;     // output rows per resize work item (bounded by shared memory: rows * P * 12 B)
   int64_t rslot;           // bytes per route map
+  int32_t use_gbox;        // per-box partial gradients fit: fully parallel resize adjoint
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -114,6 +116,8 @@ __host__ __device__ inline Layout make_layout(const EotShape& s) {
   L.off_gm = o;           o = align_up(o + B * PP3 * sizeof(float), 256);
   L.off_gu = o;           o = align_up(o + N * (size_t)L.gslot * sizeof(float), 256);
   L.off_gp_part = o;      o = align_up(o + 16 * PP3 * sizeof(float), 256);
+  L.use_gbox = (N * PP3 * sizeof(float) <= ((size_t)1 << 30) && !(s.flags & EOT_FLAG_SERIAL_ADJOINT)) ? 1 : 0;
+  L.off_gbox = o;         o = align_up(o + (L.use_gbox ? N * PP3 * sizeof(float) : 0), 256);
   L.off_offsets = o;      o = align_up(o + (B + 1) * sizeof(int32_t), 256);
   L.total = o;
   return L;

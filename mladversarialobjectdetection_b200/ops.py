@@ -48,6 +48,7 @@ class PatchGeometry:
     noise_amp: float = 0.01         # attacker.py:426
     min_patch_area: float = 4.0     # attacker.py:347
     max_scale: float = 1.0
+    serial_adjoint: bool = False    # EOT_FLAG_SERIAL_ADJOINT (memory-lean backward path)
 
 
 def _shape(images: torch.Tensor, patch: torch.Tensor, n_boxes: int, g: PatchGeometry, want_mask: bool) -> EotShape:
@@ -72,7 +73,7 @@ def _shape(images: torch.Tensor, patch: torch.Tensor, n_boxes: int, g: PatchGeom
         raise ValueError("patch must be square, 3-channel, with unit channel stride")
     s.patch_size = P
     s.total_boxes = n_boxes
-    s.flags = _lib.EOT_FLAG_MASK_OUTPUT if want_mask else 0
+    s.flags = (_lib.EOT_FLAG_MASK_OUTPUT if want_mask else 0) | (2 if g.serial_adjoint else 0)
     s.tolerance, s.noise_amp, s.min_patch_area, s.max_scale = g.tolerance, g.noise_amp, g.min_patch_area, g.max_scale
     s.patch_stride_n, s.patch_stride_y, s.patch_stride_x = sn, sy, sx
     return s

@@ -13,8 +13,8 @@ F = np.float32
 REL_L2 = 1e-4
 
 
-def _check_backward(bt, patch, scale, seed, smooth_grad=False):
-    out, _, ctx, d = run_forward(patch, scale, bt)
+def _check_backward(bt, patch, scale, seed, smooth_grad=False, geom=None):
+    out, _, ctx, d = run_forward(patch, scale, bt, geom)
     rng = np.random.default_rng(seed)
     G = rng.normal(size=bt.images.shape).astype(F)
     if smooth_grad:
@@ -42,6 +42,15 @@ def _check_backward(bt, patch, scale, seed, smooth_grad=False):
 def test_backward_rel_l2(B, H, P, scale, seed):
     bt = synth.make_batch(B, H, H, seed=seed, max_boxes=6)
     _check_backward(bt, synth.make_patch(P, seed=seed), scale, seed)
+
+
+def test_backward_serial_adjoint_path():
+    # the memory-lean path (no per-box partial buffer) must give the same gradient
+    bt = synth.make_batch(6, 192, 192, seed=27, max_boxes=5)
+    patch = synth.make_patch(60, seed=27)
+    g1, _, G, _ = _check_backward(bt, patch, 0.4, 27)
+    g2, _, _, _ = _check_backward(bt, patch, 0.4, 27, geom=ops.PatchGeometry(serial_adjoint=True))
+    assert torch.allclose(g1, g2, rtol=1e-5, atol=1e-7 * float(g1.abs().max()))
 
 
 def test_backward_dark_patch_clips_active():
