@@ -37,8 +37,9 @@ __device__ __forceinline__ void routed_grad3(const uint8_t* __restrict__ route, 
 
 __global__ void __launch_bounds__(kThreads) k_bwd_window(EotShape s, Layout L, char* ws, const float* __restrict__ G) {
   const BoxPlan* plans = reinterpret_cast<const BoxPlan*>(ws + L.off_plans);
-  const int2* items = reinterpret_cast<const int2*>(ws + L.off_items_resize);
-  const int n_items = reinterpret_cast<const int*>(ws + L.off_counters)[0];
+  __shared__ int2 s_base[kMaxBaseSmem];
+  const int2* base = stage_base(reinterpret_cast<const int2*>(ws + L.off_base), s.total_boxes, s_base);
+  const int n_items = base[s.total_boxes].x;
   const float* ubuf = reinterpret_cast<const float*>(ws + L.off_u);
   float* gubuf = reinterpret_cast<float*>(ws + L.off_gu);
   const uint8_t* routes = reinterpret_cast<const uint8_t*>(ws + L.off_route);
@@ -46,7 +47,7 @@ __global__ void __launch_bounds__(kThreads) k_bwd_window(EotShape s, Layout L, c
   const int RR = L.resize_rows;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-    const int2 item = items[it];
+    const int2 item = find_item(base, s.total_boxes, 0, it);
     const int j = item.x;
     const BoxPlan me = plans[j];
     const int ps = me.ps, D = me.d;

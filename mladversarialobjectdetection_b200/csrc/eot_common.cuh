@@ -56,14 +56,16 @@ struct Layout {
   size_t off_ysum_patch;   // double[B]
   size_t off_gy_sum;       // double[B]   (backward: sum of dL/dY per image)
   size_t off_oor;          // int32[B]    image b holds a value outside [-1,1] (then clip(background) is not the identity)
-  size_t off_counters;     // int32[8]: 0 resize items, 1 composite items, 2 error flag, 3 bwd items
+  size_t off_done;         // int32[5][B]  fused forward: finished work items per image and stage (geometry, patch
+                           //              statistics, image pass, match, resize)
+  size_t off_counters;     // int32[8]: 2 error flag, 4 work ticket, 5 finished geometry blocks
   size_t off_plans;        // BoxPlan[N]
   size_t off_starts;       // int32[N][Lmin]
   size_t off_weights;      // float[N][wcap]
   size_t off_match;        // float[B][P*P*3]
   size_t off_u;            // float4[N][slot/4]: clipped (r,g,b) of the transformed patch + inner-clip pass bits
-  size_t off_items_resize; // int2[N*ceil(Lmin/resize_rows)]
-  size_t off_items_comp;   // int2[N*ceil(Lmin/kCompRows)]
+  size_t off_cnt;          // int2[N]    work items of box j: (resize strips, composite row blocks); 0 when invalid
+  size_t off_base;         // int2[N+1]  exclusive prefix sums of off_cnt (box order == image order)
   size_t off_inv;          // int2[N][P]  for patch index i: first/last output index whose span holds i
   size_t off_route;        // uint8[N][rslot] per window pixel: bit c = channel c of the output came from this box (and passes the clip)
   size_t off_gm;           // float[B][P*P*3] backward: dL/d(matched patch) per image
@@ -102,14 +104,15 @@ __host__ __device__ inline Layout make_layout(const EotShape& s) {
   L.off_ysum_patch = o;   o = align_up(o + B * sizeof(double), 256);
   L.off_gy_sum = o;       o = align_up(o + B * sizeof(double), 256);
   L.off_oor = o;          o = align_up(o + B * sizeof(int32_t), 256);
+  L.off_done = o;         o = align_up(o + 5 * B * sizeof(int32_t), 256);
   L.off_counters = o;     o = align_up(o + 8 * sizeof(int32_t), 256);
   L.off_plans = o;        o = align_up(o + N * sizeof(BoxPlan), 256);
   L.off_starts = o;       o = align_up(o + N * (size_t)lmin * sizeof(int32_t), 256);
   L.off_weights = o;      o = align_up(o + N * (size_t)L.wcap * sizeof(float), 256);
   L.off_match = o;        o = align_up(o + B * PP3 * sizeof(float), 256);
   L.off_u = o;            o = align_up(o + N * (size_t)L.slot * sizeof(float), 256);
-  L.off_items_resize = o; o = align_up(o + N * (size_t)((lmin + L.resize_rows - 1) / L.resize_rows) * 8, 256);
-  L.off_items_comp = o;   o = align_up(o + N * (size_t)((lmin + kCompRows - 1) / kCompRows) * 8, 256);
+  L.off_cnt = o;          o = align_up(o + N * 8, 256);
+  L.off_base = o;         o = align_up(o + (N + 1) * 8, 256);
   L.off_inv = o;          o = align_up(o + N * (size_t)s.patch_size * 8, 256);
   L.rslot = (int64_t)align_up((size_t)lfull * lfull, 32);
   L.off_route = o;        o = align_up(o + N * (size_t)L.rslot, 256);
@@ -176,6 +179,24 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t k0, uint32_
     c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
   }
   return make_uint4(c0, c1, c2, c3);
+}
+
+// Work item i of kind `which` (0: resize strip, 1: composite row block) -> (box, index inside the box).
+// base[] holds the exclusive prefix sums of the per-box item counts, in box (== image) order.
+__device__ __forceinline__ int2 find_item(const int2* __restrict__ base, int N, int which, int i) {
+  const int* b = reinterpret_cast<const int*>(base) + which;
+  int lo = 0, hi = N;                      // last j with base[j] <= i
+  while (hi - lo > 1) { const int m = (lo + hi) >> 1; if (b[2 * m] <= i) lo = m; else hi = m; }
+  return make_int2(lo, i - b[2 * lo]);
+}
+
+// Copies the prefix table to shared memory when it fits (the binary search then costs no global latency).
+constexpr int kMaxBaseSmem = 1025;
+__device__ __forceinline__ const int2* stage_base(const int2* base, int N, int2* smem) {
+  if (N + 1 > kMaxBaseSmem) return base;
+  for (int i = threadIdx.x; i <= N; i += blockDim.x) smem[i] = base[i];
+  __syncthreads();
+  return smem;
 }
 
 // TF Uint32ToFloat + random_uniform range map: u*(hi-lo)+lo with lo=-amp, hi=amp.

@@ -147,12 +147,11 @@ __device__ __forceinline__ int2 inverse_span_search(const int* starts, int n_out
   return make_int2(lo, a - 1);
 }
 
-// One CTA per box: plan, span table, inverse-span table, work items.
-__device__ void geometry_block(const EotShape& s, const Layout& L, int j, const float* __restrict__ boxes,
+// One CTA per box: plan, span table, inverse-span table, work-item counts.
+__device__ int geometry_block(const EotShape& s, const Layout& L, int j, const float* __restrict__ boxes,
                                const int32_t* __restrict__ offsets, const EotBoxParams* __restrict__ params,
                                const float* __restrict__ scale, char* ws, EotBoxGeometry* geom_out) {
   __shared__ BoxPlan spl;
-  __shared__ int base_r, base_c;
   int* counters = ws ? reinterpret_cast<int*>(ws + L.off_counters) : nullptr;
   if (threadIdx.x == 0) {
     int a = 0, b = s.batch;                       // image of box j: last b with offsets[b] <= j
@@ -161,31 +160,81 @@ __device__ void geometry_block(const EotShape& s, const Layout& L, int j, const 
                            (int64_t)j * L.slot, counters ? counters + 2 : nullptr);
     if (pl.valid) pl.span = span_cfg(pl.ps, s.patch_size).span;
     spl = pl;
-    if (ws) reinterpret_cast<BoxPlan*>(ws + L.off_plans)[j] = pl;
+    if (ws) {
+      reinterpret_cast<BoxPlan*>(ws + L.off_plans)[j] = pl;
+      reinterpret_cast<int2*>(ws + L.off_cnt)[j] =
+          pl.valid ? make_int2((pl.ps + L.resize_rows - 1) / L.resize_rows, (pl.d + kCompRows - 1) / kCompRows) : make_int2(0, 0);
+    }
     if (geom_out) {
       EotBoxGeometry g = {pl.y0, pl.x0, pl.ps, pl.d, pl.pad_lo, pl.pad_hi, pl.valid, pl.span};
       geom_out[j] = g;
     }
-    if (ws && pl.valid) {
-      base_r = atomicAdd(counters + 0, (pl.ps + L.resize_rows - 1) / L.resize_rows);
-      base_c = atomicAdd(counters + 1, (pl.d + kCompRows - 1) / kCompRows);
-    }
   }
   __syncthreads();
-  if (!ws || !spl.valid) return;
+  const int image = spl.image;
+  if (!ws || !spl.valid) return image;
   const int ps = spl.ps, P = s.patch_size;
   int* starts = reinterpret_cast<int*>(ws + L.off_starts) + (size_t)j * L.lmin;
   float* weights = reinterpret_cast<float*>(ws + L.off_weights) + (size_t)j * L.wcap;
   const SpanCfg cfg = span_cfg(ps, P);
   for (int o = threadIdx.x; o < ps; o += blockDim.x) span_row(o, cfg, P, starts + o, weights + (size_t)o * cfg.span);
-  const int nres = (ps + L.resize_rows - 1) / L.resize_rows, ncomp = (spl.d + kCompRows - 1) / kCompRows;
-  int2* items_r = reinterpret_cast<int2*>(ws + L.off_items_resize);
-  int2* items_c = reinterpret_cast<int2*>(ws + L.off_items_comp);
-  for (int i = threadIdx.x; i < nres; i += blockDim.x) items_r[base_r + i] = make_int2(j, i);
-  for (int i = threadIdx.x; i < ncomp; i += blockDim.x) items_c[base_c + i] = make_int2(j, i);
   __syncthreads();                                  // starts[] of this box are complete
   int2* inv = reinterpret_cast<int2*>(ws + L.off_inv) + (size_t)j * P;
   for (int i = threadIdx.x; i < P; i += blockDim.x) inv[i] = inverse_span_search(starts, ps, cfg.span, i);
+  return image;
+}
+
+// Exclusive prefix sums of the per-box work-item counts (one CTA; N is a few hundred to a few thousand).
+__device__ void scan_block(int N, const int2* cnt, int2* base, int2* part /* [blockDim.x] shared */) {
+  const int T = blockDim.x;
+  const int per = (N + T - 1) / T;
+  const int j0 = threadIdx.x * per, j1 = min(N, j0 + per);
+  int2 sum = make_int2(0, 0);
+  for (int j = j0; j < j1; ++j) { const int2 c = __ldcg(cnt + j); sum.x += c.x; sum.y += c.y; }
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  for (int d = 1; d < T; d <<= 1) {
+    int2 v = make_int2(0, 0);
+    if ((int)threadIdx.x >= d) v = part[threadIdx.x - d];
+    __syncthreads();
+    part[threadIdx.x].x += v.x;
+    part[threadIdx.x].y += v.y;
+    __syncthreads();
+  }
+  int2 run = threadIdx.x ? part[threadIdx.x - 1] : make_int2(0, 0);
+  for (int j = j0; j < j1; ++j) {
+    base[j] = run;
+    const int2 c = __ldcg(cnt + j);
+    run.x += c.x;
+    run.y += c.y;
+  }
+  if ((int)threadIdx.x == T - 1) base[N] = part[T - 1];
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) k_scan(int N, const int2* __restrict__ cnt, int2* base) {
+  __shared__ int2 part[1024];
+  const int per = (N + 1023) / 1024;
+  const int j0 = threadIdx.x * per, j1 = min(N, j0 + per);
+  int2 sum = make_int2(0, 0);
+  for (int j = j0; j < j1; ++j) { sum.x += cnt[j].x; sum.y += cnt[j].y; }
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {
+    int2 v = make_int2(0, 0);
+    if ((int)threadIdx.x >= d) v = part[threadIdx.x - d];
+    __syncthreads();
+    part[threadIdx.x].x += v.x;
+    part[threadIdx.x].y += v.y;
+    __syncthreads();
+  }
+  int2 run = threadIdx.x ? part[threadIdx.x - 1] : make_int2(0, 0);
+  for (int j = j0; j < j1; ++j) {
+    base[j] = run;
+    run.x += cnt[j].x;
+    run.y += cnt[j].y;
+  }
+  if (threadIdx.x == 1023) base[N] = part[1023];
 }
 
 __global__ void __launch_bounds__(kThreads) k_geometry_only(EotShape s, Layout L, const float* __restrict__ boxes,
@@ -240,34 +289,38 @@ __device__ __forceinline__ void image_pass_block(int HW, int b, int chunk, const
     const float4* in4 = reinterpret_cast<const float4*>(in);
     float4* o4 = reinterpret_cast<float4*>(o);
     float4* m4 = reinterpret_cast<float4*>(mk);
-    float4 v[kPassPixPerThread / 4][3];
+    // two batches of 2 x (3 x float4): 96 bytes per thread in flight per batch, modest register footprint
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      float4 v[2][3];
 #pragma unroll
-    for (int st = 0; st < kPassPixPerThread / 4; ++st) {
-      const int pix = pix0 + (st * kThreads + threadIdx.x) * 4;
-      if (pix < HW) {
-        const int q = (pix >> 2) * 3;
-        v[st][0] = __ldg(in4 + q);
-        v[st][1] = __ldg(in4 + q + 1);
-        v[st][2] = __ldg(in4 + q + 2);
+      for (int k = 0; k < 2; ++k) {
+        const int pix = pix0 + ((half * 2 + k) * kThreads + threadIdx.x) * 4;
+        if (pix < HW) {
+          const int q = (pix >> 2) * 3;
+          v[k][0] = __ldg(in4 + q);
+          v[k][1] = __ldg(in4 + q + 1);
+          v[k][2] = __ldg(in4 + q + 2);
+        }
       }
-    }
 #pragma unroll
-    for (int st = 0; st < kPassPixPerThread / 4; ++st) {
-      const int pix = pix0 + (st * kThreads + threadIdx.x) * 4;
-      if (pix < HW) {
-        const int q = (pix >> 2) * 3;
-        const float4 a = v[st][0], bb = v[st][1], c = v[st][2];
-        if (o) { o4[q] = a; o4[q + 1] = bb; o4[q + 2] = c; }
-        if (mk) { const float4 z = make_float4(0.f, 0.f, 0.f, 0.f); m4[q] = z; m4[q + 1] = z; m4[q + 2] = z; }
-        acc += (double)luma_of(a.x, a.y, a.z);
-        acc += (double)luma_of(a.w, bb.x, bb.y);
-        acc += (double)luma_of(bb.z, bb.w, c.x);
-        acc += (double)luma_of(c.y, c.z, c.w);
-        const float m0 = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w)));
-        const float m1 = fmaxf(fmaxf(fabsf(bb.x), fabsf(bb.y)), fmaxf(fabsf(bb.z), fabsf(bb.w)));
-        const float m2 = fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fmaxf(fabsf(c.z), fabsf(c.w)));
-        const float sum = (a.x + a.y + a.z + a.w) + (bb.x + bb.y + bb.z + bb.w) + (c.x + c.y + c.z + c.w);
-        oor = oor || !(fmaxf(fmaxf(m0, m1), m2) <= 1.0f) || (sum != sum);      // fmaxf drops NaN: test the sum too
+      for (int k = 0; k < 2; ++k) {
+        const int pix = pix0 + ((half * 2 + k) * kThreads + threadIdx.x) * 4;
+        if (pix < HW) {
+          const int q = (pix >> 2) * 3;
+          const float4 a = v[k][0], bb = v[k][1], c = v[k][2];
+          if (o) { o4[q] = a; o4[q + 1] = bb; o4[q + 2] = c; }
+          if (mk) { const float4 z = make_float4(0.f, 0.f, 0.f, 0.f); m4[q] = z; m4[q + 1] = z; m4[q + 2] = z; }
+          acc += (double)luma_of(a.x, a.y, a.z);
+          acc += (double)luma_of(a.w, bb.x, bb.y);
+          acc += (double)luma_of(bb.z, bb.w, c.x);
+          acc += (double)luma_of(c.y, c.z, c.w);
+          const float m0 = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w)));
+          const float m1 = fmaxf(fmaxf(fabsf(bb.x), fabsf(bb.y)), fmaxf(fabsf(bb.z), fabsf(bb.w)));
+          const float m2 = fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fmaxf(fabsf(c.z), fabsf(c.w)));
+          const float sum = (a.x + a.y + a.z + a.w) + (bb.x + bb.y + bb.z + bb.w) + (c.x + c.y + c.z + c.w);
+          oor = oor || !(fmaxf(fmaxf(m0, m1), m2) <= 1.0f) || (sum != sum);      // fmaxf drops NaN: test the sum too
+        }
       }
     }
   } else {
@@ -291,36 +344,46 @@ __device__ __forceinline__ void image_pass_block(int HW, int b, int chunk, const
 }
 
 // One launch, three independent roles selected by the block index (they only meet at k_match):
-//   [0, N)                         geometry of box j
-//   [N, N + B*pchunks)             patch luma statistics
-//   [N + B*pchunks, ... + B*cpi)   image pass (copy + luma sum), the HBM-bound bulk
+//   [0, n_geom)                         geometry of box j                   (n_geom = N or 0)
+//   [.., + n_stat_imgs*pchunks)         patch luma statistics               (n_stat_imgs = B or 0)
+//   [.., + (b1-b0)*cpi)                 image pass (copy + luma sum) of images [b0,b1), the HBM-bound bulk
 template <bool kVec>
 __global__ void __launch_bounds__(kThreads) k_prepass(EotShape s, Layout L, const float* __restrict__ patch,
                                                       const float* __restrict__ print_wb, const float* __restrict__ boxes,
                                                       const int32_t* __restrict__ offsets,
                                                       const EotBoxParams* __restrict__ params,
                                                       const float* __restrict__ scale, const float* __restrict__ images,
-                                                      float* out, float* mask, char* ws, int pchunks, int cpi) {
+                                                      float* out, float* mask, char* ws, int n_geom, int n_stat_imgs,
+                                                      int pchunks, int cpi, int b0) {
   __shared__ double red[32];
   int blk = blockIdx.x;
-  const int N = s.total_boxes;
-  if (blk < N) {
+  if (blk < n_geom) {
+    __shared__ int s_last;
+    __shared__ int2 s_part[kThreads];
     geometry_block(s, L, blk, boxes, offsets, params, scale, ws, nullptr);
+    __threadfence();
+    __syncthreads();
+    int* counters = reinterpret_cast<int*>(ws + L.off_counters);
+    if (threadIdx.x == 0) s_last = (atomicAdd(counters + 5, 1) == n_geom - 1);
+    __syncthreads();
+    if (s_last) {                                        // last geometry block: prefix sums of the work-item counts
+      __threadfence();
+      scan_block(n_geom, reinterpret_cast<const int2*>(ws + L.off_cnt), reinterpret_cast<int2*>(ws + L.off_base), s_part);
+    }
     return;
   }
-  blk -= N;
-  if (blk < s.batch * pchunks) {
+  blk -= n_geom;
+  if (blk < n_stat_imgs * pchunks) {
     const int b = blk / pchunks;
     patch_stats_block(s, b, blk - b * pchunks, pchunks, patch, print_wb, reinterpret_cast<double*>(ws + L.off_ysum_patch), red);
+    if (blk == 0 && threadIdx.x == 0) {                  // CSR copy for the backward
+      int32_t* off_copy = reinterpret_cast<int32_t*>(ws + L.off_offsets);
+      for (int i = 0; i <= s.batch; ++i) off_copy[i] = offsets[i];
+    }
     return;
   }
-  blk -= s.batch * pchunks;
-  const int b = blk / cpi, chunk = blk - b * cpi;
-  if (chunk == 0 && threadIdx.x == 0) {                 // CSR copy for the backward
-    int32_t* off_copy = reinterpret_cast<int32_t*>(ws + L.off_offsets);
-    off_copy[b] = offsets[b];
-    if (b == s.batch - 1) off_copy[b + 1] = offsets[b + 1];
-  }
+  blk -= n_stat_imgs * pchunks;
+  const int b = b0 + blk / cpi, chunk = blk % cpi;
   image_pass_block<kVec>(s.height * s.width, b, chunk, images, out, mask, reinterpret_cast<double*>(ws + L.off_ysum_img),
                          reinterpret_cast<int*>(ws + L.off_oor), red);
 }
@@ -328,9 +391,16 @@ __global__ void __launch_bounds__(kThreads) k_prepass(EotShape s, Layout L, cons
 // ------------------------------------------------------------------------------------------------
 // print adjust + brightness match of the patch for image b (attacker.py:372; brightness_matcher.py:43-73)
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void match_block(const EotShape& s, const Layout& L, const float* __restrict__ patch,
+                                            const float* __restrict__ print_wb, char* ws, int b, int part, int nparts);
+
 __global__ void __launch_bounds__(kThreads) k_match(EotShape s, Layout L, const float* __restrict__ patch,
-                                                    const float* __restrict__ print_wb, char* ws) {
-  const int b = blockIdx.y;
+                                                    const float* __restrict__ print_wb, char* ws, int b0) {
+  match_block(s, L, patch, print_wb, ws, b0 + blockIdx.y, blockIdx.x, gridDim.x);
+}
+
+__device__ __forceinline__ void match_block(const EotShape& s, const Layout& L, const float* __restrict__ patch,
+                                            const float* __restrict__ print_wb, char* ws, int b, int part, int nparts) {
   const int P = s.patch_size;
   const double* ysum_img = reinterpret_cast<const double*>(ws + L.off_ysum_img);
   const double* ysum_patch = reinterpret_cast<const double*>(ws + L.off_ysum_patch);
@@ -339,7 +409,7 @@ __global__ void __launch_bounds__(kThreads) k_match(EotShape s, Layout L, const 
   const float* wb = print_wb + (size_t)b * 6;
   const float* base = patch + (s.num_patches > 1 ? (int64_t)b * s.patch_stride_n : 0);
   float* m = reinterpret_cast<float*>(ws + L.off_match) + (size_t)b * P * P * 3;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < P * P; t += gridDim.x * blockDim.x) {
+  for (int t = part * blockDim.x + threadIdx.x; t < P * P; t += nparts * blockDim.x) {
     const int py = t / P, px = t - py * P;
     const float* p = base + (int64_t)py * s.patch_stride_y + (int64_t)px * s.patch_stride_x;
     const TexelYuv y = texel_yuv(__ldg(p), __ldg(p + 1), __ldg(p + 2), wb);
@@ -502,12 +572,14 @@ __device__ __forceinline__ void resize_item(const EotShape& s, const Layout& L, 
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 4) k_resize(EotShape s, Layout L, char* ws) {
+__global__ void __launch_bounds__(kThreads, 4) k_resize(EotShape s, Layout L, char* ws, const int32_t* __restrict__ offsets,
+                                                        int b0, int b1) {
   extern __shared__ float resize_smem[];
-  const int2* items = reinterpret_cast<const int2*>(ws + L.off_items_resize);
-  const int n_items = reinterpret_cast<const int*>(ws + L.off_counters)[0];
-  for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-    resize_item(s, L, ws, items[it], resize_smem);
+  __shared__ int2 s_base[kMaxBaseSmem];
+  const int2* base = stage_base(reinterpret_cast<const int2*>(ws + L.off_base), s.total_boxes, s_base);
+  const int lo = base[offsets[b0]].x, hi = base[offsets[b1]].x;
+  for (int it = lo + blockIdx.x; it < hi; it += gridDim.x) {
+    resize_item(s, L, ws, find_item(base, s.total_boxes, 0, it), resize_smem);
     __syncthreads();
   }
 }
@@ -728,13 +800,185 @@ __device__ __forceinline__ void composite_item(const EotShape& s, const Layout& 
 }
 
 __global__ void __launch_bounds__(kThreads, 3) k_composite(EotShape s, Layout L, char* ws,
-                                                        const float* __restrict__ images, float* out, float* mask) {
+                                                        const float* __restrict__ images, float* out, float* mask,
+                                                        const int32_t* __restrict__ offsets, int b0, int b1) {
   __shared__ CompositeSmem sm;
-  const int2* items = reinterpret_cast<const int2*>(ws + L.off_items_comp);
-  const int n_items = reinterpret_cast<const int*>(ws + L.off_counters)[1];
-  for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-    composite_item(s, L, ws, images, out, mask, items[it], sm);
+  __shared__ int2 s_base[kMaxBaseSmem];
+  const int2* base = stage_base(reinterpret_cast<const int2*>(ws + L.off_base), s.total_boxes, s_base);
+  const int lo = base[offsets[b0]].y, hi = base[offsets[b1]].y;
+  for (int it = lo + blockIdx.x; it < hi; it += gridDim.x) {
+    composite_item(s, L, ws, images, out, mask, find_item(base, s.total_boxes, 1, it), sm);
     __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused persistent forward: ONE launch for the whole of Patcher.call.
+//
+// Every CTA stays resident and draws work tickets from a global counter.  Tickets are laid out so that
+// each item only depends on items with LOWER ticket numbers, all of which have already been handed to a
+// resident CTA -- so a CTA may spin (bounded) on a per-image "finished items" counter without deadlock:
+//
+//   [ geometry of every box | patch luma statistics of every image ]
+//   slot k = 0 .. B+LAG-1:  image pass of image k (cpi chunks)  |  window work of image k-LAG:
+//                           match (MP parts) -> resize (NPR parts) -> composite (NPC parts)
+//
+// The HBM-bound image pass of later images therefore overlaps the instruction-bound window work of
+// earlier ones inside the same SMs, and the second touch of a window (background read, route/texel
+// traffic) happens while its lines are still in L2.  Producer: writes, __threadfence, barrier, one
+// atomicAdd on the stage counter.  Consumer: one thread polls the counter, __threadfence, barrier.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFusedNPR = 24;    // resize parts per image
+constexpr int kFusedNPC = 48;   // composite parts per image
+constexpr int kFusedStages = 4;  // slot k holds: pass(k), match(k-1), resize(k-2), composite(k-3)
+constexpr int kPassChunksPerTicket = 2;
+
+struct FusedPlan {
+  int n_geom, n_stat_tickets, pchunks, cpi, mp;   // mp = match parts per image
+  int pass_tickets;                                // image-pass tickets per image
+  int slot;                                        // tickets per slot
+  int total_tickets;
+};
+
+// acquire / release on the stage counters by ONE thread per CTA (PTX memory model: the CTA barrier
+// around them makes the ordering cumulative for the whole CTA).  No gpu-scope fence in every thread:
+// that would invalidate the SM's L1 at each of the ~10^4 tickets and starve the composite's tap reuse.
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add(int* p, int n) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(n) : "memory");
+}
+
+__device__ __forceinline__ bool wait_counter(const int* ctr, int need, int* err_flag) {
+  if (need <= 0) return true;
+  for (int spin = 0; spin < (1 << 22); ++spin) {
+    if (ld_acquire(ctr) >= need) return true;
+    __nanosleep(64);
+  }
+  atomicExch(err_flag, 3);      // dependency never arrived: give up instead of hanging the GPU
+  return false;
+}
+
+__device__ __forceinline__ void signal_counter(int* ctr, int n = 1) {
+  __syncthreads();
+  if (threadIdx.x == 0) red_release_add(ctr, n);
+}
+
+template <bool kVec>
+__global__ void __launch_bounds__(kThreads, 4) k_forward_fused(EotShape s, Layout L, FusedPlan fp, const float* __restrict__ patch,
+                                                               const float* __restrict__ print_wb,
+                                                               const float* __restrict__ boxes,
+                                                               const int32_t* __restrict__ offsets,
+                                                               const EotBoxParams* __restrict__ params,
+                                                               const float* __restrict__ scale,
+                                                               const float* __restrict__ images, float* out, float* mask,
+                                                               char* ws) {
+  extern __shared__ float dyn_smem[];                 // resize strip buffers
+  __shared__ CompositeSmem csm;
+  __shared__ double red[32];
+  __shared__ int2 pre[kMaxWin + 1];                   // per-image prefix of (resize strips, composite row blocks)
+  __shared__ int s_ticket[2], s_ok;
+  int* counters = reinterpret_cast<int*>(ws + L.off_counters);
+  int* err_flag = counters + 2;
+  int* done = reinterpret_cast<int*>(ws + L.off_done);
+  const int B = s.batch, N = s.total_boxes;
+  int* done_geom = done, *done_stat = done + B, *done_pass = done + 2 * B, *done_match = done + 3 * B, *done_resize = done + 4 * B;
+  const int S = fp.n_geom + fp.n_stat_tickets;
+  const int HW = s.height * s.width;
+  for (;;) {
+    // (no ticket prefetch: a ticket held but not started would delay everything that depends on it)
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket[0] = atomicAdd(counters + 4, 1);
+    __syncthreads();
+    int t = s_ticket[0];
+    if (t >= fp.total_tickets) break;
+    // ---- setup tickets ----
+    if (t < fp.n_geom) {
+      const int img = geometry_block(s, L, t, boxes, offsets, params, scale, ws, nullptr);
+      signal_counter(done_geom + img);
+      if (threadIdx.x == 0) s_ok = (atomicAdd(counters + 5, 1) == N - 1);
+      __syncthreads();
+      if (s_ok) {                                     // last geometry block: prefix sums for the backward's work list
+        __threadfence();
+        scan_block(N, reinterpret_cast<const int2*>(ws + L.off_cnt), reinterpret_cast<int2*>(ws + L.off_base),
+                   reinterpret_cast<int2*>(dyn_smem));
+      }
+      continue;
+    }
+    if (t < S) {
+      const int q = t - fp.n_geom;
+      const int b = q / fp.pchunks;
+      patch_stats_block(s, b, q - b * fp.pchunks, fp.pchunks, patch, print_wb, reinterpret_cast<double*>(ws + L.off_ysum_patch), red);
+      if (q == 0 && threadIdx.x == 0) {
+        int32_t* off_copy = reinterpret_cast<int32_t*>(ws + L.off_offsets);
+        for (int i = 0; i <= B; ++i) off_copy[i] = offsets[i];
+      }
+      signal_counter(done_stat + b);
+      continue;
+    }
+    // ---- slot tickets ----
+    t -= S;
+    const int slot = t / fp.slot;
+    int r = t - slot * fp.slot;
+    if (r < fp.pass_tickets) {                                    // image pass: kPassChunksPerTicket chunks of image `slot`
+      if (slot >= B) continue;
+      int n_done = 0;
+      for (int c = r * kPassChunksPerTicket; c < min(fp.cpi, (r + 1) * kPassChunksPerTicket); ++c, ++n_done)
+        image_pass_block<kVec>(HW, slot, c, images, out, mask, reinterpret_cast<double*>(ws + L.off_ysum_img),
+                               reinterpret_cast<int*>(ws + L.off_oor), red);
+      signal_counter(done_pass + slot, n_done);
+      continue;
+    }
+    r -= fp.pass_tickets;
+    int stage, w;                                                 // 1 match, 2 resize, 3 composite ; image w
+    if (r < fp.mp) { stage = 1; w = slot - 1; }
+    else if (r < fp.mp + kFusedNPR) { stage = 2; w = slot - 2; r -= fp.mp; }
+    else { stage = 3; w = slot - 3; r -= fp.mp + kFusedNPR; }
+    if (w < 0 || w >= B) continue;
+    const int first = offsets[w], nb_all = offsets[w + 1] - first;
+    if (stage == 1) {
+      if (nb_all > 0) {
+        if (threadIdx.x == 0) s_ok = wait_counter(done_pass + w, fp.cpi, err_flag) && wait_counter(done_stat + w, fp.pchunks, err_flag);
+        __syncthreads();
+        if (s_ok) match_block(s, L, patch, print_wb, ws, w, r, fp.mp);
+      }
+      signal_counter(done_match + w);
+      continue;
+    }
+    const bool is_resize = stage == 2;
+    const int part = r;
+    const int nparts = is_resize ? kFusedNPR : kFusedNPC;
+    if (nb_all > 0) {
+      if (threadIdx.x == 0) {
+        bool ok = wait_counter(done_geom + w, nb_all, err_flag);
+        ok = ok && (is_resize ? wait_counter(done_match + w, fp.mp, err_flag) : wait_counter(done_resize + w, kFusedNPR, err_flag));
+        s_ok = ok;
+      }
+      __syncthreads();
+      if (s_ok) {
+        const int nb = min(nb_all, kMaxWin);
+        const int2* cnt = reinterpret_cast<const int2*>(ws + L.off_cnt) + first;
+        if (threadIdx.x == 0) {
+          int2 run = make_int2(0, 0);
+          for (int i = 0; i < nb; ++i) { pre[i] = run; const int2 c = __ldcg(cnt + i); run.x += c.x; run.y += c.y; }
+          pre[nb] = run;
+        }
+        __syncthreads();
+        const int total = is_resize ? pre[nb].x : pre[nb].y;
+        for (int it = part; it < total; it += nparts) {
+          int lo = 0, hi = nb;                                    // last box with prefix <= it
+          while (hi - lo > 1) { const int m = (lo + hi) >> 1; if ((is_resize ? pre[m].x : pre[m].y) <= it) lo = m; else hi = m; }
+          const int2 item = make_int2(first + lo, it - (is_resize ? pre[lo].x : pre[lo].y));
+          if (is_resize) resize_item(s, L, ws, item, dyn_smem);
+          else composite_item(s, L, ws, images, out, mask, item, csm);
+          __syncthreads();
+        }
+      }
+    }
+    if (is_resize) signal_counter(done_resize + w);
   }
 }
 
@@ -789,10 +1033,103 @@ extern "C" int eot_box_geometry(const EotShape* shape, const float* boxes, const
   return EOT_OK;
 }
 
-extern "C" int eot_apply_fwd(const EotShape* shape, const float* patch, const float* scale, const float* images,
-                             const float* boxes, const int32_t* box_offsets, const EotBoxParams* params,
-                             const float* print_wb, float* out_images, float* out_masks, void* workspace,
-                             size_t workspace_bytes, void* stream) {
+namespace eot {
+
+// Enqueues the whole forward.  With an auxiliary stream the batch is cut into chunks of images: the
+// HBM-bound image pass of chunk c+1 (main stream) overlaps the instruction-bound window work of chunk c
+// (auxiliary stream); the two meet through events only.  Without one everything runs in order on `st`.
+static int launch_forward(const EotShape& s, const Layout& L, const float* patch, const float* scale, const float* images,
+                          const float* boxes, const int32_t* box_offsets, const EotBoxParams* params,
+                          const float* print_wb, float* out_images, float* mask, char* ws, cudaStream_t st,
+                          cudaStream_t aux, int chunks) {
+  const int B = s.batch, P = s.patch_size, HW = s.height * s.width, N = s.total_boxes;
+  EOT_CHECK_CUDA(cudaMemsetAsync(ws + L.off_ysum_img, 0, L.off_plans - L.off_ysum_img, st));
+  const int pchunks = max(1, min((P * P + kThreads * 4 - 1) / (kThreads * 4), 64));
+  const int cpi = (HW + kPassPixPerBlock - 1) / kPassPixPerBlock;
+  const bool vec = (HW % 4 == 0) && (((uintptr_t)images | (uintptr_t)out_images | (uintptr_t)(mask ? mask : out_images)) & 15) == 0;
+  const int nsm = sm_count();
+  const size_t smem = resize_smem_bytes(s, L);
+  if (smem > 48 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto prepass = [&](cudaStream_t q, int n_geom, int n_stat, int b0, int b1) {
+    const long long nblocks = (long long)n_geom + (long long)n_stat * pchunks + (long long)(b1 - b0) * cpi;
+    if (nblocks <= 0) return;
+    if (vec)
+      k_prepass<true><<<(unsigned)nblocks, kThreads, 0, q>>>(s, L, patch, print_wb, boxes, box_offsets, params, scale, images,
+                                                             out_images, mask, ws, n_geom, n_stat, pchunks, cpi, b0);
+    else
+      k_prepass<false><<<(unsigned)nblocks, kThreads, 0, q>>>(s, L, patch, print_wb, boxes, box_offsets, params, scale, images,
+                                                              out_images, mask, ws, n_geom, n_stat, pchunks, cpi, b0);
+    count_launches(1);
+  };
+  auto windows = [&](cudaStream_t q, int b0, int b1) {
+    k_match<<<dim3(pchunks, b1 - b0), kThreads, 0, q>>>(s, L, patch, print_wb, ws, b0);
+    k_resize<<<nsm * 4, kThreads, smem, q>>>(s, L, ws, box_offsets, b0, b1);
+    k_composite<<<nsm * 6, kThreads, 0, q>>>(s, L, ws, images, out_images, mask, box_offsets, b0, b1);
+    count_launches(3);
+  };
+  if ((long long)N + (long long)B * pchunks + (long long)B * cpi >= (1ll << 31)) { set_error("eot_apply_fwd: grid too large"); return EOT_ERR_BAD_SHAPE; }
+  if (!aux && N > 0 && (s.flags & EOT_FLAG_FUSED)) {             // experimental: one persistent launch
+    FusedPlan fp;
+    fp.n_geom = N;
+    fp.pchunks = pchunks;
+    fp.n_stat_tickets = B * pchunks;
+    fp.cpi = cpi;
+    fp.mp = max(1, (P * P + 4095) / 4096);
+    fp.pass_tickets = (cpi + kPassChunksPerTicket - 1) / kPassChunksPerTicket;
+    fp.slot = fp.pass_tickets + fp.mp + kFusedNPR + kFusedNPC;
+    const long long tickets = (long long)N + (long long)B * pchunks + (long long)(B + kFusedStages - 1) * fp.slot;
+    if (tickets >= (1ll << 31)) { set_error("eot_apply_fwd: too many work tickets"); return EOT_ERR_BAD_SHAPE; }
+    fp.total_tickets = (int)tickets;
+    const size_t dsm = max(smem, (size_t)256 * sizeof(int2));
+    if (vec) {
+      if (dsm > 40 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_forward_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+      k_forward_fused<true><<<nsm * 4, kThreads, dsm, st>>>(s, L, fp, patch, print_wb, boxes, box_offsets, params, scale, images,
+                                                            out_images, mask, ws);
+    } else {
+      if (dsm > 40 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_forward_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+      k_forward_fused<false><<<nsm * 4, kThreads, dsm, st>>>(s, L, fp, patch, print_wb, boxes, box_offsets, params, scale, images,
+                                                             out_images, mask, ws);
+    }
+    count_launches(1);
+    EOT_CHECK_CUDA(cudaPeekAtLastError());
+    return EOT_OK;
+  }
+  if (!aux || chunks <= 1 || N == 0) {
+    prepass(st, N, B, 0, B);
+    if (N > 0) windows(st, 0, B);
+    EOT_CHECK_CUDA(cudaPeekAtLastError());
+    return EOT_OK;
+  }
+  if (chunks > B) chunks = B;
+  if (chunks > 16) chunks = 16;
+  cudaEvent_t ev[18];
+  for (int i = 0; i < chunks + 2; ++i) EOT_CHECK_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+  EOT_CHECK_CUDA(cudaEventRecord(ev[chunks], st));               // memset done
+  EOT_CHECK_CUDA(cudaStreamWaitEvent(aux, ev[chunks], 0));
+  prepass(aux, N, B, 0, 0);                                       // geometry (+ prefix scan) + patch statistics only
+  const int per = (B + chunks - 1) / chunks;
+  for (int c = 0; c < chunks; ++c) {
+    const int b0 = c * per, b1 = min(B, b0 + per);
+    if (b0 >= b1) { chunks = c; break; }
+    prepass(st, 0, 0, b0, b1);
+    EOT_CHECK_CUDA(cudaEventRecord(ev[c], st));
+  }
+  for (int c = 0; c < chunks; ++c) {
+    const int b0 = c * per, b1 = min(B, b0 + per);
+    EOT_CHECK_CUDA(cudaStreamWaitEvent(aux, ev[c], 0));
+    windows(aux, b0, b1);
+  }
+  EOT_CHECK_CUDA(cudaEventRecord(ev[chunks + 1], aux));
+  EOT_CHECK_CUDA(cudaStreamWaitEvent(st, ev[chunks + 1], 0));
+  for (int i = 0; i < chunks + 2; ++i) cudaEventDestroy(ev[i]);    // released once the recorded work completes
+  EOT_CHECK_CUDA(cudaPeekAtLastError());
+  return EOT_OK;
+}
+
+static int forward_entry(const EotShape* shape, const float* patch, const float* scale, const float* images,
+                         const float* boxes, const int32_t* box_offsets, const EotBoxParams* params, const float* print_wb,
+                         float* out_images, float* out_masks, void* workspace, size_t workspace_bytes, void* stream,
+                         void* aux_stream, int chunks) {
   if (int rc = check_shape(shape)) return rc;
   if (!patch || !scale || !images || !box_offsets || !print_wb || !out_images || !workspace ||
       (shape->total_boxes > 0 && (!boxes || !params))) {
@@ -808,35 +1145,28 @@ extern "C" int eot_apply_fwd(const EotShape* shape, const float* patch, const fl
     return EOT_ERR_WORKSPACE_TOO_SMALL;
   }
   if (((uintptr_t)workspace & 255) != 0) { set_error("workspace must be 256-byte aligned"); return EOT_ERR_MISALIGNED; }
-  cudaStream_t st = (cudaStream_t)stream;
-  char* ws = static_cast<char*>(workspace);
-  float* mask = want_mask ? out_masks : nullptr;
-  const int B = s.batch, P = s.patch_size, HW = s.height * s.width;
+  return launch_forward(s, L, patch, scale, images, boxes, box_offsets, params, print_wb, out_images,
+                        want_mask ? out_masks : nullptr, static_cast<char*>(workspace), (cudaStream_t)stream,
+                        (cudaStream_t)aux_stream, chunks);
+}
 
-  EOT_CHECK_CUDA(cudaMemsetAsync(ws + L.off_ysum_img, 0, L.off_plans - L.off_ysum_img, st));
-  const int pchunks = max(1, min((P * P + kThreads * 4 - 1) / (kThreads * 4), 64));
-  const int cpi = (HW + kPassPixPerBlock - 1) / kPassPixPerBlock;
-  const long long nblocks = (long long)s.total_boxes + (long long)B * pchunks + (long long)B * cpi;
-  if (nblocks >= (1ll << 31)) { set_error("eot_apply_fwd: grid too large"); return EOT_ERR_BAD_SHAPE; }
-  const bool vec = (HW % 4 == 0) && (((uintptr_t)images | (uintptr_t)out_images | (uintptr_t)(mask ? mask : out_images)) & 15) == 0;
-  if (vec)
-    k_prepass<true><<<(unsigned)nblocks, kThreads, 0, st>>>(s, L, patch, print_wb, boxes, box_offsets, params, scale, images,
-                                                            out_images, mask, ws, pchunks, cpi);
-  else
-    k_prepass<false><<<(unsigned)nblocks, kThreads, 0, st>>>(s, L, patch, print_wb, boxes, box_offsets, params, scale, images,
-                                                             out_images, mask, ws, pchunks, cpi);
-  count_launches(1);
-  if (s.total_boxes > 0) {
-    k_match<<<dim3(pchunks, B), kThreads, 0, st>>>(s, L, patch, print_wb, ws);
-    const int nsm = sm_count();
-    const size_t smem = resize_smem_bytes(s, L);
-    if (smem > 48 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_resize<<<nsm * 4, kThreads, smem, st>>>(s, L, ws);
-    k_composite<<<nsm * 8, kThreads, 0, st>>>(s, L, ws, images, out_images, mask);
-    count_launches(3);
-  }
-  EOT_CHECK_CUDA(cudaPeekAtLastError());
-  return EOT_OK;
+}  // namespace eot
+
+extern "C" int eot_apply_fwd(const EotShape* shape, const float* patch, const float* scale, const float* images,
+                             const float* boxes, const int32_t* box_offsets, const EotBoxParams* params,
+                             const float* print_wb, float* out_images, float* out_masks, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  return forward_entry(shape, patch, scale, images, boxes, box_offsets, params, print_wb, out_images, out_masks, workspace,
+                       workspace_bytes, stream, nullptr, 1);
+}
+
+extern "C" int eot_apply_fwd_overlapped(const EotShape* shape, const float* patch, const float* scale, const float* images,
+                                        const float* boxes, const int32_t* box_offsets, const EotBoxParams* params,
+                                        const float* print_wb, float* out_images, float* out_masks, void* workspace,
+                                        size_t workspace_bytes, void* stream, void* aux_stream, int chunks) {
+  if (!aux_stream || aux_stream == stream) { set_error("eot_apply_fwd_overlapped: needs a distinct auxiliary stream"); return EOT_ERR_NULL_POINTER; }
+  return forward_entry(shape, patch, scale, images, boxes, box_offsets, params, print_wb, out_images, out_masks, workspace,
+                       workspace_bytes, stream, aux_stream, chunks);
 }
 
 extern "C" int eot_check_workspace(const EotShape* shape, const void* workspace, void* stream) {
