@@ -181,6 +181,10 @@ __device__ int geometry_block(const EotShape& s, const Layout& L, int j, const f
   __syncthreads();                                  // starts[] of this box are complete
   int2* inv = reinterpret_cast<int2*>(ws + L.off_inv) + (size_t)j * P;
   for (int i = threadIdx.x; i < P; i += blockDim.x) inv[i] = inverse_span_search(starts, ps, cfg.span, i);
+  // route map of the box starts all-zero; the composite only writes the non-zero bytes
+  uint4* rz = reinterpret_cast<uint4*>(ws + L.off_route + (size_t)j * L.rslot);
+  const int n16 = (spl.d * spl.d + 15) / 16;
+  for (int i = threadIdx.x; i < n16; i += blockDim.x) rz[i] = make_uint4(0u, 0u, 0u, 0u);
   return image;
 }
 
@@ -490,22 +494,35 @@ __device__ __forceinline__ void resize_item(const EotShape& s, const Layout& L, 
   __syncthreads();
   // rows pass over the flattened (row, column) index so that every warp is full
   if (span == 3) {                                       // up-sampling / near unit scale: plain bilinear, 3 taps
-    int r = 0, f = threadIdx.x;
-    while (f >= P3) { f -= P3; ++r; }
-    while (r < rows) {
-      const int oy = oy0 + r;
-      const int st = s_st[oy];
-      const float* w = s_w + oy * 3;
-      // weights past the true span are stored as 0 and the clamped row is finite, so the extra taps add +0
-      const float* m0 = m + st * P3 + f;
-      const float* m1 = m + min(st + 1, P - 1) * P3 + f;
-      const float* m2 = m + min(st + 2, P - 1) * P3 + f;
-      float acc = 0.0f + w[0] * m0[0];
-      acc = acc + w[1] * m1[0];
-      acc = acc + w[2] * m2[0];
-      inter[r * P3 + f] = acc;
-      f += blockDim.x;
-      while (f >= P3) { f -= P3; ++r; }
+    // four outputs per thread and iteration: 12 independent L2 loads in flight before the first use
+    const int total = rows * P3;
+    for (int i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {
+      float v[4][3];
+      float wk[4][3];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int idx = i0 + q * blockDim.x;
+        if (idx < total) {
+          const int r = idx / P3, f = idx - r * P3;
+          const int oy = oy0 + r;
+          const int st = s_st[oy];
+          // weights past the true span are stored as 0 and the clamped row is finite, so the extra taps add +0
+          v[q][0] = m[st * P3 + f];
+          v[q][1] = m[min(st + 1, P - 1) * P3 + f];
+          v[q][2] = m[min(st + 2, P - 1) * P3 + f];
+          wk[q][0] = s_w[oy * 3]; wk[q][1] = s_w[oy * 3 + 1]; wk[q][2] = s_w[oy * 3 + 2];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int idx = i0 + q * blockDim.x;
+        if (idx < total) {
+          float acc = 0.0f + wk[q][0] * v[q][0];
+          acc = acc + wk[q][1] * v[q][1];
+          acc = acc + wk[q][2] * v[q][2];
+          inter[idx] = acc;
+        }
+      }
     }
   } else {
     int r = 0, f = threadIdx.x;
@@ -681,6 +698,89 @@ __device__ __forceinline__ void composite_item(const EotShape& s, const Layout& 
   float* mask_win = mask ? mask + (((size_t)me.image * H + me.y0) * W + me.x0) * 3 : nullptr;
   float* sv = sm.stage[warp];
   const int p0 = lane / 3, p1 = (lane + 32) / 3, p2 = (lane + 64) / 3;   // pixel of the element a lane stores
+  if (!any_later && !any_earlier) {
+    // ---- lean path: this item's rows touch no other window (the common case) ----
+    // Branch-free sampling: the four taps are always loaded from clamped texel coordinates and replaced
+    // by the -2 fill where they fall outside the core, which is what the padded image would hold.
+    const int ps = me.ps;
+    const float4 fill = make_float4(-2.0f, -2.0f, -2.0f, 0.0f);
+    for (int gy = ya + warp; gy < yb; gy += kThreads / 32) {
+      const int y = gy - me.y0;
+      const float yf = (float)y;
+      int xa = 0, xb = D - 1;
+      if (!full) core_range(S, yf, D, &xa, &xb);
+      xa = max(xa, 0);
+      xb = min(xb, D - 1);
+      const int row_off = y * W * 3;
+      uint8_t* rrow = my_route + y * D;
+      const float cxr = S.t1 * yf, cyr = S.t4 * yf, pr = S.t7 * yf;
+      for (int xs = xa & ~31; xs <= xb; xs += 32) {
+        const int x = xs + lane;
+        const bool act = x >= xa && x <= xb;
+        const float xf = (float)x;
+        float ix = (S.t0 * xf + cxr) + S.t2;
+        float iy = (S.t3 * xf + cyr) + S.t5;
+        bool degenerate = false;
+        if (!S.affine) {
+          const float proj = (S.t6 * xf + pr) + 1.0f;
+          degenerate = proj == 0.0f;
+          ix = ix / proj;
+          iy = iy / proj;
+        }
+        const float x0f = floorf(ix), y0f = floorf(iy);
+        const float x1f = x0f + 1.0f, y1f = y0f + 1.0f;
+        const bool bx0 = (x0f >= S.lo) && (x0f < S.hi), bx1 = (x1f >= S.lo) && (x1f < S.hi);
+        const bool by0 = (y0f >= S.lo) && (y0f < S.hi), by1 = (y1f >= S.lo) && (y1f < S.hi);
+        const float wx1 = x1f - ix, wx0 = ix - x0f, wy1 = y1f - iy, wy0 = iy - y0f;
+        // clamp in float first: the coordinates of far-away pixels may not fit an int
+        const float pmax = (float)(ps - 1);
+        const int xi0 = (int)fminf(fmaxf(x0f - S.lo, 0.0f), pmax), xi1 = (int)fminf(fmaxf(x1f - S.lo, 0.0f), pmax);
+        const int yi0 = (int)fminf(fmaxf(y0f - S.lo, 0.0f), pmax), yi1 = (int)fminf(fmaxf(y1f - S.lo, 0.0f), pmax);
+        const float4* r0 = S.u + yi0 * ps;
+        const float4* r1 = S.u + yi1 * ps;
+        float4 v00 = r0[xi0], v01 = r0[xi1], v10 = r1[xi0], v11 = r1[xi1];
+        if (!(by0 && bx0)) v00 = fill;
+        if (!(by0 && bx1)) v01 = fill;
+        if (!(by1 && bx0)) v10 = fill;
+        if (!(by1 && bx1)) v11 = fill;
+        float R[3];
+        blend3(v00, v01, v10, v11, wx1, wx0, wy1, wy0, R);
+        if (degenerate) R[0] = R[1] = R[2] = -2.0f;
+        const bool s0 = !(R[0] < -1.0f), s1 = !(R[1] < -1.0f), s2 = !(R[2] < -1.0f);
+        const unsigned bits = (unsigned)(s0 && R[0] <= 1.0f) | ((unsigned)(s1 && R[1] <= 1.0f) << 1) |
+                              ((unsigned)(s2 && R[2] <= 1.0f) << 2);
+        const bool all3 = s0 && s1 && s2;
+        float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f;
+        if (act && (!all3 || mask_win)) {
+          const float* op = img_win + row_off + x * 3;
+          o0 = __ldg(op); o1 = __ldg(op + 1); o2 = __ldg(op + 2);
+        }
+        const bool store = act && (s0 || s1 || s2 || oor || mask_win != nullptr);
+        if (act && bits) rrow[x] = (uint8_t)bits;
+        if (store) {
+          sv[lane * 3] = clampf(s0 ? R[0] : o0, -1.0f, 1.0f);
+          sv[lane * 3 + 1] = clampf(s1 ? R[1] : o1, -1.0f, 1.0f);
+          sv[lane * 3 + 2] = clampf(s2 ? R[2] : o2, -1.0f, 1.0f);
+        }
+        const unsigned smask = __ballot_sync(0xffffffffu, store);
+        if (smask) {
+          const int seg = row_off + xs * 3;
+          if (mask_win && store) {
+            mask_win[seg + lane * 3] = o0 - sv[lane * 3];
+            mask_win[seg + lane * 3 + 1] = o1 - sv[lane * 3 + 1];
+            mask_win[seg + lane * 3 + 2] = o2 - sv[lane * 3 + 2];
+          }
+          __syncwarp();
+          float* op = out_win + seg + lane;
+          if ((smask >> p0) & 1u) op[0] = sv[lane];
+          if ((smask >> p1) & 1u) op[32] = sv[lane + 32];
+          if ((smask >> p2) & 1u) op[64] = sv[lane + 64];
+          __syncwarp();
+        }
+      }
+    }
+    return;
+  }
   for (int gy = ya + warp; gy < yb; gy += kThreads / 32) {
     const int y = gy - me.y0;
     const float yf = (float)y;
@@ -711,19 +811,7 @@ __device__ __forceinline__ void composite_item(const EotShape& s, const Layout& 
     uint8_t* rrow = my_route + y * D;
     for (int xs = 0; xs < D; xs += 32) {
       const int x = xs + lane;
-      if (xs + 31 < xa || xs > xb) {                         // whole segment is background of this box
-        if (x < D && !any_later) rrow[x] = 0;
-        else if (x < D) {
-          bool mine = true;
-          for (int w = jl >> 5; w < nwords && mine; ++w) {
-            unsigned m = sm.ovmask[w];
-            if (w == (jl >> 5)) m &= ~((2u << (jl & 31)) - 1u);
-            while (m) { const int q = (w << 5) + __ffs(m) - 1; m &= m - 1; if (covers(sm.win[q], gy, me.x0 + x)) { mine = false; break; } }
-          }
-          if (mine) rrow[x] = 0;
-        }
-        continue;
-      }
+      if (xs + 31 < xa || xs > xb) continue;                 // whole segment is background of this box (route stays 0)
       const int gx = me.x0 + x;
       bool write = x < D;
       if (write && any_later) {                               // a later box covering this pixel owns it
@@ -742,7 +830,7 @@ __device__ __forceinline__ void composite_item(const EotShape& s, const Layout& 
 #pragma unroll
         for (int c = 0; c < 3; ++c)
           if (!(R[c] < -1.0f)) { v[c] = R[c]; found |= 1u << c; if (R[c] <= 1.0f) bits |= 1u << c; }
-        rrow[x] = (uint8_t)bits;
+        if (bits) rrow[x] = (uint8_t)bits;
         if (found != 7u || mask) {
           const float* op = img_win + row_off + x * 3;
           orig[0] = __ldg(op); orig[1] = __ldg(op + 1); orig[2] = __ldg(op + 2);
@@ -769,7 +857,7 @@ __device__ __forceinline__ void composite_item(const EotShape& s, const Layout& 
                     v[c] = Rq[c]; found |= 1u << c; if (Rq[c] <= 1.0f) qbits |= 1u << c;
                   }
               }
-              routes[(size_t)(first + q) * L.rslot + (size_t)(gy - wq.x) * wq.z + (gx - wq.y)] = (uint8_t)qbits;
+              if (qbits) routes[(size_t)(first + q) * L.rslot + (size_t)(gy - wq.x) * wq.z + (gx - wq.y)] = (uint8_t)qbits;
             }
           }
         }
@@ -799,7 +887,7 @@ __device__ __forceinline__ void composite_item(const EotShape& s, const Layout& 
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 3) k_composite(EotShape s, Layout L, char* ws,
+__global__ void __launch_bounds__(kThreads, 4) k_composite(EotShape s, Layout L, char* ws,
                                                         const float* __restrict__ images, float* out, float* mask,
                                                         const int32_t* __restrict__ offsets, int b0, int b1) {
   __shared__ CompositeSmem sm;
@@ -1064,7 +1152,7 @@ static int launch_forward(const EotShape& s, const Layout& L, const float* patch
   auto windows = [&](cudaStream_t q, int b0, int b1) {
     k_match<<<dim3(pchunks, b1 - b0), kThreads, 0, q>>>(s, L, patch, print_wb, ws, b0);
     k_resize<<<nsm * 4, kThreads, smem, q>>>(s, L, ws, box_offsets, b0, b1);
-    k_composite<<<nsm * 6, kThreads, 0, q>>>(s, L, ws, images, out_images, mask, box_offsets, b0, b1);
+    k_composite<<<nsm * 8, kThreads, 0, q>>>(s, L, ws, images, out_images, mask, box_offsets, b0, b1);
     count_launches(3);
   };
   if ((long long)N + (long long)B * pchunks + (long long)B * cpi >= (1ll << 31)) { set_error("eot_apply_fwd: grid too large"); return EOT_ERR_BAD_SHAPE; }
