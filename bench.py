@@ -155,7 +155,7 @@ def run_reference(args):
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "reference = op-for-op CPU restatement (oracle/) of the TF path; TensorFlow is not installed"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -261,7 +261,7 @@ def run_ours(args):
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
     it = args.kernel_iters
-    sc = attacker._scale_regressor
+    sc = torch.tensor(0.4, dtype=torch.float32, device=dev)     # the reference's initial scale (attacker.py:44), fixed for the kernel numbers
     params = attacker._patcher.sampler.box_params(0, rank * B, boxes.row_splits, boxes.values.shape[0])
     wb = attacker._patcher.sampler.print_wb(0, rank * B, B, dev)
     out = torch.empty_like(images)
@@ -330,12 +330,26 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, world), "clocks": clock_info, "e2e": e2e,
             "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
             "apply_kernel_hbm_gbs": {"fwd": kernels[0]["achieved"], "bwd": kernels[1]["achieved"]}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the real stdout; everything else any library prints to fd 1 (NCCL banner ...) is
+    redirected to stderr for the whole run."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)

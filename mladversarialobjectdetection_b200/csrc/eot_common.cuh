@@ -79,6 +79,7 @@ struct Layout {
   int32_t wcap;            // floats per weight table
   int32_t lmin;            // max patch side
   int32_t resize_rows;     // output rows per resize work item (bounded by shared memory: rows * P * 12 B)
+  uint32_t p3_magic;       // ceil(2^32 / (3P)): idx / (3P) == umulhi(idx, p3_magic) for idx < 2^16
   int64_t rslot;           // bytes per route map
   int32_t use_gbox;        // per-box partial gradients fit: fully parallel resize adjoint
 };
@@ -98,6 +99,7 @@ __host__ __device__ inline Layout make_layout(const EotShape& s) {
   L.gslot = (int64_t)align_up((size_t)lmin * lmin * 3, 32);
   int rr = 12288 / (s.patch_size * 3);       // <= 48 KB of float32 intermediate rows
   L.resize_rows = rr > 16 ? 16 : (rr < 1 ? 1 : rr);
+  L.p3_magic = (uint32_t)((((uint64_t)1 << 32) + (uint64_t)(s.patch_size * 3) - 1) / (uint64_t)(s.patch_size * 3));
   const size_t PP3 = (size_t)s.patch_size * s.patch_size * 3;
   size_t o = 0;
   L.off_ysum_img = o;     o = align_up(o + B * sizeof(double), 256);

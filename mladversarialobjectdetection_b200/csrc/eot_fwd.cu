@@ -472,6 +472,115 @@ __host__ __device__ inline size_t resize_smem_bytes(const EotShape& s, const Lay
   return ((size_t)L.resize_rows * s.patch_size * 3 + (size_t)L.wcap + (size_t)L.lmin) * sizeof(float);
 }
 
+// SPAN > 0: compile-time tap count (3 = up-sampling / unit scale, 5 and 7 = moderate down-sampling), every tap
+// loop fully unrolled; weights past the true span are stored as 0 and the clamped source index is finite, so the
+// padded taps add +0 -- the same sums as the oracle's.  SPAN == 0: run-time span (any scale).
+template <int SPAN>
+__device__ __forceinline__ void resize_passes(const EotShape& s, const Layout& L, int P, int ps, int span, int oy0, int rows,
+                                              const float* __restrict__ m, const int* s_st, const float* s_w, float* inter,
+                                              float4* u4, float delta, uint32_t key0, uint32_t key1) {
+  const int P3 = P * 3;
+  const int total = rows * P3;
+  constexpr int kRB = 2;                                     // outputs per thread and iteration
+  // rows pass over the flattened (row, column) index so that every warp is full; kRB outputs per thread and
+  // iteration keep the L2 loads of all taps in flight before the first use
+  for (int i0 = threadIdx.x; i0 < total; i0 += kRB * blockDim.x) {
+    if (SPAN > 0) {
+      float v[kRB][SPAN > 0 ? SPAN : 1];
+      int oyq[kRB];
+#pragma unroll
+      for (int q = 0; q < kRB; ++q) {
+        const int idx = i0 + q * blockDim.x;
+        if (idx < total) {
+          const int r = __umulhi((unsigned)idx, L.p3_magic);          // idx / P3 for idx < 2^16
+          const int f = idx - r * P3;
+          const int oy = oy0 + r;
+          oyq[q] = oy;
+          const int st = s_st[oy];
+#pragma unroll
+          for (int k = 0; k < SPAN; ++k) v[q][k] = m[min(st + k, P - 1) * P3 + f];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kRB; ++q) {
+        const int idx = i0 + q * blockDim.x;
+        if (idx < total) {
+          const float* w = s_w + oyq[q] * SPAN;
+          float acc = 0.0f;
+#pragma unroll
+          for (int k = 0; k < SPAN; ++k) acc = acc + w[k] * v[q][k];
+          inter[idx] = acc;
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int q = 0; q < kRB; ++q) {
+        const int idx = i0 + q * blockDim.x;
+        if (idx < total) {
+          const int r = __umulhi((unsigned)idx, L.p3_magic);
+          const int f = idx - r * P3;
+          const int oy = oy0 + r;
+          const int st = s_st[oy];
+          const float* w = s_w + oy * span;
+          const int nk = min(span, P - st);
+          const float* mp = m + st * P3 + f;
+          float acc = 0.0f;
+          for (int k = 0; k < nk; ++k) acc = acc + w[k] * mp[k * P3];
+          inter[idx] = acc;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int p_begin = oy0 * ps, p_end = (oy0 + rows) * ps;   // flat texel range of the strip
+  for (int q = (p_begin >> 2) + threadIdx.x; q <= ((p_end - 1) >> 2); q += blockDim.x) {
+    uint32_t words[12];
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      const uint4 rnd = philox4x32_10((uint32_t)(3 * q + g), key0, key1);
+      words[4 * g] = rnd.x; words[4 * g + 1] = rnd.y; words[4 * g + 2] = rnd.z; words[4 * g + 3] = rnd.w;
+    }
+    int p = 4 * q;
+    int oy = p / ps, ox = p - oy * ps;
+#pragma unroll
+    for (int t = 0; t < 4; ++t, ++p) {
+      if (p >= p_begin && p < p_end) {
+        const int st = s_st[ox];
+        const float* irow = inter + (oy - oy0) * P3;
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+        if (SPAN > 0) {
+          const float* w = s_w + ox * SPAN;
+#pragma unroll
+          for (int k = 0; k < SPAN; ++k) {
+            const float wk = w[k];
+            const float* ip = irow + min(st + k, P - 1) * 3;
+            a0 = a0 + wk * ip[0];
+            a1 = a1 + wk * ip[1];
+            a2 = a2 + wk * ip[2];
+          }
+        } else {
+          const float* w = s_w + ox * span;
+          const int nk = min(span, P - st);
+          const float* ip = irow + st * 3;
+          for (int k = 0; k < nk; ++k) {
+            const float wk = w[k];
+            a0 = a0 + wk * ip[k * 3];
+            a1 = a1 + wk * ip[k * 3 + 1];
+            a2 = a2 + wk * ip[k * 3 + 2];
+          }
+        }
+        const float v0 = (a0 + noise_from_word(words[3 * t], s.noise_amp)) + delta;
+        const float v1 = (a1 + noise_from_word(words[3 * t + 1], s.noise_amp)) + delta;
+        const float v2 = (a2 + noise_from_word(words[3 * t + 2], s.noise_amp)) + delta;
+        const unsigned bits = (unsigned)(v0 >= -1.0f && v0 <= 1.0f) | ((unsigned)(v1 >= -1.0f && v1 <= 1.0f) << 1) |
+                              ((unsigned)(v2 >= -1.0f && v2 <= 1.0f) << 2);
+        u4[p] = make_float4(clampf(v0, -1.0f, 1.0f), clampf(v1, -1.0f, 1.0f), clampf(v2, -1.0f, 1.0f), __uint_as_float(bits));
+      }
+      if (++ox == ps) { ox = 0; ++oy; }
+    }
+  }
+}
+
 __device__ __forceinline__ void resize_item(const EotShape& s, const Layout& L, char* ws, int2 item, float* smem) {
   const int P = s.patch_size, P3 = P * 3;
   float* inter = smem;                                       // [resize_rows][P3]
@@ -492,101 +601,10 @@ __device__ __forceinline__ void resize_item(const EotShape& s, const Layout& L, 
   for (int i = threadIdx.x; i < ps; i += blockDim.x) s_st[i] = starts[i];
   for (int i = threadIdx.x; i < ps * span; i += blockDim.x) s_w[i] = wts[i];
   __syncthreads();
-  // rows pass over the flattened (row, column) index so that every warp is full
-  if (span == 3) {                                       // up-sampling / near unit scale: plain bilinear, 3 taps
-    // four outputs per thread and iteration: 12 independent L2 loads in flight before the first use
-    const int total = rows * P3;
-    for (int i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {
-      float v[4][3];
-      float wk[4][3];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int idx = i0 + q * blockDim.x;
-        if (idx < total) {
-          const int r = idx / P3, f = idx - r * P3;
-          const int oy = oy0 + r;
-          const int st = s_st[oy];
-          // weights past the true span are stored as 0 and the clamped row is finite, so the extra taps add +0
-          v[q][0] = m[st * P3 + f];
-          v[q][1] = m[min(st + 1, P - 1) * P3 + f];
-          v[q][2] = m[min(st + 2, P - 1) * P3 + f];
-          wk[q][0] = s_w[oy * 3]; wk[q][1] = s_w[oy * 3 + 1]; wk[q][2] = s_w[oy * 3 + 2];
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int idx = i0 + q * blockDim.x;
-        if (idx < total) {
-          float acc = 0.0f + wk[q][0] * v[q][0];
-          acc = acc + wk[q][1] * v[q][1];
-          acc = acc + wk[q][2] * v[q][2];
-          inter[idx] = acc;
-        }
-      }
-    }
-  } else {
-    int r = 0, f = threadIdx.x;
-    while (f >= P3) { f -= P3; ++r; }
-    while (r < rows) {
-      const int oy = oy0 + r;
-      const int st = s_st[oy];
-      const float* w = s_w + oy * span;
-      const int nk = min(span, P - st);
-      const float* mp = m + st * P3 + f;
-      float acc = 0.0f;
-      for (int k = 0; k < nk; ++k) acc = acc + w[k] * mp[k * P3];
-      inter[r * P3 + f] = acc;
-      f += blockDim.x;
-      while (f >= P3) { f -= P3; ++r; }
-    }
-  }
-  __syncthreads();
-  const int p_begin = oy0 * ps, p_end = (oy0 + rows) * ps;   // flat texel range of the strip
-  for (int q = (p_begin >> 2) + threadIdx.x; q <= ((p_end - 1) >> 2); q += blockDim.x) {
-    uint32_t words[12];
-#pragma unroll
-    for (int g = 0; g < 3; ++g) {
-      const uint4 rnd = philox4x32_10((uint32_t)(3 * q + g), key0, key1);
-      words[4 * g] = rnd.x; words[4 * g + 1] = rnd.y; words[4 * g + 2] = rnd.z; words[4 * g + 3] = rnd.w;
-    }
-    int p = 4 * q;
-    int oy = p / ps, ox = p - oy * ps;
-#pragma unroll
-    for (int t = 0; t < 4; ++t, ++p) {
-      if (p >= p_begin && p < p_end) {
-        const int st = s_st[ox];
-        const float* w = s_w + ox * span;
-        const float* irow = inter + (oy - oy0) * P3;
-        float a0, a1, a2;
-        if (span == 3) {
-          const float* i0 = irow + st * 3;
-          const float* i1 = irow + min(st + 1, P - 1) * 3;
-          const float* i2 = irow + min(st + 2, P - 1) * 3;
-          const float w0 = w[0], w1 = w[1], w2 = w[2];
-          a0 = 0.0f + w0 * i0[0]; a1 = 0.0f + w0 * i0[1]; a2 = 0.0f + w0 * i0[2];
-          a0 = a0 + w1 * i1[0];   a1 = a1 + w1 * i1[1];   a2 = a2 + w1 * i1[2];
-          a0 = a0 + w2 * i2[0];   a1 = a1 + w2 * i2[1];   a2 = a2 + w2 * i2[2];
-        } else {
-          const int nk = min(span, P - st);
-          const float* ip = irow + st * 3;
-          a0 = a1 = a2 = 0.0f;
-          for (int k = 0; k < nk; ++k) {
-            const float wk = w[k];
-            a0 = a0 + wk * ip[k * 3];
-            a1 = a1 + wk * ip[k * 3 + 1];
-            a2 = a2 + wk * ip[k * 3 + 2];
-          }
-        }
-        const float v0 = (a0 + noise_from_word(words[3 * t], s.noise_amp)) + delta;
-        const float v1 = (a1 + noise_from_word(words[3 * t + 1], s.noise_amp)) + delta;
-        const float v2 = (a2 + noise_from_word(words[3 * t + 2], s.noise_amp)) + delta;
-        const unsigned bits = (unsigned)(v0 >= -1.0f && v0 <= 1.0f) | ((unsigned)(v1 >= -1.0f && v1 <= 1.0f) << 1) |
-                              ((unsigned)(v2 >= -1.0f && v2 <= 1.0f) << 2);
-        u4[p] = make_float4(clampf(v0, -1.0f, 1.0f), clampf(v1, -1.0f, 1.0f), clampf(v2, -1.0f, 1.0f), __uint_as_float(bits));
-      }
-      if (++ox == ps) { ox = 0; ++oy; }
-    }
-  }
+  if (span == 3) resize_passes<3>(s, L, P, ps, span, oy0, rows, m, s_st, s_w, inter, u4, delta, key0, key1);
+  else if (span == 5) resize_passes<5>(s, L, P, ps, span, oy0, rows, m, s_st, s_w, inter, u4, delta, key0, key1);
+  else if (span == 7) resize_passes<7>(s, L, P, ps, span, oy0, rows, m, s_st, s_w, inter, u4, delta, key0, key1);
+  else resize_passes<0>(s, L, P, ps, span, oy0, rows, m, s_st, s_w, inter, u4, delta, key0, key1);
 }
 
 __global__ void __launch_bounds__(kThreads, 4) k_resize(EotShape s, Layout L, char* ws, const int32_t* __restrict__ offsets,
