@@ -9,7 +9,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libeotpatch.so")
+LIB_PATH = os.environ.get("EOTPATCH_LIB") or os.path.join(_HERE, "libeotpatch.so")   # override: A/B of two builds
 
 EOT_FLAG_MASK_OUTPUT = 1
 SCORE_MAX_LEVELS = 8
