@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(kThreads) k_bwd_window(EotShape s, Layout L, c
           for (int c = 0; c < 3; ++c) g[c] = wy1 * (wx1 * v00[c] + wx0 * v01[c]) + wy0 * (wx1 * v10[c] + wx0 * v11[c]);
         }
         const int t = ty * ps + tx;
-        const unsigned bits = __float_as_uint(u4[t].w);                  // inner clip pass bits (attacker.py:428)
+        const unsigned bits = __float_as_uint(u4[u_index(ps, ty, tx)].w);  // inner clip pass bits (attacker.py:428)
 #pragma unroll
         for (int c = 0; c < 3; ++c) gu[t * 3 + c] = ((bits >> c) & 1u) ? g[c] : 0.0f;
       }

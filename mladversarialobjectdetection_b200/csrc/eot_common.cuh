@@ -33,7 +33,7 @@ namespace eot {
 #define EOT_C255_127 ((float)(255.0 / 127.0))   // brightness_matcher.py:41
 #define EOT_SQRT2 1.41421354f                   // float32(2. ** .5), attacker.py:470
 
-constexpr int kCompRows = 16;         // window rows per composite work item (one warp per row)
+constexpr int kCompRows = 16;         // image rows per composite work item (one CTA: 8 warps x 2 rows)
 constexpr int kThreads = 256;
 
 // Per-box plan written by the geometry kernel; 128 bytes.
@@ -63,7 +63,8 @@ struct Layout {
   size_t off_starts;       // int32[N][Lmin]
   size_t off_weights;      // float[N][wcap]
   size_t off_match;        // float[B][P*P*3]
-  size_t off_u;            // float4[N][slot/4]: clipped (r,g,b) of the transformed patch + inner-clip pass bits
+  size_t off_u;            // float4[N][slot/4]: (ps+4)^2 texels per box = clipped (r,g,b) of the transformed patch +
+                           //            inner-clip pass bits, inside a two-texel ring of the -2 pad / fill value
   size_t off_cnt;          // int2[N]    work items of box j: (resize strips, composite row blocks); 0 when invalid
   size_t off_base;         // int2[N+1]  exclusive prefix sums of off_cnt (box order == image order)
   size_t off_inv;          // int2[N][P]  for patch index i: first/last output index whose span holds i
@@ -95,9 +96,9 @@ __host__ __device__ inline Layout make_layout(const EotShape& s) {
   if (lmin > lfull) lmin = lfull;
   L.lmin = lmin;
   L.wcap = 2 * s.patch_size + 3 * lmin + 8;
-  L.slot = (int64_t)align_up((size_t)lmin * lmin * 4, 32);
+  L.slot = (int64_t)align_up((size_t)(lmin + 4) * (lmin + 4) * 4, 32);
   L.gslot = (int64_t)align_up((size_t)lmin * lmin * 3, 32);
-  int rr = 12288 / (s.patch_size * 3);       // <= 48 KB of float32 intermediate rows
+  int rr = 2560 / s.patch_size;              // <= 40 KB of RGBX float32 intermediate rows
   L.resize_rows = rr > 16 ? 16 : (rr < 1 ? 1 : rr);
   L.p3_magic = (uint32_t)((((uint64_t)1 << 32) + (uint64_t)(s.patch_size * 3) - 1) / (uint64_t)(s.patch_size * 3));
   const size_t PP3 = (size_t)s.patch_size * s.patch_size * 3;
@@ -174,11 +175,11 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t k0, uint32_
   uint32_t c1 = 0, c2 = 0, c3 = 0;
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
-    if (r > 0) { k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;            // one IMAD.WIDE each
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ (k0 + (uint32_t)r * 0x9E3779B9u);
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ (k1 + (uint32_t)r * 0xBB67AE85u);
+    c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
   }
   return make_uint4(c0, c1, c2, c3);
 }
@@ -227,26 +228,31 @@ __device__ __forceinline__ TexelYuv texel_yuv(float p0, float p1, float p2, cons
 
 // ImageProjectiveTransformV3 BILINEAR / CONSTANT sampling of the (virtually) padded transformed
 // patch of one box at a window pixel, three channels at once.  u holds clip((resize + noise) + delta)
-// (attacker.py:425-428) as RGBX texels; everything outside the
-// ps x ps core -- the -2 pad ring of attacker.py:435 and the -2 fill of :437 -- reads as -2.
+// (attacker.py:425-428) as RGBX texels in a (ps+4)^2 buffer whose two-texel ring holds -2: the pad ring of
+// attacker.py:435 and the fill of :437 both read as -2, so clamping the floor coordinate to
+// [pad_lo-2, pad_lo+ps] makes all four taps unconditional loads at base, base+1, base+S, base+S+1.
 // For the reference's pure rotation the projective row is zero, proj == 1 exactly and x / 1 == x, so
 // the two divisions are skipped without changing a bit.
 struct Sampler {
   float t0, t1, t2, t3, t4, t5, t6, t7;
-  float lo, hi;          // core bounds in padded coordinates
-  int pad_lo, ps;
-  const float4* u;       // [ps*ps] texels: (r,g,b) already clipped to [-1,1]; .w = inner-clip pass bits
+  float lo2, hi;         // clamp range of the floor coordinates (padded window coordinates)
+  int org;               // pad_lo - 2: padded coordinate of ring texel 0
+  int S;                 // ps + 4: row stride of the ringed texel buffer
+  const float4* u;
   bool affine;
 };
+
+__device__ __forceinline__ int u_stride(int ps) { return ps + 4; }
+__device__ __forceinline__ int u_index(int ps, int ty, int tx) { return (ty + 2) * (ps + 4) + (tx + 2); }
 
 __device__ __forceinline__ Sampler make_sampler(const BoxPlan& pl, const float* ubuf) {
   Sampler S;
   S.t0 = pl.T[0]; S.t1 = pl.T[1]; S.t2 = pl.T[2]; S.t3 = pl.T[3];
   S.t4 = pl.T[4]; S.t5 = pl.T[5]; S.t6 = pl.T[6]; S.t7 = pl.T[7];
-  S.lo = (float)pl.pad_lo;
+  S.lo2 = (float)(pl.pad_lo - 2);
   S.hi = (float)(pl.pad_lo + pl.ps);
-  S.pad_lo = pl.pad_lo;
-  S.ps = pl.ps;
+  S.org = pl.pad_lo - 2;
+  S.S = pl.ps + 4;
   S.u = reinterpret_cast<const float4*>(ubuf + pl.u_off);
   S.affine = (pl.T[6] == 0.0f && pl.T[7] == 0.0f);
   return S;
@@ -259,35 +265,49 @@ __device__ __forceinline__ void blend3(const float4 v00, const float4 v01, const
   R[2] = wy1 * (wx1 * v00.z + wx0 * v01.z) + wy0 * (wx1 * v10.z + wx0 * v11.z);
 }
 
-__device__ __forceinline__ void sample3(const Sampler& S, float xf, float yf, float R[3]) {
-  float ix = (S.t0 * xf + S.t1 * yf) + S.t2;
-  float iy = (S.t3 * xf + S.t4 * yf) + S.t5;
-  if (!S.affine) {
-    const float proj = (S.t6 * xf + S.t7 * yf) + 1.0f;
-    if (proj == 0.0f) { R[0] = R[1] = R[2] = -2.0f; return; }
-    ix = ix / proj;
-    iy = iy / proj;
-  }
+// The four taps and bilinear weights of one window pixel; loading is separated from blending so that the loads of
+// several pixels can be in flight together.  (ix, iy): source coordinates in the padded window.
+struct Taps { float4 v00, v01, v10, v11; float wx1, wx0, wy1, wy0; };
+__device__ __forceinline__ Taps load_taps(const Sampler& S, float ix, float iy) {
+  Taps t;
   const float x0f = floorf(ix), y0f = floorf(iy);
-  const float x1f = x0f + 1.0f, y1f = y0f + 1.0f;
-  const bool bx0 = (x0f >= S.lo) && (x0f < S.hi), bx1 = (x1f >= S.lo) && (x1f < S.hi);
-  const bool by0 = (y0f >= S.lo) && (y0f < S.hi), by1 = (y1f >= S.lo) && (y1f < S.hi);
-  const float wx1 = x1f - ix, wx0 = ix - x0f, wy1 = y1f - iy, wy0 = iy - y0f;
-  const float4 fill = make_float4(-2.0f, -2.0f, -2.0f, 0.0f);
-  if (!((bx0 || bx1) && (by0 || by1))) {      // all four taps are pad / fill
-    blend3(fill, fill, fill, fill, wx1, wx0, wy1, wy0, R);
-    return;
+  t.wx1 = (x0f + 1.0f) - ix; t.wx0 = ix - x0f; t.wy1 = (y0f + 1.0f) - iy; t.wy0 = iy - y0f;
+  const int xi = (int)fminf(fmaxf(x0f, S.lo2), S.hi) - S.org;
+  const int yi = (int)fminf(fmaxf(y0f, S.lo2), S.hi) - S.org;
+  const float4* p = S.u + (yi * S.S + xi);
+  t.v00 = p[0]; t.v01 = p[1]; t.v10 = p[S.S]; t.v11 = p[S.S + 1];
+  return t;
+}
+
+// (ix, iy): source coordinates in the padded window (already divided by the projective term).
+__device__ __forceinline__ void sample_at(const Sampler& S, float ix, float iy, float R[3]) {
+  const float x0f = floorf(ix), y0f = floorf(iy);
+  const float wx1 = (x0f + 1.0f) - ix, wx0 = ix - x0f, wy1 = (y0f + 1.0f) - iy, wy0 = iy - y0f;
+  const int xi = (int)fminf(fmaxf(x0f, S.lo2), S.hi) - S.org;
+  const int yi = (int)fminf(fmaxf(y0f, S.lo2), S.hi) - S.org;
+  const float4* p = S.u + (yi * S.S + xi);
+  blend3(p[0], p[1], p[S.S], p[S.S + 1], wx1, wx0, wy1, wy0, R);
+}
+
+// ---- flags between work items of one launch ----------------------------------------------------------
+// acquire / release by ONE thread per CTA (the CTA barrier around them makes the ordering cumulative for
+// the whole CTA).  No gpu-scope fence in every thread.
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add(int* p, int n) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(n) : "memory");
+}
+__device__ __forceinline__ bool wait_counter(const int* ctr, int need, int* err_flag) {
+  if (need <= 0) return true;
+  for (int spin = 0; spin < (1 << 22); ++spin) {
+    if (ld_acquire(ctr) >= need) return true;
+    __nanosleep(64);
   }
-  const float4* p00 = S.u + (((int)y0f - S.pad_lo) * S.ps + ((int)x0f - S.pad_lo));
-  if (bx0 && bx1 && by0 && by1) {             // interior: 4 unconditional 128-bit loads
-    blend3(p00[0], p00[1], p00[S.ps], p00[S.ps + 1], wx1, wx0, wy1, wy0, R);
-    return;
-  }
-  const float4 v00 = (by0 && bx0) ? p00[0] : fill;
-  const float4 v01 = (by0 && bx1) ? p00[1] : fill;
-  const float4 v10 = (by1 && bx0) ? p00[S.ps] : fill;
-  const float4 v11 = (by1 && bx1) ? p00[S.ps + 1] : fill;
-  blend3(v00, v01, v10, v11, wx1, wx0, wy1, wy0, R);
+  atomicExch(err_flag, 3);      // dependency never arrived: give up instead of hanging the GPU
+  return false;
 }
 #endif  // __CUDACC__
 

@@ -163,7 +163,7 @@ __device__ int geometry_block(const EotShape& s, const Layout& L, int j, const f
     if (ws) {
       reinterpret_cast<BoxPlan*>(ws + L.off_plans)[j] = pl;
       reinterpret_cast<int2*>(ws + L.off_cnt)[j] =
-          pl.valid ? make_int2((pl.ps + L.resize_rows - 1) / L.resize_rows, (pl.d + kCompRows - 1) / kCompRows) : make_int2(0, 0);
+          pl.valid ? make_int2((pl.ps + L.resize_rows - 1) / L.resize_rows, 0) : make_int2(0, 0);
     }
     if (geom_out) {
       EotBoxGeometry g = {pl.y0, pl.x0, pl.ps, pl.d, pl.pad_lo, pl.pad_hi, pl.valid, pl.span};
@@ -185,6 +185,18 @@ __device__ int geometry_block(const EotShape& s, const Layout& L, int j, const f
   uint4* rz = reinterpret_cast<uint4*>(ws + L.off_route + (size_t)j * L.rslot);
   const int n16 = (spl.d * spl.d + 15) / 16;
   for (int i = threadIdx.x; i < n16; i += blockDim.x) rz[i] = make_uint4(0u, 0u, 0u, 0u);
+  // -2 ring (pad of attacker.py:435 / fill of :437) around the ps x ps core the resize items write
+  float4* u4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(ws + L.off_u) + spl.u_off);
+  const int S = u_stride(ps);
+  const float4 fill = make_float4(-2.0f, -2.0f, -2.0f, 0.0f);
+  for (int i = threadIdx.x; i < 4 * S; i += blockDim.x) {
+    const int r = i / S, c = i - r * S;
+    u4[(r < 2 ? r : S - 4 + r) * S + c] = fill;
+  }
+  for (int i = threadIdx.x; i < 4 * ps; i += blockDim.x) {
+    const int r = i >> 2, k = i & 3;
+    u4[(r + 2) * S + (k < 2 ? k : S - 4 + k)] = fill;
+  }
   return image;
 }
 
@@ -464,74 +476,91 @@ __global__ void __launch_bounds__(kThreads) k_bm_apply(const float* __restrict__
 // resize + noise + delta + clip for one strip of L.resize_rows output rows of one box
 // (attacker.py:425-428; ScaleAndTranslate GatherRows then GatherColumns).
 // The box's span table is staged in shared memory first (no dependent global loads in the loops).
-// Rows pass: a thread owns a column of the [P,3] row and walks the strip's rows.  Columns pass: a lane
-// owns a quad of 4 consecutive texels = 12 elements = exactly 3 Philox groups.  Accumulation order ==
-// the oracle's.  Output texel: (clip r, clip g, clip b, inner-clip pass bits).
+// Rows pass: a lane owns four texels (12 floats = 3 x 128-bit loads per tap) of a source row and writes
+// them as RGBX texels into the shared intermediate.  Columns pass: a lane owns a quad of 4 consecutive
+// output texels = 12 elements = exactly 3 Philox groups; one 128-bit shared load per tap.  Accumulation
+// order == the oracle's.  Output texel: (clip r, clip g, clip b, inner-clip pass bits).
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t resize_smem_bytes(const EotShape& s, const Layout& L) {
-  return ((size_t)L.resize_rows * s.patch_size * 3 + (size_t)L.wcap + (size_t)L.lmin) * sizeof(float);
+  return ((size_t)L.resize_rows * s.patch_size * 4 + (size_t)L.wcap + (size_t)L.lmin) * sizeof(float);
 }
 
 // SPAN > 0: compile-time tap count (3 = up-sampling / unit scale, 5 and 7 = moderate down-sampling), every tap
 // loop fully unrolled; weights past the true span are stored as 0 and the clamped source index is finite, so the
 // padded taps add +0 -- the same sums as the oracle's.  SPAN == 0: run-time span (any scale).
 template <int SPAN>
-__device__ __forceinline__ void resize_passes(const EotShape& s, const Layout& L, int P, int ps, int span, int oy0, int rows,
-                                              const float* __restrict__ m, const int* s_st, const float* s_w, float* inter,
+__device__ __forceinline__ void resize_passes(const EotShape& s, int P, int ps, int span, int oy0, int rows,
+                                              const float* m, const int* s_st, const float* s_w, float4* inter,
                                               float4* u4, float delta, uint32_t key0, uint32_t key1) {
   const int P3 = P * 3;
-  const int total = rows * P3;
-  constexpr int kRB = 2;                                     // outputs per thread and iteration
-  // rows pass over the flattened (row, column) index so that every warp is full; kRB outputs per thread and
-  // iteration keep the L2 loads of all taps in flight before the first use
-  for (int i0 = threadIdx.x; i0 < total; i0 += kRB * blockDim.x) {
-    if (SPAN > 0) {
-      float v[kRB][SPAN > 0 ? SPAN : 1];
-      int oyq[kRB];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  constexpr int NT = SPAN > 0 ? SPAN : 1;
+  // ---- rows pass ----
+  if ((P & 3) == 0) {
+    const int nq = P >> 2;                                    // texel quads per source row
+    for (int r = warp; r < rows; r += nwarps) {
+      const int oy = oy0 + r;
+      const int st = s_st[oy];
+      const float* w = s_w + oy * (SPAN > 0 ? SPAN : span);
+      const int nk = SPAN > 0 ? SPAN : min(span, P - st);
+      for (int tq = lane; tq < nq; tq += 32) {
+        float acc[12];
 #pragma unroll
-      for (int q = 0; q < kRB; ++q) {
-        const int idx = i0 + q * blockDim.x;
-        if (idx < total) {
-          const int r = __umulhi((unsigned)idx, L.p3_magic);          // idx / P3 for idx < 2^16
-          const int f = idx - r * P3;
-          const int oy = oy0 + r;
-          oyq[q] = oy;
-          const int st = s_st[oy];
+        for (int i = 0; i < 12; ++i) acc[i] = 0.0f;
+        if (SPAN > 0) {
+          float4 v[NT][3];
 #pragma unroll
-          for (int k = 0; k < SPAN; ++k) v[q][k] = m[min(st + k, P - 1) * P3 + f];
+          for (int k = 0; k < NT; ++k) {
+            const float4* mp = reinterpret_cast<const float4*>(m + (size_t)min(st + k, P - 1) * P3) + 3 * tq;
+            v[k][0] = mp[0]; v[k][1] = mp[1]; v[k][2] = mp[2];
+          }
+#pragma unroll
+          for (int k = 0; k < NT; ++k) {
+            const float wk = w[k];
+            const float x[12] = {v[k][0].x, v[k][0].y, v[k][0].z, v[k][0].w, v[k][1].x, v[k][1].y, v[k][1].z, v[k][1].w,
+                                 v[k][2].x, v[k][2].y, v[k][2].z, v[k][2].w};
+#pragma unroll
+            for (int i = 0; i < 12; ++i) acc[i] = acc[i] + wk * x[i];
+          }
+        } else {
+          for (int k = 0; k < nk; ++k) {
+            const float4* mp = reinterpret_cast<const float4*>(m + (size_t)(st + k) * P3) + 3 * tq;
+            const float4 a = mp[0], b = mp[1], c = mp[2];
+            const float wk = w[k];
+            const float x[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int i = 0; i < 12; ++i) acc[i] = acc[i] + wk * x[i];
+          }
         }
+        float4* o = inter + r * P + 4 * tq;
+        o[0] = make_float4(acc[0], acc[1], acc[2], 0.0f);
+        o[1] = make_float4(acc[3], acc[4], acc[5], 0.0f);
+        o[2] = make_float4(acc[6], acc[7], acc[8], 0.0f);
+        o[3] = make_float4(acc[9], acc[10], acc[11], 0.0f);
       }
-#pragma unroll
-      for (int q = 0; q < kRB; ++q) {
-        const int idx = i0 + q * blockDim.x;
-        if (idx < total) {
-          const float* w = s_w + oyq[q] * SPAN;
-          float acc = 0.0f;
-#pragma unroll
-          for (int k = 0; k < SPAN; ++k) acc = acc + w[k] * v[q][k];
-          inter[idx] = acc;
+    }
+  } else {                                                    // any P: one lane per texel, scalar loads
+    for (int r = warp; r < rows; r += nwarps) {
+      const int oy = oy0 + r;
+      const int st = s_st[oy];
+      const float* w = s_w + oy * (SPAN > 0 ? SPAN : span);
+      const int nk = SPAN > 0 ? SPAN : min(span, P - st);
+      for (int x = lane; x < P; x += 32) {
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+        for (int k = 0; k < nk; ++k) {
+          const float* mp = m + (size_t)min(st + k, P - 1) * P3 + x * 3;
+          const float wk = w[k];
+          a0 = a0 + wk * mp[0];
+          a1 = a1 + wk * mp[1];
+          a2 = a2 + wk * mp[2];
         }
-      }
-    } else {
-#pragma unroll 1
-      for (int q = 0; q < kRB; ++q) {
-        const int idx = i0 + q * blockDim.x;
-        if (idx < total) {
-          const int r = __umulhi((unsigned)idx, L.p3_magic);
-          const int f = idx - r * P3;
-          const int oy = oy0 + r;
-          const int st = s_st[oy];
-          const float* w = s_w + oy * span;
-          const int nk = min(span, P - st);
-          const float* mp = m + st * P3 + f;
-          float acc = 0.0f;
-          for (int k = 0; k < nk; ++k) acc = acc + w[k] * mp[k * P3];
-          inter[idx] = acc;
-        }
+        inter[r * P + x] = make_float4(a0, a1, a2, 0.0f);
       }
     }
   }
   __syncthreads();
+  // ---- columns pass + noise + delta + clip ----
+  const int S = u_stride(ps);
   const int p_begin = oy0 * ps, p_end = (oy0 + rows) * ps;   // flat texel range of the strip
   for (int q = (p_begin >> 2) + threadIdx.x; q <= ((p_end - 1) >> 2); q += blockDim.x) {
     uint32_t words[12];
@@ -546,27 +575,27 @@ __device__ __forceinline__ void resize_passes(const EotShape& s, const Layout& L
     for (int t = 0; t < 4; ++t, ++p) {
       if (p >= p_begin && p < p_end) {
         const int st = s_st[ox];
-        const float* irow = inter + (oy - oy0) * P3;
+        const float4* irow = inter + (oy - oy0) * P;
         float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
         if (SPAN > 0) {
           const float* w = s_w + ox * SPAN;
 #pragma unroll
-          for (int k = 0; k < SPAN; ++k) {
+          for (int k = 0; k < NT; ++k) {
             const float wk = w[k];
-            const float* ip = irow + min(st + k, P - 1) * 3;
-            a0 = a0 + wk * ip[0];
-            a1 = a1 + wk * ip[1];
-            a2 = a2 + wk * ip[2];
+            const float4 v = irow[min(st + k, P - 1)];
+            a0 = a0 + wk * v.x;
+            a1 = a1 + wk * v.y;
+            a2 = a2 + wk * v.z;
           }
         } else {
           const float* w = s_w + ox * span;
           const int nk = min(span, P - st);
-          const float* ip = irow + st * 3;
           for (int k = 0; k < nk; ++k) {
             const float wk = w[k];
-            a0 = a0 + wk * ip[k * 3];
-            a1 = a1 + wk * ip[k * 3 + 1];
-            a2 = a2 + wk * ip[k * 3 + 2];
+            const float4 v = irow[st + k];
+            a0 = a0 + wk * v.x;
+            a1 = a1 + wk * v.y;
+            a2 = a2 + wk * v.z;
           }
         }
         const float v0 = (a0 + noise_from_word(words[3 * t], s.noise_amp)) + delta;
@@ -574,7 +603,8 @@ __device__ __forceinline__ void resize_passes(const EotShape& s, const Layout& L
         const float v2 = (a2 + noise_from_word(words[3 * t + 2], s.noise_amp)) + delta;
         const unsigned bits = (unsigned)(v0 >= -1.0f && v0 <= 1.0f) | ((unsigned)(v1 >= -1.0f && v1 <= 1.0f) << 1) |
                               ((unsigned)(v2 >= -1.0f && v2 <= 1.0f) << 2);
-        u4[p] = make_float4(clampf(v0, -1.0f, 1.0f), clampf(v1, -1.0f, 1.0f), clampf(v2, -1.0f, 1.0f), __uint_as_float(bits));
+        u4[(oy + 2) * S + ox + 2] =
+            make_float4(clampf(v0, -1.0f, 1.0f), clampf(v1, -1.0f, 1.0f), clampf(v2, -1.0f, 1.0f), __uint_as_float(bits));
       }
       if (++ox == ps) { ox = 0; ++oy; }
     }
@@ -583,8 +613,8 @@ __device__ __forceinline__ void resize_passes(const EotShape& s, const Layout& L
 
 __device__ __forceinline__ void resize_item(const EotShape& s, const Layout& L, char* ws, int2 item, float* smem) {
   const int P = s.patch_size, P3 = P * 3;
-  float* inter = smem;                                       // [resize_rows][P3]
-  float* s_w = smem + L.resize_rows * P3;                    // [ps][span]
+  float4* inter = reinterpret_cast<float4*>(smem);           // [resize_rows][P] RGBX
+  float* s_w = smem + (size_t)L.resize_rows * P * 4;         // [ps][span]
   int* s_st = reinterpret_cast<int*>(s_w + L.wcap);          // [ps]
   const BoxPlan* pl = reinterpret_cast<const BoxPlan*>(ws + L.off_plans) + item.x;
   const int j = item.x;
@@ -601,305 +631,187 @@ __device__ __forceinline__ void resize_item(const EotShape& s, const Layout& L, 
   for (int i = threadIdx.x; i < ps; i += blockDim.x) s_st[i] = starts[i];
   for (int i = threadIdx.x; i < ps * span; i += blockDim.x) s_w[i] = wts[i];
   __syncthreads();
-  if (span == 3) resize_passes<3>(s, L, P, ps, span, oy0, rows, m, s_st, s_w, inter, u4, delta, key0, key1);
-  else if (span == 5) resize_passes<5>(s, L, P, ps, span, oy0, rows, m, s_st, s_w, inter, u4, delta, key0, key1);
-  else if (span == 7) resize_passes<7>(s, L, P, ps, span, oy0, rows, m, s_st, s_w, inter, u4, delta, key0, key1);
-  else resize_passes<0>(s, L, P, ps, span, oy0, rows, m, s_st, s_w, inter, u4, delta, key0, key1);
+  if (span == 3) resize_passes<3>(s, P, ps, span, oy0, rows, m, s_st, s_w, inter, u4, delta, key0, key1);
+  else if (span == 5) resize_passes<5>(s, P, ps, span, oy0, rows, m, s_st, s_w, inter, u4, delta, key0, key1);
+  else if (span == 7) resize_passes<7>(s, P, ps, span, oy0, rows, m, s_st, s_w, inter, u4, delta, key0, key1);
+  else resize_passes<0>(s, P, ps, span, oy0, rows, m, s_st, s_w, inter, u4, delta, key0, key1);
 }
 
 __global__ void __launch_bounds__(kThreads, 4) k_resize(EotShape s, Layout L, char* ws, const int32_t* __restrict__ offsets,
                                                         int b0, int b1) {
-  extern __shared__ float resize_smem[];
+  extern __shared__ __align__(16) float resize_smem[];
   __shared__ int2 s_base[kMaxBaseSmem];
   const int2* base = stage_base(reinterpret_cast<const int2*>(ws + L.off_base), s.total_boxes, s_base);
   const int lo = base[offsets[b0]].x, hi = base[offsets[b1]].x;
+  __shared__ int2 s_item;
   for (int it = lo + blockIdx.x; it < hi; it += gridDim.x) {
-    resize_item(s, L, ws, find_item(base, s.total_boxes, 0, it), resize_smem);
+    if (threadIdx.x == 0) s_item = find_item(base, s.total_boxes, 0, it);
+    __syncthreads();
+    resize_item(s, L, ws, s_item, resize_smem);
     __syncthreads();
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// composite (attacker.py:436-444 in gather form).  Sequential-paste semantics: an element's final
-// value is clip(R_j) of the LAST box j (in paste order) covering it with R_j >= -1, else
-// clip(original); elements outside every window are untouched by this kernel.  A pixel covered by
-// several windows is written only by the items of the last covering box.
+// composite (attacker.py:436-444) in gather form over IMAGE tiles.
 //
-// One work item = kCompRows window rows of one box; one warp per row, one lane per pixel (sampling
-// coordinates shared by the three channels); the row segment is transposed through shared memory so
-// that global loads and stores are contiguous 128-byte warp accesses.  Each pixel also leaves a
-// route byte per covering box (bit c: channel c of the output came from this box and passes the
-// outer clip) -- the backward's TensorScatterUpdate / SelectV2 / clip routing without re-sampling.
+// Sequential-paste semantics: an element's final value is clip(R_j) of the LAST box j (in paste order)
+// covering it with R_j >= -1, else clip(original); pixels outside every window are untouched.  One work
+// item = a band of kCompRows rows of one image; the boxes whose windows meet the band are staged in shared
+// memory once; a warp owns a row and sweeps it in 32-pixel tiles, one lane per pixel (sampling coordinates
+// shared by the three channels).  Per tile the candidate boxes are visited newest first, warp-uniformly;
+// a box is sampled only where the pixel is inside its window, still misses a channel, and at least one of
+// the four taps can touch the ps x ps core (everything else blends to -2 exactly as the padded image
+// would).  Every output pixel is written once, by one thread: no ordering between work items, no waits.
+//
+// Each pixel leaves a route byte in the map of every box that provided one of its channels (bit c: channel
+// c of the output came from this box and passes the outer clip): the backward's TensorScatterUpdate /
+// SelectV2 / clip routing without re-sampling.
 // ------------------------------------------------------------------------------------------------
-constexpr int kMaxWin = 256;   // person boxes per image held in shared memory (the reference's NMS keeps <= 100)
+constexpr int kMaxBandBoxes = 32;   // boxes of one image whose windows meet one band (more: flagged, first 32 handled)
 
-struct CompositeSmem {
-  int4 win[kMaxWin];                 // y0, x0, d, valid of every box of the image
-  unsigned ovmask[kMaxWin / 32];     // boxes whose window intersects this item's rows
-  float stage[kThreads / 32][96];    // one 32-pixel row segment per warp, for coalesced stores
+struct BandBox {
+  float t0, t1, t2, t3, t4, t5, t6, t7;
+  float lo2, hi;              // clamp range of the floor coordinates
+  int org, S;
+  int y0, x0, d, j;
+  const float4* u;
+  uint8_t* route;
 };
 
-__device__ __forceinline__ bool covers(const int4 w, int gy, int gx) {
-  return gy >= w.x && gy < w.x + w.z && gx >= w.y && gx < w.y + w.z;
-}
+struct CompositeSmem {
+  BandBox box[kMaxBandBoxes];
+  int n;
+};
 
-// Conservative range of window columns x in row y whose sample can touch the ps x ps core (affine T):
-// outside it all four taps are pad/fill, R == -2 and the pixel keeps its background.
-__device__ __forceinline__ void core_range(const Sampler& S, float yf, int D, int* xa, int* xb) {
-  float lo = 0.0f, hi = (float)(D - 1);
-  const float a[2] = {S.t0, S.t3};
-  const float c[2] = {S.t1 * yf + S.t2, S.t4 * yf + S.t5};
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const float l = S.lo - 1.5f - c[i], h = S.hi + 0.5f - c[i];      // need l < a*x < h (half-pixel safety margin)
-    if (fabsf(a[i]) < 1e-6f) {
-      if (!(0.0f > l - 1.0f && 0.0f < h + 1.0f)) { lo = 1.0f; hi = 0.0f; }
-    } else {
-      const float x1 = l / a[i], x2 = h / a[i];
-      lo = fmaxf(lo, fminf(x1, x2) - 1.0f);
-      hi = fminf(hi, fmaxf(x1, x2) + 1.0f);
-    }
-  }
-  *xa = (int)floorf(lo);
-  *xb = (int)ceilf(hi);
-}
-
-__device__ __forceinline__ void composite_item(const EotShape& s, const Layout& L, char* ws,
-                                               const float* __restrict__ images, float* out, float* mask, int2 item,
-                                               CompositeSmem& sm) {
+__device__ __forceinline__ void composite_band(const EotShape& s, const Layout& L, char* ws,
+                                               const float* __restrict__ images, float* out, float* mask, int b, int band,
+                                               const int32_t* __restrict__ offsets, CompositeSmem& sm) {
   const BoxPlan* plans = reinterpret_cast<const BoxPlan*>(ws + L.off_plans);
-  const float* ubuf = reinterpret_cast<const float*>(ws + L.off_u);
-  uint8_t* routes = reinterpret_cast<uint8_t*>(ws + L.off_route);
   const int H = s.height, W = s.width;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j = item.x;
-  const BoxPlan me = plans[j];
-  const int first = me.first_box;
-  int nb = me.last_box - first;
-  if (nb > kMaxWin) {                                  // unsupported: flag and treat the first kMaxWin only
-    if (threadIdx.x == 0) atomicExch(reinterpret_cast<int*>(ws + L.off_counters) + 2, 2);
-    nb = kMaxWin;
-  }
-  const int jl = j - first;
-  const int D = me.d;
-  const int ya = me.y0 + item.y * kCompRows, yb = min(me.y0 + D, ya + kCompRows);
-  const int nwords = (nb + 31) >> 5;
-  bool any_later = false, any_earlier = false;
-  if (nb > 1) {
-    for (int q = threadIdx.x; q < nwords * 32; q += blockDim.x) {
-      int4 w = make_int4(0, 0, 0, 0);
-      if (q < nb) {
-        const BoxPlan* o = plans + first + q;
-        w = make_int4(o->y0, o->x0, o->d, o->valid);
-        sm.win[q] = w;
+  const int ya = band * kCompRows, yb = min(H, ya + kCompRows);
+  if (warp == 0) {                                              // stage the boxes meeting the band, in paste order
+    const float* ubuf = reinterpret_cast<const float*>(ws + L.off_u);
+    uint8_t* routes = reinterpret_cast<uint8_t*>(ws + L.off_route);
+    const int first = offsets[b], last = offsets[b + 1];
+    int n = 0;
+    for (int q0 = first; q0 < last; q0 += 32) {
+      const int q = q0 + lane;
+      bool hit = false;
+      if (q < last) {
+        const BoxPlan* o = plans + q;
+        hit = o->valid && o->y0 < yb && o->y0 + o->d > ya;
       }
-      const bool ov = q < nb && q != jl && w.w && w.x < yb && w.x + w.z > ya && w.y < me.x0 + D && w.y + w.z > me.x0;
-      const unsigned bits = __ballot_sync(0xffffffffu, ov);
-      if ((q & 31) == 0) sm.ovmask[q >> 5] = bits;
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      const int pos = n + __popc(m & ((1u << lane) - 1u));
+      if (hit && pos < kMaxBandBoxes) {
+        const BoxPlan* o = plans + q;
+        BandBox& bx = sm.box[pos];
+        bx.t0 = o->T[0]; bx.t1 = o->T[1]; bx.t2 = o->T[2]; bx.t3 = o->T[3];
+        bx.t4 = o->T[4]; bx.t5 = o->T[5]; bx.t6 = o->T[6]; bx.t7 = o->T[7];
+        bx.lo2 = (float)(o->pad_lo - 2);
+        bx.hi = (float)(o->pad_lo + o->ps);
+        bx.org = o->pad_lo - 2;
+        bx.S = o->ps + 4;
+        bx.y0 = o->y0; bx.x0 = o->x0; bx.d = o->d; bx.j = q;
+        bx.u = reinterpret_cast<const float4*>(ubuf + o->u_off);
+        bx.route = routes + (size_t)q * L.rslot;
+      }
+      n += __popc(m);
     }
-    __syncthreads();
-    for (int w = 0; w < nwords; ++w) {
-      const unsigned m = sm.ovmask[w];
-      const unsigned below = w < (jl >> 5) ? 0xffffffffu : (w > (jl >> 5) ? 0u : ((1u << (jl & 31)) - 1u));
-      any_earlier = any_earlier || (m & below);
-      any_later = any_later || (m & ~below);
+    if (n > kMaxBandBoxes) {
+      if (lane == 0) atomicExch(reinterpret_cast<int*>(ws + L.off_counters) + 2, 2);
+      n = kMaxBandBoxes;
     }
+    if (lane == 0) sm.n = n;
   }
-  const Sampler S = make_sampler(me, ubuf);
-  uint8_t* my_route = routes + (size_t)j * L.rslot;
-  const bool oor = reinterpret_cast<const int*>(ws + L.off_oor)[me.image] != 0;
-  // every pixel of the window has to be visited when the background clip is not the identity, when the
-  // Masker's mask needs the original, when an earlier paste may show through, or for a projective T
-  const bool full = oor || mask != nullptr || !S.affine;
-  const float* img_win = images + (((size_t)me.image * H + me.y0) * W + me.x0) * 3;     // window origin
-  float* out_win = out + (((size_t)me.image * H + me.y0) * W + me.x0) * 3;
-  float* mask_win = mask ? mask + (((size_t)me.image * H + me.y0) * W + me.x0) * 3 : nullptr;
-  float* sv = sm.stage[warp];
-  const int p0 = lane / 3, p1 = (lane + 32) / 3, p2 = (lane + 64) / 3;   // pixel of the element a lane stores
-  if (!any_later && !any_earlier) {
-    // ---- lean path: this item's rows touch no other window (the common case) ----
-    // Branch-free sampling: the four taps are always loaded from clamped texel coordinates and replaced
-    // by the -2 fill where they fall outside the core, which is what the padded image would hold.
-    const int ps = me.ps;
-    const float4 fill = make_float4(-2.0f, -2.0f, -2.0f, 0.0f);
-    for (int gy = ya + warp; gy < yb; gy += kThreads / 32) {
-      const int y = gy - me.y0;
-      const float yf = (float)y;
-      int xa = 0, xb = D - 1;
-      if (!full) core_range(S, yf, D, &xa, &xb);
-      xa = max(xa, 0);
-      xb = min(xb, D - 1);
-      const int row_off = y * W * 3;
-      uint8_t* rrow = my_route + y * D;
-      const float cxr = S.t1 * yf, cyr = S.t4 * yf, pr = S.t7 * yf;
-      for (int xs = xa & ~31; xs <= xb; xs += 32) {
-        const int x = xs + lane;
-        const bool act = x >= xa && x <= xb;
-        const float xf = (float)x;
-        float ix = (S.t0 * xf + cxr) + S.t2;
-        float iy = (S.t3 * xf + cyr) + S.t5;
+  __syncthreads();
+  const int n = sm.n;
+  if (n == 0) return;
+  const bool oor = reinterpret_cast<const int*>(ws + L.off_oor)[b] != 0;
+  // with a background clip that is not the identity, or the Masker's mask, every pixel inside a window is written
+  const bool all_px = oor || mask != nullptr;
+  const size_t img_off = (size_t)b * H * W * 3;
+  const float* img = images + img_off;
+  float* o_img = out + img_off;
+  float* m_img = mask ? mask + img_off : nullptr;
+  for (int gy = ya + warp; gy < yb; gy += kThreads / 32) {
+    // candidate boxes of this row and the union of their column ranges
+    unsigned cand = 0;
+    int xlo = W, xhi = -1;
+    {
+      bool hit = false;
+      int bx0 = W, bx1 = -1;
+      if (lane < n) {
+        const BandBox& bx = sm.box[lane];
+        hit = gy >= bx.y0 && gy < bx.y0 + bx.d;
+        if (hit) { bx0 = bx.x0; bx1 = bx.x0 + bx.d - 1; }
+      }
+      cand = __ballot_sync(0xffffffffu, hit);
+      if (!cand) continue;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, o));
+        bx1 = max(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
+      }
+      xlo = bx0; xhi = bx1;
+    }
+    const int row_off = gy * W * 3;
+    for (int xs = xlo & ~31; xs <= xhi; xs += 32) {
+      const int gx = xs + lane;
+      unsigned found = 0;
+      bool in_any = false;
+      float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f;
+      unsigned rest = cand;
+      while (rest) {                                            // newest paste first (warp-uniform loop)
+        const int i = 31 - __clz(rest);
+        rest &= ~(1u << i);
+        const BandBox& bx = sm.box[i];
+        const int x = gx - bx.x0;
+        const bool inwin = x >= 0 && x < bx.d;
+        in_any = in_any || inwin;
+        if (!__any_sync(0xffffffffu, inwin && found != 7u)) continue;
+        const float xf = (float)x, yf = (float)(gy - bx.y0);
+        float ix = (bx.t0 * xf + bx.t1 * yf) + bx.t2;
+        float iy = (bx.t3 * xf + bx.t4 * yf) + bx.t5;
         bool degenerate = false;
-        if (!S.affine) {
-          const float proj = (S.t6 * xf + pr) + 1.0f;
+        if (bx.t6 != 0.0f || bx.t7 != 0.0f) {
+          const float proj = (bx.t6 * xf + bx.t7 * yf) + 1.0f;
           degenerate = proj == 0.0f;
           ix = ix / proj;
           iy = iy / proj;
         }
         const float x0f = floorf(ix), y0f = floorf(iy);
-        const float x1f = x0f + 1.0f, y1f = y0f + 1.0f;
-        const bool bx0 = (x0f >= S.lo) && (x0f < S.hi), bx1 = (x1f >= S.lo) && (x1f < S.hi);
-        const bool by0 = (y0f >= S.lo) && (y0f < S.hi), by1 = (y1f >= S.lo) && (y1f < S.hi);
-        const float wx1 = x1f - ix, wx0 = ix - x0f, wy1 = y1f - iy, wy0 = iy - y0f;
-        // clamp in float first: the coordinates of far-away pixels may not fit an int
-        const float pmax = (float)(ps - 1);
-        const int xi0 = (int)fminf(fmaxf(x0f - S.lo, 0.0f), pmax), xi1 = (int)fminf(fmaxf(x1f - S.lo, 0.0f), pmax);
-        const int yi0 = (int)fminf(fmaxf(y0f - S.lo, 0.0f), pmax), yi1 = (int)fminf(fmaxf(y1f - S.lo, 0.0f), pmax);
-        const float4* r0 = S.u + yi0 * ps;
-        const float4* r1 = S.u + yi1 * ps;
-        float4 v00 = r0[xi0], v01 = r0[xi1], v10 = r1[xi0], v11 = r1[xi1];
-        if (!(by0 && bx0)) v00 = fill;
-        if (!(by0 && bx1)) v01 = fill;
-        if (!(by1 && bx0)) v10 = fill;
-        if (!(by1 && bx1)) v11 = fill;
+        // at least one tap inside the core <=> floor coordinate in [pad_lo - 1, pad_lo + ps - 1] on both axes
+        const bool core = x0f > bx.lo2 && x0f < bx.hi && y0f > bx.lo2 && y0f < bx.hi;
+        const bool take = inwin && found != 7u && core && !degenerate;
+        if (!__any_sync(0xffffffffu, take)) continue;
+        const float wx1 = (x0f + 1.0f) - ix, wx0 = ix - x0f, wy1 = (y0f + 1.0f) - iy, wy0 = iy - y0f;
+        const int xi = (int)fminf(fmaxf(x0f, bx.lo2), bx.hi) - bx.org;
+        const int yi = (int)fminf(fmaxf(y0f, bx.lo2), bx.hi) - bx.org;
+        const float4* p = bx.u + (yi * bx.S + xi);
         float R[3];
-        blend3(v00, v01, v10, v11, wx1, wx0, wy1, wy0, R);
-        if (degenerate) R[0] = R[1] = R[2] = -2.0f;
-        const bool s0 = !(R[0] < -1.0f), s1 = !(R[1] < -1.0f), s2 = !(R[2] < -1.0f);
-        const unsigned bits = (unsigned)(s0 && R[0] <= 1.0f) | ((unsigned)(s1 && R[1] <= 1.0f) << 1) |
-                              ((unsigned)(s2 && R[2] <= 1.0f) << 2);
-        const bool all3 = s0 && s1 && s2;
-        float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f;
-        if (act && (!all3 || mask_win)) {
-          const float* op = img_win + row_off + x * 3;
-          o0 = __ldg(op); o1 = __ldg(op + 1); o2 = __ldg(op + 2);
-        }
-        const bool store = act && (s0 || s1 || s2 || oor || mask_win != nullptr);
-        if (act && bits) rrow[x] = (uint8_t)bits;
-        if (store) {
-          sv[lane * 3] = clampf(s0 ? R[0] : o0, -1.0f, 1.0f);
-          sv[lane * 3 + 1] = clampf(s1 ? R[1] : o1, -1.0f, 1.0f);
-          sv[lane * 3 + 2] = clampf(s2 ? R[2] : o2, -1.0f, 1.0f);
-        }
-        const unsigned smask = __ballot_sync(0xffffffffu, store);
-        if (smask) {
-          const int seg = row_off + xs * 3;
-          if (mask_win && store) {
-            mask_win[seg + lane * 3] = o0 - sv[lane * 3];
-            mask_win[seg + lane * 3 + 1] = o1 - sv[lane * 3 + 1];
-            mask_win[seg + lane * 3 + 2] = o2 - sv[lane * 3 + 2];
-          }
-          __syncwarp();
-          float* op = out_win + seg + lane;
-          if ((smask >> p0) & 1u) op[0] = sv[lane];
-          if ((smask >> p1) & 1u) op[32] = sv[lane + 32];
-          if ((smask >> p2) & 1u) op[64] = sv[lane + 64];
-          __syncwarp();
+        blend3(p[0], p[1], p[bx.S], p[bx.S + 1], wx1, wx0, wy1, wy0, R);
+        if (take) {
+          unsigned bits = 0;
+          if (!(found & 1u) && !(R[0] < -1.0f)) { v0 = R[0]; found |= 1u; bits |= (unsigned)(R[0] <= 1.0f); }
+          if (!(found & 2u) && !(R[1] < -1.0f)) { v1 = R[1]; found |= 2u; bits |= (unsigned)(R[1] <= 1.0f) << 1; }
+          if (!(found & 4u) && !(R[2] < -1.0f)) { v2 = R[2]; found |= 4u; bits |= (unsigned)(R[2] <= 1.0f) << 2; }
+          if (bits) bx.route[(gy - bx.y0) * bx.d + x] = (uint8_t)bits;
         }
       }
-    }
-    return;
-  }
-  for (int gy = ya + warp; gy < yb; gy += kThreads / 32) {
-    const int y = gy - me.y0;
-    const float yf = (float)y;
-    int xa = 0, xb = D - 1;
-    bool row_earlier = false;
-    if (!full) {
-      core_range(S, yf, D, &xa, &xb);
-      if (any_earlier) {                                   // widen to the earlier windows crossing this row
-        for (int w = jl >> 5; w >= 0; --w) {
-          unsigned m = sm.ovmask[w];
-          if (w == (jl >> 5)) m &= (1u << (jl & 31)) - 1u;
-          while (m) {
-            const int q = (w << 5) + __ffs(m) - 1;
-            m &= m - 1;
-            const int4 wq = sm.win[q];
-            if (gy >= wq.x && gy < wq.x + wq.z) {
-              row_earlier = true;
-              xa = min(xa, max(0, wq.y - me.x0));
-              xb = max(xb, min(D - 1, wq.y + wq.z - 1 - me.x0));
-            }
-          }
+      if (found || (in_any && all_px)) {
+        const int e = row_off + gx * 3;
+        float b0 = 0.0f, b1 = 0.0f, b2 = 0.0f;
+        if (found != 7u || m_img) { b0 = __ldg(img + e); b1 = __ldg(img + e + 1); b2 = __ldg(img + e + 2); }
+        const float o0 = clampf((found & 1u) ? v0 : b0, -1.0f, 1.0f);
+        const float o1 = clampf((found & 2u) ? v1 : b1, -1.0f, 1.0f);
+        const float o2 = clampf((found & 4u) ? v2 : b2, -1.0f, 1.0f);
+        o_img[e] = o0; o_img[e + 1] = o1; o_img[e + 2] = o2;
+        if (m_img) {                                            // Masker: mask = original - pasted (attack_detection.py:429-430)
+          m_img[e] = b0 - o0; m_img[e + 1] = b1 - o1; m_img[e + 2] = b2 - o2;
         }
-      }
-    } else {
-      row_earlier = any_earlier;
-    }
-    const int row_off = y * W * 3;                          // offset of this window row from the window origin
-    uint8_t* rrow = my_route + y * D;
-    for (int xs = 0; xs < D; xs += 32) {
-      const int x = xs + lane;
-      if (xs + 31 < xa || xs > xb) continue;                 // whole segment is background of this box (route stays 0)
-      const int gx = me.x0 + x;
-      bool write = x < D;
-      if (write && any_later) {                               // a later box covering this pixel owns it
-        for (int w = jl >> 5; w < nwords && write; ++w) {
-          unsigned m = sm.ovmask[w];
-          if (w == (jl >> 5)) m &= ~((2u << (jl & 31)) - 1u);
-          while (m) { const int q = (w << 5) + __ffs(m) - 1; m &= m - 1; if (covers(sm.win[q], gy, gx)) { write = false; break; } }
-        }
-      }
-      bool store = false;
-      float orig[3] = {0.0f, 0.0f, 0.0f};
-      if (write) {
-        float v[3], R[3];
-        sample3(S, (float)x, yf, R);
-        unsigned found = 0, bits = 0;
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-          if (!(R[c] < -1.0f)) { v[c] = R[c]; found |= 1u << c; if (R[c] <= 1.0f) bits |= 1u << c; }
-        if (bits) rrow[x] = (uint8_t)bits;
-        if (found != 7u || mask) {
-          const float* op = img_win + row_off + x * 3;
-          orig[0] = __ldg(op); orig[1] = __ldg(op + 1); orig[2] = __ldg(op + 2);
-#pragma unroll
-          for (int c = 0; c < 3; ++c) if (!((found >> c) & 1u)) v[c] = orig[c];
-        }
-        if (row_earlier) {                                     // earlier pastes underneath, newest first
-          for (int w = jl >> 5; w >= 0; --w) {
-            unsigned m = sm.ovmask[w];
-            if (w == (jl >> 5)) m &= (1u << (jl & 31)) - 1u;
-            while (m) {
-              const int q = (w << 5) + 31 - __clz(m);
-              m &= ~(1u << (q & 31));
-              const int4 wq = sm.win[q];
-              if (!covers(wq, gy, gx)) continue;
-              unsigned qbits = 0;
-              if (found != 7u) {
-                const Sampler Sq = make_sampler(plans[first + q], ubuf);
-                float Rq[3];
-                sample3(Sq, (float)(gx - wq.y), (float)(gy - wq.x), Rq);
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                  if (!((found >> c) & 1u) && !(Rq[c] < -1.0f)) {
-                    v[c] = Rq[c]; found |= 1u << c; if (Rq[c] <= 1.0f) qbits |= 1u << c;
-                  }
-              }
-              if (qbits) routes[(size_t)(first + q) * L.rslot + (size_t)(gy - wq.x) * wq.z + (gx - wq.y)] = (uint8_t)qbits;
-            }
-          }
-        }
-        store = found != 0u || oor || mask != nullptr;          // untouched in-range background stays as copied
-        if (store) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) sv[lane * 3 + c] = clampf(v[c], -1.0f, 1.0f);
-        }
-      }
-      const unsigned smask = __ballot_sync(0xffffffffu, store);
-      if (smask) {
-        const int seg = row_off + xs * 3;
-        if (mask_win) {                                        // Masker: mask = original - pasted (per pixel, 3 scalars)
-          if (store) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) mask_win[seg + lane * 3 + c] = orig[c] - sv[lane * 3 + c];
-          }
-        }
-        __syncwarp();
-        float* op = out_win + seg + lane;
-        if ((smask >> p0) & 1u) op[0] = sv[lane];
-        if ((smask >> p1) & 1u) op[32] = sv[lane + 32];
-        if ((smask >> p2) & 1u) op[64] = sv[lane + 64];
-        __syncwarp();
       }
     }
   }
@@ -909,11 +821,11 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(EotShape s, Layout L,
                                                         const float* __restrict__ images, float* out, float* mask,
                                                         const int32_t* __restrict__ offsets, int b0, int b1) {
   __shared__ CompositeSmem sm;
-  __shared__ int2 s_base[kMaxBaseSmem];
-  const int2* base = stage_base(reinterpret_cast<const int2*>(ws + L.off_base), s.total_boxes, s_base);
-  const int lo = base[offsets[b0]].y, hi = base[offsets[b1]].y;
-  for (int it = lo + blockIdx.x; it < hi; it += gridDim.x) {
-    composite_item(s, L, ws, images, out, mask, find_item(base, s.total_boxes, 1, it), sm);
+  const int bands = (s.height + kCompRows - 1) / kCompRows;
+  const int total = (b1 - b0) * bands;
+  for (int it = blockIdx.x; it < total; it += gridDim.x) {
+    const int b = b0 + it / bands;
+    composite_band(s, L, ws, images, out, mask, b, it % bands, offsets, sm);
     __syncthreads();
   }
 }
@@ -934,6 +846,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(EotShape s, Layout L,
 // traffic) happens while its lines are still in L2.  Producer: writes, __threadfence, barrier, one
 // atomicAdd on the stage counter.  Consumer: one thread polls the counter, __threadfence, barrier.
 // ------------------------------------------------------------------------------------------------
+constexpr int kMaxWin = 256;     // boxes per image whose work-item prefix the fused kernel keeps in shared memory
 constexpr int kFusedNPR = 24;    // resize parts per image
 constexpr int kFusedNPC = 48;   // composite parts per image
 constexpr int kFusedStages = 4;  // slot k holds: pass(k), match(k-1), resize(k-2), composite(k-3)
@@ -945,28 +858,6 @@ struct FusedPlan {
   int slot;                                        // tickets per slot
   int total_tickets;
 };
-
-// acquire / release on the stage counters by ONE thread per CTA (PTX memory model: the CTA barrier
-// around them makes the ordering cumulative for the whole CTA).  No gpu-scope fence in every thread:
-// that would invalidate the SM's L1 at each of the ~10^4 tickets and starve the composite's tap reuse.
-__device__ __forceinline__ int ld_acquire(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void red_release_add(int* p, int n) {
-  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(n) : "memory");
-}
-
-__device__ __forceinline__ bool wait_counter(const int* ctr, int need, int* err_flag) {
-  if (need <= 0) return true;
-  for (int spin = 0; spin < (1 << 22); ++spin) {
-    if (ld_acquire(ctr) >= need) return true;
-    __nanosleep(64);
-  }
-  atomicExch(err_flag, 3);      // dependency never arrived: give up instead of hanging the GPU
-  return false;
-}
 
 __device__ __forceinline__ void signal_counter(int* ctr, int n = 1) {
   __syncthreads();
@@ -982,7 +873,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_forward_fused(EotShape s, Layou
                                                                const float* __restrict__ scale,
                                                                const float* __restrict__ images, float* out, float* mask,
                                                                char* ws) {
-  extern __shared__ float dyn_smem[];                 // resize strip buffers
+  extern __shared__ __align__(16) float dyn_smem[];    // resize strip buffers
   __shared__ CompositeSmem csm;
   __shared__ double red[32];
   __shared__ int2 pre[kMaxWin + 1];                   // per-image prefix of (resize strips, composite row blocks)
@@ -1056,7 +947,6 @@ __global__ void __launch_bounds__(kThreads, 4) k_forward_fused(EotShape s, Layou
     }
     const bool is_resize = stage == 2;
     const int part = r;
-    const int nparts = is_resize ? kFusedNPR : kFusedNPC;
     if (nb_all > 0) {
       if (threadIdx.x == 0) {
         bool ok = wait_counter(done_geom + w, nb_all, err_flag);
@@ -1065,22 +955,28 @@ __global__ void __launch_bounds__(kThreads, 4) k_forward_fused(EotShape s, Layou
       }
       __syncthreads();
       if (s_ok) {
-        const int nb = min(nb_all, kMaxWin);
-        const int2* cnt = reinterpret_cast<const int2*>(ws + L.off_cnt) + first;
-        if (threadIdx.x == 0) {
-          int2 run = make_int2(0, 0);
-          for (int i = 0; i < nb; ++i) { pre[i] = run; const int2 c = __ldcg(cnt + i); run.x += c.x; run.y += c.y; }
-          pre[nb] = run;
-        }
-        __syncthreads();
-        const int total = is_resize ? pre[nb].x : pre[nb].y;
-        for (int it = part; it < total; it += nparts) {
-          int lo = 0, hi = nb;                                    // last box with prefix <= it
-          while (hi - lo > 1) { const int m = (lo + hi) >> 1; if ((is_resize ? pre[m].x : pre[m].y) <= it) lo = m; else hi = m; }
-          const int2 item = make_int2(first + lo, it - (is_resize ? pre[lo].x : pre[lo].y));
-          if (is_resize) resize_item(s, L, ws, item, dyn_smem);
-          else composite_item(s, L, ws, images, out, mask, item, csm);
+        if (is_resize) {
+          const int nb = min(nb_all, kMaxWin);
+          const int2* cnt = reinterpret_cast<const int2*>(ws + L.off_cnt) + first;
+          if (threadIdx.x == 0) {
+            int2 run = make_int2(0, 0);
+            for (int i = 0; i < nb; ++i) { pre[i] = run; const int2 c = __ldcg(cnt + i); run.x += c.x; run.y += c.y; }
+            pre[nb] = run;
+          }
           __syncthreads();
+          const int total = pre[nb].x;
+          for (int it = part; it < total; it += kFusedNPR) {
+            int lo = 0, hi = nb;                                  // last box with prefix <= it
+            while (hi - lo > 1) { const int m = (lo + hi) >> 1; if (pre[m].x <= it) lo = m; else hi = m; }
+            resize_item(s, L, ws, make_int2(first + lo, it - pre[lo].x), dyn_smem);
+            __syncthreads();
+          }
+        } else {
+          const int bands = (s.height + kCompRows - 1) / kCompRows;
+          for (int band = part; band < bands; band += kFusedNPC) {
+            composite_band(s, L, ws, images, out, mask, w, band, offsets, csm);
+            __syncthreads();
+          }
         }
       }
     }
@@ -1155,7 +1051,7 @@ static int launch_forward(const EotShape& s, const Layout& L, const float* patch
   const bool vec = (HW % 4 == 0) && (((uintptr_t)images | (uintptr_t)out_images | (uintptr_t)(mask ? mask : out_images)) & 15) == 0;
   const int nsm = sm_count();
   const size_t smem = resize_smem_bytes(s, L);
-  if (smem > 48 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 32 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // static + dynamic may pass 48 KB
   auto prepass = [&](cudaStream_t q, int n_geom, int n_stat, int b0, int b1) {
     const long long nblocks = (long long)n_geom + (long long)n_stat * pchunks + (long long)(b1 - b0) * cpi;
     if (nblocks <= 0) return;
@@ -1170,7 +1066,7 @@ static int launch_forward(const EotShape& s, const Layout& L, const float* patch
   auto windows = [&](cudaStream_t q, int b0, int b1) {
     k_match<<<dim3(pchunks, b1 - b0), kThreads, 0, q>>>(s, L, patch, print_wb, ws, b0);
     k_resize<<<nsm * 4, kThreads, smem, q>>>(s, L, ws, box_offsets, b0, b1);
-    k_composite<<<nsm * 8, kThreads, 0, q>>>(s, L, ws, images, out_images, mask, box_offsets, b0, b1);
+    k_composite<<<nsm * 4, kThreads, 0, q>>>(s, L, ws, images, out_images, mask, box_offsets, b0, b1);
     count_launches(3);
   };
   if ((long long)N + (long long)B * pchunks + (long long)B * cpi >= (1ll << 31)) { set_error("eot_apply_fwd: grid too large"); return EOT_ERR_BAD_SHAPE; }
@@ -1188,11 +1084,11 @@ static int launch_forward(const EotShape& s, const Layout& L, const float* patch
     fp.total_tickets = (int)tickets;
     const size_t dsm = max(smem, (size_t)256 * sizeof(int2));
     if (vec) {
-      if (dsm > 40 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_forward_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+      if (dsm > 24 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_forward_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
       k_forward_fused<true><<<nsm * 4, kThreads, dsm, st>>>(s, L, fp, patch, print_wb, boxes, box_offsets, params, scale, images,
                                                             out_images, mask, ws);
     } else {
-      if (dsm > 40 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_forward_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+      if (dsm > 24 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_forward_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
       k_forward_fused<false><<<nsm * 4, kThreads, dsm, st>>>(s, L, fp, patch, print_wb, boxes, box_offsets, params, scale, images,
                                                              out_images, mask, ws);
     }
@@ -1244,6 +1140,7 @@ static int forward_entry(const EotShape* shape, const float* patch, const float*
   }
   const bool want_mask = (shape->flags & EOT_FLAG_MASK_OUTPUT) != 0;
   if (want_mask && !out_masks) { set_error("EOT_FLAG_MASK_OUTPUT set but out_masks is NULL"); return EOT_ERR_NULL_POINTER; }
+  if (want_mask && out_images == images) { set_error("the Masker's mask needs the original image: out_images may not alias images"); return EOT_ERR_BAD_SHAPE; }
   const EotShape s = normalised(*shape);
   const Layout L = make_layout(s);
   if (workspace_bytes < L.total) {
