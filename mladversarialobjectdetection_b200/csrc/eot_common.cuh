@@ -59,6 +59,7 @@ struct Layout {
   size_t off_done;         // int32[5][B]  fused forward: finished work items per image and stage (geometry, patch
                            //              statistics, image pass, match, resize)
   size_t off_counters;     // int32[8]: 2 error flag, 4 work ticket, 5 finished geometry blocks
+  size_t off_tickets;      // int32[32]  composite band tickets (one counter per image group of the two-stream entry)
   size_t off_plans;        // BoxPlan[N]
   size_t off_starts;       // int32[N][Lmin]
   size_t off_weights;      // float[N][wcap]
@@ -109,6 +110,7 @@ __host__ __device__ inline Layout make_layout(const EotShape& s) {
   L.off_oor = o;          o = align_up(o + B * sizeof(int32_t), 256);
   L.off_done = o;         o = align_up(o + 5 * B * sizeof(int32_t), 256);
   L.off_counters = o;     o = align_up(o + 8 * sizeof(int32_t), 256);
+  L.off_tickets = o;      o = align_up(o + 32 * sizeof(int32_t), 256);
   L.off_plans = o;        o = align_up(o + N * sizeof(BoxPlan), 256);
   L.off_starts = o;       o = align_up(o + N * (size_t)lmin * sizeof(int32_t), 256);
   L.off_weights = o;      o = align_up(o + N * (size_t)L.wcap * sizeof(float), 256);

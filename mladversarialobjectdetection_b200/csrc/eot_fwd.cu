@@ -673,6 +673,7 @@ constexpr int kMaxBandBoxes = 32;   // boxes of one image whose windows meet one
 struct BandBox {
   float t0, t1, t2, t3, t4, t5, t6, t7;
   float lo2, hi;              // clamp range of the floor coordinates
+  float ia0, ia3;             // 1/t0, 1/t3 (0 when the coefficient is ~0): column range of the core per row
   int org, S;
   int y0, x0, d, j;
   const float4* u;
@@ -683,6 +684,26 @@ struct CompositeSmem {
   BandBox box[kMaxBandBoxes];
   int n;
 };
+
+// Conservative range of window columns x in window row y whose sample can touch the ps x ps core (affine T):
+// outside it all four taps are pad/fill and the box contributes nothing.
+__device__ __forceinline__ void core_range(const BandBox& bx, float yf, int* xa, int* xb) {
+  float lo = 0.0f, hi = (float)(bx.d - 1);
+  const float clo = bx.lo2 + 2.0f, chi = bx.hi;               // core bounds in padded coordinates
+  const float c0 = bx.t1 * yf + bx.t2, c1 = bx.t4 * yf + bx.t5;
+  {
+    const float l = clo - 1.5f - c0, h = chi + 0.5f - c0;      // need l < t0*x < h (half-pixel safety margin)
+    if (bx.ia0 == 0.0f) { if (!(0.0f > l - 1.0f && 0.0f < h + 1.0f)) { lo = 1.0f; hi = 0.0f; } }
+    else { const float x1 = l * bx.ia0, x2 = h * bx.ia0; lo = fmaxf(lo, fminf(x1, x2) - 1.0f); hi = fminf(hi, fmaxf(x1, x2) + 1.0f); }
+  }
+  {
+    const float l = clo - 1.5f - c1, h = chi + 0.5f - c1;
+    if (bx.ia3 == 0.0f) { if (!(0.0f > l - 1.0f && 0.0f < h + 1.0f)) { lo = 1.0f; hi = 0.0f; } }
+    else { const float x1 = l * bx.ia3, x2 = h * bx.ia3; lo = fmaxf(lo, fminf(x1, x2) - 1.0f); hi = fminf(hi, fmaxf(x1, x2) + 1.0f); }
+  }
+  *xa = (int)floorf(lo);
+  *xb = (int)ceilf(hi);
+}
 
 __device__ __forceinline__ void composite_band(const EotShape& s, const Layout& L, char* ws,
                                                const float* __restrict__ images, float* out, float* mask, int b, int band,
@@ -712,6 +733,8 @@ __device__ __forceinline__ void composite_band(const EotShape& s, const Layout& 
         bx.t4 = o->T[4]; bx.t5 = o->T[5]; bx.t6 = o->T[6]; bx.t7 = o->T[7];
         bx.lo2 = (float)(o->pad_lo - 2);
         bx.hi = (float)(o->pad_lo + o->ps);
+        bx.ia0 = fabsf(o->T[0]) < 1e-6f ? 0.0f : 1.0f / o->T[0];
+        bx.ia3 = fabsf(o->T[3]) < 1e-6f ? 0.0f : 1.0f / o->T[3];
         bx.org = o->pad_lo - 2;
         bx.S = o->ps + 4;
         bx.y0 = o->y0; bx.x0 = o->x0; bx.d = o->d; bx.j = q;
@@ -737,68 +760,88 @@ __device__ __forceinline__ void composite_band(const EotShape& s, const Layout& 
   float* o_img = out + img_off;
   float* m_img = mask ? mask + img_off : nullptr;
   for (int gy = ya + warp; gy < yb; gy += kThreads / 32) {
-    // candidate boxes of this row and the union of their column ranges
-    unsigned cand = 0;
-    int xlo = W, xhi = -1;
-    {
-      bool hit = false;
-      int bx0 = W, bx1 = -1;
-      if (lane < n) {
-        const BandBox& bx = sm.box[lane];
-        hit = gy >= bx.y0 && gy < bx.y0 + bx.d;
-        if (hit) { bx0 = bx.x0; bx1 = bx.x0 + bx.d - 1; }
+    // lane i: the column range of this row in which box i can matter (its whole window when every window pixel is
+    // written or T is projective, else the conservative range of the rotated core)
+    int rx0 = 1, rx1 = 0;
+    if (lane < n) {
+      const BandBox& bx = sm.box[lane];
+      if (gy >= bx.y0 && gy < bx.y0 + bx.d) {
+        int xa = 0, xb = bx.d - 1;
+        if (!all_px && bx.t6 == 0.0f && bx.t7 == 0.0f) {
+          core_range(bx, (float)(gy - bx.y0), &xa, &xb);
+          xa = max(xa, 0);
+          xb = min(xb, bx.d - 1);
+        }
+        rx0 = bx.x0 + xa;
+        rx1 = bx.x0 + xb;
       }
-      cand = __ballot_sync(0xffffffffu, hit);
-      if (!cand) continue;
+    }
+    if (!__any_sync(0xffffffffu, rx0 <= rx1)) continue;
+    int xlo = rx0 <= rx1 ? rx0 : W, xhi = rx0 <= rx1 ? rx1 : -1;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, o));
-        bx1 = max(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
-      }
-      xlo = bx0; xhi = bx1;
+    for (int o = 16; o > 0; o >>= 1) {
+      xlo = min(xlo, __shfl_xor_sync(0xffffffffu, xlo, o));
+      xhi = max(xhi, __shfl_xor_sync(0xffffffffu, xhi, o));
     }
     const int row_off = gy * W * 3;
+    // the box whose constants sit in registers (tiles of one row mostly meet the same single box)
+    int cur = -1;
+    float t0 = 0.f, t3 = 0.f, c0 = 0.f, c1 = 0.f, t6 = 0.f, c2 = 0.f, lo2 = 0.f, hi = 0.f;
+    int org = 0, S = 0, bx0 = 0, bd = 0;
+    const float4* bu = nullptr;
+    uint8_t* brow = nullptr;
+    bool proj_on = false;
     for (int xs = xlo & ~31; xs <= xhi; xs += 32) {
       const int gx = xs + lane;
+      unsigned rest = __ballot_sync(0xffffffffu, rx0 <= rx1 && rx0 <= xs + 31 && rx1 >= xs);
+      if (!rest) continue;
       unsigned found = 0;
       bool in_any = false;
       float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f;
-      unsigned rest = cand;
       while (rest) {                                            // newest paste first (warp-uniform loop)
         const int i = 31 - __clz(rest);
         rest &= ~(1u << i);
-        const BandBox& bx = sm.box[i];
-        const int x = gx - bx.x0;
-        const bool inwin = x >= 0 && x < bx.d;
+        if (i != cur) {
+          const BandBox& bx = sm.box[i];
+          const float yf = (float)(gy - bx.y0);
+          cur = i;
+          t0 = bx.t0; t3 = bx.t3; c0 = bx.t1 * yf; c1 = bx.t4 * yf; c2 = bx.t7 * yf; t6 = bx.t6;
+          proj_on = bx.t6 != 0.0f || bx.t7 != 0.0f;
+          lo2 = bx.lo2; hi = bx.hi; org = bx.org; S = bx.S; bx0 = bx.x0; bd = bx.d;
+          bu = bx.u;
+          brow = bx.route + (gy - bx.y0) * bx.d;
+        }
+        const BandBox& bxs = sm.box[i];
+        const int x = gx - bx0;
+        const bool inwin = x >= 0 && x < bd;
         in_any = in_any || inwin;
-        if (!__any_sync(0xffffffffu, inwin && found != 7u)) continue;
-        const float xf = (float)x, yf = (float)(gy - bx.y0);
-        float ix = (bx.t0 * xf + bx.t1 * yf) + bx.t2;
-        float iy = (bx.t3 * xf + bx.t4 * yf) + bx.t5;
+        const float xf = (float)x;
+        float ix = (t0 * xf + c0) + bxs.t2;
+        float iy = (t3 * xf + c1) + bxs.t5;
         bool degenerate = false;
-        if (bx.t6 != 0.0f || bx.t7 != 0.0f) {
-          const float proj = (bx.t6 * xf + bx.t7 * yf) + 1.0f;
+        if (proj_on) {
+          const float proj = (t6 * xf + c2) + 1.0f;
           degenerate = proj == 0.0f;
           ix = ix / proj;
           iy = iy / proj;
         }
         const float x0f = floorf(ix), y0f = floorf(iy);
         // at least one tap inside the core <=> floor coordinate in [pad_lo - 1, pad_lo + ps - 1] on both axes
-        const bool core = x0f > bx.lo2 && x0f < bx.hi && y0f > bx.lo2 && y0f < bx.hi;
+        const bool core = x0f > lo2 && x0f < hi && y0f > lo2 && y0f < hi;
         const bool take = inwin && found != 7u && core && !degenerate;
         if (!__any_sync(0xffffffffu, take)) continue;
         const float wx1 = (x0f + 1.0f) - ix, wx0 = ix - x0f, wy1 = (y0f + 1.0f) - iy, wy0 = iy - y0f;
-        const int xi = (int)fminf(fmaxf(x0f, bx.lo2), bx.hi) - bx.org;
-        const int yi = (int)fminf(fmaxf(y0f, bx.lo2), bx.hi) - bx.org;
-        const float4* p = bx.u + (yi * bx.S + xi);
+        const int xi = (int)fminf(fmaxf(x0f, lo2), hi) - org;
+        const int yi = (int)fminf(fmaxf(y0f, lo2), hi) - org;
+        const float4* p = bu + (yi * S + xi);
         float R[3];
-        blend3(p[0], p[1], p[bx.S], p[bx.S + 1], wx1, wx0, wy1, wy0, R);
+        blend3(p[0], p[1], p[S], p[S + 1], wx1, wx0, wy1, wy0, R);
         if (take) {
           unsigned bits = 0;
           if (!(found & 1u) && !(R[0] < -1.0f)) { v0 = R[0]; found |= 1u; bits |= (unsigned)(R[0] <= 1.0f); }
           if (!(found & 2u) && !(R[1] < -1.0f)) { v1 = R[1]; found |= 2u; bits |= (unsigned)(R[1] <= 1.0f) << 1; }
           if (!(found & 4u) && !(R[2] < -1.0f)) { v2 = R[2]; found |= 4u; bits |= (unsigned)(R[2] <= 1.0f) << 2; }
-          if (bits) bx.route[(gy - bx.y0) * bx.d + x] = (uint8_t)bits;
+          if (bits) brow[x] = (uint8_t)bits;
         }
       }
       if (found || (in_any && all_px)) {
@@ -817,15 +860,22 @@ __device__ __forceinline__ void composite_band(const EotShape& s, const Layout& 
   }
 }
 
+// Bands are handed out by an atomic ticket (their cost varies from nothing to several overlapping windows).
 __global__ void __launch_bounds__(kThreads, 4) k_composite(EotShape s, Layout L, char* ws,
                                                         const float* __restrict__ images, float* out, float* mask,
-                                                        const int32_t* __restrict__ offsets, int b0, int b1) {
+                                                        const int32_t* __restrict__ offsets, int b0, int b1, int group) {
   __shared__ CompositeSmem sm;
+  __shared__ int s_it;
   const int bands = (s.height + kCompRows - 1) / kCompRows;
   const int total = (b1 - b0) * bands;
-  for (int it = blockIdx.x; it < total; it += gridDim.x) {
+  int* ticket = reinterpret_cast<int*>(ws + L.off_tickets) + group;
+  for (;;) {
+    if (threadIdx.x == 0) s_it = atomicAdd(ticket, 1);
+    __syncthreads();
+    const int it = s_it;
+    if (it >= total) break;
     const int b = b0 + it / bands;
-    composite_band(s, L, ws, images, out, mask, b, it % bands, offsets, sm);
+    composite_band(s, L, ws, images, out, mask, b, it - (it / bands) * bands, offsets, sm);
     __syncthreads();
   }
 }
@@ -1063,10 +1113,10 @@ static int launch_forward(const EotShape& s, const Layout& L, const float* patch
                                                               out_images, mask, ws, n_geom, n_stat, pchunks, cpi, b0);
     count_launches(1);
   };
-  auto windows = [&](cudaStream_t q, int b0, int b1) {
+  auto windows = [&](cudaStream_t q, int b0, int b1, int group) {
     k_match<<<dim3(pchunks, b1 - b0), kThreads, 0, q>>>(s, L, patch, print_wb, ws, b0);
     k_resize<<<nsm * 4, kThreads, smem, q>>>(s, L, ws, box_offsets, b0, b1);
-    k_composite<<<nsm * 4, kThreads, 0, q>>>(s, L, ws, images, out_images, mask, box_offsets, b0, b1);
+    k_composite<<<nsm * 4, kThreads, 0, q>>>(s, L, ws, images, out_images, mask, box_offsets, b0, b1, group);
     count_launches(3);
   };
   if ((long long)N + (long long)B * pchunks + (long long)B * cpi >= (1ll << 31)) { set_error("eot_apply_fwd: grid too large"); return EOT_ERR_BAD_SHAPE; }
@@ -1098,7 +1148,7 @@ static int launch_forward(const EotShape& s, const Layout& L, const float* patch
   }
   if (!aux || chunks <= 1 || N == 0) {
     prepass(st, N, B, 0, B);
-    if (N > 0) windows(st, 0, B);
+    if (N > 0) windows(st, 0, B, 0);
     EOT_CHECK_CUDA(cudaPeekAtLastError());
     return EOT_OK;
   }
@@ -1119,7 +1169,7 @@ static int launch_forward(const EotShape& s, const Layout& L, const float* patch
   for (int c = 0; c < chunks; ++c) {
     const int b0 = c * per, b1 = min(B, b0 + per);
     EOT_CHECK_CUDA(cudaStreamWaitEvent(aux, ev[c], 0));
-    windows(aux, b0, b1);
+    windows(aux, b0, b1, c);
   }
   EOT_CHECK_CUDA(cudaEventRecord(ev[chunks + 1], aux));
   EOT_CHECK_CUDA(cudaStreamWaitEvent(st, ev[chunks + 1], 0));
