@@ -205,11 +205,29 @@ class Head(nn.Module):
         self.out_pw = nn.Conv2d(c, out, 1)
         nn.init.constant_(self.out_pw.bias, bias_init)
 
+        self.folded = None
+
+    def fold_batchnorm(self):
+        """Inference-mode BatchNorm is a per-channel affine map: fold it into the shared pointwise conv, one
+        (weight, bias) pair per level (the reference runs the victim with is_training_bn=False)."""
+        ws, bs = nn.ParameterList(), nn.ParameterList()
+        for i in range(len(self.dw)):
+            for bn in self.bn[i]:
+                k = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+                ws.append(nn.Parameter((self.pw[i].weight * k.view(-1, 1, 1, 1)).detach(), requires_grad=False))
+                bs.append(nn.Parameter(((self.pw[i].bias - bn.running_mean) * k + bn.bias).detach(), requires_grad=False))
+        self.fold_w, self.fold_b = ws, bs
+        self.folded = len(self.bn[0])
+
     def forward(self, feats):
         outs = []
         for lvl, x in enumerate(feats):
             for i in range(len(self.dw)):
-                x = Fn.silu(self.bn[i][lvl](self.pw[i](self.dw[i](x))))
+                if self.folded:
+                    k = i * self.folded + lvl
+                    x = Fn.silu(Fn.conv2d(self.dw[i](x), self.fold_w[k], self.fold_b[k]))
+                else:
+                    x = Fn.silu(self.bn[i][lvl](self.pw[i](self.dw[i](x))))
             outs.append(self.out_pw(self.out_dw(x)))
         return outs
 
@@ -244,7 +262,35 @@ class EfficientDetVictim(nn.Module):
         return cls, box
 
 
-def get_victim_model(name: str = "efficientdet-d0", device="cuda", seed: int = 0, image_size: int = None) -> EfficientDetVictim:
+def _fold_conv_bn(conv: nn.Conv2d, bn: nn.BatchNorm2d) -> nn.Conv2d:
+    k = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    out = nn.Conv2d(conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding, conv.dilation,
+                    conv.groups, bias=True)
+    bias = conv.bias if conv.bias is not None else torch.zeros_like(bn.running_mean)
+    with torch.no_grad():
+        out.weight.copy_(conv.weight * k.view(-1, 1, 1, 1))
+        out.bias.copy_((bias - bn.running_mean) * k + bn.bias)
+    return out
+
+
+def fold_batchnorm(model: "EfficientDetVictim") -> None:
+    """conv -> BatchNorm(eval) pairs become one conv with bias (exact algebra; the usual inference-graph rewrite).
+    The victim always runs with is_training_bn=False (tf2/infer_lib.py:171), so nothing else ever sees the BN."""
+    for mod in model.modules():
+        if isinstance(mod, ConvBN):
+            mod[0] = _fold_conv_bn(mod[0], mod[1])
+            mod[1] = nn.Identity()
+        elif isinstance(mod, SepConvBN):
+            mod[1] = _fold_conv_bn(mod[1], mod[2])
+            mod[2] = nn.Identity()
+        elif isinstance(mod, Head):
+            mod.fold_batchnorm()
+    for p in model.parameters():
+        p.requires_grad_(False)
+
+
+def get_victim_model(name: str = "efficientdet-d0", device="cuda", seed: int = 0, image_size: int = None,
+                     fold_bn: bool = True) -> EfficientDetVictim:
     """Counterpart of util.get_victim_model (util.py:177-189) with random-init weights."""
     cfg = get_config(name)
     if image_size is not None:
@@ -253,6 +299,8 @@ def get_victim_model(name: str = "efficientdet-d0", device="cuda", seed: int = 0
     torch.manual_seed(seed)
     model = EfficientDetVictim(cfg)
     _calibrate_batchnorm(model)
+    if fold_bn:
+        fold_batchnorm(model)
     torch.random.set_rng_state(g)
     return model.to(device=device, memory_format=torch.channels_last)
 
