@@ -52,48 +52,83 @@ __host__ __device__ inline ScoreLayout score_layout(const ScoreShape& s) {
   return L;
 }
 
-__device__ __forceinline__ float2 ldg_nc_f2(const float2* p) {
-  float2 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
-  return v;
+struct TileRef { const float* src; int b, l, a0, n_valid; };
+
+__device__ __forceinline__ TileRef locate_tile(const ScoreShape& s, const ScoreLevels& lv, int t, int tiles_per_image) {
+  TileRef r;
+  r.b = t / tiles_per_image;
+  int tt = t - r.b * tiles_per_image;
+  int l = 0;
+  while (l + 1 < s.num_levels && tt >= lv.tile_base[l + 1]) ++l;
+  tt -= lv.tile_base[l];
+  r.l = l;
+  r.a0 = tt * kTile;
+  r.n_valid = min(kTile, lv.n_anchors[l] - r.a0);
+  r.src = lv.cls[l] + ((size_t)r.b * lv.n_anchors[l] + r.a0) * s.num_classes;
+  return r;
 }
 
-__global__ void __launch_bounds__(kScoreWarps * 32) k_score_fwd(ScoreShape s, ScoreLevels lv, const float* __restrict__ anchors,
-                                                                unsigned long long* keys, int* ncand,
-                                                                float* __restrict__ cand_score, int total_tiles) {
-  extern __shared__ float2 tile_smem[];
+// asynchronous global -> shared copy of one tile (8-byte cp.async: any even class count, no 16-byte alignment needed)
+__device__ __forceinline__ void stage_tile_async(float2* dst, const TileRef& r, int C2, int lane) {
+  const float2* src = reinterpret_cast<const float2*>(r.src);
+  const int nf2 = r.n_valid * C2;
+  const unsigned d0 = (unsigned)__cvta_generic_to_shared(dst);
+#pragma unroll 9
+  for (int i = lane; i < nf2; i += 32)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0 + (unsigned)i * 8u), "l"(src + i) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// One warp owns two tile buffers: the copy of its next tile (32 anchors x C logits, 11.5 KB for C = 90) is in flight
+// while the lanes scan the current one out of shared memory, one anchor per lane.
+__global__ void __launch_bounds__(kScoreWarps * 32, 1) k_score_fwd(ScoreShape s, ScoreLevels lv, const float* __restrict__ anchors,
+                                                                   unsigned long long* keys, int* ncand,
+                                                                   float* __restrict__ cand_score, int total_tiles) {
+  extern __shared__ __align__(16) float2 tile_smem[];
   const int C = s.num_classes, C2 = C >> 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float2* sm = tile_smem + (size_t)warp * kTile * C2;
+  float2* buf0 = tile_smem + (size_t)warp * 2 * kTile * C2;
   const int tiles_per_image = lv.tile_base[s.num_levels];
-  for (int t = blockIdx.x * kScoreWarps + warp; t < total_tiles; t += gridDim.x * kScoreWarps) {
-    const int b = t / tiles_per_image;
-    int tt = t - b * tiles_per_image;
-    int l = 0;
-    while (l + 1 < s.num_levels && tt >= lv.tile_base[l + 1]) ++l;
-    tt -= lv.tile_base[l];
-    const int n_l = lv.n_anchors[l];
-    const int a0 = tt * kTile;
-    const int n_valid = min(kTile, n_l - a0);
-    const float2* src = reinterpret_cast<const float2*>(lv.cls[l] + ((size_t)b * n_l + a0) * C);
-    const int nf2 = n_valid * C2;
-#pragma unroll 9
-    for (int i = lane; i < nf2; i += 32) sm[i] = ldg_nc_f2(src + i);
+  const int stride = gridDim.x * kScoreWarps;
+  int t = blockIdx.x * kScoreWarps + warp;
+  int cur = 0;
+  TileRef r;
+  if (t < total_tiles) {
+    r = locate_tile(s, lv, t, tiles_per_image);
+    stage_tile_async(buf0, r, C2, lane);
+  }
+  for (; t < total_tiles; t += stride) {
+    TileRef rn;
+    const bool more = t + stride < total_tiles;
+    if (more) {
+      rn = locate_tile(s, lv, t + stride, tiles_per_image);
+      stage_tile_async(buf0 + (size_t)(cur ^ 1) * kTile * C2, rn, C2, lane);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
     __syncwarp();
+    const float2* sm = buf0 + (size_t)cur * kTile * C2;
+    const int b = r.b, l = r.l, a0 = r.a0, n_valid = r.n_valid, n_l = lv.n_anchors[l];
     unsigned long long key = 0ull;
     float cs = -1.0f;
     if (lane < n_valid) {
+      // tf.argmax returns the FIRST maximal index: class 0 (person) is the arg-max iff x[0] >= max(x[1:]),
+      // and then the max logit is x[0] itself -- no index tracking needed.  Two independent chains for ILP.
       const float2* mine = sm + (size_t)lane * C2;
       float2 v = mine[0];
-      float best = v.x;
-      int idx = 0;
-      if (v.y > best) { best = v.y; idx = 1; }
-      for (int k = 1; k < C2; ++k) {
-        v = mine[k];
-        if (v.x > best) { best = v.x; idx = 2 * k; }
-        if (v.y > best) { best = v.y; idx = 2 * k + 1; }
+      const float best = v.x;
+      float m0 = v.y, m1 = -INFINITY;
+      int k = 1;
+#pragma unroll 11
+      for (; k + 1 < C2; k += 2) {
+        const float2 u = mine[k], w = mine[k + 1];
+        m0 = fmaxf(fmaxf(m0, u.x), u.y);
+        m1 = fmaxf(fmaxf(m1, w.x), w.y);
       }
-      if (idx == 0) {   // person is the arg-max class (first maximal index wins ties, as tf.argmax)
+      if (k < C2) { const float2 u = mine[k]; m0 = fmaxf(fmaxf(m0, u.x), u.y); }
+      const float others = fmaxf(m0, m1);
+      if (best >= others) {   // person is the arg-max class
         const int a_local = a0 + lane;
         const float4 tb = __ldg(reinterpret_cast<const float4*>(lv.box[l] + ((size_t)b * n_l + a_local) * 4));
         const float4 an = __ldg(reinterpret_cast<const float4*>(anchors + (size_t)(lv.anchor_base[l] + a_local) * 4));
@@ -122,7 +157,9 @@ __global__ void __launch_bounds__(kScoreWarps * 32) k_score_fwd(ScoreShape s, Sc
       atomicMax(keys + b, key);
       atomicAdd(ncand + b, (int)cnt);
     }
-    __syncwarp();
+    __syncwarp();                                              // every lane is done with this buffer
+    r = rn;
+    cur ^= 1;
   }
 }
 
@@ -284,10 +321,11 @@ extern "C" int score_max_fwd(const ScoreShape* shape, const float* const* cls_le
   float* cand = reinterpret_cast<float*>(ws + L.off_cand);
   const long long total_tiles = (long long)lv.tile_base[s.num_levels] * s.batch;
   if (total_tiles >= (1ll << 31)) { set_error("score_max_fwd: too many anchor tiles"); return EOT_ERR_BAD_SHAPE; }
-  const size_t smem = (size_t)kScoreWarps * kTile * s.num_classes * sizeof(float);
+  const size_t smem = (size_t)kScoreWarps * 2 * kTile * s.num_classes * sizeof(float);   // two tile buffers per warp
+  if (smem > 220 * 1024 || (s.num_classes & 1)) { set_error("score_max_fwd: num_classes %d not supported (even, <= 107)", s.num_classes); return EOT_ERR_BAD_SHAPE; }
   EOT_CHECK_CUDA(cudaFuncSetAttribute(k_score_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int need = (int)((total_tiles + kScoreWarps - 1) / kScoreWarps);
-  const int grid = need < sm_count() * 16 ? need : sm_count() * 16;
+  const int grid = need < sm_count() ? need : sm_count();      // persistent: one CTA (8 warps x 2 tile buffers = 184 KB) per SM
   k_score_fwd<<<grid, kScoreWarps * 32, smem, st>>>(s, lv, anchors, keys, ncand, cand, (int)total_tiles);
   k_score_finalize<<<(s.batch + 127) / 128, 128, 0, st>>>(s.batch, keys, ncand, max_scores, argmax_anchor, num_candidates);
   const int tgrid = (s.total_anchors + kThreads * 8 - 1) / (kThreads * 8);
