@@ -90,8 +90,8 @@ __global__ void __launch_bounds__(kThreads) k_bwd_window(EotShape s, Layout L, c
         }
         const int t = ty * ps + tx;
         const unsigned bits = __float_as_uint(u4[u_index(ps, ty, tx)].w);  // inner clip pass bits (attacker.py:428)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) gu[t * 3 + c] = ((bits >> c) & 1u) ? g[c] : 0.0f;
+        reinterpret_cast<float4*>(gu)[t] = make_float4((bits & 1u) ? g[0] : 0.0f, (bits & 2u) ? g[1] : 0.0f,
+                                                       (bits & 4u) ? g[2] : 0.0f, 0.0f);
       }
     }
   }
@@ -140,13 +140,14 @@ __global__ void __launch_bounds__(kThreads) k_bwd_resize(EotShape s, Layout L, c
     for (int c0 = 0; c0 < rows; c0 += kBwdChunk) {
       const int crow = min(kBwdChunk, rows - c0);
       for (int f = threadIdx.x; f < ps3; f += blockDim.x) {
+        const int fo = (f / 3) * 4 + f % 3;                          // g_u texels are RGBX
         for (int r = 0; r < crow; ++r) {
           const int py = py0 + c0 + r;
           const int2 rng = s_inv[py];
           float a = 0.0f;
           for (int oy = rng.x; oy <= rng.y; ++oy) {
             const int kk = py - s_st[oy];
-            if (kk >= 0 && kk < span) a += s_w[oy * span + kk] * gu[oy * ps3 + f];
+            if (kk >= 0 && kk < span) a += s_w[oy * span + kk] * gu[oy * ps * 4 + fo];
           }
           tmp[r * tstride + f] = a;
         }
@@ -208,93 +209,106 @@ __global__ void __launch_bounds__(kThreads) k_bwd_resize(EotShape s, Layout L, c
   if (threadIdx.x == 0) atomicAdd(reinterpret_cast<double*>(ws + L.off_gy_sum) + b, gy_acc);
 }
 
-// Fully parallel variant: one CTA per (box, chunk of kBwdChunk patch rows) writes that box's share of
-// dL/d(matched patch) to its own slot; k_bwd_match then sums an image's boxes in a fixed order (no atomics,
-// deterministic) and applies the first half of the BrightnessMatcher backward.
-constexpr int kBwdMaxTaps = 24;
-
-__host__ __device__ inline size_t bwd_resize2_smem_bytes(const EotShape& s, const Layout& L) {
-  return ((size_t)kBwdChunk * L.lmin * 3 + (size_t)L.wcap + (size_t)L.lmin + 2 * (size_t)s.patch_size) * sizeof(float);
+// Fully parallel variant: the transpose of the antialiased resize has the same shape as the forward resize once the
+// weights are stored transposed (the geometry role does that: off_wt / off_stt), so it runs the same two passes:
+//   rows:    inter[r][ox]    = sum_k wT[py][k] * g_u[st(py)+k][ox]          (RGBX texels, 128-bit loads)
+//   columns: gbox[py][px][c] = sum_k wT[px][k] * inter[r][st(px)+k][c]
+// One CTA per (box, strip of patch rows) writes that box's share of dL/d(matched patch) to its own slot;
+// k_bwd_match then sums an image's boxes in a fixed order (no atomics, deterministic).
+__host__ __device__ inline size_t bwd_resize3_smem_bytes(const EotShape& s, const Layout& L) {
+  return (size_t)2560 * 16 + (size_t)L.lmin * 16 + (size_t)s.patch_size * L.tcap * 4 + (size_t)(s.patch_size + 1) * 8;
 }
 
-__global__ void __launch_bounds__(kThreads) k_bwd_resize2(EotShape s, Layout L, char* ws) {
-  extern __shared__ float smem[];
-  __shared__ int tap_off[kBwdChunk][kBwdMaxTaps];
-  __shared__ float tap_w[kBwdChunk][kBwdMaxTaps];
-  __shared__ int tap_cnt[kBwdChunk];
-  const int P = s.patch_size, P3 = P * 3;
-  const int tstride = L.lmin * 3;
-  float* tmp = smem;                                               // [kBwdChunk][lmin*3]
-  float* s_w = tmp + (size_t)kBwdChunk * tstride;                  // [ps][span]
-  int* s_st = reinterpret_cast<int*>(s_w + L.wcap);                // [ps]
-  int2* s_inv = reinterpret_cast<int2*>(s_st + L.lmin);            // [P]
-  const int j = blockIdx.y;
-  const BoxPlan* pl = reinterpret_cast<const BoxPlan*>(ws + L.off_plans) + j;
-  if (!pl->valid) return;
-  const int py0 = blockIdx.x * kBwdChunk;
-  const int crow = min(kBwdChunk, P - py0);
-  const int ps = pl->ps, ps3 = ps * 3, span = pl->span;
-  const int* starts = reinterpret_cast<const int*>(ws + L.off_starts) + (size_t)j * L.lmin;
-  const float* wts = reinterpret_cast<const float*>(ws + L.off_weights) + (size_t)j * L.wcap;
-  const int2* inv = reinterpret_cast<const int2*>(ws + L.off_inv) + (size_t)j * P;
-  const float* gu = reinterpret_cast<const float*>(ws + L.off_gu) + (size_t)j * L.gslot;
-  float* gbox = reinterpret_cast<float*>(ws + L.off_gbox) + (size_t)j * P * P3;
-  for (int i = threadIdx.x; i < ps; i += blockDim.x) s_st[i] = starts[i];
-  for (int i = threadIdx.x; i < ps * span; i += blockDim.x) s_w[i] = wts[i];
-  for (int i = threadIdx.x; i < P; i += blockDim.x) s_inv[i] = inv[i];
-  __syncthreads();
-  if (threadIdx.x < kBwdChunk * kBwdMaxTaps) {                     // tap list of each patch row of the chunk
-    const int r = threadIdx.x / kBwdMaxTaps, k = threadIdx.x - r * kBwdMaxTaps;
-    if (r < crow) {
-      const int py = py0 + r;
-      const int2 rng = s_inv[py];
-      if (k == 0) tap_cnt[r] = rng.y - rng.x + 1;
-      const int oy = rng.x + k;
-      float w = 0.0f;
-      if (oy <= rng.y) {
-        const int kk = py - s_st[oy];
-        if (kk >= 0 && kk < span) w = s_w[oy * span + kk];
-      }
-      tap_off[r][k] = oy * ps3;
-      tap_w[r][k] = w;
-    }
-  }
-  __syncthreads();
-  for (int f = threadIdx.x; f < ps3; f += blockDim.x) {
-    for (int r = 0; r < crow; ++r) {
-      const int cnt = tap_cnt[r];
-      float a = 0.0f;
-      if (cnt <= kBwdMaxTaps) {
-        for (int k = 0; k < cnt; ++k) a += tap_w[r][k] * gu[tap_off[r][k] + f];
-      } else {                                                     // very strong up-sampling: walk the tables
-        const int py = py0 + r;
-        const int2 rng = s_inv[py];
-        for (int oy = rng.x; oy <= rng.y; ++oy) {
-          const int kk = py - s_st[oy];
-          if (kk >= 0 && kk < span) a += s_w[oy * span + kk] * gu[oy * ps3 + f];
+// TK > 0: compile-time tap count (every load of a texel issued before the first use; taps past the true count carry
+// weight 0 and a clamped index); TK == 0: run-time count.
+template <int TK>
+__device__ __forceinline__ void bwd_resize_passes(int P, int ps, int tcap, int py0, int rows, const float4* __restrict__ gu,
+                                                  const float* s_wt, const int2* s_st, float4* inter, float* gbox) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  constexpr int NT = TK > 0 ? TK : 1;
+  for (int r = warp; r < rows; r += nwarps) {                      // rows pass: a warp per patch row, a lane per texel column
+    const int py = py0 + r;
+    const int2 sc = s_st[py];
+    const float* w = s_wt + py * tcap;
+    for (int ox = lane; ox < ps; ox += 32) {
+      float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+      if (TK > 0) {
+        float4 v[NT];
+#pragma unroll
+        for (int k = 0; k < NT; ++k) v[k] = gu[(size_t)min(sc.x + k, ps - 1) * ps + ox];
+#pragma unroll
+        for (int k = 0; k < NT; ++k) { const float wk = w[k]; a0 += wk * v[k].x; a1 += wk * v[k].y; a2 += wk * v[k].z; }
+      } else {
+        for (int k = 0; k < sc.y; ++k) {
+          const float4 v = gu[(size_t)(sc.x + k) * ps + ox];
+          const float wk = w[k];
+          a0 += wk * v.x; a1 += wk * v.y; a2 += wk * v.z;
         }
       }
-      tmp[r * tstride + f] = a;
+      inter[r * ps + ox] = make_float4(a0, a1, a2, 0.0f);
     }
   }
   __syncthreads();
-  for (int f = threadIdx.x; f < P3; f += blockDim.x) {
-    const int px = f / 3, c = f - px * 3;
-    const int2 rng = s_inv[px];
-    float a[kBwdChunk];
+  const int P3 = P * 3;
+  for (int idx = threadIdx.x; idx < rows * P; idx += blockDim.x) {  // columns pass
+    const int r = idx / P, px = idx - r * P;
+    const int2 sc = s_st[px];
+    const float* w = s_wt + px * tcap;
+    const float4* irow = inter + r * ps;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+    if (TK > 0) {
 #pragma unroll
-    for (int r = 0; r < kBwdChunk; ++r) a[r] = 0.0f;
-    for (int ox = rng.x; ox <= rng.y; ++ox) {
-      const int kk = px - s_st[ox];
-      if (kk < 0 || kk >= span) continue;
-      const float w = s_w[ox * span + kk];
-      const float* tp = tmp + ox * 3 + c;
-#pragma unroll
-      for (int r = 0; r < kBwdChunk; ++r) a[r] += w * tp[r * tstride];
+      for (int k = 0; k < NT; ++k) {
+        const float4 v = irow[min(sc.x + k, ps - 1)];
+        const float wk = w[k];
+        a0 += wk * v.x; a1 += wk * v.y; a2 += wk * v.z;
+      }
+    } else {
+      for (int k = 0; k < sc.y; ++k) {
+        const float4 v = irow[sc.x + k];
+        const float wk = w[k];
+        a0 += wk * v.x; a1 += wk * v.y; a2 += wk * v.z;
+      }
     }
-#pragma unroll
-    for (int r = 0; r < kBwdChunk; ++r)
-      if (r < crow) gbox[(size_t)(py0 + r) * P3 + f] = a[r];
+    float* o = gbox + (size_t)(py0 + r) * P3 + px * 3;
+    o[0] = a0; o[1] = a1; o[2] = a2;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 3) k_bwd_resize3(EotShape s, Layout L, char* ws) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ int2 s_base[kMaxBaseSmem];
+  __shared__ int2 s_item;
+  const int P = s.patch_size, P3 = P * 3;
+  const int inter_texels = max(2560, L.lmin);                      // rows * ps <= 2560 unless a single row is longer
+  float4* inter = reinterpret_cast<float4*>(smem);                // [rows][ps]
+  int2* s_st = reinterpret_cast<int2*>(smem + (size_t)inter_texels * 4);   // [P+1]
+  float* s_wt = reinterpret_cast<float*>(s_st + (P + 1));          // [P][tstride]
+  const int2* base = stage_base(reinterpret_cast<const int2*>(ws + L.off_base), s.total_boxes, s_base);
+  const int n_items = base[s.total_boxes].y;
+  for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    if (threadIdx.x == 0) s_item = find_item(base, s.total_boxes, 1, it);
+    __syncthreads();
+    const int j = s_item.x;
+    const BoxPlan* pl = reinterpret_cast<const BoxPlan*>(ws + L.off_plans) + j;
+    const int ps = pl->ps;
+    const int2* stt = reinterpret_cast<const int2*>(ws + L.off_stt) + (size_t)j * (P + 1);
+    for (int i = threadIdx.x; i <= P; i += blockDim.x) s_st[i] = stt[i];
+    __syncthreads();
+    const int tstride = s_st[P].x, RR = s_st[P].y;
+    const int py0 = s_item.y * RR;
+    const int rows = min(RR, P - py0);
+    const float* wt = reinterpret_cast<const float*>(ws + L.off_wt) + (size_t)j * P * L.tcap;
+    const float4* gu = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ws + L.off_gu) + (size_t)j * L.gslot);
+    float* gbox = reinterpret_cast<float*>(ws + L.off_gbox) + (size_t)j * P * P3;
+    for (int i = threadIdx.x; i < P * tstride; i += blockDim.x) s_wt[i] = wt[i];
+    __syncthreads();
+    if (tstride == 3) bwd_resize_passes<3>(P, ps, tstride, py0, rows, gu, s_wt, s_st, inter, gbox);
+    else if (tstride == 4) bwd_resize_passes<4>(P, ps, tstride, py0, rows, gu, s_wt, s_st, inter, gbox);
+    else if (tstride == 5) bwd_resize_passes<5>(P, ps, tstride, py0, rows, gu, s_wt, s_st, inter, gbox);
+    else if (tstride == 6) bwd_resize_passes<6>(P, ps, tstride, py0, rows, gu, s_wt, s_st, inter, gbox);
+    else bwd_resize_passes<0>(P, ps, tstride, py0, rows, gu, s_wt, s_st, inter, gbox);
+    __syncthreads();
   }
 }
 
@@ -411,10 +425,10 @@ extern "C" int eot_apply_bwd(const EotShape* shape, const float* patch, const fl
   const int nsm = sm_count();
   k_bwd_window<<<nsm * 8, kThreads, 0, st>>>(s, L, ws, grad_images);
   if (L.use_gbox) {
-    const size_t smem2 = bwd_resize2_smem_bytes(s, L);
+    const size_t smem2 = bwd_resize3_smem_bytes(s, L);
     if (smem2 > 200 * 1024) { set_error("eot_apply_bwd: shared-memory tile too large (L=%d)", L.lmin); return EOT_ERR_BAD_SHAPE; }
-    if (smem2 > 48 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_bwd_resize2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    k_bwd_resize2<<<dim3((P + kBwdChunk - 1) / kBwdChunk, s.total_boxes), kThreads, smem2, st>>>(s, L, ws);
+    if (smem2 > 32 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_bwd_resize3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    k_bwd_resize3<<<nsm * 3, kThreads, smem2, st>>>(s, L, ws);
     const int mchunks = max(1, min((PP + kThreads - 1) / kThreads, 64));
     k_bwd_match<<<dim3(mchunks, B), kThreads, 0, st>>>(s, L, ws, patch, print_wb, offsets);
     count_launches(1);

@@ -66,9 +66,13 @@ struct Layout {
   size_t off_match;        // float[B][P*P*3]
   size_t off_u;            // float4[N][slot/4]: (ps+4)^2 texels per box = clipped (r,g,b) of the transformed patch +
                            //            inner-clip pass bits, inside a two-texel ring of the -2 pad / fill value
-  size_t off_cnt;          // int2[N]    work items of box j: (resize strips, composite row blocks); 0 when invalid
+  size_t off_cnt;          // int2[N]    work items of box j: (forward resize strips, backward resize strips); 0 when invalid
   size_t off_base;         // int2[N+1]  exclusive prefix sums of off_cnt (box order == image order)
   size_t off_inv;          // int2[N][P]  for patch index i: first/last output index whose span holds i
+  size_t off_wt;           // float[N][P*tcap] transposed resize weights, row stride = the box's own max tap count:
+                           //              tap k of patch index i = weight of output index st+k
+  size_t off_stt;          // int2[N][P+1] (first output index, tap count) of patch index i (clamped into [0, ps));
+                           //              entry P = (max tap count, patch rows per backward strip)
   size_t off_route;        // uint8[N][rslot] per window pixel: bit c = channel c of the output came from this box (and passes the clip)
   size_t off_gm;           // float[B][P*P*3] backward: dL/d(matched patch) per image
   size_t off_gu;           // float[N][gslot]  backward: dL/d(u) per box
@@ -77,7 +81,8 @@ struct Layout {
   size_t off_offsets;      // int32[B+1] copy of the CSR row splits (the backward has no other source)
   size_t total;
   int64_t slot;            // floats per u slot (4 per texel)
-  int64_t gslot;           // floats per g_u slot (3 per texel)
+  int64_t gslot;           // floats per g_u slot (RGBX: 4 per texel)
+  int32_t tcap;            // taps per patch index in the transposed weight table
   int32_t wcap;            // floats per weight table
   int32_t lmin;            // max patch side
   int32_t resize_rows;     // output rows per resize work item (bounded by shared memory: rows * P * 12 B)
@@ -98,7 +103,8 @@ __host__ __device__ inline Layout make_layout(const EotShape& s) {
   L.lmin = lmin;
   L.wcap = 2 * s.patch_size + 3 * lmin + 8;
   L.slot = (int64_t)align_up((size_t)(lmin + 4) * (lmin + 4) * 4, 32);
-  L.gslot = (int64_t)align_up((size_t)lmin * lmin * 3, 32);
+  L.gslot = (int64_t)align_up((size_t)lmin * lmin * 4, 32);
+  L.tcap = 3 * ((lmin + s.patch_size - 1) / s.patch_size) + 3;
   int rr = 2560 / s.patch_size;              // <= 40 KB of RGBX float32 intermediate rows
   L.resize_rows = rr > 16 ? 16 : (rr < 1 ? 1 : rr);
   L.p3_magic = (uint32_t)((((uint64_t)1 << 32) + (uint64_t)(s.patch_size * 3) - 1) / (uint64_t)(s.patch_size * 3));
@@ -119,6 +125,8 @@ __host__ __device__ inline Layout make_layout(const EotShape& s) {
   L.off_cnt = o;          o = align_up(o + N * 8, 256);
   L.off_base = o;         o = align_up(o + (N + 1) * 8, 256);
   L.off_inv = o;          o = align_up(o + N * (size_t)s.patch_size * 8, 256);
+  L.off_wt = o;           o = align_up(o + N * (size_t)s.patch_size * L.tcap * sizeof(float), 256);
+  L.off_stt = o;          o = align_up(o + N * (size_t)(s.patch_size + 1) * 8, 256);
   L.rslot = (int64_t)align_up((size_t)lfull * lfull, 32);
   L.off_route = o;        o = align_up(o + N * (size_t)L.rslot, 256);
   L.off_gm = o;           o = align_up(o + B * PP3 * sizeof(float), 256);
@@ -129,6 +137,12 @@ __host__ __device__ inline Layout make_layout(const EotShape& s) {
   L.off_offsets = o;      o = align_up(o + (B + 1) * sizeof(int32_t), 256);
   L.total = o;
   return L;
+}
+
+// patch rows per strip of the backward resize adjoint: <= 40 KB of RGBX intermediate rows of ps texels
+__host__ __device__ inline int bwd_strip_rows(int ps) {
+  int rr = 2560 / (ps > 0 ? ps : 1);
+  return rr > 32 ? 32 : (rr < 1 ? 1 : rr);
 }
 
 // ---- error plumbing (host) -------------------------------------------------------------------------

@@ -14,6 +14,7 @@
 #include "eot_common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace eot {
 
@@ -152,8 +153,10 @@ __device__ int geometry_block(const EotShape& s, const Layout& L, int j, const f
                                const int32_t* __restrict__ offsets, const EotBoxParams* __restrict__ params,
                                const float* __restrict__ scale, char* ws, EotBoxGeometry* geom_out) {
   __shared__ BoxPlan spl;
+  __shared__ int s_maxcnt;
   int* counters = ws ? reinterpret_cast<int*>(ws + L.off_counters) : nullptr;
   if (threadIdx.x == 0) {
+    s_maxcnt = 0;
     int a = 0, b = s.batch;                       // image of box j: last b with offsets[b] <= j
     while (a < b) { const int m = (a + b) >> 1; if (offsets[m + 1] <= j) a = m + 1; else b = m; }
     BoxPlan pl = make_plan(boxes + (size_t)j * 4, *scale, params[j], s, a, offsets[a], offsets[a + 1],
@@ -180,7 +183,39 @@ __device__ int geometry_block(const EotShape& s, const Layout& L, int j, const f
   for (int o = threadIdx.x; o < ps; o += blockDim.x) span_row(o, cfg, P, starts + o, weights + (size_t)o * cfg.span);
   __syncthreads();                                  // starts[] of this box are complete
   int2* inv = reinterpret_cast<int2*>(ws + L.off_inv) + (size_t)j * P;
-  for (int i = threadIdx.x; i < P; i += blockDim.x) inv[i] = inverse_span_search(starts, ps, cfg.span, i);
+  float* wt = reinterpret_cast<float*>(ws + L.off_wt) + (size_t)j * P * L.tcap;
+  int2* stt = reinterpret_cast<int2*>(ws + L.off_stt) + (size_t)j * (P + 1);
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    const int2 rng = inverse_span_search(starts, ps, cfg.span, i);
+    inv[i] = rng;
+    int cnt = rng.y - rng.x + 1;
+    if (cnt < 0) cnt = 0;
+    if (cnt > L.tcap) { cnt = L.tcap; if (counters) atomicExch(counters + 2, 4); }
+    stt[i] = make_int2(min(max(rng.x, 0), ps - 1), cnt);
+    atomicMax(&s_maxcnt, cnt);
+  }
+  __syncthreads();
+  // transposed weights (ScaleAndTranslateGrad = scatter of the same weights): row i of W^T, dense from rng.x, row
+  // stride = the largest tap count of this box
+  const int tstride = max(s_maxcnt, 1);
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    const int2 rng = inv[i];
+    const int cnt = stt[i].y;
+    for (int k = 0; k < tstride; ++k) {
+      const int o = rng.x + k;
+      float w = 0.0f;
+      if (k < cnt) {
+        const int kk = i - starts[o];
+        if (kk >= 0 && kk < cfg.span) w = weights[(size_t)o * cfg.span + kk];
+      }
+      wt[(size_t)i * tstride + k] = w;
+    }
+  }
+  if (threadIdx.x == 0) {
+    const int rows = bwd_strip_rows(ps);
+    stt[P] = make_int2(tstride, rows);
+    reinterpret_cast<int2*>(ws + L.off_cnt)[j].y = (P + rows - 1) / rows;   // backward resize strips of this box
+  }
   // route map of the box starts all-zero; the composite only writes the non-zero bytes
   uint4* rz = reinterpret_cast<uint4*>(ws + L.off_route + (size_t)j * L.rslot);
   const int n16 = (spl.d * spl.d + 15) / 16;
@@ -907,6 +942,7 @@ struct FusedPlan {
   int pass_tickets;                                // image-pass tickets per image
   int slot;                                        // tickets per slot
   int total_tickets;
+  int lag;                                         // images between dependent stages in the ticket order
 };
 
 __device__ __forceinline__ void signal_counter(int* ctr, int n = 1) {
@@ -981,9 +1017,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_forward_fused(EotShape s, Layou
     }
     r -= fp.pass_tickets;
     int stage, w;                                                 // 1 match, 2 resize, 3 composite ; image w
-    if (r < fp.mp) { stage = 1; w = slot - 1; }
-    else if (r < fp.mp + kFusedNPR) { stage = 2; w = slot - 2; r -= fp.mp; }
-    else { stage = 3; w = slot - 3; r -= fp.mp + kFusedNPR; }
+    if (r < fp.mp) { stage = 1; w = slot - fp.lag; }
+    else if (r < fp.mp + kFusedNPR) { stage = 2; w = slot - 2 * fp.lag; r -= fp.mp; }
+    else { stage = 3; w = slot - 3 * fp.lag; r -= fp.mp + kFusedNPR; }
     if (w < 0 || w >= B) continue;
     const int first = offsets[w], nb_all = offsets[w + 1] - first;
     if (stage == 1) {
@@ -1129,7 +1165,12 @@ static int launch_forward(const EotShape& s, const Layout& L, const float* patch
     fp.mp = max(1, (P * P + 4095) / 4096);
     fp.pass_tickets = (cpi + kPassChunksPerTicket - 1) / kPassChunksPerTicket;
     fp.slot = fp.pass_tickets + fp.mp + kFusedNPR + kFusedNPC;
-    const long long tickets = (long long)N + (long long)B * pchunks + (long long)(B + kFusedStages - 1) * fp.slot;
+    {
+      const char* e = getenv("EOT_FUSED_LAG");                    // tuning knob (images between dependent stages)
+      fp.lag = e ? atoi(e) : 8;
+      if (fp.lag < 1) fp.lag = 1;
+    }
+    const long long tickets = (long long)N + (long long)B * pchunks + (long long)(B + (kFusedStages - 1) * fp.lag) * fp.slot;
     if (tickets >= (1ll << 31)) { set_error("eot_apply_fwd: too many work tickets"); return EOT_ERR_BAD_SHAPE; }
     fp.total_tickets = (int)tickets;
     const size_t dsm = max(smem, (size_t)256 * sizeof(int2));

@@ -23,6 +23,7 @@ ap.add_argument("--what", default="fwd,bwd,score")
 ap.add_argument("--max-boxes", type=int, default=8)
 ap.add_argument("--time", action="store_true")
 ap.add_argument("--overlap", type=int, default=0, help="chunks of the two-stream forward (0 = single stream)")
+ap.add_argument("--fused", action="store_true", help="single persistent launch for the whole forward")
 args = ap.parse_args()
 B, H, P = args.batch, args.image, args.patch
 dev = "cuda"
@@ -34,7 +35,8 @@ patch = torch.from_numpy(synth.make_patch(P)).to(dev)
 scale = torch.tensor(0.4, device=dev)
 out = torch.empty_like(images)
 aux = torch.cuda.Stream() if args.overlap else None
-_, _, ctx = ops.apply_forward(patch, scale, images, boxes, offsets, params, wb, out=out)
+geo = ops.PatchGeometry(fused=args.fused)
+_, _, ctx = ops.apply_forward(patch, scale, images, boxes, offsets, params, wb, geo, out=out)
 G = torch.randn_like(images)
 gp = torch.empty_like(patch)
 what = args.what.split(",")
@@ -52,7 +54,7 @@ state = {}
 def one():
     res = {}
     if "fwd" in what:
-        ops.apply_forward(patch, scale, images, boxes, offsets, params, wb, out=out, workspace=ctx.workspace,
+        ops.apply_forward(patch, scale, images, boxes, offsets, params, wb, geo, out=out, workspace=ctx.workspace,
                           aux_stream=aux, chunks=args.overlap)
     if "bwd" in what:
         ops.apply_backward(ctx, G, grad_patch=gp)
