@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-first-pass", action="store_true", help="skip the clean victim pass (NOT the headline)")
+    ap.add_argument("--launch-list", action="store_true",
+                    help="profiling aid (ncu launch lists): 1 warm-up + the timed steps only, prints no bench line")
     return ap.parse_args()
 
 
@@ -56,7 +58,8 @@ def workload_config(args, n_gpus):
                         f"{args.patch}x{args.patch} patch, 1-{args.max_boxes} boxes/img, affine EOT"
                         + (" + projective row" if args.perspective > 0 else ""),
             "global_batch": args.batch * n_gpus, "per_gpu_batch": args.batch, "image": args.image, "patch": args.patch,
-            "victim": args.victim + " (random init, torch/cuDNN stand-in for the Keras model)",
+            "victim": args.victim + " (random init, torch/cuDNN stand-in for the Keras model; inference BatchNorm folded "
+                                    "into the convs; cuDNN convs at the framework's default TF32 setting, as TF 2.8)",
             "parallelism": f"dp{n_gpus}", "first_pass_included": not args.no_first_pass,
             "l2": "inputs larger than L2 (images %.0f MB/GPU > 126 MB)" % (args.batch * args.image ** 2 * 12 / 1e6)}
 
@@ -195,6 +198,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.launch_list:                       # under ncu: the numbers of this mode are never bench values
+        step()
+        torch.cuda.synchronize()
+        for _ in range(args.steps):
+            step()
+        torch.cuda.synchronize()
+        return
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
