@@ -115,3 +115,19 @@ def test_tv_grad_and_adam_clip():
         v64 = np.clip(v64 - m64 * alpha / (np.sqrt(s64) + 1e-7), -1, 1)
     torch.cuda.synchronize()
     np.testing.assert_allclose(var.cpu().numpy(), v64, atol=2e-6)
+
+
+def test_backward_many_mutually_overlapping_boxes():
+    bt = synth.make_batch(2, 192, 192, seed=72, max_boxes=14, min_boxes=14)
+    rng = np.random.default_rng(72)
+    for j in range(bt.offsets[0], bt.offsets[1]):
+        cy, cx = rng.uniform(70, 120, 2)
+        h, w = rng.uniform(60, 130), rng.uniform(30, 70)
+        bt.boxes[j] = [max(cy - h / 2, 0), max(cx - w / 2, 0), min(cy + h / 2, 192), min(cx + w / 2, 192)]
+    _check_backward(bt, synth.make_patch(36, seed=72), 0.4, 72)
+
+
+def test_backward_out_of_range_image():
+    bt = synth.make_batch(3, 160, 160, seed=71, max_boxes=3, min_boxes=1)
+    bt.images[0] *= F(1.6)
+    _check_backward(bt, synth.make_patch(40, seed=71), 0.4, 71)

@@ -183,3 +183,33 @@ def test_forward_fused_and_unfused_paths_are_identical():
     ops.check_workspace(ctx_f)
     G = torch.randn_like(fused)
     assert torch.equal(ops.apply_backward(ctx_f, G), ops.apply_backward(ctx_u, G))
+
+
+def test_forward_out_of_range_image_clips_whole_window():
+    # attacker.py:441 clips the WHOLE d x d window, background included; pixels outside every window keep values > 1
+    bt = synth.make_batch(3, 160, 160, seed=71, max_boxes=3, min_boxes=1)
+    bt.images[0] *= F(1.6)
+    bt.images[2, :40] = F(-1.3)
+    got = _check_forward(bt, synth.make_patch(40, seed=71), 0.4)
+    assert np.abs(got[0]).max() > 1.0          # untouched background outside the windows
+    assert np.abs(got[1]).max() <= 1.0
+
+
+def test_forward_many_mutually_overlapping_boxes():
+    # 14 boxes crowded into one image: every pixel sees several windows; the last paste must win per channel
+    bt = synth.make_batch(2, 192, 192, seed=72, max_boxes=14, min_boxes=14)
+    rng = np.random.default_rng(72)
+    for j in range(bt.offsets[0], bt.offsets[1]):
+        cy, cx = rng.uniform(70, 120, 2)
+        h, w = rng.uniform(60, 130), rng.uniform(30, 70)
+        bt.boxes[j] = [max(cy - h / 2, 0), max(cx - w / 2, 0), min(cy + h / 2, 192), min(cx + w / 2, 192)]
+    _check_forward(bt, synth.make_patch(36, seed=72), 0.4)
+
+
+def test_masker_mask_with_overlapping_windows():
+    # mask = original - pasted over the union of the windows (attack_detection.py:429-430), later pastes on top
+    bt = synth.make_batch(2, 160, 160, seed=73, max_boxes=3, min_boxes=3)
+    for b in range(2):
+        bt.boxes[bt.offsets[b] + 1] = bt.boxes[bt.offsets[b]] + F(6.0)
+    bt.boxes = np.clip(bt.boxes, 0, 160).astype(F)
+    _check_forward(bt, synth.make_patch(32, seed=73), 0.4, geom=ops.PatchGeometry(tolerance=0.5, noise_amp=0.1), want_mask=True)
