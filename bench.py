@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-first-pass", action="store_true", help="skip the clean victim pass (NOT the headline)")
+    ap.add_argument("--no-graphs", action="store_true", help="launch the victim passes kernel by kernel (no CUDA graphs)")
     ap.add_argument("--launch-list", action="store_true",
                     help="profiling aid (ncu launch lists): 1 warm-up + the timed steps only, prints no bench line")
     return ap.parse_args()
@@ -61,6 +62,7 @@ def workload_config(args, n_gpus):
             "victim": args.victim + " (random init, torch/cuDNN stand-in for the Keras model; inference BatchNorm folded "
                                     "into the convs; cuDNN convs at the framework's default TF32 setting, as TF 2.8)",
             "parallelism": f"dp{n_gpus}", "first_pass_included": not args.no_first_pass,
+            "cuda_graphs": "victim passes (clean forward+score; attacked forward+score+objective grad+backward)" if not args.no_graphs else "off",
             "l2": "inputs larger than L2 (images %.0f MB/GPU > 126 MB)" % (args.batch * args.image ** 2 * 12 / 1e6)}
 
 
@@ -182,7 +184,8 @@ def run_ours(args):
 
     B, H, P = args.batch, args.image, args.patch
     model = victim.get_victim_model(args.victim, device=dev, image_size=H)
-    attacker = PatchAttacker(model, patch_size=P, device=dev, seed=7, perspective=args.perspective)
+    attacker = PatchAttacker(model, patch_size=P, device=dev, seed=7, perspective=args.perspective,
+                             cuda_graphs=not args.no_graphs)
     attacker.compile(learning_rate=1e-2)
     attacker.always_first_pass = not args.no_first_pass
     attacker._patcher.first_image = rank * B

@@ -76,7 +76,8 @@ class PatchAttacker:
     """attack with malicious patches (reference: attacker.py:24)."""
 
     def __init__(self, model, initial_patch=None, config_override=None, visualize_freq=200, *,
-                 patch_size: int = 640, device=None, seed: int = 0, process_group=None, perspective: float = 0.0):
+                 patch_size: int = 640, device=None, seed: int = 0, process_group=None, perspective: float = 0.0,
+                 cuda_graphs: bool = False):
         self.model = model
         self.config = model.config
         if config_override:
@@ -104,6 +105,11 @@ class PatchAttacker:
         self._adam_v = torch.zeros(n, dtype=torch.float32, device=self.device)
         self._anchors = None
         self.metrics = {}
+        # CUDA graphs of the two fixed-shape victim passes (clean forward + score; attacked forward + score +
+        # objective gradient + victim backward): the ~2000 framework launches of a step become two replays.
+        # The patcher itself stays outside (its box count changes from step to step).
+        self.cuda_graphs = bool(cuda_graphs)
+        self._graphs = None
 
     # -- Keras-like surface ------------------------------------------------------------------------
     def compile(self, optimizer=None, learning_rate: Optional[float] = None, run_eagerly=False):
@@ -146,9 +152,64 @@ class PatchAttacker:
         cls_outputs, box_outputs, M, argmax, ncand, ctx = self._score(images)
         return cls_outputs, M, argmax, ncand, ctx
 
+    # -- CUDA-graph replay of the victim passes ------------------------------------------------------
+    def _build_graphs(self, images: torch.Tensor):
+        dev = images.device
+        g = dict(shape=tuple(images.shape))
+        g["clean_in"] = torch.empty_like(images)
+        g["patched"] = torch.empty_like(images).requires_grad_(True)
+        g["clean_in"].copy_(images)
+        with torch.no_grad():
+            g["patched"].copy_(images)
+        torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)   # the capture stream differs by design
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):                                   # warm-up: cuDNN algorithm search, lazy allocations
+                with torch.no_grad():
+                    self._score(g["clean_in"])
+                cls_outputs, M, argmax, ncand, sctx = self.second_pass(g["patched"])
+                dcls, dscale, data_loss = ops.score_max_backward(sctx, self._scale_regressor)
+                torch.autograd.backward(cls_outputs, dcls)
+                g["patched"].grad = None
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g1 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1):
+            with torch.no_grad():
+                c_cls, c_box, _, _, _, c_ctx = self._score(g["clean_in"])
+        g["g1"], g["clean_box"], g["clean_ctx"] = g1, c_box, c_ctx
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g2):
+            cls_outputs, M, argmax, ncand, sctx = self.second_pass(g["patched"])
+            dcls, dscale, data_loss = ops.score_max_backward(sctx, self._scale_regressor)
+            torch.autograd.backward(cls_outputs, dcls)
+        g.update(g2=g2, M=M, argmax=argmax, ncand=ncand, dscale=dscale, data_loss=data_loss, grad=g["patched"].grad)
+        self._graphs = g
+
+    def _call_graphed(self, images: torch.Tensor, boxes, transforms):
+        if self._graphs is None or self._graphs["shape"] != tuple(images.shape):
+            self._build_graphs(images)
+        g = self._graphs
+        if boxes is None or self.always_first_pass:
+            from . import postprocess
+            g["clean_in"].copy_(images)
+            g["g1"].replay()
+            det_boxes, _ = postprocess.person_boxes_after_nms(self.config, g["clean_ctx"], g["clean_box"],
+                                                              self._anchor_table(images), images.shape[1:3], thresh=True)
+            if boxes is None:
+                boxes = det_boxes
+        self._patcher([boxes, images], transforms=transforms, out=g["patched"].detach())
+        g["g2"].replay()
+        grad_patch = self._patcher.backward(g["grad"])
+        self._last = dict(max_scores=g["M"], data_loss=g["data_loss"], dscale=g["dscale"], ncand=g["ncand"])
+        return [g["dscale"], grad_patch]
+
     def call(self, images: torch.Tensor, *, training=True, boxes: Optional[RaggedBoxes] = None, transforms=None):
         """called on each batch (attacker.py:172-219).  Returns [dL/dscale, dL/dpatch] when training, else
         (max_scores, argmax_anchor).  `boxes` overrides the first pass' detections (synthetic benchmarks)."""
+        if training and self.cuda_graphs:
+            return self._call_graphed(images, boxes, transforms)
         det_boxes, _ = self.first_pass(images) if boxes is None or self.always_first_pass else (None, None)
         if boxes is None:
             boxes = det_boxes

@@ -153,3 +153,26 @@ def test_save_and_resume_weights_roundtrip():
     assert torch.equal(att2._patch, att._patch) and abs(float(att2._scale_regressor) - 0.4) < 1e-7
     with pytest.raises(FileExistsError):
         att.save_weights(d)                                     # os.makedirs without exist_ok (attacker.py:334)
+
+
+def test_cuda_graph_replay_equals_eager_step(no_tf32):
+    H, P, B = 128, 32, 3
+    model = victim.get_victim_model("efficientdet-d0", device="cuda", image_size=H, seed=5)
+    model.class_net.out_pw.bias.data.view(9, 90)[:, 0] += 6.0
+    bt = synth.make_batch(B, H, H, seed=79, max_boxes=3, min_boxes=1)
+    images = torch.from_numpy(bt.images).cuda()
+    boxes = RaggedBoxes(torch.from_numpy(bt.boxes).cuda(), torch.from_numpy(bt.offsets).cuda())
+    tr = (ops.params_to_tensor(bt.params, "cuda"), torch.from_numpy(bt.print_wb).cuda())
+    res = []
+    for graphs in (False, True):
+        att = PatchAttacker(model, patch_size=P, device="cuda", seed=3, cuda_graphs=graphs)
+        att.compile(learning_rate=1e-2)
+        for _ in range(3):                                  # several steps: the replayed graph must see the updated patch / scale
+            m = att.train_step(images, boxes=boxes, transforms=tr)
+        torch.cuda.synchronize()
+        res.append((att._patch.clone(), float(att._scale_regressor), float(m["loss"])))
+    # cuDNN picks algorithms independently for the two runs: equal up to float32 reduction order
+    assert torch.allclose(res[0][0], res[1][0], atol=2e-3)
+    assert (res[0][0] - res[1][0]).abs().mean() < 2e-4
+    assert abs(res[0][1] - res[1][1]) < 1e-4
+    assert abs(res[0][2] - res[1][2]) < 1e-3 * max(1.0, abs(res[0][2]))
