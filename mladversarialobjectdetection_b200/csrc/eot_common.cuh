@@ -33,7 +33,16 @@ namespace eot {
 #define EOT_C255_127 ((float)(255.0 / 127.0))   // brightness_matcher.py:41
 #define EOT_SQRT2 1.41421354f                   // float32(2. ** .5), attacker.py:470
 
-constexpr int kCompRows = 16;         // image rows per composite work item (one CTA: 8 warps x 2 rows)
+#ifndef EOT_COMP_ROWS
+#define EOT_COMP_ROWS 8
+#endif
+#ifndef EOT_RESIZE_ROWS_CAP
+#define EOT_RESIZE_ROWS_CAP 16
+#endif
+#ifndef EOT_BWD_ROWS_CAP
+#define EOT_BWD_ROWS_CAP 32
+#endif
+constexpr int kCompRows = EOT_COMP_ROWS;  // image rows per composite work item (one CTA: a warp per row)
 constexpr int kThreads = 256;
 
 // Per-box plan written by the geometry kernel; 128 bytes.
@@ -106,7 +115,7 @@ __host__ __device__ inline Layout make_layout(const EotShape& s) {
   L.gslot = (int64_t)align_up((size_t)lmin * lmin * 4, 32);
   L.tcap = 3 * ((lmin + s.patch_size - 1) / s.patch_size) + 3;
   int rr = 2560 / s.patch_size;              // <= 40 KB of RGBX float32 intermediate rows
-  L.resize_rows = rr > 16 ? 16 : (rr < 1 ? 1 : rr);
+  L.resize_rows = rr > EOT_RESIZE_ROWS_CAP ? EOT_RESIZE_ROWS_CAP : (rr < 1 ? 1 : rr);
   L.p3_magic = (uint32_t)((((uint64_t)1 << 32) + (uint64_t)(s.patch_size * 3) - 1) / (uint64_t)(s.patch_size * 3));
   const size_t PP3 = (size_t)s.patch_size * s.patch_size * 3;
   size_t o = 0;
@@ -142,7 +151,7 @@ __host__ __device__ inline Layout make_layout(const EotShape& s) {
 // patch rows per strip of the backward resize adjoint: <= 40 KB of RGBX intermediate rows of ps texels
 __host__ __device__ inline int bwd_strip_rows(int ps) {
   int rr = 2560 / (ps > 0 ? ps : 1);
-  return rr > 32 ? 32 : (rr < 1 ? 1 : rr);
+  return rr > EOT_BWD_ROWS_CAP ? EOT_BWD_ROWS_CAP : (rr < 1 ? 1 : rr);
 }
 
 // ---- error plumbing (host) -------------------------------------------------------------------------

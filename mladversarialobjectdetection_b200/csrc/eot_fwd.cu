@@ -318,7 +318,10 @@ __device__ void patch_stats_block(const EotShape& s, int b, int chunk, int nchun
 // image pass: out = image (128-bit loads/stores, 4 pixels = 3 x float4 per thread per step) and
 // sum of Y over the image (brightness_matcher.py:55,59,62,64) in float64.
 // ------------------------------------------------------------------------------------------------
-constexpr int kPassPixPerThread = 16;   // 4 steps of 4 pixels
+#ifndef EOT_PASS_PIX
+#define EOT_PASS_PIX 16
+#endif
+constexpr int kPassPixPerThread = EOT_PASS_PIX;   // batches of 2 x 4 pixels
 constexpr int kPassPixPerBlock = kThreads * kPassPixPerThread;
 
 __device__ __forceinline__ float luma_of(float r, float g, float b) {
@@ -342,7 +345,7 @@ __device__ __forceinline__ void image_pass_block(int HW, int b, int chunk, const
     float4* m4 = reinterpret_cast<float4*>(mk);
     // two batches of 2 x (3 x float4): 96 bytes per thread in flight per batch, modest register footprint
 #pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
+    for (int half = 0; half < kPassPixPerThread / 8; ++half) {
       float4 v[2][3];
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
