@@ -21,18 +21,18 @@ namespace eot {
 constexpr int kBwdGroups = 16;   // image groups of k_bwd_texel
 constexpr int kBwdChunk = 8;     // patch rows per tap fetch in k_bwd_resize
 
-// gradient that reaches R_j at window pixel (xi, yi) of a box, 3 channels: the route byte says which
-// channels of the pasted pixel came from this box (SelectV2), passed the outer clip and were not
-// overwritten by a later paste (TensorScatterUpdate grad).
-__device__ __forceinline__ void routed_grad3(const uint8_t* __restrict__ route, const float* __restrict__ Gwin, int D, int W,
-                                             int xi, int yi, float g[3]) {
-  const unsigned bits = route[yi * D + xi];
+// gradient that reaches R_j at a window pixel of a box, 3 channels: the route byte says which channels of the pasted
+// pixel came from this box (SelectV2), passed the outer clip and were not overwritten by a later paste
+// (TensorScatterUpdate grad).  `px` = pixel index inside the image plane window (32-bit: H*W*3 < 2^31 is checked).
+__device__ __forceinline__ void routed_grad3(const uint8_t* __restrict__ route, const float* __restrict__ Gwin, int rt, int px,
+                                             float g[3]) {
+  const unsigned bits = route[rt];
   g[0] = g[1] = g[2] = 0.0f;
   if (!bits) return;
-  const float* gp = Gwin + ((size_t)yi * W + xi) * 3;
-#pragma unroll
-  for (int c = 0; c < 3; ++c)
-    if ((bits >> c) & 1u) g[c] = __ldg(gp + c);
+  const float* gp = Gwin + px * 3;
+  if (bits & 1u) g[0] = __ldg(gp);
+  if (bits & 2u) g[1] = __ldg(gp + 1);
+  if (bits & 4u) g[2] = __ldg(gp + 2);
 }
 
 __global__ void __launch_bounds__(kThreads) k_bwd_window(EotShape s, Layout L, char* ws, const float* __restrict__ G) {
@@ -52,46 +52,61 @@ __global__ void __launch_bounds__(kThreads) k_bwd_window(EotShape s, Layout L, c
     const BoxPlan me = plans[j];
     const int ps = me.ps, D = me.d;
     const float4* u4 = reinterpret_cast<const float4*>(ubuf + me.u_off);
-    float* gu = gubuf + (size_t)j * L.gslot;
+    float4* gu = reinterpret_cast<float4*>(gubuf + (size_t)j * L.gslot);
     const uint8_t* route = routes + (size_t)j * L.rslot;
     const float* Gwin = G + (((size_t)me.image * H + me.y0) * W + me.x0) * 3;
     const int oy0 = item.y * RR;
     const int rows = min(RR, ps - oy0);
     const bool affine = (me.Ti[6] == 0.0f && me.Ti[7] == 0.0f);
-    const float Df = (float)D;
+    const float Dm1 = (float)(D - 1);
+    const int S = u_stride(ps);
     for (int r = warp; r < rows; r += kThreads / 32) {
       const int ty = oy0 + r;
       const float yf = (float)(ty + me.pad_lo);
+      const float cx = me.Ti[1] * yf, cy = me.Ti[4] * yf, cp = me.Ti[7] * yf;
+      const float4* urow = u4 + (ty + 2) * S + 2;
       for (int tx = lane; tx < ps; tx += 32) {
         const float xf = (float)(tx + me.pad_lo);
         float g[3] = {0.0f, 0.0f, 0.0f};
-        float ix = (me.Ti[0] * xf + me.Ti[1] * yf) + me.Ti[2];
-        float iy = (me.Ti[3] * xf + me.Ti[4] * yf) + me.Ti[5];
+        float ix = (me.Ti[0] * xf + cx) + me.Ti[2];
+        float iy = (me.Ti[3] * xf + cy) + me.Ti[5];
         bool ok = true;
         if (!affine) {
-          const float proj = (me.Ti[6] * xf + me.Ti[7] * yf) + 1.0f;
+          const float proj = (me.Ti[6] * xf + cp) + 1.0f;
           ok = proj != 0.0f;
           if (ok) { ix = ix / proj; iy = iy / proj; }
         }
         if (ok) {
           const float x0f = floorf(ix), y0f = floorf(iy);
-          const float x1f = x0f + 1.0f, y1f = y0f + 1.0f;
-          const bool bx0 = x0f >= 0.0f && x0f < Df, bx1 = x1f >= 0.0f && x1f < Df;
-          const bool by0 = y0f >= 0.0f && y0f < Df, by1 = y1f >= 0.0f && y1f < Df;
-          const int xi0 = (int)x0f, yi0 = (int)y0f;
-          float v00[3] = {0.f, 0.f, 0.f}, v01[3] = {0.f, 0.f, 0.f}, v10[3] = {0.f, 0.f, 0.f}, v11[3] = {0.f, 0.f, 0.f};
-          if (by0 && bx0) routed_grad3(route, Gwin, D, W, xi0, yi0, v00);
-          if (by0 && bx1) routed_grad3(route, Gwin, D, W, xi0 + 1, yi0, v01);
-          if (by1 && bx0) routed_grad3(route, Gwin, D, W, xi0, yi0 + 1, v10);
-          if (by1 && bx1) routed_grad3(route, Gwin, D, W, xi0 + 1, yi0 + 1, v11);
-          const float wx1 = x1f - ix, wx0 = ix - x0f, wy1 = y1f - iy, wy0 = iy - y0f;
+          const float wx0 = ix - x0f, wx1 = (x0f + 1.0f) - ix, wy0 = iy - y0f, wy1 = (y0f + 1.0f) - iy;
+          float v00[3], v01[3], v10[3], v11[3];
+          if (x0f >= 0.0f && x0f < Dm1 && y0f >= 0.0f && y0f < Dm1) {        // all four taps inside the window
+            const int xi0 = (int)x0f, yi0 = (int)y0f;
+            const int rt = yi0 * D + xi0, px = yi0 * W + xi0;
+            routed_grad3(route, Gwin, rt, px, v00);
+            routed_grad3(route, Gwin, rt + 1, px + 1, v01);
+            routed_grad3(route, Gwin, rt + D, px + W, v10);
+            routed_grad3(route, Gwin, rt + D + 1, px + W + 1, v11);
+          } else {
+            const float x1f = x0f + 1.0f, y1f = y0f + 1.0f, Df = (float)D;
+            const bool bx0 = x0f >= 0.0f && x0f < Df, bx1 = x1f >= 0.0f && x1f < Df;
+            const bool by0 = y0f >= 0.0f && y0f < Df, by1 = y1f >= 0.0f && y1f < Df;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v00[c] = v01[c] = v10[c] = v11[c] = 0.0f;
+            if ((bx0 || bx1) && (by0 || by1)) {
+              const int xi0 = (int)x0f, yi0 = (int)y0f;
+              const int rt = yi0 * D + xi0, px = yi0 * W + xi0;
+              if (by0 && bx0) routed_grad3(route, Gwin, rt, px, v00);
+              if (by0 && bx1) routed_grad3(route, Gwin, rt + 1, px + 1, v01);
+              if (by1 && bx0) routed_grad3(route, Gwin, rt + D, px + W, v10);
+              if (by1 && bx1) routed_grad3(route, Gwin, rt + D + 1, px + W + 1, v11);
+            }
+          }
 #pragma unroll
           for (int c = 0; c < 3; ++c) g[c] = wy1 * (wx1 * v00[c] + wx0 * v01[c]) + wy0 * (wx1 * v10[c] + wx0 * v11[c]);
         }
-        const int t = ty * ps + tx;
-        const unsigned bits = __float_as_uint(u4[u_index(ps, ty, tx)].w);  // inner clip pass bits (attacker.py:428)
-        reinterpret_cast<float4*>(gu)[t] = make_float4((bits & 1u) ? g[0] : 0.0f, (bits & 2u) ? g[1] : 0.0f,
-                                                       (bits & 4u) ? g[2] : 0.0f, 0.0f);
+        const unsigned bits = __float_as_uint(urow[tx].w);                 // inner clip pass bits (attacker.py:428)
+        gu[ty * ps + tx] = make_float4((bits & 1u) ? g[0] : 0.0f, (bits & 2u) ? g[1] : 0.0f, (bits & 4u) ? g[2] : 0.0f, 0.0f);
       }
     }
   }

@@ -37,7 +37,7 @@ namespace eot {
 #define EOT_COMP_ROWS 8
 #endif
 #ifndef EOT_RESIZE_ROWS_CAP
-#define EOT_RESIZE_ROWS_CAP 16
+#define EOT_RESIZE_ROWS_CAP 12
 #endif
 #ifndef EOT_BWD_ROWS_CAP
 #define EOT_BWD_ROWS_CAP 32

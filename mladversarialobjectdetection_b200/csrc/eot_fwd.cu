@@ -1198,8 +1198,16 @@ static int launch_forward(const EotShape& s, const Layout& L, const float* patch
   }
   if (chunks > B) chunks = B;
   if (chunks > 16) chunks = 16;
-  cudaEvent_t ev[18];
-  for (int i = 0; i < chunks + 2; ++i) EOT_CHECK_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+  // events are created once per host thread and device and reused (creating them per call costs more than the kernels)
+  struct EventPool { int device = -1; cudaEvent_t ev[18] = {}; };
+  static thread_local EventPool pool;
+  int dev_id = 0;
+  EOT_CHECK_CUDA(cudaGetDevice(&dev_id));
+  if (pool.device != dev_id) {
+    for (int i = 0; i < 18; ++i) EOT_CHECK_CUDA(cudaEventCreateWithFlags(&pool.ev[i], cudaEventDisableTiming));
+    pool.device = dev_id;
+  }
+  cudaEvent_t* ev = pool.ev;
   EOT_CHECK_CUDA(cudaEventRecord(ev[chunks], st));               // memset done
   EOT_CHECK_CUDA(cudaStreamWaitEvent(aux, ev[chunks], 0));
   prepass(aux, N, B, 0, 0);                                       // geometry (+ prefix scan) + patch statistics only
@@ -1217,7 +1225,6 @@ static int launch_forward(const EotShape& s, const Layout& L, const float* patch
   }
   EOT_CHECK_CUDA(cudaEventRecord(ev[chunks + 1], aux));
   EOT_CHECK_CUDA(cudaStreamWaitEvent(st, ev[chunks + 1], 0));
-  for (int i = 0; i < chunks + 2; ++i) cudaEventDestroy(ev[i]);    // released once the recorded work completes
   EOT_CHECK_CUDA(cudaPeekAtLastError());
   return EOT_OK;
 }

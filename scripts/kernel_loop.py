@@ -34,7 +34,7 @@ params, wb = ops.params_to_tensor(bt.params, dev), torch.from_numpy(bt.print_wb)
 patch = torch.from_numpy(synth.make_patch(P)).to(dev)
 scale = torch.tensor(0.4, device=dev)
 out = torch.empty_like(images)
-aux = torch.cuda.Stream() if args.overlap else None
+aux = torch.cuda.Stream(priority=-1) if args.overlap else None
 geo = ops.PatchGeometry(fused=args.fused)
 _, _, ctx = ops.apply_forward(patch, scale, images, boxes, offsets, params, wb, geo, out=out)
 G = torch.randn_like(images)
