@@ -46,7 +46,6 @@ typedef struct EotBoxParams {
 } EotBoxParams;
 
 #define EOT_FLAG_MASK_OUTPUT 1u /* Masker: also write mask = original - pasted (attack_detection.py:429-430) */
-#define EOT_FLAG_FUSED 4u        /* forward: experimental single persistent launch (ticketed dataflow over all stages) */
 #define EOT_FLAG_SERIAL_ADJOINT 2u /* backward: per-image serial resize adjoint (no per-box partial buffer; the
                                      default when that buffer would exceed 1 GiB) */
 
@@ -95,15 +94,6 @@ int eot_apply_fwd(const EotShape* shape, const float* patch, const float* scale,
                   const float* boxes, const int32_t* box_offsets, const EotBoxParams* params,
                   const float* print_wb, float* out_images, float* out_masks, void* workspace,
                   size_t workspace_bytes, void* stream);
-
-/* Same result as eot_apply_fwd, enqueued on two streams: the batch is cut into `chunks` groups of images and the
- * HBM-bound image pass of group c+1 (on `stream`) overlaps the window work of group c (on `aux_stream`).  On return
- * `stream` is ordered after everything (the caller keeps using `stream` only).  Both streams must belong to the
- * current device; `aux_stream` must differ from `stream`. */
-int eot_apply_fwd_overlapped(const EotShape* shape, const float* patch, const float* scale, const float* images,
-                             const float* boxes, const int32_t* box_offsets, const EotBoxParams* params,
-                             const float* print_wb, float* out_images, float* out_masks, void* workspace,
-                             size_t workspace_bytes, void* stream, void* aux_stream, int chunks);
 
 /* `tape.gradient(loss, patch)` through the patcher (attacker.py:217; chain of SURVEY.md 3.2):
  * grad_images = dL/d(out_images) [B,H,W,3]; grad_patch [P,P,3] (shared patch only).

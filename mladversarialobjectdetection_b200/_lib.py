@@ -15,7 +15,7 @@ EOT_FLAG_MASK_OUTPUT = 1
 SCORE_MAX_LEVELS = 8
 
 # every symbol include/eotpatch.h declares (tests check the export list against the header)
-SYMBOLS = ["eot_last_error", "eot_version", "eot_launch_count", "eot_workspace_bytes", "eot_box_geometry", "eot_apply_fwd", "eot_apply_fwd_overlapped",
+SYMBOLS = ["eot_last_error", "eot_version", "eot_launch_count", "eot_workspace_bytes", "eot_box_geometry", "eot_apply_fwd",
            "eot_apply_bwd", "eot_brightness_match", "eot_check_workspace", "score_workspace_bytes", "score_max_fwd", "score_max_bwd",
            "patch_tv_grad", "adam_clip_update"]
 
@@ -50,8 +50,6 @@ def _declare(lib):
     lib.eot_workspace_bytes.argtypes = [ctypes.POINTER(EotShape), ctypes.POINTER(sz)]
     lib.eot_box_geometry.argtypes = [ctypes.POINTER(EotShape), vp, vp, vp, vp, vp, vp]
     lib.eot_apply_fwd.argtypes = [ctypes.POINTER(EotShape), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
-    lib.eot_apply_fwd_overlapped.argtypes = [ctypes.POINTER(EotShape), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp, vp,
-                                             ctypes.c_int]
     lib.eot_apply_bwd.argtypes = [ctypes.POINTER(EotShape), vp, vp, vp, vp, sz, vp, ctypes.c_int, vp]
     lib.eot_brightness_match.argtypes = [vp, i64, vp, i64, vp, vp, sz, vp]
     lib.eot_check_workspace.argtypes = [ctypes.POINTER(EotShape), vp, vp]

@@ -5,12 +5,15 @@
 //                  ImageProjectiveTransformV3 -- the SAME bilinear warp applied to the gradient with
 //                  the inverted transform, fill 0 -- reading dL/d(window) through the route bytes the
 //                  forward composite left (TensorScatterUpdate / SelectV2 / outer clip routing), then
-//                  the inner clip mask of attacker.py:428.  -> g_u[box]
-//   k_bwd_resize   exact transpose of the antialiased resize (ScaleAndTranslateGrad), one CTA per
-//                  (image, block of patch rows) looping over the image's boxes, accumulating in a
-//                  shared-memory patch-gradient tile (no global atomics); then the first half of the
-//                  BrightnessMatcher backward (clip mask, K'^T) and the per-image sum of dL/dY
-//                  (warp-shuffle tree + one atomic per CTA).
+//                  the inner clip mask of attacker.py:428.  -> g_u[box] (RGBX texels)
+//   k_bwd_resize3  exact transpose of the antialiased resize (ScaleAndTranslateGrad) as the forward's
+//                  two passes over the transposed weight tables the geometry role wrote; persistent
+//                  CTAs over (box, strip of patch rows); per-box partial gradient, no atomics.
+//   k_bwd_match    deterministic per-image sum of the boxes' partials, first half of the
+//                  BrightnessMatcher backward (clip mask, K'^T), per-image sum of dL/dY.
+//   k_bwd_resize   memory-lean serial variant of the two above (EOT_FLAG_SERIAL_ADJOINT): one CTA per
+//                  (image, block of patch rows) looping over the image's boxes with a shared-memory
+//                  patch-gradient accumulator and a warp-shuffle tree for the dL/dY sum.
 //   k_bwd_texel    second half: subtract the per-image mean of dL/dY, K^T, rescale, print-adjust
 //                  clip mask and weights; partial sums over image groups.
 //   k_bwd_reduce   deterministic sum of the partials (+ optional accumulate).

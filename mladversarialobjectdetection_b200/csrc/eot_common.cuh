@@ -65,10 +65,8 @@ struct Layout {
   size_t off_ysum_patch;   // double[B]
   size_t off_gy_sum;       // double[B]   (backward: sum of dL/dY per image)
   size_t off_oor;          // int32[B]    image b holds a value outside [-1,1] (then clip(background) is not the identity)
-  size_t off_done;         // int32[5][B]  fused forward: finished work items per image and stage (geometry, patch
-                           //              statistics, image pass, match, resize)
-  size_t off_counters;     // int32[8]: 2 error flag, 4 work ticket, 5 finished geometry blocks
-  size_t off_tickets;      // int32[32]  composite band tickets (one counter per image group of the two-stream entry)
+  size_t off_counters;     // int32[8]: 2 error flag, 5 finished geometry blocks
+  size_t off_tickets;      // int32[32]  composite band tickets
   size_t off_plans;        // BoxPlan[N]
   size_t off_starts;       // int32[N][Lmin]
   size_t off_weights;      // float[N][wcap]
@@ -123,7 +121,6 @@ __host__ __device__ inline Layout make_layout(const EotShape& s) {
   L.off_ysum_patch = o;   o = align_up(o + B * sizeof(double), 256);
   L.off_gy_sum = o;       o = align_up(o + B * sizeof(double), 256);
   L.off_oor = o;          o = align_up(o + B * sizeof(int32_t), 256);
-  L.off_done = o;         o = align_up(o + 5 * B * sizeof(int32_t), 256);
   L.off_counters = o;     o = align_up(o + 8 * sizeof(int32_t), 256);
   L.off_tickets = o;      o = align_up(o + 32 * sizeof(int32_t), 256);
   L.off_plans = o;        o = align_up(o + N * sizeof(BoxPlan), 256);
@@ -314,26 +311,6 @@ __device__ __forceinline__ void sample_at(const Sampler& S, float ix, float iy, 
   blend3(p[0], p[1], p[S.S], p[S.S + 1], wx1, wx0, wy1, wy0, R);
 }
 
-// ---- flags between work items of one launch ----------------------------------------------------------
-// acquire / release by ONE thread per CTA (the CTA barrier around them makes the ordering cumulative for
-// the whole CTA).  No gpu-scope fence in every thread.
-__device__ __forceinline__ int ld_acquire(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void red_release_add(int* p, int n) {
-  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(n) : "memory");
-}
-__device__ __forceinline__ bool wait_counter(const int* ctr, int need, int* err_flag) {
-  if (need <= 0) return true;
-  for (int spin = 0; spin < (1 << 22); ++spin) {
-    if (ld_acquire(ctr) >= need) return true;
-    __nanosleep(64);
-  }
-  atomicExch(err_flag, 3);      // dependency never arrived: give up instead of hanging the GPU
-  return false;
-}
 #endif  // __CUDACC__
 
 }  // namespace eot

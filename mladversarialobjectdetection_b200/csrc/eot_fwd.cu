@@ -2,19 +2,20 @@
 // (reference: attacker.py:344-498, attack_detection.py:321-498, brightness_matcher.py:25-73).
 //
 // Kernels (all on the caller's stream, no host sync; ragged counts come in as CSR):
-//   k_patch_stats     mean Y of the print-adjusted patch, per image          (B x P^2, tiny)
-//   k_geometry        Patcher.create + area filter + int cast, span tables, work lists
-//   k_image_pass      ONE streaming pass over the batch: copy image -> out (128-bit I/O) while
-//                     accumulating mean Y of the target image               (the HBM-bound part)
+//   k_prepass         ONE launch, three roles by block index:
+//                       geometry    Patcher.create + area filter + int cast, span / inverse-span / transposed
+//                                   tables, -2 ring of the texel buffer, zeroed route map, work-item counts
+//                       statistics  mean Y of the print-adjusted patch, per image
+//                       image pass  copy image -> out (128-bit I/O) while accumulating mean Y of the target
+//                                   image in float64 (the HBM-bound part)
 //   k_match           print adjust + brightness match -> matched patch per image
 //   k_resize          antialiased triangle resize (rows then columns, sequential float32
-//                     accumulation as ScaleAndTranslate) + noise + brightness delta -> u_j
-//   k_composite       per window element: projective bilinear sample of the padded u_j, `< -1`
-//                     mask, background select, clip, store (gather form of the sequential paste)
+//                     accumulation as ScaleAndTranslate) + noise + brightness delta -> u_j (RGBX texels)
+//   k_composite       gather over image tiles: projective bilinear sample of the ring-padded u_j of the
+//                     covering boxes, newest first, `< -1` mask, background select, clip, store, route bytes
 #include "eot_common.cuh"
 
 #include <math.h>
-#include <stdlib.h>
 
 namespace eot {
 
@@ -261,31 +262,6 @@ __device__ void scan_block(int N, const int2* cnt, int2* base, int2* part /* [bl
   }
   if ((int)threadIdx.x == T - 1) base[N] = part[T - 1];
   __syncthreads();
-}
-
-__global__ void __launch_bounds__(1024) k_scan(int N, const int2* __restrict__ cnt, int2* base) {
-  __shared__ int2 part[1024];
-  const int per = (N + 1023) / 1024;
-  const int j0 = threadIdx.x * per, j1 = min(N, j0 + per);
-  int2 sum = make_int2(0, 0);
-  for (int j = j0; j < j1; ++j) { sum.x += cnt[j].x; sum.y += cnt[j].y; }
-  part[threadIdx.x] = sum;
-  __syncthreads();
-  for (int d = 1; d < 1024; d <<= 1) {
-    int2 v = make_int2(0, 0);
-    if ((int)threadIdx.x >= d) v = part[threadIdx.x - d];
-    __syncthreads();
-    part[threadIdx.x].x += v.x;
-    part[threadIdx.x].y += v.y;
-    __syncthreads();
-  }
-  int2 run = threadIdx.x ? part[threadIdx.x - 1] : make_int2(0, 0);
-  for (int j = j0; j < j1; ++j) {
-    base[j] = run;
-    run.x += cnt[j].x;
-    run.y += cnt[j].y;
-  }
-  if (threadIdx.x == 1023) base[N] = part[1023];
 }
 
 __global__ void __launch_bounds__(kThreads) k_geometry_only(EotShape s, Layout L, const float* __restrict__ boxes,
@@ -919,161 +895,6 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(EotShape s, Layout L,
 }
 
 // ------------------------------------------------------------------------------------------------
-// Fused persistent forward: ONE launch for the whole of Patcher.call.
-//
-// Every CTA stays resident and draws work tickets from a global counter.  Tickets are laid out so that
-// each item only depends on items with LOWER ticket numbers, all of which have already been handed to a
-// resident CTA -- so a CTA may spin (bounded) on a per-image "finished items" counter without deadlock:
-//
-//   [ geometry of every box | patch luma statistics of every image ]
-//   slot k = 0 .. B+LAG-1:  image pass of image k (cpi chunks)  |  window work of image k-LAG:
-//                           match (MP parts) -> resize (NPR parts) -> composite (NPC parts)
-//
-// The HBM-bound image pass of later images therefore overlaps the instruction-bound window work of
-// earlier ones inside the same SMs, and the second touch of a window (background read, route/texel
-// traffic) happens while its lines are still in L2.  Producer: writes, __threadfence, barrier, one
-// atomicAdd on the stage counter.  Consumer: one thread polls the counter, __threadfence, barrier.
-// ------------------------------------------------------------------------------------------------
-constexpr int kMaxWin = 256;     // boxes per image whose work-item prefix the fused kernel keeps in shared memory
-constexpr int kFusedNPR = 24;    // resize parts per image
-constexpr int kFusedNPC = 48;   // composite parts per image
-constexpr int kFusedStages = 4;  // slot k holds: pass(k), match(k-1), resize(k-2), composite(k-3)
-constexpr int kPassChunksPerTicket = 2;
-
-struct FusedPlan {
-  int n_geom, n_stat_tickets, pchunks, cpi, mp;   // mp = match parts per image
-  int pass_tickets;                                // image-pass tickets per image
-  int slot;                                        // tickets per slot
-  int total_tickets;
-  int lag;                                         // images between dependent stages in the ticket order
-};
-
-__device__ __forceinline__ void signal_counter(int* ctr, int n = 1) {
-  __syncthreads();
-  if (threadIdx.x == 0) red_release_add(ctr, n);
-}
-
-template <bool kVec>
-__global__ void __launch_bounds__(kThreads, 4) k_forward_fused(EotShape s, Layout L, FusedPlan fp, const float* __restrict__ patch,
-                                                               const float* __restrict__ print_wb,
-                                                               const float* __restrict__ boxes,
-                                                               const int32_t* __restrict__ offsets,
-                                                               const EotBoxParams* __restrict__ params,
-                                                               const float* __restrict__ scale,
-                                                               const float* __restrict__ images, float* out, float* mask,
-                                                               char* ws) {
-  extern __shared__ __align__(16) float dyn_smem[];    // resize strip buffers
-  __shared__ CompositeSmem csm;
-  __shared__ double red[32];
-  __shared__ int2 pre[kMaxWin + 1];                   // per-image prefix of (resize strips, composite row blocks)
-  __shared__ int s_ticket[2], s_ok;
-  int* counters = reinterpret_cast<int*>(ws + L.off_counters);
-  int* err_flag = counters + 2;
-  int* done = reinterpret_cast<int*>(ws + L.off_done);
-  const int B = s.batch, N = s.total_boxes;
-  int* done_geom = done, *done_stat = done + B, *done_pass = done + 2 * B, *done_match = done + 3 * B, *done_resize = done + 4 * B;
-  const int S = fp.n_geom + fp.n_stat_tickets;
-  const int HW = s.height * s.width;
-  for (;;) {
-    // (no ticket prefetch: a ticket held but not started would delay everything that depends on it)
-    __syncthreads();
-    if (threadIdx.x == 0) s_ticket[0] = atomicAdd(counters + 4, 1);
-    __syncthreads();
-    int t = s_ticket[0];
-    if (t >= fp.total_tickets) break;
-    // ---- setup tickets ----
-    if (t < fp.n_geom) {
-      const int img = geometry_block(s, L, t, boxes, offsets, params, scale, ws, nullptr);
-      signal_counter(done_geom + img);
-      if (threadIdx.x == 0) s_ok = (atomicAdd(counters + 5, 1) == N - 1);
-      __syncthreads();
-      if (s_ok) {                                     // last geometry block: prefix sums for the backward's work list
-        __threadfence();
-        scan_block(N, reinterpret_cast<const int2*>(ws + L.off_cnt), reinterpret_cast<int2*>(ws + L.off_base),
-                   reinterpret_cast<int2*>(dyn_smem));
-      }
-      continue;
-    }
-    if (t < S) {
-      const int q = t - fp.n_geom;
-      const int b = q / fp.pchunks;
-      patch_stats_block(s, b, q - b * fp.pchunks, fp.pchunks, patch, print_wb, reinterpret_cast<double*>(ws + L.off_ysum_patch), red);
-      if (q == 0 && threadIdx.x == 0) {
-        int32_t* off_copy = reinterpret_cast<int32_t*>(ws + L.off_offsets);
-        for (int i = 0; i <= B; ++i) off_copy[i] = offsets[i];
-      }
-      signal_counter(done_stat + b);
-      continue;
-    }
-    // ---- slot tickets ----
-    t -= S;
-    const int slot = t / fp.slot;
-    int r = t - slot * fp.slot;
-    if (r < fp.pass_tickets) {                                    // image pass: kPassChunksPerTicket chunks of image `slot`
-      if (slot >= B) continue;
-      int n_done = 0;
-      for (int c = r * kPassChunksPerTicket; c < min(fp.cpi, (r + 1) * kPassChunksPerTicket); ++c, ++n_done)
-        image_pass_block<kVec>(HW, slot, c, images, out, mask, reinterpret_cast<double*>(ws + L.off_ysum_img),
-                               reinterpret_cast<int*>(ws + L.off_oor), red);
-      signal_counter(done_pass + slot, n_done);
-      continue;
-    }
-    r -= fp.pass_tickets;
-    int stage, w;                                                 // 1 match, 2 resize, 3 composite ; image w
-    if (r < fp.mp) { stage = 1; w = slot - fp.lag; }
-    else if (r < fp.mp + kFusedNPR) { stage = 2; w = slot - 2 * fp.lag; r -= fp.mp; }
-    else { stage = 3; w = slot - 3 * fp.lag; r -= fp.mp + kFusedNPR; }
-    if (w < 0 || w >= B) continue;
-    const int first = offsets[w], nb_all = offsets[w + 1] - first;
-    if (stage == 1) {
-      if (nb_all > 0) {
-        if (threadIdx.x == 0) s_ok = wait_counter(done_pass + w, fp.cpi, err_flag) && wait_counter(done_stat + w, fp.pchunks, err_flag);
-        __syncthreads();
-        if (s_ok) match_block(s, L, patch, print_wb, ws, w, r, fp.mp);
-      }
-      signal_counter(done_match + w);
-      continue;
-    }
-    const bool is_resize = stage == 2;
-    const int part = r;
-    if (nb_all > 0) {
-      if (threadIdx.x == 0) {
-        bool ok = wait_counter(done_geom + w, nb_all, err_flag);
-        ok = ok && (is_resize ? wait_counter(done_match + w, fp.mp, err_flag) : wait_counter(done_resize + w, kFusedNPR, err_flag));
-        s_ok = ok;
-      }
-      __syncthreads();
-      if (s_ok) {
-        if (is_resize) {
-          const int nb = min(nb_all, kMaxWin);
-          const int2* cnt = reinterpret_cast<const int2*>(ws + L.off_cnt) + first;
-          if (threadIdx.x == 0) {
-            int2 run = make_int2(0, 0);
-            for (int i = 0; i < nb; ++i) { pre[i] = run; const int2 c = __ldcg(cnt + i); run.x += c.x; run.y += c.y; }
-            pre[nb] = run;
-          }
-          __syncthreads();
-          const int total = pre[nb].x;
-          for (int it = part; it < total; it += kFusedNPR) {
-            int lo = 0, hi = nb;                                  // last box with prefix <= it
-            while (hi - lo > 1) { const int m = (lo + hi) >> 1; if (pre[m].x <= it) lo = m; else hi = m; }
-            resize_item(s, L, ws, make_int2(first + lo, it - pre[lo].x), dyn_smem);
-            __syncthreads();
-          }
-        } else {
-          const int bands = (s.height + kCompRows - 1) / kCompRows;
-          for (int band = part; band < bands; band += kFusedNPC) {
-            composite_band(s, L, ws, images, out, mask, w, band, offsets, csm);
-            __syncthreads();
-          }
-        }
-      }
-    }
-    if (is_resize) signal_counter(done_resize + w);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // host entry points
 // ------------------------------------------------------------------------------------------------
 static int check_shape(const EotShape* s) {
@@ -1126,113 +947,41 @@ extern "C" int eot_box_geometry(const EotShape* shape, const float* boxes, const
 
 namespace eot {
 
-// Enqueues the whole forward.  With an auxiliary stream the batch is cut into chunks of images: the
-// HBM-bound image pass of chunk c+1 (main stream) overlaps the instruction-bound window work of chunk c
-// (auxiliary stream); the two meet through events only.  Without one everything runs in order on `st`.
+// Enqueues the whole forward on `st`: memset of the small accumulators, the pre-pass (geometry + patch statistics +
+// image pass in one launch), then match -> resize -> composite.
 static int launch_forward(const EotShape& s, const Layout& L, const float* patch, const float* scale, const float* images,
                           const float* boxes, const int32_t* box_offsets, const EotBoxParams* params,
-                          const float* print_wb, float* out_images, float* mask, char* ws, cudaStream_t st,
-                          cudaStream_t aux, int chunks) {
+                          const float* print_wb, float* out_images, float* mask, char* ws, cudaStream_t st) {
   const int B = s.batch, P = s.patch_size, HW = s.height * s.width, N = s.total_boxes;
   EOT_CHECK_CUDA(cudaMemsetAsync(ws + L.off_ysum_img, 0, L.off_plans - L.off_ysum_img, st));
   const int pchunks = max(1, min((P * P + kThreads * 4 - 1) / (kThreads * 4), 64));
   const int cpi = (HW + kPassPixPerBlock - 1) / kPassPixPerBlock;
   const bool vec = (HW % 4 == 0) && (((uintptr_t)images | (uintptr_t)out_images | (uintptr_t)(mask ? mask : out_images)) & 15) == 0;
   const int nsm = sm_count();
-  const size_t smem = resize_smem_bytes(s, L);
-  if (smem > 32 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // static + dynamic may pass 48 KB
-  auto prepass = [&](cudaStream_t q, int n_geom, int n_stat, int b0, int b1) {
-    const long long nblocks = (long long)n_geom + (long long)n_stat * pchunks + (long long)(b1 - b0) * cpi;
-    if (nblocks <= 0) return;
-    if (vec)
-      k_prepass<true><<<(unsigned)nblocks, kThreads, 0, q>>>(s, L, patch, print_wb, boxes, box_offsets, params, scale, images,
-                                                             out_images, mask, ws, n_geom, n_stat, pchunks, cpi, b0);
-    else
-      k_prepass<false><<<(unsigned)nblocks, kThreads, 0, q>>>(s, L, patch, print_wb, boxes, box_offsets, params, scale, images,
-                                                              out_images, mask, ws, n_geom, n_stat, pchunks, cpi, b0);
-    count_launches(1);
-  };
-  auto windows = [&](cudaStream_t q, int b0, int b1, int group) {
-    k_match<<<dim3(pchunks, b1 - b0), kThreads, 0, q>>>(s, L, patch, print_wb, ws, b0);
-    k_resize<<<nsm * 4, kThreads, smem, q>>>(s, L, ws, box_offsets, b0, b1);
-    k_composite<<<nsm * 4, kThreads, 0, q>>>(s, L, ws, images, out_images, mask, box_offsets, b0, b1, group);
+  const long long nblocks = (long long)N + (long long)B * pchunks + (long long)B * cpi;
+  if (nblocks >= (1ll << 31)) { set_error("eot_apply_fwd: grid too large"); return EOT_ERR_BAD_SHAPE; }
+  if (vec)
+    k_prepass<true><<<(unsigned)nblocks, kThreads, 0, st>>>(s, L, patch, print_wb, boxes, box_offsets, params, scale, images,
+                                                            out_images, mask, ws, N, B, pchunks, cpi, 0);
+  else
+    k_prepass<false><<<(unsigned)nblocks, kThreads, 0, st>>>(s, L, patch, print_wb, boxes, box_offsets, params, scale, images,
+                                                             out_images, mask, ws, N, B, pchunks, cpi, 0);
+  count_launches(1);
+  if (N > 0) {
+    const size_t smem = resize_smem_bytes(s, L);
+    if (smem > 32 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // static + dynamic may pass 48 KB
+    k_match<<<dim3(pchunks, B), kThreads, 0, st>>>(s, L, patch, print_wb, ws, 0);
+    k_resize<<<nsm * 4, kThreads, smem, st>>>(s, L, ws, box_offsets, 0, B);
+    k_composite<<<nsm * 4, kThreads, 0, st>>>(s, L, ws, images, out_images, mask, box_offsets, 0, B, 0);
     count_launches(3);
-  };
-  if ((long long)N + (long long)B * pchunks + (long long)B * cpi >= (1ll << 31)) { set_error("eot_apply_fwd: grid too large"); return EOT_ERR_BAD_SHAPE; }
-  if (!aux && N > 0 && (s.flags & EOT_FLAG_FUSED)) {             // experimental: one persistent launch
-    FusedPlan fp;
-    fp.n_geom = N;
-    fp.pchunks = pchunks;
-    fp.n_stat_tickets = B * pchunks;
-    fp.cpi = cpi;
-    fp.mp = max(1, (P * P + 4095) / 4096);
-    fp.pass_tickets = (cpi + kPassChunksPerTicket - 1) / kPassChunksPerTicket;
-    fp.slot = fp.pass_tickets + fp.mp + kFusedNPR + kFusedNPC;
-    {
-      const char* e = getenv("EOT_FUSED_LAG");                    // tuning knob (images between dependent stages)
-      fp.lag = e ? atoi(e) : 8;
-      if (fp.lag < 1) fp.lag = 1;
-    }
-    const long long tickets = (long long)N + (long long)B * pchunks + (long long)(B + (kFusedStages - 1) * fp.lag) * fp.slot;
-    if (tickets >= (1ll << 31)) { set_error("eot_apply_fwd: too many work tickets"); return EOT_ERR_BAD_SHAPE; }
-    fp.total_tickets = (int)tickets;
-    const size_t dsm = max(smem, (size_t)256 * sizeof(int2));
-    if (vec) {
-      if (dsm > 24 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_forward_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-      k_forward_fused<true><<<nsm * 4, kThreads, dsm, st>>>(s, L, fp, patch, print_wb, boxes, box_offsets, params, scale, images,
-                                                            out_images, mask, ws);
-    } else {
-      if (dsm > 24 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_forward_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-      k_forward_fused<false><<<nsm * 4, kThreads, dsm, st>>>(s, L, fp, patch, print_wb, boxes, box_offsets, params, scale, images,
-                                                             out_images, mask, ws);
-    }
-    count_launches(1);
-    EOT_CHECK_CUDA(cudaPeekAtLastError());
-    return EOT_OK;
   }
-  if (!aux || chunks <= 1 || N == 0) {
-    prepass(st, N, B, 0, B);
-    if (N > 0) windows(st, 0, B, 0);
-    EOT_CHECK_CUDA(cudaPeekAtLastError());
-    return EOT_OK;
-  }
-  if (chunks > B) chunks = B;
-  if (chunks > 16) chunks = 16;
-  // events are created once per host thread and device and reused (creating them per call costs more than the kernels)
-  struct EventPool { int device = -1; cudaEvent_t ev[18] = {}; };
-  static thread_local EventPool pool;
-  int dev_id = 0;
-  EOT_CHECK_CUDA(cudaGetDevice(&dev_id));
-  if (pool.device != dev_id) {
-    for (int i = 0; i < 18; ++i) EOT_CHECK_CUDA(cudaEventCreateWithFlags(&pool.ev[i], cudaEventDisableTiming));
-    pool.device = dev_id;
-  }
-  cudaEvent_t* ev = pool.ev;
-  EOT_CHECK_CUDA(cudaEventRecord(ev[chunks], st));               // memset done
-  EOT_CHECK_CUDA(cudaStreamWaitEvent(aux, ev[chunks], 0));
-  prepass(aux, N, B, 0, 0);                                       // geometry (+ prefix scan) + patch statistics only
-  const int per = (B + chunks - 1) / chunks;
-  for (int c = 0; c < chunks; ++c) {
-    const int b0 = c * per, b1 = min(B, b0 + per);
-    if (b0 >= b1) { chunks = c; break; }
-    prepass(st, 0, 0, b0, b1);
-    EOT_CHECK_CUDA(cudaEventRecord(ev[c], st));
-  }
-  for (int c = 0; c < chunks; ++c) {
-    const int b0 = c * per, b1 = min(B, b0 + per);
-    EOT_CHECK_CUDA(cudaStreamWaitEvent(aux, ev[c], 0));
-    windows(aux, b0, b1, c);
-  }
-  EOT_CHECK_CUDA(cudaEventRecord(ev[chunks + 1], aux));
-  EOT_CHECK_CUDA(cudaStreamWaitEvent(st, ev[chunks + 1], 0));
   EOT_CHECK_CUDA(cudaPeekAtLastError());
   return EOT_OK;
 }
 
 static int forward_entry(const EotShape* shape, const float* patch, const float* scale, const float* images,
                          const float* boxes, const int32_t* box_offsets, const EotBoxParams* params, const float* print_wb,
-                         float* out_images, float* out_masks, void* workspace, size_t workspace_bytes, void* stream,
-                         void* aux_stream, int chunks) {
+                         float* out_images, float* out_masks, void* workspace, size_t workspace_bytes, void* stream) {
   if (int rc = check_shape(shape)) return rc;
   if (!patch || !scale || !images || !box_offsets || !print_wb || !out_images || !workspace ||
       (shape->total_boxes > 0 && (!boxes || !params))) {
@@ -1250,8 +999,7 @@ static int forward_entry(const EotShape* shape, const float* patch, const float*
   }
   if (((uintptr_t)workspace & 255) != 0) { set_error("workspace must be 256-byte aligned"); return EOT_ERR_MISALIGNED; }
   return launch_forward(s, L, patch, scale, images, boxes, box_offsets, params, print_wb, out_images,
-                        want_mask ? out_masks : nullptr, static_cast<char*>(workspace), (cudaStream_t)stream,
-                        (cudaStream_t)aux_stream, chunks);
+                        want_mask ? out_masks : nullptr, static_cast<char*>(workspace), (cudaStream_t)stream);
 }
 
 }  // namespace eot
@@ -1261,16 +1009,7 @@ extern "C" int eot_apply_fwd(const EotShape* shape, const float* patch, const fl
                              const float* print_wb, float* out_images, float* out_masks, void* workspace,
                              size_t workspace_bytes, void* stream) {
   return forward_entry(shape, patch, scale, images, boxes, box_offsets, params, print_wb, out_images, out_masks, workspace,
-                       workspace_bytes, stream, nullptr, 1);
-}
-
-extern "C" int eot_apply_fwd_overlapped(const EotShape* shape, const float* patch, const float* scale, const float* images,
-                                        const float* boxes, const int32_t* box_offsets, const EotBoxParams* params,
-                                        const float* print_wb, float* out_images, float* out_masks, void* workspace,
-                                        size_t workspace_bytes, void* stream, void* aux_stream, int chunks) {
-  if (!aux_stream || aux_stream == stream) { set_error("eot_apply_fwd_overlapped: needs a distinct auxiliary stream"); return EOT_ERR_NULL_POINTER; }
-  return forward_entry(shape, patch, scale, images, boxes, box_offsets, params, print_wb, out_images, out_masks, workspace,
-                       workspace_bytes, stream, aux_stream, chunks);
+                       workspace_bytes, stream);
 }
 
 extern "C" int eot_check_workspace(const EotShape* shape, const void* workspace, void* stream) {

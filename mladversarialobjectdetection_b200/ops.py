@@ -49,7 +49,6 @@ class PatchGeometry:
     min_patch_area: float = 4.0     # attacker.py:347
     max_scale: float = 1.0
     serial_adjoint: bool = False    # EOT_FLAG_SERIAL_ADJOINT (memory-lean backward path)
-    fused: bool = False             # EOT_FLAG_FUSED (experimental single persistent launch for the whole forward)
 
 
 def _shape(images: torch.Tensor, patch: torch.Tensor, n_boxes: int, g: PatchGeometry, want_mask: bool) -> EotShape:
@@ -74,7 +73,7 @@ def _shape(images: torch.Tensor, patch: torch.Tensor, n_boxes: int, g: PatchGeom
         raise ValueError("patch must be square, 3-channel, with unit channel stride")
     s.patch_size = P
     s.total_boxes = n_boxes
-    s.flags = (_lib.EOT_FLAG_MASK_OUTPUT if want_mask else 0) | (2 if g.serial_adjoint else 0) | (4 if g.fused else 0)
+    s.flags = (_lib.EOT_FLAG_MASK_OUTPUT if want_mask else 0) | (2 if g.serial_adjoint else 0)
     s.tolerance, s.noise_amp, s.min_patch_area, s.max_scale = g.tolerance, g.noise_amp, g.min_patch_area, g.max_scale
     s.patch_stride_n, s.patch_stride_y, s.patch_stride_x = sn, sy, sx
     return s
@@ -115,8 +114,7 @@ class ApplyContext:
 def apply_forward(patch: torch.Tensor, scale: torch.Tensor, images: torch.Tensor, boxes: torch.Tensor,
                   offsets: torch.Tensor, params: torch.Tensor, print_wb: torch.Tensor,
                   g: PatchGeometry = PatchGeometry(), *, want_mask: bool = False,
-                  out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None,
-                  aux_stream: Optional[torch.cuda.Stream] = None, chunks: int = 4):
+                  out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None):
     """`Patcher.call` / `Masker.call` on the GPU (attacker.py:490-498, attack_detection.py:478-498).
 
     boxes [N,4] + offsets [B+1] int32 are the CSR form of the reference's ragged boxes; params is the
@@ -138,17 +136,10 @@ def apply_forward(patch: torch.Tensor, scale: torch.Tensor, images: torch.Tensor
     if out is None:
         out = torch.empty_like(images)
     mask = torch.empty_like(images) if want_mask else None
-    if aux_stream is not None and chunks > 1 and n_boxes > 0:
-        # the window work of image group c overlaps the image pass of group c+1 (see eot_apply_fwd_overlapped)
-        _lib.check(_lib.load().eot_apply_fwd_overlapped(
-            ctypes.byref(shape), _ptr(patch), _ptr(scale), _ptr(images), _ptr(boxes), _ptr(offsets), _ptr(params),
-            _ptr(print_wb), _ptr(out), _ptr(mask), _ptr(workspace), ctypes.c_size_t(workspace.numel()), _stream(),
-            ctypes.c_void_p(aux_stream.cuda_stream), int(chunks)), "eot_apply_fwd_overlapped")
-    else:
-        _lib.check(_lib.load().eot_apply_fwd(ctypes.byref(shape), _ptr(patch), _ptr(scale), _ptr(images), _ptr(boxes),
-                                             _ptr(offsets), _ptr(params), _ptr(print_wb), _ptr(out), _ptr(mask),
-                                             _ptr(workspace), ctypes.c_size_t(workspace.numel()), _stream()),
-                   "eot_apply_fwd")
+    _lib.check(_lib.load().eot_apply_fwd(ctypes.byref(shape), _ptr(patch), _ptr(scale), _ptr(images), _ptr(boxes),
+                                         _ptr(offsets), _ptr(params), _ptr(print_wb), _ptr(out), _ptr(mask),
+                                         _ptr(workspace), ctypes.c_size_t(workspace.numel()), _stream()),
+               "eot_apply_fwd")
     return out, mask, ApplyContext(shape, workspace, patch, print_wb)
 
 

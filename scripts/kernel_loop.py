@@ -22,8 +22,6 @@ ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--what", default="fwd,bwd,score")
 ap.add_argument("--max-boxes", type=int, default=8)
 ap.add_argument("--time", action="store_true")
-ap.add_argument("--overlap", type=int, default=0, help="chunks of the two-stream forward (0 = single stream)")
-ap.add_argument("--fused", action="store_true", help="single persistent launch for the whole forward")
 args = ap.parse_args()
 B, H, P = args.batch, args.image, args.patch
 dev = "cuda"
@@ -34,8 +32,7 @@ params, wb = ops.params_to_tensor(bt.params, dev), torch.from_numpy(bt.print_wb)
 patch = torch.from_numpy(synth.make_patch(P)).to(dev)
 scale = torch.tensor(0.4, device=dev)
 out = torch.empty_like(images)
-aux = torch.cuda.Stream(priority=-1) if args.overlap else None
-geo = ops.PatchGeometry(fused=args.fused)
+geo = ops.PatchGeometry()
 _, _, ctx = ops.apply_forward(patch, scale, images, boxes, offsets, params, wb, geo, out=out)
 G = torch.randn_like(images)
 gp = torch.empty_like(patch)
@@ -54,8 +51,7 @@ state = {}
 def one():
     res = {}
     if "fwd" in what:
-        ops.apply_forward(patch, scale, images, boxes, offsets, params, wb, geo, out=out, workspace=ctx.workspace,
-                          aux_stream=aux, chunks=args.overlap)
+        ops.apply_forward(patch, scale, images, boxes, offsets, params, wb, geo, out=out, workspace=ctx.workspace)
     if "bwd" in what:
         ops.apply_backward(ctx, G, grad_patch=gp)
     if "score" in what or "scoref" in what:

@@ -157,34 +157,6 @@ def test_cpu_tensors_are_rejected_loudly():
                           torch.zeros(1, 48, dtype=torch.uint8), torch.from_numpy(bt.print_wb))
 
 
-@pytest.mark.parametrize("chunks", [2, 3, 8])
-def test_forward_overlapped_two_stream_path_is_identical(chunks):
-    bt = synth.make_batch(7, 192, 192, seed=91, max_boxes=5)
-    patch = synth.make_patch(48, seed=91)
-    ref, _, ctx_ref, d = run_forward(patch, 0.4, bt)
-    aux = torch.cuda.Stream()
-    sc = torch.tensor(0.4, dtype=torch.float32, device="cuda")
-    out, _, ctx = ops.apply_forward(torch.from_numpy(patch).cuda(), sc, d["images"], d["boxes"], d["offsets"], d["params"],
-                                    d["print_wb"], aux_stream=aux, chunks=chunks)
-    G = torch.randn_like(out)                       # enqueued on the current stream: must see the finished forward
-    g1 = ops.apply_backward(ctx, G)
-    g0 = ops.apply_backward(ctx_ref, G)
-    torch.cuda.synchronize()
-    assert torch.equal(out, ref)
-    assert torch.equal(g1, g0)
-
-
-def test_forward_fused_and_unfused_paths_are_identical():
-    bt = synth.make_batch(9, 224, 224, seed=92, max_boxes=6)
-    patch = synth.make_patch(64, seed=92)
-    fused, _, ctx_f, d = run_forward(patch, 0.4, bt, ops.PatchGeometry(fused=True))     # persistent ticketed launch
-    unfused, _, ctx_u, _ = run_forward(patch, 0.4, bt)
-    assert torch.equal(fused, unfused)
-    ops.check_workspace(ctx_f)
-    G = torch.randn_like(fused)
-    assert torch.equal(ops.apply_backward(ctx_f, G), ops.apply_backward(ctx_u, G))
-
-
 def test_forward_out_of_range_image_clips_whole_window():
     # attacker.py:441 clips the WHOLE d x d window, background included; pixels outside every window keep values > 1
     bt = synth.make_batch(3, 160, 160, seed=71, max_boxes=3, min_boxes=1)
