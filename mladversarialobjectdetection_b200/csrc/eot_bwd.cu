@@ -38,7 +38,13 @@ __device__ __forceinline__ void routed_grad3(const uint8_t* __restrict__ route, 
   if (bits & 4u) g[2] = __ldg(gp + 2);
 }
 
-__global__ void __launch_bounds__(kThreads) k_bwd_window(EotShape s, Layout L, char* ws, const float* __restrict__ G) {
+#ifndef EOT_BWDW_MINB
+#define EOT_BWDW_MINB 4
+#endif
+#ifndef EOT_BWDR_MINB
+#define EOT_BWDR_MINB 3
+#endif
+__global__ void __launch_bounds__(kThreads, EOT_BWDW_MINB) k_bwd_window(EotShape s, Layout L, char* ws, const float* __restrict__ G) {
   const BoxPlan* plans = reinterpret_cast<const BoxPlan*>(ws + L.off_plans);
   __shared__ int2 s_base[kMaxBaseSmem];
   const int2* base = stage_base(reinterpret_cast<const int2*>(ws + L.off_base), s.total_boxes, s_base);
@@ -293,7 +299,7 @@ __device__ __forceinline__ void bwd_resize_passes(int P, int ps, int tcap, int p
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 3) k_bwd_resize3(EotShape s, Layout L, char* ws) {
+__global__ void __launch_bounds__(kThreads, EOT_BWDR_MINB) k_bwd_resize3(EotShape s, Layout L, char* ws) {
   extern __shared__ __align__(16) float smem[];
   __shared__ int2 s_base[kMaxBaseSmem];
   __shared__ int2 s_item;
@@ -446,7 +452,7 @@ extern "C" int eot_apply_bwd(const EotShape* shape, const float* patch, const fl
     const size_t smem2 = bwd_resize3_smem_bytes(s, L);
     if (smem2 > 200 * 1024) { set_error("eot_apply_bwd: shared-memory tile too large (L=%d)", L.lmin); return EOT_ERR_BAD_SHAPE; }
     if (smem2 > 32 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_bwd_resize3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    k_bwd_resize3<<<nsm * 3, kThreads, smem2, st>>>(s, L, ws);
+    k_bwd_resize3<<<nsm * EOT_BWDR_MINB, kThreads, smem2, st>>>(s, L, ws);
     const int mchunks = max(1, min((PP + kThreads - 1) / kThreads, 64));
     k_bwd_match<<<dim3(mchunks, B), kThreads, 0, st>>>(s, L, ws, patch, print_wb, offsets);
     count_launches(1);

@@ -651,7 +651,10 @@ __device__ __forceinline__ void resize_item(const EotShape& s, const Layout& L, 
   else resize_passes<0>(s, P, ps, span, oy0, rows, m, s_st, s_w, inter, u4, delta, key0, key1);
 }
 
-__global__ void __launch_bounds__(kThreads, 4) k_resize(EotShape s, Layout L, char* ws, const int32_t* __restrict__ offsets,
+#ifndef EOT_RESIZE_MINB
+#define EOT_RESIZE_MINB 4
+#endif
+__global__ void __launch_bounds__(kThreads, EOT_RESIZE_MINB) k_resize(EotShape s, Layout L, char* ws, const int32_t* __restrict__ offsets,
                                                         int b0, int b1) {
   extern __shared__ __align__(16) float resize_smem[];
   __shared__ int2 s_base[kMaxBaseSmem];
@@ -971,7 +974,7 @@ static int launch_forward(const EotShape& s, const Layout& L, const float* patch
     const size_t smem = resize_smem_bytes(s, L);
     if (smem > 32 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // static + dynamic may pass 48 KB
     k_match<<<dim3(pchunks, B), kThreads, 0, st>>>(s, L, patch, print_wb, ws, 0);
-    k_resize<<<nsm * 4, kThreads, smem, st>>>(s, L, ws, box_offsets, 0, B);
+    k_resize<<<nsm * EOT_RESIZE_MINB, kThreads, smem, st>>>(s, L, ws, box_offsets, 0, B);
     k_composite<<<nsm * 4, kThreads, 0, st>>>(s, L, ws, images, out_images, mask, box_offsets, 0, B, 0);
     count_launches(3);
   }
