@@ -131,3 +131,10 @@ def test_backward_out_of_range_image():
     bt = synth.make_batch(3, 160, 160, seed=71, max_boxes=3, min_boxes=1)
     bt.images[0] *= F(1.6)
     _check_backward(bt, synth.make_patch(40, seed=71), 0.4, 71)
+
+
+def test_forward_backward_more_than_1024_boxes():
+    # the work-item prefix tables no longer fit shared memory (kMaxBaseSmem): global-memory search paths
+    bt = synth.make_batch(160, 64, 64, seed=91, max_boxes=8, min_boxes=7)
+    assert bt.boxes.shape[0] > 1024
+    _check_backward(bt, synth.make_patch(20, seed=91), 0.5, 91)
