@@ -45,7 +45,8 @@ def parse_args():
     ap.add_argument("--max-boxes", type=int, default=8)
     ap.add_argument("--perspective", type=float, default=0.0)
     ap.add_argument("--kernel-iters", type=int, default=20)
-    ap.add_argument("--cpu-sample-batch", type=int, default=8)
+    ap.add_argument("--cpu-sample-batch", type=int, default=64,
+                    help="images per CPU step (default: the workload's per-GPU batch; ~10 s per step on 16 host threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-first-pass", action="store_true", help="skip the clean victim pass (NOT the headline)")
     ap.add_argument("--no-graphs", action="store_true", help="launch the victim passes kernel by kernel (no CUDA graphs)")
