@@ -34,7 +34,7 @@ namespace eot {
 #define EOT_SQRT2 1.41421354f                   // float32(2. ** .5), attacker.py:470
 
 #ifndef EOT_COMP_ROWS
-#define EOT_COMP_ROWS 8
+#define EOT_COMP_ROWS 4
 #endif
 #ifndef EOT_RESIZE_ROWS_CAP
 #define EOT_RESIZE_ROWS_CAP 12

@@ -685,6 +685,10 @@ __global__ void __launch_bounds__(kThreads, EOT_RESIZE_MINB) k_resize(EotShape s
 // c of the output came from this box and passes the outer clip): the backward's TensorScatterUpdate /
 // SelectV2 / clip routing without re-sampling.
 // ------------------------------------------------------------------------------------------------
+#ifndef EOT_COMP_THREADS
+#define EOT_COMP_THREADS 128
+#endif
+constexpr int kCompThreads = EOT_COMP_THREADS;   // threads per composite CTA: one warp per band row
 constexpr int kMaxBandBoxes = 32;   // boxes of one image whose windows meet one band (more: flagged, first 32 handled)
 
 struct BandBox {
@@ -776,7 +780,7 @@ __device__ __forceinline__ void composite_band(const EotShape& s, const Layout& 
   const float* img = images + img_off;
   float* o_img = out + img_off;
   float* m_img = mask ? mask + img_off : nullptr;
-  for (int gy = ya + warp; gy < yb; gy += kThreads / 32) {
+  for (int gy = ya + warp; gy < yb; gy += kCompThreads / 32) {
     // lane i: the column range of this row in which box i can matter (its whole window when every window pixel is
     // written or T is projective, else the conservative range of the rotated core)
     int rx0 = 1, rx1 = 0;
@@ -878,7 +882,7 @@ __device__ __forceinline__ void composite_band(const EotShape& s, const Layout& 
 }
 
 // Bands are handed out by an atomic ticket (their cost varies from nothing to several overlapping windows).
-__global__ void __launch_bounds__(kThreads, 4) k_composite(EotShape s, Layout L, char* ws,
+__global__ void __launch_bounds__(kCompThreads, 1024 / kCompThreads) k_composite(EotShape s, Layout L, char* ws,
                                                         const float* __restrict__ images, float* out, float* mask,
                                                         const int32_t* __restrict__ offsets, int b0, int b1, int group) {
   __shared__ CompositeSmem sm;
@@ -975,7 +979,7 @@ static int launch_forward(const EotShape& s, const Layout& L, const float* patch
     if (smem > 32 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // static + dynamic may pass 48 KB
     k_match<<<dim3(pchunks, B), kThreads, 0, st>>>(s, L, patch, print_wb, ws, 0);
     k_resize<<<nsm * EOT_RESIZE_MINB, kThreads, smem, st>>>(s, L, ws, box_offsets, 0, B);
-    k_composite<<<nsm * 4, kThreads, 0, st>>>(s, L, ws, images, out_images, mask, box_offsets, 0, B, 0);
+    k_composite<<<nsm * (1024 / kCompThreads), kCompThreads, 0, st>>>(s, L, ws, images, out_images, mask, box_offsets, 0, B, 0);
     count_launches(3);
   }
   EOT_CHECK_CUDA(cudaPeekAtLastError());
