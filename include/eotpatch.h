@@ -150,6 +150,40 @@ int score_max_bwd(const ScoreShape* shape, const float* const* cls_levels, const
                   float* loss_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* --------------------------------------------------------------------------------------------
+ * First-pass post-processing (attacker.py:100-116,143-170): the person candidates score_max_fwd
+ * left in its workspace -> per-image NonMaxSuppressionV5 (tf2/postprocess.py:159-205; hard or
+ * Gaussian soft-NMS, TF's lazy priority-queue order) -> clip_boxes -> ragged boxes as CSR.
+ * Replaces the reference's host-synchronous tf.map_fn over the images + CPU-only NMS kernel.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct NmsShape {
+  int32_t batch;
+  int32_t total_anchors;                    /* A                                                  */
+  int32_t num_levels;
+  int32_t max_output_size;                  /* nms_configs.max_output_size (100); <= 128          */
+  int32_t max_candidates;                   /* candidates per image the workspace holds; 0 = A    */
+  int32_t level_anchors[SCORE_MAX_LEVELS];  /* anchors per image of level l (9 * H_l * W_l)       */
+  float iou_threshold;                      /* hard: nms_configs.iou_thresh; gaussian: 1.0        */
+  float score_threshold;                    /* NMS score threshold (>= 0)                         */
+  float soft_nms_sigma;                     /* 0: hard NMS; gaussian: sigma / 2                   */
+  float score_floor;                        /* filter_valid_boxes(thresh=True): score >= floor    */
+  float image_height, image_width;          /* clip_boxes                                         */
+} NmsShape;
+
+int person_nms_workspace_bytes(const NmsShape* shape, size_t* bytes);
+
+/* cand_score: [B,A] candidate score or -1 (score_max_fwd's workspace; see ScoreShape).  box_levels:
+ * HOST array of num_levels device pointers [B, H_l, W_l, 9*4].  anchors: [A,4].
+ * Outputs (all device): nms_boxes [B,max_output_size,4] / nms_scores [B,max_output_size] in
+ * selection order, zero padded (scores are the soft-NMS adjusted ones, as TF returns them);
+ * valid_len [B]; row_splits [B+1] and ragged_boxes [B*max_output_size,4] / ragged_scores (optional)
+ * = the same boxes compacted in image order.  An image with more candidates than max_candidates
+ * sets valid_len[b] = -1 and row_splits[B] = -1 (nothing is truncated silently). */
+int person_nms(const NmsShape* shape, const float* cand_score, const float* const* box_levels,
+               const float* anchors, float* nms_boxes, float* nms_scores, int32_t* valid_len,
+               int32_t* row_splits, float* ragged_boxes, float* ragged_scores, void* workspace,
+               size_t workspace_bytes, void* stream);
+
+/* --------------------------------------------------------------------------------------------
  * Patch update (attacker.py:191-193,307-316,51-54): total-variation term and Adam + constraint.
  * ------------------------------------------------------------------------------------------ */
 /* grad_patch += weight * d TV(patch)/d patch ; tv_out (optional device scalar) = TV(patch). */

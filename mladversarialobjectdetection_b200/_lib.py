@@ -17,7 +17,7 @@ SCORE_MAX_LEVELS = 8
 # every symbol include/eotpatch.h declares (tests check the export list against the header)
 SYMBOLS = ["eot_last_error", "eot_version", "eot_launch_count", "eot_workspace_bytes", "eot_box_geometry", "eot_apply_fwd",
            "eot_apply_bwd", "eot_brightness_match", "eot_check_workspace", "score_workspace_bytes", "score_max_fwd", "score_max_bwd",
-           "patch_tv_grad", "adam_clip_update"]
+           "person_nms_workspace_bytes", "person_nms", "patch_tv_grad", "adam_clip_update"]
 
 
 class EotShape(ctypes.Structure):
@@ -34,6 +34,14 @@ class ScoreShape(ctypes.Structure):
                 ("anchors_per_loc", ctypes.c_int32), ("level_locs", ctypes.c_int32 * SCORE_MAX_LEVELS),
                 ("total_anchors", ctypes.c_int32), ("image_height", ctypes.c_float),
                 ("image_width", ctypes.c_float), ("min_area", ctypes.c_float)]
+
+
+class NmsShape(ctypes.Structure):
+    _fields_ = [("batch", ctypes.c_int32), ("total_anchors", ctypes.c_int32), ("num_levels", ctypes.c_int32),
+                ("max_output_size", ctypes.c_int32), ("max_candidates", ctypes.c_int32),
+                ("level_anchors", ctypes.c_int32 * SCORE_MAX_LEVELS), ("iou_threshold", ctypes.c_float),
+                ("score_threshold", ctypes.c_float), ("soft_nms_sigma", ctypes.c_float), ("score_floor", ctypes.c_float),
+                ("image_height", ctypes.c_float), ("image_width", ctypes.c_float)]
 
 
 _lock = threading.Lock()
@@ -58,6 +66,8 @@ def _declare(lib):
                                   vp, vp, sz, vp]
     lib.score_max_bwd.argtypes = [ctypes.POINTER(ScoreShape), ctypes.POINTER(vp), vp, vp, ctypes.POINTER(vp), vp,
                                   vp, vp, sz, vp]
+    lib.person_nms_workspace_bytes.argtypes = [ctypes.POINTER(NmsShape), ctypes.POINTER(sz)]
+    lib.person_nms.argtypes = [ctypes.POINTER(NmsShape), vp, ctypes.POINTER(vp), vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.patch_tv_grad.argtypes = [vp, i32, f32, vp, vp, vp]
     lib.adam_clip_update.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i64, f32, f32, vp]
     for name in SYMBOLS:

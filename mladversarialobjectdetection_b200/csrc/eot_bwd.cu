@@ -53,13 +53,13 @@ __global__ void __launch_bounds__(kThreads, EOT_BWDW_MINB) k_bwd_window(EotShape
   float* gubuf = reinterpret_cast<float*>(ws + L.off_gu);
   const uint8_t* routes = reinterpret_cast<const uint8_t*>(ws + L.off_route);
   const int H = s.height, W = s.width;
-  const int RR = L.resize_rows;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int2* cnt = reinterpret_cast<const int2*>(ws + L.off_cnt);
   for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
     const int2 item = find_item(base, s.total_boxes, 0, it);
     const int j = item.x;
     const BoxPlan me = plans[j];
     const int ps = me.ps, D = me.d;
+    const int RR = strip_rows(ps, cnt[j].x);
     const float4* u4 = reinterpret_cast<const float4*>(ubuf + me.u_off);
     float4* gu = reinterpret_cast<float4*>(gubuf + (size_t)j * L.gslot);
     const uint8_t* route = routes + (size_t)j * L.rslot;
@@ -69,12 +69,17 @@ __global__ void __launch_bounds__(kThreads, EOT_BWDW_MINB) k_bwd_window(EotShape
     const bool affine = (me.Ti[6] == 0.0f && me.Ti[7] == 0.0f);
     const float Dm1 = (float)(D - 1);
     const int S = u_stride(ps);
-    for (int r = warp; r < rows; r += kThreads / 32) {
+    // the strip's texels flattened over the CTA (strips are sized to a multiple of its thread count)
+    const float inv_ps = 1.0f / (float)ps;
+    for (int t = threadIdx.x; t < rows * ps; t += kThreads) {
+      int r = (int)(((float)t + 0.5f) * inv_ps);
+      int tx = t - r * ps;
+      if (tx < 0) { --r; tx += ps; } else if (tx >= ps) { ++r; tx -= ps; }
       const int ty = oy0 + r;
       const float yf = (float)(ty + me.pad_lo);
       const float cx = me.Ti[1] * yf, cy = me.Ti[4] * yf, cp = me.Ti[7] * yf;
       const float4* urow = u4 + (ty + 2) * S + 2;
-      for (int tx = lane; tx < ps; tx += 32) {
+      {
         const float xf = (float)(tx + me.pad_lo);
         float g[3] = {0.0f, 0.0f, 0.0f};
         float ix = (me.Ti[0] * xf + cx) + me.Ti[2];

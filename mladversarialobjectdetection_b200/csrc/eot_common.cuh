@@ -145,6 +145,16 @@ __host__ __device__ inline Layout make_layout(const EotShape& s) {
   return L;
 }
 
+// Forward resize strips of a box (also the items of the backward's window kernel): at most `cap` output rows each,
+// balanced (rows = ceil(ps / strips)).  Sizing the strips to multiples of the CTA's thread count was measured and did
+// not pay (profiles/r01_launches.md).
+__host__ __device__ inline int fwd_strips(int ps, int cap) {
+  if (ps <= 0) return 0;
+  const int r = cap < ps ? cap : ps;
+  return (ps + r - 1) / r;
+}
+__host__ __device__ inline int strip_rows(int ps, int strips) { return strips > 0 ? (ps + strips - 1) / strips : 1; }
+
 // patch rows per strip of the backward resize adjoint: <= 40 KB of RGBX intermediate rows of ps texels
 __host__ __device__ inline int bwd_strip_rows(int ps) {
   int rr = 2560 / (ps > 0 ? ps : 1);

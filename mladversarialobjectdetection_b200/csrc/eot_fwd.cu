@@ -167,7 +167,7 @@ __device__ int geometry_block(const EotShape& s, const Layout& L, int j, const f
     if (ws) {
       reinterpret_cast<BoxPlan*>(ws + L.off_plans)[j] = pl;
       reinterpret_cast<int2*>(ws + L.off_cnt)[j] =
-          pl.valid ? make_int2((pl.ps + L.resize_rows - 1) / L.resize_rows, 0) : make_int2(0, 0);
+          pl.valid ? make_int2(fwd_strips(pl.ps, L.resize_rows), 0) : make_int2(0, 0);
     }
     if (geom_out) {
       EotBoxGeometry g = {pl.y0, pl.x0, pl.ps, pl.d, pl.pad_lo, pl.pad_hi, pl.valid, pl.span};
@@ -512,12 +512,15 @@ __device__ __forceinline__ void resize_passes(const EotShape& s, int P, int ps, 
   // ---- rows pass ----
   if ((P & 3) == 0) {
     const int nq = P >> 2;                                    // texel quads per source row
-    for (int r = warp; r < rows; r += nwarps) {
+    // (row, quad) pairs flattened over the CTA (a warp per row would idle 7 lanes of 32 at P = 100)
+    for (int idx = threadIdx.x; idx < rows * nq; idx += blockDim.x) {
+      const int r = idx / nq;
       const int oy = oy0 + r;
       const int st = s_st[oy];
       const float* w = s_w + oy * (SPAN > 0 ? SPAN : span);
       const int nk = SPAN > 0 ? SPAN : min(span, P - st);
-      for (int tq = lane; tq < nq; tq += 32) {
+      {
+        const int tq = idx - r * nq;
         float acc[12];
 #pragma unroll
         for (int i = 0; i < 12; ++i) acc[i] = 0.0f;
@@ -635,7 +638,7 @@ __device__ __forceinline__ void resize_item(const EotShape& s, const Layout& L, 
   const int ps = pl->ps, span = pl->span;
   const float delta = pl->delta;
   const uint32_t key0 = pl->key0, key1 = pl->key1;
-  const int RR = L.resize_rows;
+  const int RR = strip_rows(ps, reinterpret_cast<const int2*>(ws + L.off_cnt)[j].x);
   const int oy0 = item.y * RR;
   const int rows = min(RR, ps - oy0);
   const float* m = reinterpret_cast<const float*>(ws + L.off_match) + (size_t)pl->image * P * P3;
@@ -654,7 +657,10 @@ __device__ __forceinline__ void resize_item(const EotShape& s, const Layout& L, 
 #ifndef EOT_RESIZE_MINB
 #define EOT_RESIZE_MINB 4
 #endif
-__global__ void __launch_bounds__(kThreads, EOT_RESIZE_MINB) k_resize(EotShape s, Layout L, char* ws, const int32_t* __restrict__ offsets,
+#ifndef EOT_RESIZE_THREADS
+#define EOT_RESIZE_THREADS 256
+#endif
+__global__ void __launch_bounds__(EOT_RESIZE_THREADS, EOT_RESIZE_MINB) k_resize(EotShape s, Layout L, char* ws, const int32_t* __restrict__ offsets,
                                                         int b0, int b1) {
   extern __shared__ __align__(16) float resize_smem[];
   __shared__ int2 s_base[kMaxBaseSmem];
@@ -978,7 +984,7 @@ static int launch_forward(const EotShape& s, const Layout& L, const float* patch
     const size_t smem = resize_smem_bytes(s, L);
     if (smem > 32 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // static + dynamic may pass 48 KB
     k_match<<<dim3(pchunks, B), kThreads, 0, st>>>(s, L, patch, print_wb, ws, 0);
-    k_resize<<<nsm * EOT_RESIZE_MINB, kThreads, smem, st>>>(s, L, ws, box_offsets, 0, B);
+    k_resize<<<nsm * EOT_RESIZE_MINB, EOT_RESIZE_THREADS, smem, st>>>(s, L, ws, box_offsets, 0, B);
     k_composite<<<nsm * (1024 / kCompThreads), kCompThreads, 0, st>>>(s, L, ws, images, out_images, mask, box_offsets, 0, B, 0);
     count_launches(3);
   }

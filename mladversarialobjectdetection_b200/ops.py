@@ -269,6 +269,57 @@ def score_max_backward(ctx: ScoreContext, scale: torch.Tensor, *, want_loss: boo
 
 
 # --------------------------------------------------------------------------------------------------
+# first-pass post-processing (NMS)
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class NmsResult:
+    nms_boxes: torch.Tensor       # [B,max_out,4] selection order, zero padded
+    nms_scores: torch.Tensor      # [B,max_out]
+    valid_len: torch.Tensor       # [B] int32
+    row_splits: torch.Tensor      # [B+1] int32
+    ragged_boxes: torch.Tensor    # [B*max_out,4], first row_splits[B] rows valid
+    ragged_scores: torch.Tensor   # [B*max_out]
+
+
+def person_nms(cand_score: torch.Tensor, box_levels: Sequence[torch.Tensor], anchors: torch.Tensor,
+               image_hw: Tuple[int, int], *, max_output_size: int = 100, iou_threshold: float = 1.0,
+               score_threshold: float = 0.5, soft_nms_sigma: float = 0.25, score_floor: float = 0.5,
+               max_candidates: int = 0) -> NmsResult:
+    """Per-image NonMaxSuppressionV5 + clip_boxes over the score kernel's person candidates -> padded and CSR
+    outputs, all on the device (attacker.py:104-116,143-170; tf2/postprocess.py:159-205).  No host sync."""
+    _need_cuda(cand_score, anchors, *box_levels)
+    box_levels = [_f32c(b, "box level") for b in box_levels]
+    cand_score = _f32c(cand_score, "cand_score")
+    B, A = cand_score.shape
+    s = _lib.NmsShape()
+    s.batch, s.total_anchors, s.num_levels = B, A, len(box_levels)
+    s.max_output_size, s.max_candidates = int(max_output_size), int(max_candidates)
+    for i, bl in enumerate(box_levels):
+        if bl.shape[0] != B or bl.numel() % (B * 4):
+            raise ValueError("box level tensors must be [B,h,w,anchors*4]")
+        s.level_anchors[i] = bl.numel() // (B * 4)
+    s.iou_threshold, s.score_threshold = float(iou_threshold), float(score_threshold)
+    s.soft_nms_sigma, s.score_floor = float(soft_nms_sigma), float(score_floor)
+    s.image_height, s.image_width = float(image_hw[0]), float(image_hw[1])
+    if anchors.shape != (A, 4):
+        raise ValueError(f"anchors must be [{A},4], got {tuple(anchors.shape)}")
+    lib = _lib.load()
+    n = ctypes.c_size_t(0)
+    _lib.check(lib.person_nms_workspace_bytes(ctypes.byref(s), ctypes.byref(n)), "person_nms_workspace_bytes")
+    dev = cand_score.device
+    ws = torch.empty(int(n.value), dtype=torch.uint8, device=dev)
+    M = int(max_output_size)
+    r = NmsResult(torch.empty((B, M, 4), dtype=torch.float32, device=dev), torch.empty((B, M), dtype=torch.float32, device=dev),
+                  torch.empty(B, dtype=torch.int32, device=dev), torch.empty(B + 1, dtype=torch.int32, device=dev),
+                  torch.empty((B * M, 4), dtype=torch.float32, device=dev), torch.empty(B * M, dtype=torch.float32, device=dev))
+    _lib.check(lib.person_nms(ctypes.byref(s), _ptr(cand_score), _ptr_array(box_levels), _ptr(_f32c(anchors, "anchors")),
+                              _ptr(r.nms_boxes), _ptr(r.nms_scores), _ptr(r.valid_len), _ptr(r.row_splits),
+                              _ptr(r.ragged_boxes), _ptr(r.ragged_scores), _ptr(ws), ctypes.c_size_t(ws.numel()),
+                              _stream()), "person_nms")
+    return r
+
+
+# --------------------------------------------------------------------------------------------------
 # patch update
 # --------------------------------------------------------------------------------------------------
 def tv_grad_(patch: torch.Tensor, grad_patch: torch.Tensor, weight: float = 1e-5, want_tv: bool = True):

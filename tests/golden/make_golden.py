@@ -4,6 +4,11 @@
 
 (a) `adv_patch_create.npz` -- outputs of the REFERENCE's own `adv_patch.AdversarialPatch._create`
     (/root/reference/adv_patch.py:61-92), the only importable piece of the patch-placement logic.
+(c) `nms_np.npz`           -- hard and Gaussian soft NMS selections of the REFERENCE's own NumPy implementation
+    (/root/reference/automl/efficientdet/nms_np.py:89-191) on seeded boxes.  nms_np uses the pixel-inclusive area
+    convention ((x2-x1+1)*(y2-y1+1)) while tf.raw_ops.NonMaxSuppressionV5 does not; the boxes are a few thousand
+    units wide so the two IoUs differ by ~1e-3, and cases with an IoU / score that close to a threshold are
+    rejected, so that both definitions must select the same boxes in the same order.
 (b) `oracle_small.npz`     -- the oracle's forward/backward on a small seeded case, so that the
     oracle cannot drift silently and the GPU box (which has no /root/reference) can check both the
     oracle and the CUDA path against a committed vector.
@@ -59,7 +64,48 @@ def gen_oracle_small():
                         anchors_head=anchors[:18], anchors_tail=anchors[-9:])
 
 
+def gen_nms_np():
+    sys.path.insert(0, "/root/reference/automl/efficientdet")
+    import nms_np  # noqa: the reference's NumPy NMS
+    rng = np.random.default_rng(77)
+    cases = {}
+    k = 0
+    while k < 6:
+        n = int(rng.integers(20, 120))
+        # clusters of overlapping boxes, coordinates in thousands of units
+        centres = rng.uniform(2000, 18000, size=(int(rng.integers(3, 9)), 2))
+        c = centres[rng.integers(0, len(centres), n)] + rng.normal(0, 400, size=(n, 2))
+        wh = rng.uniform(1500, 5000, size=(n, 2))
+        x1y1 = c - wh / 2
+        x2y2 = c + wh / 2
+        scores = rng.uniform(0.05, 1.0, n)
+        dets = np.concatenate([x1y1, x2y2, scores[:, None]], 1).astype(np.float64)   # [x1,y1,x2,y2,score]
+        hard = nms_np.hard_nms(dets.copy(), 0.5)
+        soft = nms_np.soft_nms(dets.copy(), dict(method="gaussian", sigma=0.5, iou_thresh=None, score_thresh=0.2))
+        # margins: no pairwise IoU within 0.02 of the hard threshold, no soft score within 0.01 of the score
+        # threshold or of another selected score
+        a = dets[:, None, :4]; b = dets[None, :, :4]
+        iw = np.maximum(np.minimum(a[..., 2], b[..., 2]) - np.maximum(a[..., 0], b[..., 0]), 0)
+        ih = np.maximum(np.minimum(a[..., 3], b[..., 3]) - np.maximum(a[..., 1], b[..., 1]), 0)
+        area = (dets[:, 2] - dets[:, 0]) * (dets[:, 3] - dets[:, 1])
+        iou = iw * ih / (area[:, None] + area[None, :] - iw * ih)
+        ss = np.sort(soft[:, 4])
+        if (np.abs(iou - 0.5) < 0.02).any() or (np.abs(ss - 0.2) < 0.01).any() or (np.diff(ss) < 1e-3).any():
+            continue
+        # ... nor may a REJECTED box come that close to the score threshold: the selection must not move with it
+        lo = nms_np.soft_nms(dets.copy(), dict(method="gaussian", sigma=0.5, iou_thresh=None, score_thresh=0.19))
+        hi = nms_np.soft_nms(dets.copy(), dict(method="gaussian", sigma=0.5, iou_thresh=None, score_thresh=0.21))
+        if lo.shape != soft.shape or hi.shape != soft.shape:
+            continue
+        cases[f"dets{k}"] = dets
+        cases[f"hard{k}"] = hard
+        cases[f"soft{k}"] = soft
+        k += 1
+    np.savez_compressed(os.path.join(HERE, "nms_np.npz"), n_cases=k, **cases)
+
+
 if __name__ == "__main__":
     gen_adv_patch_create()
+    gen_nms_np()
     gen_oracle_small()
     print("fixtures written to", HERE)
