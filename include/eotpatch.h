@@ -184,6 +184,33 @@ int person_nms(const NmsShape* shape, const float* cand_score, const float* cons
                size_t workspace_bytes, void* stream);
 
 /* --------------------------------------------------------------------------------------------
+ * Input pipeline (train_data_generator.py:55-75 `DataSequence._map_fn`; :201-226 augmentation):
+ * decoded uint8 frames -> the [B,H,W,3] float32 batch the attack step consumes.
+ * ------------------------------------------------------------------------------------------ */
+/* frames: HOST array of `batch` DEVICE pointers, frame i is uint8 [heights[i], widths[i], 3]
+ * contiguous; heights / widths / mean_rgb[3] / stddev_rgb[3]: HOST arrays.  out: [B,H,W,3]:
+ * (v - mean) / stddev in float64, aspect-preserving bilinear resize (cv2.resize INTER_LINEAR on
+ * the float64 image) into the top-left corner, zero padding, one rounding to float32.
+ * channel_sums (optional, device double[B,3]): per-image per-channel sums of `out` for
+ * eot_augment_batch. */
+int eot_letterbox_normalize(const uint8_t* const* frames, const int32_t* heights,
+                            const int32_t* widths, int32_t batch, int32_t out_height,
+                            int32_t out_width, const double* mean_rgb, const double* stddev_rgb,
+                            float* out, double* channel_sums, void* stream);
+
+/* channel_sums[B,3] (device double) of a [B,H,W,3] batch that did not come from the call above. */
+int eot_channel_sums(const float* images, int32_t batch, int32_t height, int32_t width,
+                     double* channel_sums, void* stream);
+
+/* tf.image.random_flip_left_right + RandomFlip('horizontal') (flip[b] != 0: mirror image b; NULL:
+ * none), RandomContrast ((x - mean_hw) * contrast_factor + mean_hw per image and channel),
+ * random_brightness (+ brightness_delta), clip to [-1,1] (train_data_generator.py:218-222); the
+ * random draws are the caller's.  Out of place when flip is given. */
+int eot_augment_batch(const float* images, float* out, int32_t batch, int32_t height, int32_t width,
+                      const uint8_t* flip, const double* channel_sums, float contrast_factor,
+                      float brightness_delta, void* stream);
+
+/* --------------------------------------------------------------------------------------------
  * Patch update (attacker.py:191-193,307-316,51-54): total-variation term and Adam + constraint.
  * ------------------------------------------------------------------------------------------ */
 /* grad_patch += weight * d TV(patch)/d patch ; tv_out (optional device scalar) = TV(patch). */

@@ -17,7 +17,8 @@ SCORE_MAX_LEVELS = 8
 # every symbol include/eotpatch.h declares (tests check the export list against the header)
 SYMBOLS = ["eot_last_error", "eot_version", "eot_launch_count", "eot_workspace_bytes", "eot_box_geometry", "eot_apply_fwd",
            "eot_apply_bwd", "eot_brightness_match", "eot_check_workspace", "score_workspace_bytes", "score_max_fwd", "score_max_bwd",
-           "person_nms_workspace_bytes", "person_nms", "patch_tv_grad", "adam_clip_update"]
+           "person_nms_workspace_bytes", "person_nms", "eot_letterbox_normalize", "eot_channel_sums",
+           "eot_augment_batch", "patch_tv_grad", "adam_clip_update"]
 
 
 class EotShape(ctypes.Structure):
@@ -68,6 +69,11 @@ def _declare(lib):
                                   vp, vp, sz, vp]
     lib.person_nms_workspace_bytes.argtypes = [ctypes.POINTER(NmsShape), ctypes.POINTER(sz)]
     lib.person_nms.argtypes = [ctypes.POINTER(NmsShape), vp, ctypes.POINTER(vp), vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    f64p = ctypes.POINTER(ctypes.c_double)
+    lib.eot_letterbox_normalize.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(i32), ctypes.POINTER(i32), i32, i32, i32,
+                                            f64p, f64p, vp, vp, vp]
+    lib.eot_channel_sums.argtypes = [vp, i32, i32, i32, vp, vp]
+    lib.eot_augment_batch.argtypes = [vp, vp, i32, i32, i32, vp, vp, f32, f32, vp]
     lib.patch_tv_grad.argtypes = [vp, i32, f32, vp, vp, vp]
     lib.adam_clip_update.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i64, f32, f32, vp]
     for name in SYMBOLS:

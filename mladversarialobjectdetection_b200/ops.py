@@ -320,6 +320,63 @@ def person_nms(cand_score: torch.Tensor, box_levels: Sequence[torch.Tensor], anc
 
 
 # --------------------------------------------------------------------------------------------------
+# input pipeline
+# --------------------------------------------------------------------------------------------------
+def letterbox_normalize(frames: Sequence[torch.Tensor], output_size: Tuple[int, int], mean_rgb, stddev_rgb,
+                        out: Optional[torch.Tensor] = None, want_sums: bool = True):
+    """`DataSequence._map_fn` for a batch (train_data_generator.py:55-75): uint8 CUDA frames [h_i,w_i,3] of any
+    sizes -> ([B,H,W,3] float32, channel sums [B,3] float64 for `augment_batch`)."""
+    _need_cuda(*frames)
+    B = len(frames)
+    if B == 0:
+        raise ValueError("no frames")
+    fr = []
+    for f in frames:
+        if f.dtype != torch.uint8 or f.dim() != 3 or f.shape[2] != 3:
+            raise TypeError("frames must be uint8 [h,w,3]")
+        fr.append(f if f.is_contiguous() else f.contiguous())
+    H, W = int(output_size[0]), int(output_size[1])
+    dev = fr[0].device
+    if out is None:
+        out = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev)
+    sums = torch.empty((B, 3), dtype=torch.float64, device=dev) if want_sums else None
+    heights = (ctypes.c_int32 * B)(*[int(f.shape[0]) for f in fr])
+    widths = (ctypes.c_int32 * B)(*[int(f.shape[1]) for f in fr])
+    mean = (ctypes.c_double * 3)(*np.broadcast_to(np.asarray(mean_rgb, np.float64), (3,)).tolist())
+    std = (ctypes.c_double * 3)(*np.broadcast_to(np.asarray(stddev_rgb, np.float64), (3,)).tolist())
+    _lib.check(_lib.load().eot_letterbox_normalize(_ptr_array(fr), heights, widths, B, H, W, mean, std, _ptr(out),
+                                                   _ptr(sums), _stream()), "eot_letterbox_normalize")
+    return out, sums
+
+
+def channel_sums(images: torch.Tensor) -> torch.Tensor:
+    _need_cuda(images)
+    images = _f32c(images, "images")
+    B, H, W, _ = images.shape
+    sums = torch.empty((B, 3), dtype=torch.float64, device=images.device)
+    _lib.check(_lib.load().eot_channel_sums(_ptr(images), B, H, W, _ptr(sums), _stream()), "eot_channel_sums")
+    return sums
+
+
+def augment_batch(images: torch.Tensor, flip: Optional[torch.Tensor], contrast_factor: float, brightness_delta: float,
+                  sums: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """train_data_generator.py:218-222: flips, RandomContrast, random_brightness, clip; draws are explicit."""
+    _need_cuda(images, flip, sums)
+    images = _f32c(images, "images")
+    B, H, W, _ = images.shape
+    if sums is None:
+        sums = channel_sums(images)
+    if flip is not None and (flip.dtype != torch.uint8 or flip.numel() != B):
+        raise TypeError("flip must be uint8 [B]")
+    if out is None:
+        out = torch.empty_like(images)
+    _lib.check(_lib.load().eot_augment_batch(_ptr(images), _ptr(out), B, H, W, _ptr(flip), _ptr(sums),
+                                             ctypes.c_float(contrast_factor), ctypes.c_float(brightness_delta),
+                                             _stream()), "eot_augment_batch")
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
 # patch update
 # --------------------------------------------------------------------------------------------------
 def tv_grad_(patch: torch.Tensor, grad_patch: torch.Tensor, weight: float = 1e-5, want_tv: bool = True):

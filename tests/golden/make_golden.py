@@ -9,6 +9,10 @@
     convention ((x2-x1+1)*(y2-y1+1)) while tf.raw_ops.NonMaxSuppressionV5 does not; the boxes are a few thousand
     units wide so the two IoUs differ by ~1e-3, and cases with an IoU / score that close to a threshold are
     rejected, so that both definitions must select the same boxes in the same order.
+(d) `map_fn.npz`           -- outputs of the REFERENCE's own `DataSequence._map_fn`
+    (/root/reference/train_data_generator.py:55-75; NumPy + cv2) on seeded uint8 frames.  The module imports
+    TensorFlow at the top (absent here); the import is satisfied by an inert stub so that the reference's own
+    function body runs unmodified.
 (b) `oracle_small.npz`     -- the oracle's forward/backward on a small seeded case, so that the
     oracle cannot drift silently and the GPU box (which has no /root/reference) can check both the
     oracle and the CUDA path against a committed vector.
@@ -104,8 +108,30 @@ def gen_nms_np():
     np.savez_compressed(os.path.join(HERE, "nms_np.npz"), n_cases=k, **cases)
 
 
+def gen_map_fn():
+    import types
+    from unittest import mock
+    tf = mock.MagicMock()
+    tf.keras.utils.Sequence = type("Sequence", (), {})          # DataSequence's base class must be a real class
+    stubs = {"tensorflow": tf, "hparams_config": mock.MagicMock(), "util": mock.MagicMock(), "utils": mock.MagicMock()}
+    with mock.patch.dict(sys.modules, stubs):
+        sys.path.insert(0, "/root/reference")
+        import train_data_generator as tdg  # noqa: the reference module; only _map_fn (NumPy + cv2) is executed
+    rng = np.random.default_rng(55)
+    out = {}
+    sizes = [(48, 64), (37, 53), (80, 60), (64, 64), (128, 128), (200, 31), (9, 150)]
+    for k, (h, w) in enumerate(sizes):
+        frame = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+        for tag, mean, std in (("a", 127.0, 128.0), ("b", [123.675, 116.28, 103.53], [58.395, 57.12, 57.375])):
+            ds = tdg.DataSequence("", (64, 64), mean, std, file_list=["unused"])
+            out[f"frame{k}"] = frame
+            out[f"out{k}{tag}"] = ds._map_fn(frame).astype(np.float32)      # generator: tf.convert_to_tensor(.., float32)
+    np.savez_compressed(os.path.join(HERE, "map_fn.npz"), n=len(sizes), **out)
+
+
 if __name__ == "__main__":
     gen_adv_patch_create()
+    gen_map_fn()
     gen_nms_np()
     gen_oracle_small()
     print("fixtures written to", HERE)
