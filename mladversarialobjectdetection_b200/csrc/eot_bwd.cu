@@ -27,15 +27,15 @@ constexpr int kBwdChunk = 8;     // patch rows per tap fetch in k_bwd_resize
 // gradient that reaches R_j at a window pixel of a box, 3 channels: the route byte says which channels of the pasted
 // pixel came from this box (SelectV2), passed the outer clip and were not overwritten by a later paste
 // (TensorScatterUpdate grad).  `px` = pixel index inside the image plane window (32-bit: H*W*3 < 2^31 is checked).
+__device__ __forceinline__ void routed_grad3_bits(unsigned bits, const float* __restrict__ Gwin, int px, float g[3]) {
+  const float* gp = Gwin + px * 3;
+  g[0] = (bits & 1u) ? __ldg(gp) : 0.0f;
+  g[1] = (bits & 2u) ? __ldg(gp + 1) : 0.0f;
+  g[2] = (bits & 4u) ? __ldg(gp + 2) : 0.0f;
+}
 __device__ __forceinline__ void routed_grad3(const uint8_t* __restrict__ route, const float* __restrict__ Gwin, int rt, int px,
                                              float g[3]) {
-  const unsigned bits = route[rt];
-  g[0] = g[1] = g[2] = 0.0f;
-  if (!bits) return;
-  const float* gp = Gwin + px * 3;
-  if (bits & 1u) g[0] = __ldg(gp);
-  if (bits & 2u) g[1] = __ldg(gp + 1);
-  if (bits & 4u) g[2] = __ldg(gp + 2);
+  routed_grad3_bits(route[rt], Gwin, px, g);
 }
 
 #ifndef EOT_BWDW_MINB
@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(kThreads, EOT_BWDW_MINB) k_bwd_window(EotShape
       const float cx = me.Ti[1] * yf, cy = me.Ti[4] * yf, cp = me.Ti[7] * yf;
       const float4* urow = u4 + (ty + 2) * S + 2;
       {
+        const unsigned bits = __float_as_uint(__ldg(&urow[tx].w));         // inner clip pass bits (attacker.py:428), fetched early
         const float xf = (float)(tx + me.pad_lo);
         float g[3] = {0.0f, 0.0f, 0.0f};
         float ix = (me.Ti[0] * xf + cx) + me.Ti[2];
@@ -97,10 +98,12 @@ __global__ void __launch_bounds__(kThreads, EOT_BWDW_MINB) k_bwd_window(EotShape
           if (x0f >= 0.0f && x0f < Dm1 && y0f >= 0.0f && y0f < Dm1) {        // all four taps inside the window
             const int xi0 = (int)x0f, yi0 = (int)y0f;
             const int rt = yi0 * D + xi0, px = yi0 * W + xi0;
-            routed_grad3(route, Gwin, rt, px, v00);
-            routed_grad3(route, Gwin, rt + 1, px + 1, v01);
-            routed_grad3(route, Gwin, rt + D, px + W, v10);
-            routed_grad3(route, Gwin, rt + D + 1, px + W + 1, v11);
+            // the four route bytes first, then all (predicated) gradient loads: one round trip each, not two per row
+            const unsigned r00 = route[rt], r01 = route[rt + 1], r10 = route[rt + D], r11 = route[rt + D + 1];
+            routed_grad3_bits(r00, Gwin, px, v00);
+            routed_grad3_bits(r01, Gwin, px + 1, v01);
+            routed_grad3_bits(r10, Gwin, px + W, v10);
+            routed_grad3_bits(r11, Gwin, px + W + 1, v11);
           } else {
             const float x1f = x0f + 1.0f, y1f = y0f + 1.0f, Df = (float)D;
             const bool bx0 = x0f >= 0.0f && x0f < Df, bx1 = x1f >= 0.0f && x1f < Df;
@@ -119,7 +122,6 @@ __global__ void __launch_bounds__(kThreads, EOT_BWDW_MINB) k_bwd_window(EotShape
 #pragma unroll
           for (int c = 0; c < 3; ++c) g[c] = wy1 * (wx1 * v00[c] + wx0 * v01[c]) + wy0 * (wx1 * v10[c] + wx0 * v11[c]);
         }
-        const unsigned bits = __float_as_uint(urow[tx].w);                 // inner clip pass bits (attacker.py:428)
         gu[ty * ps + tx] = make_float4((bits & 1u) ? g[0] : 0.0f, (bits & 2u) ? g[1] : 0.0f, (bits & 4u) ? g[2] : 0.0f, 0.0f);
       }
     }

@@ -24,13 +24,15 @@ struct FrameBatch {
   const uint8_t* data[kFramesPerLaunch];
   int32_t h[kFramesPerLaunch], w[kFramesPerLaunch];       // decoded size
   int32_t sh[kFramesPerLaunch], sw[kFramesPerLaunch];     // scaled size inside the letterbox
+  double scale_y[kFramesPerLaunch], scale_x[kFramesPerLaunch];   // 1 / (scaled / decoded), as cv2 derives it
   int32_t n, first;                                       // frames in this launch, index of the first one in the batch
 };
 
 struct Standardise { double mean[3], stddev[3]; };
 
-__device__ __forceinline__ void bilinear_tap(int o, int dsize, int ssize, int* s0, int* s1, double* w0, double* w1) {
-  const double scale = 1.0 / ((double)dsize / (double)ssize);
+__host__ __device__ inline double resize_scale(int dsize, int ssize) { return 1.0 / ((double)dsize / (double)ssize); }
+
+__device__ __forceinline__ void bilinear_tap(int o, double scale, int ssize, int* s0, int* s1, double* w0, double* w1) {
   double f = ((double)o + 0.5) * scale - 0.5;
   int s = (int)floor(f);
   f = f - (double)s;
@@ -68,8 +70,8 @@ __global__ void __launch_bounds__(kThreads) k_letterbox(FrameBatch fb, Standardi
       } else {
         int x0, x1, y0, y1;
         double a0, a1, b0, b1;
-        bilinear_tap(ox, sw, w, &x0, &x1, &a0, &a1);
-        bilinear_tap(oy, sh, h, &y0, &y1, &b0, &b1);
+        bilinear_tap(ox, fb.scale_x[k], w, &x0, &x1, &a0, &a1);
+        bilinear_tap(oy, fb.scale_y[k], h, &y0, &y1, &b0, &b1);
         const uint8_t* q00 = src + ((size_t)y0 * w + x0) * 3;
         const uint8_t* q01 = src + ((size_t)y0 * w + x1) * 3;
         const uint8_t* q10 = src + ((size_t)y1 * w + x0) * 3;
@@ -119,6 +121,13 @@ __global__ void __launch_bounds__(kThreads) k_channel_sums(const float* __restri
   }
 }
 
+__device__ __forceinline__ float aug1(float v, float m, float contrast, float delta) {
+  return clampf(((v - m) * contrast + m) + delta, -1.0f, 1.0f);
+}
+
+// kVec: W % 4 == 0 and 16-byte aligned batches -- a thread owns 4 consecutive output pixels (3 x 128-bit stores); their
+// sources are 4 consecutive pixels as well (mirrored: the same quad read back to front).
+template <bool kVec>
 __global__ void __launch_bounds__(kThreads) k_augment(const float* __restrict__ in, float* out, int H, int W,
                                                       const uint8_t* __restrict__ flip,
                                                       const double* __restrict__ channel_sums, float contrast,
@@ -129,14 +138,36 @@ __global__ void __launch_bounds__(kThreads) k_augment(const float* __restrict__ 
   const double n = (double)H * (double)W;
   const float m0 = (float)(channel_sums[(size_t)b * 3] / n), m1 = (float)(channel_sums[(size_t)b * 3 + 1] / n),
               m2 = (float)(channel_sums[(size_t)b * 3 + 2] / n);
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < H * W; p += gridDim.x * blockDim.x) {
-    const int y = p / W, x = p - y * W;
-    const float* q = in + img + ((size_t)y * W + (fl ? W - 1 - x : x)) * 3;
-    const float v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2);
-    float* o = out + img + (size_t)p * 3;
-    o[0] = clampf(((v0 - m0) * contrast + m0) + delta, -1.0f, 1.0f);
-    o[1] = clampf(((v1 - m1) * contrast + m1) + delta, -1.0f, 1.0f);
-    o[2] = clampf(((v2 - m2) * contrast + m2) + delta, -1.0f, 1.0f);
+  if (kVec) {
+    const int wq = W >> 2;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < H * wq; q += gridDim.x * blockDim.x) {
+      const int y = q / wq, xq = q - y * wq;
+      const int sq = fl ? wq - 1 - xq : xq;
+      const float4* src = reinterpret_cast<const float4*>(in + img + ((size_t)y * W + 4 * sq) * 3);
+      const float4 A = __ldg(src), Bv = __ldg(src + 1), C = __ldg(src + 2);
+      float p[12] = {A.x, A.y, A.z, A.w, Bv.x, Bv.y, Bv.z, Bv.w, C.x, C.y, C.z, C.w};
+      float r[12];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int sp = fl ? 3 - i : i;
+        r[3 * i] = aug1(p[3 * sp], m0, contrast, delta);
+        r[3 * i + 1] = aug1(p[3 * sp + 1], m1, contrast, delta);
+        r[3 * i + 2] = aug1(p[3 * sp + 2], m2, contrast, delta);
+      }
+      float4* dst = reinterpret_cast<float4*>(out + img + ((size_t)y * W + 4 * xq) * 3);
+      dst[0] = make_float4(r[0], r[1], r[2], r[3]);
+      dst[1] = make_float4(r[4], r[5], r[6], r[7]);
+      dst[2] = make_float4(r[8], r[9], r[10], r[11]);
+    }
+  } else {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < H * W; p += gridDim.x * blockDim.x) {
+      const int y = p / W, x = p - y * W;
+      const float* q = in + img + ((size_t)y * W + (fl ? W - 1 - x : x)) * 3;
+      float* o = out + img + (size_t)p * 3;
+      o[0] = aug1(__ldg(q), m0, contrast, delta);
+      o[1] = aug1(__ldg(q + 1), m1, contrast, delta);
+      o[2] = aug1(__ldg(q + 2), m2, contrast, delta);
+    }
   }
 }
 
@@ -175,6 +206,7 @@ extern "C" int eot_letterbox_normalize(const uint8_t* const* frames, const int32
       }
       fb.data[k] = frames[first + k];
       fb.h[k] = h; fb.w[k] = w; fb.sh[k] = sh; fb.sw[k] = sw;
+      fb.scale_y[k] = resize_scale(sh, h); fb.scale_x[k] = resize_scale(sw, w);
     }
     const int per_frame = (out_height * out_width + kThreads - 1) / kThreads;
     int gx = (nsm * 8 + fb.n - 1) / fb.n;
@@ -208,11 +240,16 @@ extern "C" int eot_augment_batch(const float* images, float* out, int32_t batch,
   if (!images || !out || !channel_sums) { set_error("eot_augment_batch: NULL pointer"); return EOT_ERR_NULL_POINTER; }
   if (batch <= 0 || height <= 0 || width <= 0) { set_error("eot_augment_batch: bad shape"); return EOT_ERR_BAD_SHAPE; }
   if (images == out && flip) { set_error("eot_augment_batch: the flip cannot run in place"); return EOT_ERR_BAD_SHAPE; }
-  const int per = (height * width + kThreads - 1) / kThreads;
+  const bool vec = (width % 4 == 0) && (((uintptr_t)images | (uintptr_t)out) & 15) == 0;
+  const int per = (height * width / (vec ? 4 : 1) + kThreads - 1) / kThreads;
   int gx = (sm_count() * 8 + batch - 1) / batch;
   gx = gx > per ? per : (gx < 1 ? 1 : gx);
-  k_augment<<<dim3(gx, batch), kThreads, 0, (cudaStream_t)stream>>>(images, out, height, width, flip, channel_sums,
-                                                                   contrast_factor, brightness_delta);
+  if (vec)
+    k_augment<true><<<dim3(gx, batch), kThreads, 0, (cudaStream_t)stream>>>(images, out, height, width, flip, channel_sums,
+                                                                           contrast_factor, brightness_delta);
+  else
+    k_augment<false><<<dim3(gx, batch), kThreads, 0, (cudaStream_t)stream>>>(images, out, height, width, flip, channel_sums,
+                                                                            contrast_factor, brightness_delta);
   count_launches(1);
   EOT_CHECK_CUDA(cudaPeekAtLastError());
   return EOT_OK;
