@@ -255,28 +255,51 @@ __host__ __device__ inline size_t bwd_resize3_smem_bytes(const EotShape& s, cons
 template <int TK>
 __device__ __forceinline__ void bwd_resize_passes(int P, int ps, int tcap, int py0, int rows, const float4* __restrict__ gu,
                                                   const float* s_wt, const int2* s_st, float4* inter, float* gbox) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   constexpr int NT = TK > 0 ? TK : 1;
-  for (int r = warp; r < rows; r += nwarps) {                      // rows pass: a warp per patch row, a lane per texel column
-    const int py = py0 + r;
-    const int2 sc = s_st[py];
-    const float* w = s_wt + py * tcap;
-    for (int ox = lane; ox < ps; ox += 32) {
-      float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
-      if (TK > 0) {
-        float4 v[NT];
+  // rows pass, flattened over the strip's (patch row, texel column) pairs; two pairs per thread and iteration so that
+  // 2 x NT gradient texels are in flight before the first use (the loads come from L2 / DRAM: g_u is 56 MB)
+  const int total = rows * ps;
+  const float inv_ps = 1.0f / (float)ps;
+  for (int idx = threadIdx.x; idx < total; idx += 2 * blockDim.x) {
+    int id[2], rr[2], oxx[2];
+    id[0] = idx;
+    id[1] = idx + blockDim.x < total ? idx + blockDim.x : idx;      // tail: recompute the first pair (same value stored twice)
 #pragma unroll
-        for (int k = 0; k < NT; ++k) v[k] = gu[(size_t)min(sc.x + k, ps - 1) * ps + ox];
+    for (int u = 0; u < 2; ++u) {
+      int r = (int)(((float)id[u] + 0.5f) * inv_ps);
+      int ox = id[u] - r * ps;
+      if (ox < 0) { --r; ox += ps; } else if (ox >= ps) { ++r; ox -= ps; }
+      rr[u] = r; oxx[u] = ox;
+    }
+    if (TK > 0) {
+      float4 v[2][NT];
 #pragma unroll
-        for (int k = 0; k < NT; ++k) { const float wk = w[k]; a0 += wk * v[k].x; a1 += wk * v[k].y; a2 += wk * v[k].z; }
-      } else {
+      for (int u = 0; u < 2; ++u) {
+        const int st = s_st[py0 + rr[u]].x;
+#pragma unroll
+        for (int k = 0; k < NT; ++k) v[u][k] = gu[(size_t)min(st + k, ps - 1) * ps + oxx[u]];
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float* w = s_wt + (py0 + rr[u]) * tcap;
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+#pragma unroll
+        for (int k = 0; k < NT; ++k) { const float wk = w[k]; a0 += wk * v[u][k].x; a1 += wk * v[u][k].y; a2 += wk * v[u][k].z; }
+        inter[rr[u] * ps + oxx[u]] = make_float4(a0, a1, a2, 0.0f);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int2 sc = s_st[py0 + rr[u]];
+        const float* w = s_wt + (py0 + rr[u]) * tcap;
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
         for (int k = 0; k < sc.y; ++k) {
-          const float4 v = gu[(size_t)(sc.x + k) * ps + ox];
+          const float4 v = gu[(size_t)(sc.x + k) * ps + oxx[u]];
           const float wk = w[k];
           a0 += wk * v.x; a1 += wk * v.y; a2 += wk * v.z;
         }
+        inter[rr[u] * ps + oxx[u]] = make_float4(a0, a1, a2, 0.0f);
       }
-      inter[r * ps + ox] = make_float4(a0, a1, a2, 0.0f);
     }
   }
   __syncthreads();
@@ -361,10 +384,19 @@ __global__ void __launch_bounds__(kThreads) k_bwd_match(EotShape s, Layout L, ch
   double gy_acc = 0.0;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < PP; t += gridDim.x * blockDim.x) {
     float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
-    for (int j = j0; j < j1; ++j) {
-      if (!plans[j].valid) continue;
-      const float* g = gbox + ((size_t)j * PP + t) * 3;
-      a0 += g[0]; a1 += g[1]; a2 += g[2];
+    for (int j = j0; j < j1; j += 4) {                             // four boxes' loads in flight, summed in box order
+      float g[4][3];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int jj = j + u;
+        const bool ok = jj < j1 && plans[min(jj, j1 - 1)].valid;
+        const float* gp = gbox + ((size_t)min(jj, j1 - 1) * PP + t) * 3;
+        g[u][0] = ok ? __ldcg(gp) : 0.0f;
+        g[u][1] = ok ? __ldcg(gp + 1) : 0.0f;
+        g[u][2] = ok ? __ldcg(gp + 2) : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a0 += g[u][0]; a1 += g[u][1]; a2 += g[u][2]; }
     }
     const float* p = patch + (size_t)t * 3;
     const TexelYuv y = texel_yuv(__ldg(p), __ldg(p + 1), __ldg(p + 2), wb);
