@@ -211,6 +211,33 @@ int eot_augment_batch(const float* images, float* out, int32_t batch, int32_t he
                       float brightness_delta, void* stream);
 
 /* --------------------------------------------------------------------------------------------
+ * uint8 inference-time patcher: GPU twin of `adv_patch.AdversarialPatch` (adv_patch.py:40-201).
+ * Frames and patches are uint8 [h,w,3] RGB on the device; results are bit-identical to the
+ * reference's NumPy + OpenCV code (8-bit fixed-point colour conversion, INTER_LINEAR letter-box,
+ * INTER_AREA patch down-sampling).  The INTER_CUBIC branch (a box that needs the patch larger
+ * than its texture) is not provided: EOT_ERR_BAD_SHAPE.
+ * ------------------------------------------------------------------------------------------ */
+/* `_create` (adv_patch.py:61-92) for n boxes; HOST in, HOST out: placements[n,4] =
+ * (ymin_patch, xmin_patch, patch_h, patch_w).  No GPU work (sizes the noise buffer). */
+int adv_u8_box_geometry(int32_t frame_h, int32_t frame_w, double scale, const double* boxes,
+                        int32_t n, int32_t* placements);
+
+/* `print_patch` (adv_patch.py:40-59) on n_elems uint8 values. */
+int adv_u8_print_patch(const uint8_t* patch, uint8_t* printed, int64_t n_elems, void* stream);
+
+int adv_u8_workspace_bytes(int32_t patch_h, int32_t patch_w, size_t* bytes);
+
+/* `add_adv_to_img` (adv_patch.py:179-190), in place on `frame`: boxes (HOST double[n,4]: ymin,
+ * xmin, ymax, xmax) are pasted in order and every brightness match sees the earlier pastes.
+ * out_h/out_w: the `h, w` of AdversarialPatch (letter-box size of `rescale`).  noise: DEVICE
+ * float64, the np.random.uniform(-.01, .01) draws of `random_noise`, box after box, each
+ * [patch_h_i, patch_w_i, 3]. */
+int adv_u8_add_patches(uint8_t* frame, int32_t frame_h, int32_t frame_w, const uint8_t* patch_printed,
+                       int32_t patch_h, int32_t patch_w, int32_t out_h, int32_t out_w, double scale,
+                       const double* boxes, int32_t n, const double* noise, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* --------------------------------------------------------------------------------------------
  * Patch update (attacker.py:191-193,307-316,51-54): total-variation term and Adam + constraint.
  * ------------------------------------------------------------------------------------------ */
 /* grad_patch += weight * d TV(patch)/d patch ; tv_out (optional device scalar) = TV(patch). */

@@ -18,7 +18,8 @@ SCORE_MAX_LEVELS = 8
 SYMBOLS = ["eot_last_error", "eot_version", "eot_launch_count", "eot_workspace_bytes", "eot_box_geometry", "eot_apply_fwd",
            "eot_apply_bwd", "eot_brightness_match", "eot_check_workspace", "score_workspace_bytes", "score_max_fwd", "score_max_bwd",
            "person_nms_workspace_bytes", "person_nms", "eot_letterbox_normalize", "eot_channel_sums",
-           "eot_augment_batch", "patch_tv_grad", "adam_clip_update"]
+           "eot_augment_batch", "adv_u8_box_geometry", "adv_u8_print_patch", "adv_u8_workspace_bytes", "adv_u8_add_patches",
+           "patch_tv_grad", "adam_clip_update"]
 
 
 class EotShape(ctypes.Structure):
@@ -74,6 +75,11 @@ def _declare(lib):
                                             f64p, f64p, vp, vp, vp]
     lib.eot_channel_sums.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.eot_augment_batch.argtypes = [vp, vp, i32, i32, i32, vp, vp, f32, f32, vp]
+    f64 = ctypes.c_double
+    lib.adv_u8_box_geometry.argtypes = [i32, i32, f64, f64p, i32, ctypes.POINTER(i32)]
+    lib.adv_u8_print_patch.argtypes = [vp, vp, i64, vp]
+    lib.adv_u8_workspace_bytes.argtypes = [i32, i32, ctypes.POINTER(sz)]
+    lib.adv_u8_add_patches.argtypes = [vp, i32, i32, vp, i32, i32, i32, i32, f64, f64p, i32, vp, vp, sz, vp]
     lib.patch_tv_grad.argtypes = [vp, i32, f32, vp, vp, vp]
     lib.adam_clip_update.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i64, f32, f32, vp]
     for name in SYMBOLS:

@@ -13,6 +13,9 @@
     (/root/reference/train_data_generator.py:55-75; NumPy + cv2) on seeded uint8 frames.  The module imports
     TensorFlow at the top (absent here); the import is satisfied by an inert stub so that the reference's own
     function body runs unmodified.
+(e) `adv_patch_u8.npz`     -- outputs of the REFERENCE's own `adv_patch.AdversarialPatch.add_adv_to_img`
+    (/root/reference/adv_patch.py:179-190; NumPy + cv2) on seeded uint8 frames, with the raw patch and the
+    np.random.uniform noise draws it consumed (replayed from the same RandomState) stored next to them.
 (b) `oracle_small.npz`     -- the oracle's forward/backward on a small seeded case, so that the
     oracle cannot drift silently and the GPU box (which has no /root/reference) can check both the
     oracle and the CUDA path against a committed vector.
@@ -129,8 +132,42 @@ def gen_map_fn():
     np.savez_compressed(os.path.join(HERE, "map_fn.npz"), n=len(sizes), **out)
 
 
+def gen_adv_patch_u8():
+    sys.path.insert(0, "/root/reference")
+    import adv_patch  # noqa
+    out = {}
+    P = 96
+    cases = [((96, 96), [(10, 20, 90, 60), (30, 50, 70, 95)], 0.5),          # frame == output size
+             ((72, 96), [(5, 5, 60, 40), (20, 40, 71, 90), (0, 0, 30, 30)], 0.5),
+             ((192, 192), [(0, 40, 192, 120), (60, 60, 180, 150)], 0.5),      # exact 2x rescale; first box: patch side == P
+             ((150, 211), [(20, 30, 140, 100), (40, 100, 120, 200), (100, 10, 149, 60)], 0.4)]
+    for k, (hw, boxes, scale) in enumerate(cases):
+        np.random.seed(100 + k)
+        raw = (np.random.rand(P, P, 3) * 255).astype("uint8")               # what __init__ draws for patch_file=None
+        np.random.seed(100 + k)
+        ap = adv_patch.AdversarialPatch(scale=scale, h=P, w=P)
+        frame = np.random.default_rng(200 + k).integers(0, 256, size=hw + (3,), dtype=np.uint8)
+        state = np.random.get_state()
+        res = ap.add_adv_to_img(frame, boxes)
+        np.random.set_state(state)                                           # replay the noise draws of random_noise()
+        noises = []
+        for bb in boxes:
+            _, _, ph, pw = ap._create(frame, bb)
+            noises.append(np.random.uniform(low=-0.01, high=0.01, size=(ph, pw, 3)))
+        out[f"raw{k}"] = raw
+        out[f"printed{k}"] = ap._patch_img
+        out[f"frame{k}"] = frame
+        out[f"boxes{k}"] = np.asarray(boxes, np.float64)
+        out[f"scale{k}"] = scale
+        out[f"result{k}"] = res
+        for i, nz in enumerate(noises):
+            out[f"noise{k}_{i}"] = nz
+    np.savez_compressed(os.path.join(HERE, "adv_patch_u8.npz"), n=len(cases), P=P, **out)
+
+
 if __name__ == "__main__":
     gen_adv_patch_create()
+    gen_adv_patch_u8()
     gen_map_fn()
     gen_nms_np()
     gen_oracle_small()
