@@ -16,6 +16,10 @@
 (e) `adv_patch_u8.npz`     -- outputs of the REFERENCE's own `adv_patch.AdversarialPatch.add_adv_to_img`
     (/root/reference/adv_patch.py:179-190; NumPy + cv2) on seeded uint8 frames, with the raw patch and the
     np.random.uniform noise draws it consumed (replayed from the same RandomState) stored next to them.
+(f) `patcher_ref.npz`      -- output of the REFERENCE's own `attacker.Patcher.call` (/root/reference/attacker.py:344-498,
+    with /root/reference/brightness_matcher.py) executed verbatim on a NumPy stand-in for the TF / TFA ops it calls
+    (tests/golden/tf_numpy_shim.py: the reference's Python -- control flow, expression order, casts, pad / where / clip /
+    scatter sequence, box filter -- is real; the leaf kernels inside the TF wheels are the oracle's restatements).
 (b) `oracle_small.npz`     -- the oracle's forward/backward on a small seeded case, so that the
     oracle cannot drift silently and the GPU box (which has no /root/reference) can check both the
     oracle and the CUDA path against a committed vector.
@@ -165,8 +169,203 @@ def gen_adv_patch_u8():
     np.savez_compressed(os.path.join(HERE, "adv_patch_u8.npz"), n=len(cases), P=P, **out)
 
 
+def gen_patcher_ref():
+    import tf_numpy_shim as shim
+    from mladversarialobjectdetection_b200 import synth
+    from oracle import patcher, tfops
+    F = np.float32
+    attacker = shim.import_reference_attacker()
+    H = W = 64
+    P = 16
+    bt = synth.make_batch(2, H, W, max_boxes=3, min_boxes=2, seed=2718)
+    patch = synth.make_patch(P, seed=5)
+    boxes, params = bt.ragged()
+    boxes = [np.array(b, F) for b in boxes]
+    params = [np.array(p) for p in params]
+    # one box the area filter drops (patch side floor(4 * .4) = 1 -> area 1 <= 4), in the middle of image 0's list
+    tiny = np.array([[10.0, 12.0, 14.0, 15.0]], F)
+    boxes[0] = np.concatenate([boxes[0][:1], tiny, boxes[0][1:]])
+    params[0] = np.concatenate([params[0][:1], params[0][:1], params[0][1:]])
+    scale = F(0.4)
+    rng = np.random.default_rng(99)
+    print_wb = np.zeros((2, 6), F)
+    q = shim.QUEUE
+    q.items.clear()
+    for b in range(2):
+        zw, zb = rng.standard_normal(3).astype(F), rng.standard_normal(3).astype(F)
+        print_wb[b, :3] = zw * F(0.1) + F(0.5)                                   # tf.random.normal((1,1,3), .5, .1)
+        print_wb[b, 3:] = zb * F(0.01) + F(0.0)
+        q.push("normal", zw)
+        q.push("normal", zb)
+        plans = []
+        for j in range(len(boxes[b])):                                           # create(): jitter draws of every box
+            q.push("uniform", F(params[b][j]["uy"]))
+            q.push("uniform", F(params[b][j]["ux"]))
+            plans.append(patcher.create(boxes[b][j], scale, params[b][j]["uy"], params[b][j]["ux"], 0.2, H, W))
+        for j, pl in enumerate(plans):                                           # the while loop over the VALID boxes
+            if not pl.valid:
+                continue
+            n = pl.ps * pl.ps * 3
+            words = tfops.philox4x32_10(np.arange((n + 3) // 4, dtype=np.uint32), int(params[b][j]["key0"]),
+                                        int(params[b][j]["key1"])).reshape(-1)[:n]
+            q.push("uniform", ((words & np.uint32(0x7FFFFF)) | np.uint32(0x3F800000)).view(F) - F(1.0))
+            ud, ua = F(rng.random()), F(rng.random())
+            lo, hi = F(-0.3), F(0.3)
+            params[b][j]["delta"] = ud * (hi - lo) + lo                          # tf.image.random_brightness(im, .3)
+            q.push("uniform", ud)
+            lo, hi = F(-20.0 * np.pi / 180.0), F(20.0 * np.pi / 180.0)
+            ang = F(ua * (hi - lo) + lo)
+            params[b][j]["cos"], params[b][j]["sin"] = F(np.cos(ang)), F(np.sin(ang))
+            q.push("uniform", ua)
+    layer = attacker.Patcher(shim.Variable(patch.astype(F)), shim.Variable(scale), name="Patcher")
+    out_ref = np.asarray(layer([boxes, bt.images.astype(F)]), F)
+    assert not q.items, "the reference consumed fewer random draws than queued"
+    out_oracle, _, _ = patcher.patcher_forward(patch, bt.images, boxes, params, print_wb, float(scale))
+    assert np.array_equal(out_ref, out_oracle), "oracle != reference Patcher on the shim"
+    offsets = np.cumsum([0] + [len(b) for b in boxes]).astype(np.int32)
+    np.savez_compressed(os.path.join(HERE, "patcher_ref.npz"), patch=patch, images=bt.images, boxes=np.concatenate(boxes),
+                        offsets=offsets, params=np.concatenate(params).view(np.uint8), print_wb=print_wb, scale=scale,
+                        out_ref=out_ref)
+    # the stand-alone BrightnessMatcher layer as well (brightness_matcher.py:43-73)
+    bm = attacker.brightness_matcher.BrightnessMatcher(name="bm")
+    src = np.random.default_rng(7).uniform(-1, 1, (P, P, 3)).astype(F)
+    np.savez_compressed(os.path.join(HERE, "brightness_ref.npz"), src=src, tgt=bt.images[0],
+                        out_ref=np.asarray(bm((src, bt.images[0])), F))
+
+
+def gen_masker_ref():
+    """The reference's own `attack_detection.Masker.call` (attack_detection.py:321-498) on the NumPy TF shim, evaluation
+    branch (learned patch, tolerance 0) and training branch (per-image crops of other batch images, scale U(.3,.5))."""
+    import tf_numpy_shim as shim
+    from mladversarialobjectdetection_b200 import synth
+    from oracle import patcher, tfops
+    F = np.float32
+    ad = shim.import_reference_attacker(module="attack_detection")
+    H = W = 64
+    out = {}
+    for tag, training in (("eval", False), ("train", True)):
+        bt = synth.make_batch(2, H, W, max_boxes=2, min_boxes=1, seed=161 if training else 162,
+                              scale_range=(0.3, 0.5) if training else None)
+        boxes, params = bt.ragged()
+        boxes = [np.array(b, F) for b in boxes]
+        params = [np.array(p) for p in params]
+        images = bt.images.astype(F)
+        rng = np.random.default_rng(17)
+        q = shim.QUEUE
+        q.items.clear()
+        tol = 0.5 if training else 0.0
+        shared = synth.make_patch(24, seed=6)
+        scale = F(0.45)
+        if training:
+            perm = np.array([1, 0])
+            fl_lr, fl_ud = np.array([True, False]), np.array([False, True])
+            q.push("perm", perm)
+            q.push("flip", fl_lr)
+            q.push("flip", fl_ud)
+            patches = images[:, :240, :240, :][perm].copy()
+            patches[fl_lr] = patches[fl_lr][:, :, ::-1]
+            patches[fl_ud] = patches[fl_ud][:, ::-1]
+        print_wb = np.zeros((2, 6), F)
+        for b in range(2):
+            plans = []
+            for j in range(len(boxes[b])):                                       # create(): [scale], jitter y, jitter x
+                if training:
+                    us = F(rng.random())
+                    params[b][j]["scale"] = us * (F(0.5) - F(0.3)) + F(0.3)
+                    q.push("uniform", us)
+                else:
+                    params[b][j]["scale"] = F(-1.0)
+                q.push("uniform", F(params[b][j]["uy"]))
+                q.push("uniform", F(params[b][j]["ux"]))
+                sc = params[b][j]["scale"] if training else scale
+                plans.append(patcher.create(boxes[b][j], sc, params[b][j]["uy"], params[b][j]["ux"], tol, H, W))
+            assert all(p.valid for p in plans)
+            zw, zb = rng.standard_normal(3).astype(F), rng.standard_normal(3).astype(F)   # print adjust AFTER create here
+            print_wb[b, :3] = zw * F(0.1) + F(0.5)
+            print_wb[b, 3:] = zb * F(0.01) + F(0.0)
+            q.push("normal", zw)
+            q.push("normal", zb)
+            for j, pl in enumerate(plans):
+                n = pl.ps * pl.ps * 3
+                words = tfops.philox4x32_10(np.arange((n + 3) // 4, dtype=np.uint32), int(params[b][j]["key0"]),
+                                            int(params[b][j]["key1"])).reshape(-1)[:n]
+                q.push("uniform", ((words & np.uint32(0x7FFFFF)) | np.uint32(0x3F800000)).view(F) - F(1.0))
+                ud, ua = F(rng.random()), F(rng.random())
+                params[b][j]["delta"] = ud * (F(0.3) - F(-0.3)) + F(-0.3)
+                q.push("uniform", ud)
+                lo, hi = F(-20.0 * np.pi / 180.0), F(20.0 * np.pi / 180.0)
+                ang = F(ua * (hi - lo) + lo)
+                params[b][j]["cos"], params[b][j]["sin"] = F(np.cos(ang)), F(np.sin(ang))
+                q.push("uniform", ua)
+        layer = ad.Masker(shim.Variable(shared.astype(F)), shim.Variable(scale), name="Masker")
+        ref_img, ref_mask = layer([boxes, images], training=training)
+        assert not q.items
+        o_img, o_mask, _ = patcher.patcher_forward(patches if training else shared, images, boxes, params, print_wb, float(scale),
+                                                   tolerance=tol, noise_amp=0.1, want_mask=True)
+        assert np.array_equal(np.asarray(ref_img, F), o_img) and np.array_equal(np.asarray(ref_mask, F), o_mask), tag
+        offsets = np.cumsum([0] + [len(b) for b in boxes]).astype(np.int32)
+        out.update({f"{tag}_images": images, f"{tag}_boxes": np.concatenate(boxes), f"{tag}_offsets": offsets,
+                    f"{tag}_params": np.concatenate(params).view(np.uint8), f"{tag}_print_wb": print_wb,
+                    f"{tag}_patch": patches if training else shared, f"{tag}_scale": scale,
+                    f"{tag}_out": np.asarray(ref_img, F), f"{tag}_mask": np.asarray(ref_mask, F)})
+    np.savez_compressed(os.path.join(HERE, "masker_ref.npz"), **out)
+
+
+def gen_anchors_ref():
+    """The reference's own `tf2/anchors.py:Anchors` (NumPy arithmetic; TensorFlow and the object_detection imports of the
+    module stubbed out) for the image sizes / anchor scales of the configs: SHA-256 of the float32 table + every 97th row."""
+    import hashlib
+    import importlib.abc
+    import importlib.machinery
+    from unittest import mock
+
+    class Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+        def __init__(self):
+            self.created = []
+
+        def find_spec(self, name, path, target=None):
+            if name.split(".")[0] in ("tensorflow", "object_detection", "absl", "tensorflow_addons", "tensorflow_model_optimization"):
+                return importlib.machinery.ModuleSpec(name, self, is_package=True)
+
+        def create_module(self, spec):
+            m = mock.MagicMock(name=spec.name)
+            m.__path__, m.__name__, m.__spec__, m.__loader__ = [], spec.name, spec, self
+            self.created.append(spec.name)
+            return m
+
+        def exec_module(self, module):
+            pass
+    finder = Finder()
+    sys.meta_path.insert(0, finder)
+    paths = ["/root/reference/automl/efficientdet", "/root/reference/automl/efficientdet/tf2"]
+    sys.path[:0] = paths
+    saved = {k: sys.modules.pop(k) for k in ("anchors", "utils") if k in sys.modules}
+    try:
+        import tensorflow as tf
+        tf.convert_to_tensor = lambda x, dtype=None: np.asarray(x, np.float32)
+        import anchors as ref_anchors  # noqa: the reference module
+        out = {}
+        cfgs = [(512, 512, 4.0), (640, 640, 4.0), (1024, 1024, 4.0), (320, 320, 3.0), (384, 640, 4.0)]
+        for k, (h, w, scale) in enumerate(cfgs):
+            tab = np.asarray(ref_anchors.Anchors(3, 7, 3, [1.0, 2.0, 0.5], scale, (h, w)).boxes, np.float32)
+            out[f"sha{k}"] = hashlib.sha256(np.ascontiguousarray(tab).tobytes()).hexdigest()
+            out[f"rows{k}"] = tab[::97]
+            out[f"n{k}"] = len(tab)
+        np.savez_compressed(os.path.join(HERE, "anchors_ref.npz"), cfgs=np.asarray(cfgs, np.float64), **out)
+    finally:
+        sys.meta_path.remove(finder)
+        for p in paths:
+            sys.path.remove(p)
+        for name in finder.created + ["anchors", "utils"]:
+            sys.modules.pop(name, None)
+        sys.modules.update(saved)
+
+
 if __name__ == "__main__":
     gen_adv_patch_create()
+    gen_anchors_ref()
+    gen_masker_ref()
+    gen_patcher_ref()
     gen_adv_patch_u8()
     gen_map_fn()
     gen_nms_np()

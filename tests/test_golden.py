@@ -41,3 +41,17 @@ def test_oracle_matches_committed_vectors():
     anchors = objective.anchor_boxes(64)
     np.testing.assert_array_equal(anchors[:18], g["anchors_head"])
     np.testing.assert_array_equal(anchors[-9:], g["anchors_tail"])
+
+
+def test_anchor_tables_equal_reference_anchors_class():
+    """tf2/anchors.py:Anchors (the reference's own NumPy arithmetic, fixtures anchors_ref.npz): whole-table SHA-256 and
+    every 97th row, for D0 512, lite 640, D4 1024, lite0 320 (anchor_scale 3) and a non-square input."""
+    import hashlib
+    from mladversarialobjectdetection_b200.anchors import anchor_table
+    g = np.load(os.path.join(GOLD, "anchors_ref.npz"))
+    for k, (h, w, scale) in enumerate(g["cfgs"]):
+        for tab in (anchor_table((int(h), int(w)), 3, 7, 3, (1.0, 2.0, 0.5), float(scale)),
+                    objective.anchor_boxes((int(h), int(w)), anchor_scale=float(scale))):
+            assert len(tab) == int(g[f"n{k}"])
+            np.testing.assert_array_equal(tab[::97], g[f"rows{k}"])
+            assert hashlib.sha256(np.ascontiguousarray(tab.astype(np.float32)).tobytes()).hexdigest() == str(g[f"sha{k}"])

@@ -185,3 +185,36 @@ def test_masker_mask_with_overlapping_windows():
         bt.boxes[bt.offsets[b] + 1] = bt.boxes[bt.offsets[b]] + F(6.0)
     bt.boxes = np.clip(bt.boxes, 0, 160).astype(F)
     _check_forward(bt, synth.make_patch(32, seed=73), 0.4, geom=ops.PatchGeometry(tolerance=0.5, noise_amp=0.1), want_mask=True)
+
+
+def test_cuda_forward_equals_reference_patcher_fixture():
+    """CUDA path vs the output of the reference's own Patcher.call run on the NumPy TF shim (tests/golden/patcher_ref.npz)."""
+    from tests.test_reference_patcher_fixture import load_patcher_fixture
+    g, _, _ = load_patcher_fixture()
+    dev = "cuda"
+    params = np.ascontiguousarray(g["params"]).view(patcher.BOX_PARAMS).reshape(-1)
+    out, _, ctx = ops.apply_forward(torch.from_numpy(g["patch"]).to(dev), torch.tensor(float(g["scale"]), device=dev),
+                                    torch.from_numpy(g["images"]).to(dev), torch.from_numpy(g["boxes"]).to(dev),
+                                    torch.from_numpy(g["offsets"]).to(dev), ops.params_to_tensor(params, dev),
+                                    torch.from_numpy(g["print_wb"]).to(dev), ops.PatchGeometry())
+    ops.check_workspace(ctx)
+    np.testing.assert_array_equal(out.cpu().numpy(), g["out_ref"])
+    b = np.load(os.path.join(GOLD, "brightness_ref.npz"))
+    got = ops.brightness_match(torch.from_numpy(b["src"]).to(dev), torch.from_numpy(b["tgt"]).to(dev)).cpu().numpy()
+    np.testing.assert_array_equal(got, b["out_ref"])
+
+
+@pytest.mark.parametrize("tag,tol", [("eval", 0.0), ("train", 0.5)])
+def test_cuda_masker_equals_reference_masker_fixture(tag, tol):
+    """CUDA Masker path (mask output, per-image patch textures) vs the reference's own Masker.call on the NumPy TF shim."""
+    from tests.test_reference_patcher_fixture import load_masker_fixture
+    g, _, _, params = load_masker_fixture(tag)
+    dev = "cuda"
+    geom = ops.PatchGeometry(tolerance=tol, noise_amp=0.1, max_scale=0.5 if tag == "train" else 1.0)
+    out, mask, ctx = ops.apply_forward(torch.from_numpy(g[f"{tag}_patch"]).to(dev), torch.tensor(float(g[f"{tag}_scale"]), device=dev),
+                                       torch.from_numpy(g[f"{tag}_images"]).to(dev), torch.from_numpy(g[f"{tag}_boxes"]).to(dev),
+                                       torch.from_numpy(g[f"{tag}_offsets"]).to(dev), ops.params_to_tensor(params, dev),
+                                       torch.from_numpy(g[f"{tag}_print_wb"]).to(dev), geom, want_mask=True)
+    ops.check_workspace(ctx)
+    np.testing.assert_array_equal(out.cpu().numpy(), g[f"{tag}_out"])
+    np.testing.assert_array_equal(mask.cpu().numpy(), g[f"{tag}_mask"])

@@ -1,0 +1,58 @@
+"""The oracle against the REFERENCE'S OWN `attacker.Patcher.call` and `BrightnessMatcher.call`, executed verbatim in
+the build container on a NumPy stand-in for the TF ops they call (tests/golden/tf_numpy_shim.py; fixtures
+tests/golden/patcher_ref.npz / brightness_ref.npz written by tests/golden/make_golden.py).
+
+What this pins: the reference's Python -- expression order / association, casts, pad split, where / clip / scatter
+sequence, the area filter (a dropped box sits in the middle of image 0's list), the loop over boxes and images, the
+brightness matcher's formula order.  The leaf TF kernels underneath are the oracle's own restatements (unpinned)."""
+import os
+
+import numpy as np
+
+from oracle import patcher
+from oracle.patcher import BOX_PARAMS
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_patcher_fixture():
+    g = np.load(os.path.join(GOLD, "patcher_ref.npz"))
+    params = np.ascontiguousarray(g["params"]).view(BOX_PARAMS).reshape(-1)
+    off = g["offsets"]
+    boxes = [g["boxes"][off[b]:off[b + 1]] for b in range(len(off) - 1)]
+    prm = [params[off[b]:off[b + 1]] for b in range(len(off) - 1)]
+    return g, boxes, prm
+
+
+def test_oracle_equals_reference_patcher_on_the_shim():
+    g, boxes, prm = load_patcher_fixture()
+    out, _, states = patcher.patcher_forward(g["patch"], g["images"], boxes, prm, g["print_wb"], float(g["scale"]))
+    np.testing.assert_array_equal(out, g["out_ref"])
+    assert len(boxes[0]) == 3 and len(states[0].boxes) == 2          # the area filter dropped the tiny box
+    assert (out != g["images"]).any()
+
+
+def test_oracle_equals_reference_brightness_matcher_on_the_shim():
+    g = np.load(os.path.join(GOLD, "brightness_ref.npz"))
+    np.testing.assert_array_equal(patcher.brightness_match(g["src"], g["tgt"]), g["out_ref"])
+
+
+def load_masker_fixture(tag):
+    g = np.load(os.path.join(GOLD, "masker_ref.npz"))
+    params = np.ascontiguousarray(g[f"{tag}_params"]).view(BOX_PARAMS).reshape(-1)
+    off = g[f"{tag}_offsets"]
+    boxes = [g[f"{tag}_boxes"][off[b]:off[b + 1]] for b in range(len(off) - 1)]
+    prm = [params[off[b]:off[b + 1]] for b in range(len(off) - 1)]
+    return g, boxes, prm, params
+
+
+def test_oracle_equals_reference_masker_on_the_shim():
+    """attack_detection.Masker.call (attack_detection.py:321-498): evaluation branch (learned patch, tolerance 0) and
+    training branch (shuffled / flipped crops of other batch images as per-image patches, scale U(.3,.5), noise +-0.1)."""
+    for tag, tol in (("eval", 0.0), ("train", 0.5)):
+        g, boxes, prm, _ = load_masker_fixture(tag)
+        out, mask, _ = patcher.patcher_forward(g[f"{tag}_patch"], g[f"{tag}_images"], boxes, prm, g[f"{tag}_print_wb"],
+                                               float(g[f"{tag}_scale"]), tolerance=tol, noise_amp=0.1, want_mask=True)
+        np.testing.assert_array_equal(out, g[f"{tag}_out"])
+        np.testing.assert_array_equal(mask, g[f"{tag}_mask"])
+        assert mask.any()
