@@ -72,8 +72,9 @@ def decode(tb: np.ndarray, anchors: np.ndarray) -> np.ndarray:
     ha = a[..., 2] - a[..., 0]
     wa = a[..., 3] - a[..., 1]
     ty, tx, th, tw = tb[..., 0], tb[..., 1], tb[..., 2], tb[..., 3]
-    w = np.exp(tw) * wa
-    h = np.exp(th) * ha
+    with np.errstate(over="ignore"):
+        w = np.exp(tw.astype(np.float64)).astype(F) * wa         # correctly rounded float32 exp (as oracle/nms.py)
+        h = np.exp(th.astype(np.float64)).astype(F) * ha
     yc = ty * ha + yca
     xc = tx * wa + xca
     return np.stack([yc - h / F(2), xc - w / F(2), yc + h / F(2), xc + w / F(2)], axis=-1).astype(F)

@@ -20,6 +20,10 @@
     with /root/reference/brightness_matcher.py) executed verbatim on a NumPy stand-in for the TF / TFA ops it calls
     (tests/golden/tf_numpy_shim.py: the reference's Python -- control flow, expression order, casts, pad / where / clip /
     scatter sequence, box filter -- is real; the leaf kernels inside the TF wheels are the oracle's restatements).
+(g) `objective_ref.npz`    -- outputs of the REFERENCE's own `PatchAttacker.second_pass` / `first_pass` + the max-score line of
+    `call` (/root/reference/attacker.py:69-170,190), with the vendored automl code they call imported for real
+    (tf2/postprocess.py pre_nms / nms / clip_boxes, tf2/anchors.py, hparams_config.py), all on the NumPy TF shim;
+    the NonMaxSuppressionV5 / sigmoid / exp leaf kernels are the oracle's restatements.
 (b) `oracle_small.npz`     -- the oracle's forward/backward on a small seeded case, so that the
     oracle cannot drift silently and the GPU box (which has no /root/reference) can check both the
     oracle and the CUDA path against a committed vector.
@@ -361,8 +365,51 @@ def gen_anchors_ref():
         sys.modules.update(saved)
 
 
+def gen_objective_ref():
+    import tf_numpy_shim as shim
+    from oracle import nms as onms, objective
+    from tests._util import objective_fixture_inputs
+    F = np.float32
+    att = shim.import_reference_attacker(with_automl=True)
+    cfg = att.hparams_config.get_efficientdet_config("efficientdet-d0")
+    cfg.override({"nms_configs": {"iou_thresh": .5, "score_thresh": .5}})          # attacker_train.py:31
+    B, H = 2, 64
+    cfg.image_size = H
+    cls, box = objective_fixture_inputs(8, B, H)
+
+    class Model:
+        config = cfg
+
+        def __call__(self, images, pre_mode=None, post_mode=None):
+            return tuple(c.copy() for c in cls), tuple(b.copy() for b in box)
+    pa = object.__new__(att.PatchAttacker)
+    pa.config, pa.model = cfg, Model()
+    images = np.zeros((B, H, H, 3), F)
+    boxes_pred, scores_pred = pa.second_pass(images)
+    max_scores = np.maximum(shim._reduce_max(scores_pred, axis=1), F(0.0))           # attacker.py:190
+    fp_boxes, fp_scores = pa.first_pass(images)
+    # cross-check against the oracle right here
+    anchors = objective.anchor_boxes(H)
+    c_all, b_all = objective.merge_levels(cls, box, 90)
+    post = objective.objective_forward(c_all, b_all, anchors, H, H, 0.4)
+    for b in range(B):
+        assert np.array_equal(post["score"][b][post["cand"][b]], scores_pred.rows[b])
+        assert np.array_equal(post["boxes"][b][post["cand"][b]], boxes_pred.rows[b])
+    assert np.array_equal(post["max_scores"], max_scores)
+    cand = np.where(post["cand"], post["score"], F(-1.0)).astype(F)
+    rows, row_scores = onms.person_boxes_after_nms(cand, b_all, anchors, (H, H), dict(cfg.nms_configs.as_dict()), thresh=True)
+    for b in range(B):
+        assert np.array_equal(rows[b], fp_boxes.rows[b]) and np.array_equal(row_scores[b], fp_scores.rows[b])
+    out = dict(seed=8, B=B, H=H, max_scores=max_scores)
+    for b in range(B):
+        out[f"sp_scores{b}"], out[f"sp_boxes{b}"] = scores_pred.rows[b], boxes_pred.rows[b]
+        out[f"fp_scores{b}"], out[f"fp_boxes{b}"] = fp_scores.rows[b], fp_boxes.rows[b]
+    np.savez_compressed(os.path.join(HERE, "objective_ref.npz"), **out)
+
+
 if __name__ == "__main__":
     gen_adv_patch_create()
+    gen_objective_ref()
     gen_anchors_ref()
     gen_masker_ref()
     gen_patcher_ref()

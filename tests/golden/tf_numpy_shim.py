@@ -165,6 +165,77 @@ def _gather_nd(params, indices):
     return np.asarray(params)[tuple(idx[:, k] for k in range(idx.shape[1]))] if len(idx) else np.asarray(params)[:0]
 
 
+class Ragged:
+    """tf.RaggedTensor with one ragged dimension: a list of per-row arrays."""
+
+    def __init__(self, rows):
+        self.rows = [np.asarray(r) for r in rows]
+
+    def nrows(self):
+        return len(self.rows)
+
+    def __getitem__(self, key):
+        if isinstance(key, tuple):                              # r[:, :, k]
+            assert key[0] == slice(None) and key[1] == slice(None)
+            return Ragged([r[(slice(None),) + tuple(key[2:])] for r in self.rows])
+        return self.rows[int(key)]
+
+    def _zip(self, other, fn):
+        if isinstance(other, Ragged):
+            return Ragged([fn(a, b) for a, b in zip(self.rows, other.rows)])
+        return Ragged([fn(a, other) for a in self.rows])
+
+    def __sub__(self, o): return self._zip(o, lambda a, b: a - b)
+    def __mul__(self, o): return self._zip(o, lambda a, b: a * b)
+    def __truediv__(self, o): return self._zip(o, lambda a, b: a / b)
+
+    @staticmethod
+    def from_tensor(tensor, lengths):
+        return Ragged([np.asarray(tensor)[i][:int(n)] for i, n in enumerate(np.asarray(lengths))])
+
+
+def _rag(fn):
+    def op(a, b):
+        if isinstance(a, Ragged):
+            return a._zip(b, fn)
+        return fn(a, b)
+    return op
+
+
+def _boolean_mask(data, mask):
+    rows = data.rows if isinstance(data, Ragged) else list(np.asarray(data))
+    masks = mask.rows if isinstance(mask, Ragged) else list(np.asarray(mask))
+    return Ragged([np.asarray(r)[np.asarray(m, bool)] for r, m in zip(rows, masks)])
+
+
+def _reduce_max(x, axis=None):
+    if isinstance(x, Ragged):                                   # empty rows reduce to the lowest float (attacker.py:190)
+        assert axis == 1
+        return np.array([r.max() if len(r) else np.finfo(F).min for r in x.rows], F)
+    return np.max(x, axis=axis)
+
+
+def _zeros_like(x):
+    return Ragged([np.zeros_like(r) for r in x.rows]) if isinstance(x, Ragged) else np.zeros_like(x)
+
+
+def _nms_v5(boxes, scores, max_output_size, iou_threshold, score_threshold, soft_nms_sigma, pad_to_max_output_size=False):
+    from oracle import nms as onms                              # the restated leaf kernel (unpinned against TF)
+    sel, sel_scores = onms.non_max_suppression_v5(boxes, scores, int(max_output_size), float(iou_threshold),
+                                                  float(score_threshold), float(soft_nms_sigma))
+    n = len(sel)
+    if pad_to_max_output_size:
+        idx = np.zeros(int(max_output_size), np.int32); idx[:n] = sel
+        sc = np.zeros(int(max_output_size), F); sc[:n] = sel_scores
+        return idx, sc, np.int32(n)
+    return sel.astype(np.int32), sel_scores, np.int32(n)
+
+
+def _sigmoid(x):
+    x = _f(x)
+    return (1.0 / (1.0 + np.exp(-x.astype(np.float64)))).astype(F)   # correctly rounded float32 sigmoid, as the oracle
+
+
 class Layer:
     def __init__(self, *args, trainable=True, name=None, **kwargs):
         self.name = name
@@ -185,7 +256,7 @@ def build_modules():
     tf.stack = lambda xs, axis=0: np.stack([np.asarray(x) for x in xs], axis=axis)
     tf.reshape = lambda x, shape: np.reshape(x, tuple(int(s) for s in shape))
     tf.where = _where
-    tf.greater, tf.less = np.greater, np.less
+    tf.less = _rag(np.less)
     tf.gather_nd = _gather_nd
     tf.while_loop = _while_loop
     tf.map_fn = _map_rows
@@ -199,8 +270,29 @@ def build_modules():
     tf.tensor_scatter_nd_update = _scatter_nd_update
     tf.reduce_mean = lambda x: tfops.mean_f64(_f(x))
     tf.function = lambda fn=None, **kw: fn if fn is not None else (lambda f: f)
-    tf.math = types.SimpleNamespace(floor=np.floor, ceil=np.ceil)
-    tf.zeros_like = np.zeros_like
+    tf.math = types.SimpleNamespace(floor=np.floor, ceil=np.ceil, sigmoid=_sigmoid,
+                                    exp=lambda x: np.exp(_f(x).astype(np.float64)).astype(F),
+                                    argmax=lambda x, axis=-1, output_type=np.int32: np.argmax(x, axis=axis).astype(output_type))
+    tf.__path__ = []                                            # a package: tensorflow.compat.v1 etc. resolve to inert mocks
+    tf.zeros_like = _zeros_like
+    tf.Tensor = np.ndarray
+    tf.convert_to_tensor = lambda x, dtype=None: np.asarray(x, dtype=dtype)
+    tf.equal = _rag(np.equal)
+    tf.less_equal = _rag(np.less_equal)
+    tf.greater_equal = _rag(np.greater_equal)
+    tf.greater = _rag(np.greater)
+    tf.logical_and = _rag(np.logical_and)
+    tf.concat = lambda xs, axis: np.concatenate([np.asarray(x) for x in xs], axis=int(axis))
+    tf.transpose = lambda x, perm: np.transpose(x, perm)
+    tf.tile = lambda x, reps: np.tile(x, [int(r) for r in reps])
+    tf.expand_dims = lambda x, axis: np.expand_dims(x, axis)
+    tf.gather = lambda params, indices: np.asarray(params)[np.asarray(indices)]
+    tf.reduce_max = _reduce_max
+    tf.ragged = types.SimpleNamespace(boolean_mask=_boolean_mask)
+    tf.RaggedTensor = Ragged
+    tf.TensorSpec = lambda *a, **k: None
+    tf.raw_ops = types.SimpleNamespace(NonMaxSuppressionV5=_nms_v5)
+    tf.name_scope = lambda name: __import__("contextlib").nullcontext()
     tf.random = types.SimpleNamespace(uniform=_uniform, normal=_normal, shuffle=_shuffle)
     tf.image = types.SimpleNamespace(resize=_resize, random_brightness=_random_brightness, rgb_to_yuv=_rgb_to_yuv,
                                      yuv_to_rgb=_yuv_to_rgb, random_flip_left_right=_random_flip(2),
@@ -218,13 +310,18 @@ class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
     NAMES = ("tfplot", "tifffile", "matplotlib", "util", "tf2", "requests", "automl", "visualize", "generator", "metrics",
              "custom_callbacks", "train_data_generator", "hparams_config", "utils", "seaborn")
 
+    REAL = ("tf2", "tf2.postprocess", "tf2.anchors", "utils", "hparams_config")     # with with_automl=True
+
     def find_spec(self, name, path, target=None):
-        if name.split(".")[0] in self.NAMES:
+        if self.with_automl and name in self.REAL:
+            return None
+        if name.split(".")[0] in self.NAMES or name.startswith("tensorflow.") or name.split(".")[0] in ("absl", "object_detection"):
             return importlib.machinery.ModuleSpec(name, self, is_package=True)
         return None
 
-    def __init__(self):
+    def __init__(self, with_automl=False):
         self.created = []
+        self.with_automl = with_automl
 
     def create_module(self, spec):
         m = mock.MagicMock(name=spec.name)
@@ -236,20 +333,28 @@ class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
         pass
 
 
-def import_reference_attacker(reference_root="/root/reference", module="attacker"):
-    """-> the reference's `attacker` (or `attack_detection`) module, imported on top of the shim."""
+def import_reference_attacker(reference_root="/root/reference", module="attacker", with_automl=False):
+    """-> the reference's `attacker` (or `attack_detection`) module, imported on top of the shim.  with_automl: the
+    vendored automl modules the objective path calls (tf2/postprocess.py, tf2/anchors.py, utils.py, hparams_config.py)
+    are imported for real as well (on the same shim); everything else stays an inert mock."""
     tf, tfa = build_modules()
     sys.modules["tensorflow"] = tf
     sys.modules["tensorflow_addons"] = tfa
-    finder = _StubFinder()
+    finder = _StubFinder(with_automl)
     sys.meta_path.insert(0, finder)
-    sys.path.insert(0, reference_root)
+    paths = [reference_root] + ([reference_root + "/automl/efficientdet"] if with_automl else [])
+    sys.path[:0] = paths
     try:
-        for name in ("attacker", "brightness_matcher", "attack_detection"):
+        for name in ("attacker", "brightness_matcher", "attack_detection", "tf2", "tf2.postprocess", "tf2.anchors", "utils",
+                     "hparams_config", "nms_np"):
             sys.modules.pop(name, None)
-        return importlib.import_module(module)                  # the reference module
+        mod = importlib.import_module(module)                   # the reference module
+        if with_automl:
+            mod.hparams_config = importlib.import_module("hparams_config")
+        return mod
     finally:
         sys.meta_path.remove(finder)
-        sys.path.remove(reference_root)
+        for p in paths:
+            sys.path.remove(p)
         for name in finder.created:                             # the inert stand-ins must not leak into later imports
             sys.modules.pop(name, None)

@@ -133,3 +133,31 @@ def test_first_pass_emits_ragged_boxes_for_the_patcher():
     for b in range(B):
         np.testing.assert_array_equal(rows[b], want_rows[b])
         np.testing.assert_array_equal(got_scores[b], want_scores[b])
+
+
+def test_score_kernel_and_nms_equal_reference_passes_fixture():
+    """score_max_fwd + person_nms vs the reference's own second_pass / first_pass run on the NumPy TF shim
+    (tests/golden/objective_ref.npz): per-image max score, candidate scores, first-pass boxes and soft-NMS scores."""
+    import os
+    from mladversarialobjectdetection_b200 import postprocess
+    from tests._util import objective_fixture_inputs
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "objective_ref.npz"))
+    B, H = int(g["B"]), int(g["H"])
+    cls, box = objective_fixture_inputs(int(g["seed"]), B, H)
+    dev = "cuda"
+    tc, tb = [torch.from_numpy(c).to(dev) for c in cls], [torch.from_numpy(b).to(dev) for b in box]
+    ta = torch.from_numpy(anchors_mod.anchor_table((H, H)).astype(F)).to(dev)
+    M, _, ncand, ctx = ops.score_max_forward(tc, tb, ta, (H, H))
+    np.testing.assert_array_equal(M.cpu().numpy(), g["max_scores"])
+    cand = ops.score_candidate_view(ctx).cpu().numpy()
+    for b in range(B):
+        np.testing.assert_array_equal(cand[b][cand[b] >= 0], g[f"sp_scores{b}"])
+        assert int(ncand[b]) == len(g[f"sp_scores{b}"])
+
+    class Cfg:
+        nms_configs = GAUSS
+    boxes, scores = postprocess.person_boxes_after_nms(Cfg, ctx, tb, ta, (H, H), thresh=True)
+    rows = boxes.to_rows()
+    for b in range(B):
+        np.testing.assert_array_equal(rows[b], g[f"fp_boxes{b}"])
+        np.testing.assert_array_equal(scores[b], g[f"fp_scores{b}"])

@@ -56,3 +56,26 @@ def test_oracle_equals_reference_masker_on_the_shim():
         np.testing.assert_array_equal(out, g[f"{tag}_out"])
         np.testing.assert_array_equal(mask, g[f"{tag}_mask"])
         assert mask.any()
+
+
+def test_oracle_equals_reference_second_and_first_pass_on_the_shim():
+    """PatchAttacker.second_pass / first_pass + the max-score line (attacker.py:69-170,190) with the real vendored
+    pre_nms / nms / clip_boxes / Anchors underneath (fixtures objective_ref.npz)."""
+    from oracle import nms as onms, objective
+    from tests._util import objective_fixture_inputs
+    g = np.load(os.path.join(GOLD, "objective_ref.npz"))
+    B, H = int(g["B"]), int(g["H"])
+    cls, box = objective_fixture_inputs(int(g["seed"]), B, H)
+    anchors = objective.anchor_boxes(H)
+    c_all, b_all = objective.merge_levels(cls, box, 90)
+    post = objective.objective_forward(c_all, b_all, anchors, H, H, 0.4)
+    np.testing.assert_array_equal(post["max_scores"], g["max_scores"])
+    cand = np.where(post["cand"], post["score"], np.float32(-1.0)).astype(np.float32)
+    cfg = dict(method="gaussian", sigma=None, iou_thresh=0.5, score_thresh=0.5, max_output_size=100)
+    rows, row_scores = onms.person_boxes_after_nms(cand, b_all, anchors, (H, H), cfg, thresh=True)
+    for b in range(B):
+        np.testing.assert_array_equal(post["score"][b][post["cand"][b]], g[f"sp_scores{b}"])
+        np.testing.assert_array_equal(post["boxes"][b][post["cand"][b]], g[f"sp_boxes{b}"])
+        np.testing.assert_array_equal(rows[b], g[f"fp_boxes{b}"])
+        np.testing.assert_array_equal(row_scores[b], g[f"fp_scores{b}"])
+        assert len(g[f"fp_boxes{b}"]) > 5
