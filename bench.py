@@ -341,10 +341,17 @@ def run_ours(args):
     _, _, mctx = ops.apply_forward(mpatch, sc, mimg, mbox, moff, mpar, mwb, mgeo, want_mask=True, out=mout)
     t_mask = event_time_ms(lambda: ops.apply_forward(mpatch, sc, mimg, mbox, moff, mpar, mwb, mgeo, want_mask=True, out=mout,
                                                      workspace=mctx.workspace), it)
+    from mladversarialobjectdetection_b200.adv_patch import AdversarialPatch
+    ap_u8 = AdversarialPatch(scale=0.5, h=640, w=640, patch=rng.integers(0, 256, size=(640, 640, 3), dtype=np.uint8), seed=1)
+    vframe = torch.from_numpy(rng.integers(0, 256, size=(480, 640, 3), dtype=np.uint8)).to(dev)
+    vboxes = [(40, 60, 440, 200), (100, 250, 420, 400), (60, 430, 300, 620), (200, 20, 470, 140)]
+    t_u8 = event_time_ms(lambda: ap_u8.add_adv_to_img(vframe, vboxes), it)
     neighbours = [
         entry("eot_apply_fwd as Masker (config 5: 24 x 640x640, 240x240 crops, mask output)", 36.0 * mH * mH * mB, t_mask),
         entry("eot_letterbox_normalize (64 frames 480x640 uint8 -> 512x512 float32)", float(B) * (fh * fw * 3 + 12.0 * H * H), t_lb),
         entry("eot_augment_batch (flip + contrast + brightness + clip)", 24.0 * H * H * B, t_aug),
+        {"kernel": "adv_u8_add_patches (uint8 inference twin: 480x640 frame, 640x640 patch, 4 boxes; incl. noise draw + frame clone)",
+         "bound": "latency", "ms": t_u8, "frames_per_s": 1.0 / (t_u8 * 1e-3)},
         {"kernel": "person_nms (first pass: decode + soft-NMS + clip + CSR, 240 candidates / image)", "bound": "latency",
          "ms": t_nms, "images_per_s": B / (t_nms * 1e-3)},
     ]
