@@ -888,7 +888,10 @@ __device__ __forceinline__ void composite_band(const EotShape& s, const Layout& 
 }
 
 // Bands are handed out by an atomic ticket (their cost varies from nothing to several overlapping windows).
-__global__ void __launch_bounds__(kCompThreads, 1024 / kCompThreads) k_composite(EotShape s, Layout L, char* ws,
+#ifndef EOT_COMP_MINB
+#define EOT_COMP_MINB (1024 / EOT_COMP_THREADS)
+#endif
+__global__ void __launch_bounds__(kCompThreads, EOT_COMP_MINB) k_composite(EotShape s, Layout L, char* ws,
                                                         const float* __restrict__ images, float* out, float* mask,
                                                         const int32_t* __restrict__ offsets, int b0, int b1, int group) {
   __shared__ CompositeSmem sm;
@@ -985,7 +988,7 @@ static int launch_forward(const EotShape& s, const Layout& L, const float* patch
     if (smem > 32 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // static + dynamic may pass 48 KB
     k_match<<<dim3(pchunks, B), kThreads, 0, st>>>(s, L, patch, print_wb, ws, 0);
     k_resize<<<nsm * EOT_RESIZE_MINB, EOT_RESIZE_THREADS, smem, st>>>(s, L, ws, box_offsets, 0, B);
-    k_composite<<<nsm * (1024 / kCompThreads), kCompThreads, 0, st>>>(s, L, ws, images, out_images, mask, box_offsets, 0, B, 0);
+    k_composite<<<nsm * EOT_COMP_MINB, kCompThreads, 0, st>>>(s, L, ws, images, out_images, mask, box_offsets, 0, B, 0);
     count_launches(3);
   }
   EOT_CHECK_CUDA(cudaPeekAtLastError());

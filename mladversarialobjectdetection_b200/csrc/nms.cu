@@ -98,27 +98,59 @@ __global__ void __launch_bounds__(kNmsThreads) k_person_nms(NmsShape s, NmsLayou
   const float floor_ = s.score_floor;
   const float thr = s.score_threshold;
 
-  // ---- 1. ordered compaction: warp w owns the contiguous anchor range [w*seg, (w+1)*seg) ----
-  const int seg = ((A + NW - 1) / NW + 31) & ~31;
+  // ---- 1. ordered compaction: warp w owns the contiguous anchor range [w*seg, (w+1)*seg); a lane reads four
+  //         consecutive scores per step (128-bit loads, no cross-lane traffic unless a step holds a candidate) ----
+  const bool vec4 = (A % 4 == 0) && ((reinterpret_cast<uintptr_t>(cs) & 15) == 0);
+  const int step = vec4 ? 128 : 32;
+  const int seg = ((A + NW - 1) / NW + step - 1) / step * step;
   const int a_lo = min(A, warp * seg), a_hi = min(A, a_lo + seg);
   int cnt = 0;
-  for (int a = a_lo + lane; a - lane < a_hi; a += 32) {
-    const float v = a < a_hi ? __ldg(cs + a) : -1.0f;
-    cnt += __popc(__ballot_sync(0xffffffffu, v >= floor_ && v > thr));
+  if (vec4) {
+#pragma unroll 4
+    for (int a = a_lo + 4 * lane; a < a_hi; a += 128) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(cs + a));
+      cnt += (int)(v.x >= floor_ && v.x > thr) + (int)(v.y >= floor_ && v.y > thr) + (int)(v.z >= floor_ && v.z > thr) +
+             (int)(v.w >= floor_ && v.w > thr);
+    }
+  } else {
+    for (int a = a_lo + lane; a < a_hi; a += 32) {
+      const float v = __ldg(cs + a);
+      cnt += (int)(v >= floor_ && v > thr);
+    }
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   if (lane == 0) s_wcount[warp] = cnt;
   __syncthreads();
   int base = 0, total = 0;
 #pragma unroll
   for (int w = 0; w < NW; ++w) { if (w < warp) base += s_wcount[w]; total += s_wcount[w]; }
   if (threadIdx.x == 0) s_n = min(total, K);
-  for (int a = a_lo + lane; a - lane < a_hi; a += 32) {
-    const float v = a < a_hi ? __ldg(cs + a) : -1.0f;
-    const bool hit = v >= floor_ && v > thr;
-    const unsigned m = __ballot_sync(0xffffffffu, hit);
-    const int pos = base + __popc(m & ((1u << lane) - 1u));
-    if (hit && pos < K) { g_idx[pos] = a; g_score[pos] = v; }
-    base += __popc(m);
+  if (cnt > 0) {                                              // warp-uniform: this warp's range holds candidates
+    for (int a0 = a_lo; a0 < a_hi; a0 += step) {
+      float v[4] = {-1.0f, -1.0f, -1.0f, -1.0f};
+      const int a = a0 + (vec4 ? 4 * lane : lane);
+      if (a < a_hi) {
+        if (vec4) { const float4 q = __ldg(reinterpret_cast<const float4*>(cs + a)); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+        else v[0] = __ldg(cs + a);
+      }
+      int mine = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) mine += (int)(v[k] >= floor_ && v[k] > thr);
+      if (!__any_sync(0xffffffffu, mine > 0)) continue;
+      int incl = mine;                                        // inclusive prefix over the lanes = anchor order
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+      int pos = base + incl - mine;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (v[k] >= floor_ && v[k] > thr) {
+          if (pos < K) { g_idx[pos] = a + k; g_score[pos] = v[k]; }
+          ++pos;
+        }
+      }
+      base += __shfl_sync(0xffffffffu, incl, 31);
+    }
   }
   __syncthreads();
   const int n = s_n;
