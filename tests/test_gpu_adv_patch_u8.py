@@ -67,3 +67,17 @@ def test_unsupported_and_invalid_boxes_raise_before_any_launch():
         ap.add_adv_to_img(frame, [(0, 0, 200, 100)])                   # needs a 100 px patch from a 32 px texture
     with pytest.raises(RuntimeError, match="empty patch"):
         ap.add_adv_to_img(frame, [(5, 5, 6, 6)])
+
+
+def test_non_square_patch_texture_and_non_square_letterbox():
+    """h != w everywhere: 96x64 patch texture (different area ratios per axis), AdversarialPatch(h=80, w=120)."""
+    rng = np.random.default_rng(21)
+    raw = rng.integers(0, 256, size=(96, 64, 3), dtype=np.uint8)
+    frame = rng.integers(0, 256, size=(150, 200, 3), dtype=np.uint8)
+    boxes = [(10, 10, 130, 80), (40, 90, 120, 190)]
+    ap = AdversarialPatch(scale=0.4, h=80, w=120, patch=raw)
+    pl = ap.placements(150, 200, boxes)
+    noises = [rng.uniform(-0.01, 0.01, size=(int(p[2]), int(p[3]), 3)) for p in pl]
+    got = ap.add_adv_to_img(frame, boxes, noise=noises)
+    want = o.add_adv_to_img(frame, boxes, o.print_patch(raw), (80, 120), 0.4, noises)
+    np.testing.assert_array_equal(got, want)

@@ -76,3 +76,16 @@ def test_errors():
         ops.letterbox_normalize([torch.zeros((4, 4, 3), dtype=torch.uint8)], (8, 8), 127.0, 128.0)
     with pytest.raises(RuntimeError, match="scales to"):
         ops.letterbox_normalize([torch.zeros((1, 4000, 3), dtype=torch.uint8, device="cuda")], (8, 8), 127.0, 128.0)
+
+
+def test_augment_scalar_path_odd_width_and_channel_sums():
+    """W % 4 != 0 takes the scalar kernel; eot_channel_sums feeds the contrast means when the batch did not come from
+    the letter-box kernel."""
+    rng = np.random.default_rng(12)
+    x = rng.uniform(-1, 1, (3, 17, 57, 3)).astype(np.float32)
+    flip = np.array([0, 1, 1], np.uint8)
+    xt = torch.from_numpy(x).cuda()
+    sums = ops.channel_sums(xt)
+    np.testing.assert_allclose(sums.cpu().numpy(), x.astype(np.float64).sum(axis=(1, 2)), rtol=1e-12, atol=1e-9)
+    got = ops.augment_batch(xt, torch.from_numpy(flip).cuda(), 0.9, -0.1, sums=sums).cpu().numpy()
+    np.testing.assert_allclose(got, ip.augment(x, flip, 0.9, -0.1), rtol=0, atol=2.4e-7)
