@@ -250,6 +250,17 @@ int adam_clip_update(float* var, float* m, float* v, const float* grad, int64_t 
                      float beta1, float beta2, float eps, int64_t step, float lo, float hi,
                      void* stream);
 
+/* --------------------------------------------------------------------------------------------
+ * Epilogue helpers of the torch stand-in of the victim (victim.py) -- not a reference interface:
+ * the convolutions stay on the framework's cuDNN path; the per-channel bias add and the SiLU that
+ * PyTorch runs as two separate (partly non-vectorised) passes are one pass over the NHWC tensor.
+ * x / y / dy / dx: [n_pixels, channels] float32, channels % 4 == 0, 16-byte aligned; y may alias x.
+ * ------------------------------------------------------------------------------------------ */
+int nhwc_bias_act_fwd(const float* x, const float* bias, float* y, int64_t n_pixels,
+                      int32_t channels, int32_t act /* 0 identity, 1 SiLU */, void* stream);
+int nhwc_bias_silu_bwd(const float* x, const float* bias, const float* dy, float* dx,
+                       int64_t n_pixels, int32_t channels, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -377,6 +377,28 @@ def augment_batch(images: torch.Tensor, flip: Optional[torch.Tensor], contrast_f
 
 
 # --------------------------------------------------------------------------------------------------
+# victim stand-in epilogues (not a reference interface; see csrc/victim_ops.cu)
+# --------------------------------------------------------------------------------------------------
+def nhwc_bias_act(x: torch.Tensor, bias: torch.Tensor, act: bool, out: torch.Tensor) -> torch.Tensor:
+    """out = act(x + bias[c]) for a channels_last [N,C,H,W] float32 tensor (out may be x)."""
+    N, C, H, W = x.shape
+    _lib.check(_lib.load().nhwc_bias_act_fwd(_ptr(x), _ptr(bias), _ptr(out), N * H * W, C, 1 if act else 0, _stream()),
+               "nhwc_bias_act_fwd")
+    return out
+
+
+def nhwc_bias_silu_backward(x: torch.Tensor, bias: torch.Tensor, grad: torch.Tensor) -> torch.Tensor:
+    """dL/dx of silu(x + bias[c]) given dL/dy (channels_last float32)."""
+    N, C, H, W = x.shape
+    if not grad.is_contiguous(memory_format=torch.channels_last):
+        grad = grad.contiguous(memory_format=torch.channels_last)
+    dx = torch.empty_like(x)
+    _lib.check(_lib.load().nhwc_bias_silu_bwd(_ptr(x), _ptr(bias), _ptr(grad), _ptr(dx), N * H * W, C, _stream()),
+               "nhwc_bias_silu_bwd")
+    return dx
+
+
+# --------------------------------------------------------------------------------------------------
 # patch update
 # --------------------------------------------------------------------------------------------------
 def tv_grad_(patch: torch.Tensor, grad_patch: torch.Tensor, weight: float = 1e-5, want_tv: bool = True):

@@ -71,12 +71,66 @@ def _round_filters(c: int, mult: float, divisor: int = 8) -> int:
     return int(new)
 
 
+# ---- fused bias + activation epilogue (CUDA only) ---------------------------------------------------------------
+# After BatchNorm folding every convolution carries a bias.  PyTorch's cuDNN path applies it as a separate broadcast
+# add (a non-vectorised kernel in channels_last: a quarter of the victim's time at D0 / 512^2) and SiLU as a further
+# pass; libeotpatch's nhwc_bias_act_fwd / nhwc_bias_silu_bwd do both in one 128-bit pass.  The convolution itself stays
+# on cuDNN.  On the CPU (oracle arm, CPU tests) the plain torch ops run.
+FUSED_EPILOGUE = True
+
+
+class _BiasAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, bias, act):
+        from . import ops
+        ctx.save_for_backward(x, bias)
+        ctx.act = act
+        return ops.nhwc_bias_act(x, bias, act, out=torch.empty_like(x))
+
+    @staticmethod
+    def backward(ctx, grad):
+        from . import ops
+        x, bias = ctx.saved_tensors
+        if not ctx.act:
+            return grad, None, None
+        return ops.nhwc_bias_silu_backward(x, bias, grad), None, None
+
+
+def _nhwc_ok(y: torch.Tensor) -> bool:
+    return (y.is_cuda and y.dtype == torch.float32 and y.dim() == 4 and y.shape[1] % 4 == 0 and y.shape[2] * y.shape[3] > 1
+            and y.is_contiguous(memory_format=torch.channels_last))
+
+
+def conv_bias_act(x: torch.Tensor, weight, bias, stride, padding, dilation, groups, act: bool) -> torch.Tensor:
+    """act(conv2d(x, weight) + bias): cuDNN convolution + one fused epilogue pass on CUDA, torch ops elsewhere."""
+    if FUSED_EPILOGUE and x.is_cuda and bias is not None:
+        y = Fn.conv2d(x, weight, None, stride, padding, dilation, groups)
+        if _nhwc_ok(y):
+            if torch.is_grad_enabled() and y.requires_grad:
+                return _BiasAct.apply(y, bias, act)
+            from . import ops
+            return ops.nhwc_bias_act(y, bias, act, out=y)                  # nothing to differentiate: in place
+        y = y + bias.view(1, -1, 1, 1)
+        return Fn.silu(y) if act else y
+    y = Fn.conv2d(x, weight, bias, stride, padding, dilation, groups)
+    return Fn.silu(y) if act else y
+
+
+def _module_conv_bias_act(conv: nn.Conv2d, x, act: bool):
+    return conv_bias_act(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups, act)
+
+
 class ConvBN(nn.Sequential):
     def __init__(self, cin, cout, k=1, stride=1, groups=1, act=True):
         layers = [nn.Conv2d(cin, cout, k, stride, k // 2, groups=groups, bias=False), nn.BatchNorm2d(cout, eps=1e-3)]
         if act:
             layers.append(nn.SiLU(inplace=True))
         super().__init__(*layers)
+
+    def forward(self, x):
+        if isinstance(self[1], nn.Identity):                                # BatchNorm folded into the conv
+            return _module_conv_bias_act(self[0], x, act=len(self) == 3)
+        return super().forward(x)
 
 
 class MBConv(nn.Module):
@@ -134,6 +188,11 @@ class SepConvBN(nn.Sequential):
     def __init__(self, c, act=False):
         super().__init__(nn.Conv2d(c, c, 3, 1, 1, groups=c, bias=False), nn.Conv2d(c, c, 1, bias=True),
                          nn.BatchNorm2d(c, eps=1e-3))
+
+    def forward(self, x):
+        if isinstance(self[2], nn.Identity):
+            return _module_conv_bias_act(self[1], self[0](x), act=False)
+        return super().forward(x)
 
 
 class Fuse(nn.Module):
@@ -225,7 +284,7 @@ class Head(nn.Module):
             for i in range(len(self.dw)):
                 if self.folded:
                     k = i * self.folded + lvl
-                    x = Fn.silu(Fn.conv2d(self.dw[i](x), self.fold_w[k], self.fold_b[k]))
+                    x = conv_bias_act(self.dw[i](x), self.fold_w[k], self.fold_b[k], 1, 0, 1, 1, act=True)
                 else:
                     x = Fn.silu(self.bn[i][lvl](self.pw[i](self.dw[i](x))))
             outs.append(self.out_pw(self.out_dw(x)))

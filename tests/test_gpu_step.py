@@ -176,3 +176,36 @@ def test_cuda_graph_replay_equals_eager_step(no_tf32):
     assert (res[0][0] - res[1][0]).abs().mean() < 2e-4
     assert abs(res[0][1] - res[1][1]) < 1e-4
     assert abs(res[0][2] - res[1][2]) < 1e-3 * max(1.0, abs(res[0][2]))
+
+
+def test_fused_bias_silu_epilogue_matches_torch_ops():
+    """victim.conv_bias_act (cuDNN conv + libeotpatch's one-pass bias/SiLU epilogue) vs conv2d(bias) + silu of torch,
+    forward and input gradient, channels_last, with and without activation; and the whole victim with the switch off."""
+    torch.manual_seed(0)
+    x = torch.randn(4, 16, 24, 20, device="cuda").contiguous(memory_format=torch.channels_last)
+    w = torch.randn(32, 16, 3, 3, device="cuda").contiguous(memory_format=torch.channels_last) * 0.1
+    b = torch.randn(32, device="cuda")
+    for act in (True, False):
+        xa = x.clone().requires_grad_(True)
+        ya = victim.conv_bias_act(xa, w, b, 1, 1, 1, 1, act)
+        xb = x.clone().requires_grad_(True)
+        yb = torch.nn.functional.conv2d(xb, w, b, 1, 1)
+        yb = torch.nn.functional.silu(yb) if act else yb
+        g = torch.randn_like(yb)
+        ya.backward(g)
+        yb.backward(g)
+        torch.testing.assert_close(ya, yb, rtol=2e-6, atol=2e-6)
+        torch.testing.assert_close(xa.grad, xb.grad, rtol=1e-4, atol=1e-5)
+        with torch.no_grad():
+            torch.testing.assert_close(victim.conv_bias_act(x, w, b, 1, 1, 1, 1, act), yb, rtol=2e-6, atol=2e-6)
+    model = victim.get_victim_model("efficientdet-d0", device="cuda", image_size=128, seed=5)
+    img = torch.rand(2, 128, 128, 3, device="cuda") * 2 - 1
+    with torch.no_grad():
+        cls_f, box_f = model(img)
+        victim.FUSED_EPILOGUE = False
+        try:
+            cls_t, box_t = model(img)
+        finally:
+            victim.FUSED_EPILOGUE = True
+    for a, b_ in zip(cls_f + box_f, cls_t + box_t):
+        torch.testing.assert_close(a, b_, rtol=1e-3, atol=1e-3)
