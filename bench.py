@@ -61,7 +61,8 @@ def workload_config(args, n_gpus):
                         + (" + projective row" if args.perspective > 0 else ""),
             "global_batch": args.batch * n_gpus, "per_gpu_batch": args.batch, "image": args.image, "patch": args.patch,
             "victim": args.victim + " (random init, torch/cuDNN stand-in for the Keras model; inference BatchNorm folded "
-                                    "into the convs; cuDNN convs at the framework's default TF32 setting, as TF 2.8)",
+                                    "into the convs; cuDNN convs at the framework's default TF32 setting, as TF 2.8; per-channel "
+                                    "bias + SiLU and the squeeze-excite gate applied by one-pass libeotpatch epilogue kernels)",
             "parallelism": f"dp{n_gpus}", "first_pass_included": not args.no_first_pass,
             "cuda_graphs": "victim passes (clean forward+score; attacked forward+score+objective grad+backward)" if not args.no_graphs else "off",
             "l2": "inputs larger than L2 (images %.0f MB/GPU > 126 MB)" % (args.batch * args.image ** 2 * 12 / 1e6)}

@@ -254,12 +254,21 @@ int adam_clip_update(float* var, float* m, float* v, const float* grad, int64_t 
  * Epilogue helpers of the torch stand-in of the victim (victim.py) -- not a reference interface:
  * the convolutions stay on the framework's cuDNN path; the per-channel bias add and the SiLU that
  * PyTorch runs as two separate (partly non-vectorised) passes are one pass over the NHWC tensor.
- * x / y / dy / dx: [n_pixels, channels] float32, channels % 4 == 0, 16-byte aligned; y may alias x.
+ * x / y / dy / dx: [n_pixels, channels] float32, channels % 4 == 0 (the forward also takes even
+ * channel counts), 16-byte aligned; y may alias x.
  * ------------------------------------------------------------------------------------------ */
 int nhwc_bias_act_fwd(const float* x, const float* bias, float* y, int64_t n_pixels,
                       int32_t channels, int32_t act /* 0 identity, 1 SiLU */, void* stream);
 int nhwc_bias_silu_bwd(const float* x, const float* bias, const float* dy, float* dx,
                        int64_t n_pixels, int32_t channels, void* stream);
+/* Squeeze-and-excitation gate of MBConv on [n_images, hw, channels]: out = y * gate[n,c]
+ * (+ shift[n,c] * shift_mul when shift != NULL: the backward's dy = dout * gate + dmean / HW). */
+int nhwc_channel_scale(const float* y, const float* gate, const float* shift, float shift_mul,
+                       float* out, int32_t n_images, int64_t hw, int32_t channels, void* stream);
+/* out[n,c] = sum_hw a * b (dgate of the product above), deterministic two-stage reduction;
+ * workspace: 16 * n_images * channels floats. */
+int nhwc_channel_dot(const float* a, const float* b, float* out, float* workspace, int32_t n_images,
+                     int32_t hw, int32_t channels, void* stream);
 
 #ifdef __cplusplus
 }

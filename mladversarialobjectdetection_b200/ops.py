@@ -398,6 +398,26 @@ def nhwc_bias_silu_backward(x: torch.Tensor, bias: torch.Tensor, grad: torch.Ten
     return dx
 
 
+def nhwc_channel_scale(y: torch.Tensor, gate: torch.Tensor, shift: Optional[torch.Tensor] = None, shift_mul: float = 0.0,
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = y * gate[n,c] (+ shift[n,c] * shift_mul) for channels_last [N,C,H,W]; gate / shift are [N,C] contiguous."""
+    N, C, H, W = y.shape
+    if out is None:
+        out = torch.empty_like(y)
+    _lib.check(_lib.load().nhwc_channel_scale(_ptr(y), _ptr(gate), _ptr(shift), ctypes.c_float(shift_mul), _ptr(out), N, H * W, C,
+                                              _stream()), "nhwc_channel_scale")
+    return out
+
+
+def nhwc_channel_dot(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """[N,C] = sum over H,W of a * b (channels_last [N,C,H,W]); deterministic."""
+    N, C, H, W = a.shape
+    out = torch.empty((N, C), dtype=torch.float32, device=a.device)
+    ws = torch.empty(16 * N * C, dtype=torch.float32, device=a.device)
+    _lib.check(_lib.load().nhwc_channel_dot(_ptr(a), _ptr(b), _ptr(out), _ptr(ws), N, H * W, C, _stream()), "nhwc_channel_dot")
+    return out
+
+
 # --------------------------------------------------------------------------------------------------
 # patch update
 # --------------------------------------------------------------------------------------------------

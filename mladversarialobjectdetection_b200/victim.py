@@ -101,11 +101,17 @@ def _nhwc_ok(y: torch.Tensor) -> bool:
             and y.is_contiguous(memory_format=torch.channels_last))
 
 
+def _nhwc_ok2(y: torch.Tensor, act: bool) -> bool:
+    """forward-only / identity epilogue also takes even channel counts (the 810-channel class logits)"""
+    return (not act and y.is_cuda and y.dtype == torch.float32 and y.dim() == 4 and y.shape[1] % 2 == 0
+            and y.shape[2] * y.shape[3] > 1 and y.is_contiguous(memory_format=torch.channels_last))
+
+
 def conv_bias_act(x: torch.Tensor, weight, bias, stride, padding, dilation, groups, act: bool) -> torch.Tensor:
     """act(conv2d(x, weight) + bias): cuDNN convolution + one fused epilogue pass on CUDA, torch ops elsewhere."""
     if FUSED_EPILOGUE and x.is_cuda and bias is not None:
         y = Fn.conv2d(x, weight, None, stride, padding, dilation, groups)
-        if _nhwc_ok(y):
+        if _nhwc_ok(y) or _nhwc_ok2(y, act):
             if torch.is_grad_enabled() and y.requires_grad:
                 return _BiasAct.apply(y, bias, act)
             from . import ops
@@ -114,6 +120,48 @@ def conv_bias_act(x: torch.Tensor, weight, bias, stride, padding, dilation, grou
         return Fn.silu(y) if act else y
     y = Fn.conv2d(x, weight, bias, stride, padding, dilation, groups)
     return Fn.silu(y) if act else y
+
+
+class _SqueezeExcite(torch.autograd.Function):
+    """y * sigmoid(W2 silu(W1 mean_hw(y) + b1) + b2) with the two full-tensor passes (the gate product and, backward,
+    dy = dout * gate + dmean / HW and dgate = sum_hw dout * y) in libeotpatch; the [N,C]-sized MLP stays in torch."""
+
+    @staticmethod
+    def forward(ctx, y, w1, b1, w2, b2):
+        from . import ops
+        s = y.mean((2, 3))
+        h_pre = torch.addmm(b1, s, w1.t())
+        h = Fn.silu(h_pre)
+        g = torch.sigmoid(torch.addmm(b2, h, w2.t())).contiguous()
+        ctx.save_for_backward(y, g, h_pre, h, w1, w2)
+        return ops.nhwc_channel_scale(y, g)
+
+    @staticmethod
+    def backward(ctx, dout):
+        from . import ops
+        y, g, h_pre, h, w1, w2 = ctx.saved_tensors
+        if not dout.is_contiguous(memory_format=torch.channels_last):
+            dout = dout.contiguous(memory_format=torch.channels_last)
+        dg = ops.nhwc_channel_dot(dout, y)
+        dg_pre = dg * g * (1.0 - g)
+        dh = dg_pre @ w2
+        sg = torch.sigmoid(h_pre)
+        ds = ((dh * (sg * (1.0 + h_pre * (1.0 - sg)))) @ w1).contiguous()
+        dy = ops.nhwc_channel_scale(dout, g, ds, 1.0 / float(y.shape[2] * y.shape[3]))
+        return dy, None, None, None, None
+
+
+def squeeze_excite(y: torch.Tensor, se_reduce: nn.Conv2d, se_expand: nn.Conv2d) -> torch.Tensor:
+    if FUSED_EPILOGUE and _nhwc_ok(y):
+        w1, w2 = se_reduce.weight.flatten(1), se_expand.weight.flatten(1)
+        if torch.is_grad_enabled() and y.requires_grad:
+            return _SqueezeExcite.apply(y, w1, se_reduce.bias, w2, se_expand.bias)
+        from . import ops
+        h = Fn.silu(torch.addmm(se_reduce.bias, y.mean((2, 3)), w1.t()))
+        g = torch.sigmoid(torch.addmm(se_expand.bias, h, w2.t())).contiguous()
+        return ops.nhwc_channel_scale(y, g, out=y)                        # nothing to differentiate: in place
+    s = y.mean((2, 3), keepdim=True)
+    return y * torch.sigmoid(se_expand(Fn.silu(se_reduce(s))))
 
 
 def _module_conv_bias_act(conv: nn.Conv2d, x, act: bool):
@@ -146,9 +194,7 @@ class MBConv(nn.Module):
         self.skip = stride == 1 and cin == cout
 
     def forward(self, x):
-        y = self.dw(self.expand(x))
-        s = y.mean((2, 3), keepdim=True)
-        y = y * torch.sigmoid(self.se_expand(Fn.silu(self.se_reduce(s))))
+        y = squeeze_excite(self.dw(self.expand(x)), self.se_reduce, self.se_expand)
         y = self.project(y)
         return x + y if self.skip else y
 
@@ -287,7 +333,7 @@ class Head(nn.Module):
                     x = conv_bias_act(self.dw[i](x), self.fold_w[k], self.fold_b[k], 1, 0, 1, 1, act=True)
                 else:
                     x = Fn.silu(self.bn[i][lvl](self.pw[i](self.dw[i](x))))
-            outs.append(self.out_pw(self.out_dw(x)))
+            outs.append(_module_conv_bias_act(self.out_pw, self.out_dw(x), act=False))
         return outs
 
 

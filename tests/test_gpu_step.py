@@ -209,3 +209,36 @@ def test_fused_bias_silu_epilogue_matches_torch_ops():
             victim.FUSED_EPILOGUE = True
     for a, b_ in zip(cls_f + box_f, cls_t + box_t):
         torch.testing.assert_close(a, b_, rtol=1e-3, atol=1e-3)
+
+
+def test_fused_squeeze_excite_matches_torch_ops():
+    torch.manual_seed(1)
+    blk = victim.MBConv(24, 24, 6, 3, 1).cuda().eval().to(memory_format=torch.channels_last)
+    for p in blk.parameters():
+        p.requires_grad_(False)
+    y = torch.randn(3, 144, 20, 28, device="cuda").contiguous(memory_format=torch.channels_last)
+    ya = y.clone().requires_grad_(True)
+    oa = victim.squeeze_excite(ya, blk.se_reduce, blk.se_expand)
+    yb = y.clone().requires_grad_(True)
+    s = yb.mean((2, 3), keepdim=True)
+    ob = yb * torch.sigmoid(blk.se_expand(torch.nn.functional.silu(blk.se_reduce(s))))
+    g = torch.randn_like(ob)
+    oa.backward(g)
+    ob.backward(g)
+    torch.testing.assert_close(oa, ob, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(ya.grad, yb.grad, rtol=1e-4, atol=1e-5)
+    with torch.no_grad():
+        torch.testing.assert_close(victim.squeeze_excite(y.clone(), blk.se_reduce, blk.se_expand), ob, rtol=1e-5, atol=1e-6)
+    # 810-channel identity epilogue (even, not a multiple of 4) with gradient
+    x = torch.randn(2, 64, 9, 7, device="cuda").contiguous(memory_format=torch.channels_last)
+    w = torch.randn(810, 64, 1, 1, device="cuda") * 0.1
+    b = torch.randn(810, device="cuda")
+    xa = x.clone().requires_grad_(True)
+    xb = x.clone().requires_grad_(True)
+    oa = victim.conv_bias_act(xa, w, b, 1, 0, 1, 1, False)
+    ob = torch.nn.functional.conv2d(xb, w, b)
+    gg = torch.randn_like(ob)
+    oa.backward(gg)
+    ob.backward(gg)
+    torch.testing.assert_close(oa, ob, rtol=2e-6, atol=2e-6)
+    torch.testing.assert_close(xa.grad, xb.grad, rtol=1e-4, atol=1e-5)
