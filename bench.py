@@ -216,7 +216,7 @@ def run_ours(args):
     clocks = ClockSampler(local) if rank == 0 else None
     time.sleep(0.3)
     mark = clocks.mark() if clocks else 0
-    l0 = lib.eot_launch_count()
+    l0 = lib.eot_launch_count() + attacker.graph_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -225,7 +225,7 @@ def run_ours(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = int(lib.eot_launch_count() - l0)
+    launches = int(lib.eot_launch_count() + attacker.graph_launches - l0)      # C-ABI calls + kernels inside graph replays
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -110,6 +110,7 @@ class PatchAttacker:
         # The patcher itself stays outside (its box count changes from step to step).
         self.cuda_graphs = bool(cuda_graphs)
         self._graphs = None
+        self.graph_launches = 0           # libeotpatch kernels launched through CUDA-graph replays (see _build_graphs)
 
     # -- Keras-like surface ------------------------------------------------------------------------
     def compile(self, optimizer=None, learning_rate: Optional[float] = None, run_eagerly=False):
@@ -174,16 +175,22 @@ class PatchAttacker:
                 g["patched"].grad = None
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        from . import _lib
+        count = _lib.load().eot_launch_count
+        n0 = count()
         g1 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g1):
             with torch.no_grad():
                 c_cls, c_box, _, _, _, c_ctx = self._score(g["clean_in"])
         g["g1"], g["clean_box"], g["clean_ctx"] = g1, c_box, c_ctx
+        n1 = count()
         g2 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g2):
             cls_outputs, M, argmax, ncand, sctx = self.second_pass(g["patched"])
             dcls, dscale, data_loss = ops.score_max_backward(sctx, self._scale_regressor)
             torch.autograd.backward(cls_outputs, dcls)
+        # libeotpatch kernels recorded in each graph: a replay launches them without passing through the C ABI's counter
+        g["launches"] = (int(n1 - n0), int(count() - n1))
         g.update(g2=g2, M=M, argmax=argmax, ncand=ncand, dscale=dscale, data_loss=data_loss, grad=g["patched"].grad)
         self._graphs = g
 
@@ -195,12 +202,14 @@ class PatchAttacker:
             from . import postprocess
             g["clean_in"].copy_(images)
             g["g1"].replay()
+            self.graph_launches += g["launches"][0]
             det_boxes, _ = postprocess.person_boxes_after_nms(self.config, g["clean_ctx"], g["clean_box"],
                                                               self._anchor_table(images), images.shape[1:3], thresh=True)
             if boxes is None:
                 boxes = det_boxes
         self._patcher([boxes, images], transforms=transforms, out=g["patched"].detach())
         g["g2"].replay()
+        self.graph_launches += g["launches"][1]
         grad_patch = self._patcher.backward(g["grad"])
         self._last = dict(max_scores=g["M"], data_loss=g["data_loss"], dscale=g["dscale"], ncand=g["ncand"])
         return [g["dscale"], grad_patch]
