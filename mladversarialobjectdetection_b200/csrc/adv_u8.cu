@@ -309,6 +309,8 @@ extern "C" int adv_u8_add_patches(uint8_t* frame, int32_t frame_h, int32_t frame
     if (pl[2] <= 0 || pl[3] <= 0) { set_error("adv_u8_add_patches: box %d gives an empty patch (cv2.resize would fail)", i); return EOT_ERR_BAD_SHAPE; }
     if (pl[2] > patch_h) { set_error("adv_u8_add_patches: box %d needs a %d px patch from a %d px texture: INTER_CUBIC up-sampling is not provided", i, pl[2], patch_h); return EOT_ERR_BAD_SHAPE; }
     if (pl[0] < 0 || pl[1] < 0 || pl[0] + pl[2] > frame_h || pl[1] + pl[3] > frame_w) { set_error("adv_u8_add_patches: box %d does not fit the frame", i); return EOT_ERR_BAD_SHAPE; }
+    // resize() compares the heights only (adv_patch.py:154-160): equal height + different width would fail in the paste
+    if (pl[2] == patch_h && pl[3] != patch_w) { set_error("adv_u8_add_patches: box %d: patch height matches the texture but the width does not", i); return EOT_ERR_BAD_SHAPE; }
   }
   EOT_CHECK_CUDA(cudaMemsetAsync(sums, 0, 16, st));
   k_adv_patch_ysum<<<grid_for(n_px), kThreads, 0, st>>>(patch_printed, n_px, sums);
@@ -324,8 +326,7 @@ extern "C" int adv_u8_add_patches(uint8_t* frame, int32_t frame_h, int32_t frame
     int mode = 2, ix = 1, iy = 1;
     const double sc_x = (double)patch_w / (double)pw, sc_y = (double)patch_h / (double)ph;
     if (patch_h == ph) {
-      mode = 0;                                                      // resize() compares the heights only (adv_patch.py:154-160)
-      if (patch_w != pw) { set_error("adv_u8_add_patches: non-square patch with equal height is not supported"); return EOT_ERR_BAD_SHAPE; }
+      mode = 0;                                                      // same height: no resize (validated above)
     } else {
       ix = (int)lrint(sc_x); iy = (int)lrint(sc_y);
       if (fabs(sc_x - ix) < 2.220446049250313e-16 && fabs(sc_y - iy) < 2.220446049250313e-16) mode = 1;
