@@ -269,6 +269,13 @@ int nhwc_channel_scale(const float* y, const float* gate, const float* shift, fl
  * workspace: 16 * n_images * channels floats. */
 int nhwc_channel_dot(const float* a, const float* b, float* out, float* workspace, int32_t n_images,
                      int32_t hw, int32_t channels, void* stream);
+/* BiFPN fast normalised fusion: out = silu(sum_i weights[i] * xs[i]) for n = 2 or 3 same-layout
+ * inputs (xs / dxs: HOST arrays of device pointers; weights: device [n]); backward
+ * dxs[i] = weights[i] * dout * silu'(z) (dxs[i] may be NULL to skip an input). */
+int nhwc_fuse_silu_fwd(const float* const* xs, int32_t n, const float* weights, float* out,
+                       int64_t n_elems, void* stream);
+int nhwc_fuse_silu_bwd(const float* const* xs, int32_t n, const float* weights, const float* dout,
+                       float* const* dxs, int64_t n_elems, void* stream);
 
 #ifdef __cplusplus
 }

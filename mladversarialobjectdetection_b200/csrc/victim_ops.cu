@@ -120,6 +120,47 @@ __global__ void __launch_bounds__(kThreads) k_channel_dot_final(const float* __r
   out[i] = s;
 }
 
+// ---- BiFPN fast normalised fusion (Fuse): out = silu(sum_i w_i x_i), n <= 3 same-shaped inputs; backward
+// dx_i = w_i * dout * silu'(z).  PyTorch: n broadcast multiplies + n-1 adds + silu (and as many again backward).
+struct FuseArgs { const float* x[3]; float* dx[3]; };
+template <int N>
+__global__ void __launch_bounds__(kThreads) k_fuse_silu(FuseArgs a, const float* __restrict__ w, float* out, long long n4) {
+  float wv[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) wv[k] = __ldg(w + k);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const float4 v = reinterpret_cast<const float4*>(a.x[k])[i];
+      if (k == 0) z = make_float4(v.x * wv[0], v.y * wv[0], v.z * wv[0], v.w * wv[0]);
+      else { z.x += v.x * wv[k]; z.y += v.y * wv[k]; z.z += v.z * wv[k]; z.w += v.w * wv[k]; }
+    }
+    reinterpret_cast<float4*>(out)[i] = make_float4(silu_f(z.x), silu_f(z.y), silu_f(z.z), silu_f(z.w));
+  }
+}
+template <int N>
+__global__ void __launch_bounds__(kThreads) k_fuse_silu_bwd(FuseArgs a, const float* __restrict__ w, const float* __restrict__ dout,
+                                                            long long n4) {
+  float wv[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) wv[k] = __ldg(w + k);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const float4 v = reinterpret_cast<const float4*>(a.x[k])[i];
+      if (k == 0) z = make_float4(v.x * wv[0], v.y * wv[0], v.z * wv[0], v.w * wv[0]);
+      else { z.x += v.x * wv[k]; z.y += v.y * wv[k]; z.z += v.z * wv[k]; z.w += v.w * wv[k]; }
+    }
+    const float4 g = reinterpret_cast<const float4*>(dout)[i];
+    const float4 dz = make_float4(g.x * dsilu_f(z.x), g.y * dsilu_f(z.y), g.z * dsilu_f(z.z), g.w * dsilu_f(z.w));
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      if (a.dx[k]) reinterpret_cast<float4*>(a.dx[k])[i] = make_float4(dz.x * wv[k], dz.y * wv[k], dz.z * wv[k], dz.w * wv[k]);
+  }
+}
+
 static int epilogue_grid(long long n4) {
   long long g = (n4 + kThreads - 1) / kThreads;
   const long long cap = (long long)sm_count() * 16;
@@ -195,6 +236,41 @@ extern "C" int nhwc_channel_dot(const float* a, const float* b, float* out, floa
   const int nc = n_images * channels;
   k_channel_dot_final<<<(nc + kThreads - 1) / kThreads, kThreads, 0, st>>>(workspace, out, nc);
   count_launches(2);
+  EOT_CHECK_CUDA(cudaPeekAtLastError());
+  return EOT_OK;
+}
+
+extern "C" int nhwc_fuse_silu_fwd(const float* const* xs, int32_t n, const float* weights, float* out, int64_t n_elems, void* stream) {
+  if (!xs || !weights || !out) { set_error("nhwc_fuse_silu_fwd: NULL pointer"); return EOT_ERR_NULL_POINTER; }
+  if (n < 2 || n > 3 || n_elems <= 0 || n_elems % 4 != 0) { set_error("nhwc_fuse_silu_fwd: needs 2 or 3 inputs and a multiple of 4 elements"); return EOT_ERR_BAD_SHAPE; }
+  FuseArgs a = {};
+  uintptr_t al = (uintptr_t)out;
+  for (int k = 0; k < n; ++k) { if (!xs[k]) { set_error("nhwc_fuse_silu_fwd: input %d is NULL", k); return EOT_ERR_NULL_POINTER; } a.x[k] = xs[k]; al |= (uintptr_t)xs[k]; }
+  if (al & 15) { set_error("nhwc_fuse_silu_fwd: pointers must be 16-byte aligned"); return EOT_ERR_MISALIGNED; }
+  const long long n4 = n_elems / 4;
+  if (n == 2) k_fuse_silu<2><<<epilogue_grid(n4), kThreads, 0, (cudaStream_t)stream>>>(a, weights, out, n4);
+  else k_fuse_silu<3><<<epilogue_grid(n4), kThreads, 0, (cudaStream_t)stream>>>(a, weights, out, n4);
+  count_launches(1);
+  EOT_CHECK_CUDA(cudaPeekAtLastError());
+  return EOT_OK;
+}
+
+extern "C" int nhwc_fuse_silu_bwd(const float* const* xs, int32_t n, const float* weights, const float* dout, float* const* dxs,
+                                  int64_t n_elems, void* stream) {
+  if (!xs || !weights || !dout || !dxs) { set_error("nhwc_fuse_silu_bwd: NULL pointer"); return EOT_ERR_NULL_POINTER; }
+  if (n < 2 || n > 3 || n_elems <= 0 || n_elems % 4 != 0) { set_error("nhwc_fuse_silu_bwd: needs 2 or 3 inputs and a multiple of 4 elements"); return EOT_ERR_BAD_SHAPE; }
+  FuseArgs a = {};
+  uintptr_t al = (uintptr_t)dout;
+  for (int k = 0; k < n; ++k) {
+    if (!xs[k]) { set_error("nhwc_fuse_silu_bwd: input %d is NULL", k); return EOT_ERR_NULL_POINTER; }
+    a.x[k] = xs[k]; a.dx[k] = dxs[k];
+    al |= (uintptr_t)xs[k] | (uintptr_t)dxs[k];
+  }
+  if (al & 15) { set_error("nhwc_fuse_silu_bwd: pointers must be 16-byte aligned"); return EOT_ERR_MISALIGNED; }
+  const long long n4 = n_elems / 4;
+  if (n == 2) k_fuse_silu_bwd<2><<<epilogue_grid(n4), kThreads, 0, (cudaStream_t)stream>>>(a, weights, dout, n4);
+  else k_fuse_silu_bwd<3><<<epilogue_grid(n4), kThreads, 0, (cudaStream_t)stream>>>(a, weights, dout, n4);
+  count_launches(1);
   EOT_CHECK_CUDA(cudaPeekAtLastError());
   return EOT_OK;
 }

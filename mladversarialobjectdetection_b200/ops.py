@@ -409,6 +409,24 @@ def nhwc_channel_scale(y: torch.Tensor, gate: torch.Tensor, shift: Optional[torc
     return out
 
 
+def nhwc_fuse_silu(xs: Sequence[torch.Tensor], w: torch.Tensor) -> torch.Tensor:
+    """silu(sum_i w[i] * xs[i]) for 2 or 3 tensors of identical shape and memory layout."""
+    out = torch.empty_like(xs[0])
+    _lib.check(_lib.load().nhwc_fuse_silu_fwd(_ptr_array(xs), len(xs), _ptr(w), _ptr(out), out.numel(), _stream()),
+               "nhwc_fuse_silu_fwd")
+    return out
+
+
+def nhwc_fuse_silu_backward(xs: Sequence[torch.Tensor], w: torch.Tensor, dout: torch.Tensor, need: Sequence[bool]):
+    dxs = [torch.empty_like(x) if nd else None for x, nd in zip(xs, need)]
+    arr = (ctypes.c_void_p * len(xs))()
+    for i, d in enumerate(dxs):
+        arr[i] = 0 if d is None else d.data_ptr()
+    _lib.check(_lib.load().nhwc_fuse_silu_bwd(_ptr_array(xs), len(xs), _ptr(w), _ptr(dout), arr, dout.numel(), _stream()),
+               "nhwc_fuse_silu_bwd")
+    return dxs
+
+
 def nhwc_channel_dot(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """[N,C] = sum over H,W of a * b (channels_last [N,C,H,W]); deterministic."""
     N, C, H, W = a.shape

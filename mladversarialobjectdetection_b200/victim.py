@@ -164,6 +164,40 @@ def squeeze_excite(y: torch.Tensor, se_reduce: nn.Conv2d, se_expand: nn.Conv2d) 
     return y * torch.sigmoid(se_expand(Fn.silu(se_reduce(s))))
 
 
+class _FuseSilu(torch.autograd.Function):
+    """silu(sum_i w_i x_i) of the BiFPN's fast normalised fusion in one pass (weights are frozen: no dL/dw)."""
+
+    @staticmethod
+    def forward(ctx, w, *xs):
+        from . import ops
+        ctx.save_for_backward(w, *xs)
+        return ops.nhwc_fuse_silu(xs, w)
+
+    @staticmethod
+    def backward(ctx, dout):
+        from . import ops
+        w, *xs = ctx.saved_tensors
+        if dout.stride() != xs[0].stride():
+            dout = dout.contiguous(memory_format=torch.channels_last)
+        return (None, *ops.nhwc_fuse_silu_backward(xs, w, dout, ctx.needs_input_grad[1:]))
+
+
+def fuse_silu(xs: Sequence[torch.Tensor], w: torch.Tensor) -> torch.Tensor:
+    x0 = xs[0]
+    if (FUSED_EPILOGUE and len(xs) in (2, 3) and x0.is_cuda and x0.dtype == torch.float32 and x0.numel() % 4 == 0
+            and x0.is_contiguous(memory_format=torch.channels_last)
+            and all(x.shape == x0.shape and x.stride() == x0.stride() and x.dtype == x0.dtype for x in xs[1:])):
+        w = w.contiguous()
+        if torch.is_grad_enabled() and any(x.requires_grad for x in xs):
+            return _FuseSilu.apply(w, *xs)
+        from . import ops
+        return ops.nhwc_fuse_silu(xs, w)
+    y = xs[0] * w[0]
+    for i in range(1, len(xs)):
+        y = y + xs[i] * w[i]
+    return Fn.silu(y)
+
+
 def _module_conv_bias_act(conv: nn.Conv2d, x, act: bool):
     return conv_bias_act(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups, act)
 
@@ -252,10 +286,7 @@ class Fuse(nn.Module):
     def forward(self, xs: Sequence[torch.Tensor]):
         w = Fn.relu(self.w)
         w = w / (w.sum() + 1e-4)
-        y = xs[0] * w[0]
-        for i in range(1, len(xs)):
-            y = y + xs[i] * w[i]
-        return self.conv(Fn.silu(y))
+        return self.conv(fuse_silu(xs, w))
 
 
 def _down(x):

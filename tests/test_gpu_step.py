@@ -242,3 +242,30 @@ def test_fused_squeeze_excite_matches_torch_ops():
     ob.backward(gg)
     torch.testing.assert_close(oa, ob, rtol=2e-6, atol=2e-6)
     torch.testing.assert_close(xa.grad, xb.grad, rtol=1e-4, atol=1e-5)
+
+
+def test_fused_bifpn_fusion_matches_torch_ops():
+    torch.manual_seed(2)
+    for n in (2, 3):
+        xs = [torch.randn(2, 64, 16, 12, device="cuda").contiguous(memory_format=torch.channels_last) for _ in range(n)]
+        w = torch.rand(n, device="cuda")
+        w = w / w.sum()
+        xa = [x.clone().requires_grad_(True) for x in xs]
+        xb = [x.clone().requires_grad_(True) for x in xs]
+        xa[1].requires_grad_(False)                                     # an input that needs no gradient is skipped
+        oa = victim.fuse_silu(xa, w)
+        y = xb[0] * w[0]
+        for i in range(1, n):
+            y = y + xb[i] * w[i]
+        ob = torch.nn.functional.silu(y)
+        g = torch.randn_like(ob)
+        oa.backward(g)
+        ob.backward(g)
+        torch.testing.assert_close(oa, ob, rtol=1e-5, atol=1e-6)
+        for i in range(n):
+            if i == 1:
+                assert xa[i].grad is None
+            else:
+                torch.testing.assert_close(xa[i].grad, xb[i].grad, rtol=1e-4, atol=1e-6)
+        with torch.no_grad():
+            torch.testing.assert_close(victim.fuse_silu(xs, w), ob, rtol=1e-5, atol=1e-6)
