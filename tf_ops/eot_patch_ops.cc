@@ -234,3 +234,97 @@ class EotScoreMaxOp : public tf::OpKernel {
   float h_, w_;
 };
 REGISTER_KERNEL_BUILDER(Name("EotScoreMax").Device(tf::DEVICE_GPU), EotScoreMaxOp);
+
+// First pass after the victim (attacker.py:100-116,143-170): person candidates -> NonMaxSuppressionV5 -> clip_boxes ->
+// ragged boxes, in one op instead of tf.map_fn over the images with the CPU-only NMS kernel.
+REGISTER_OP("EotFirstPassBoxes")
+    .Input("cls_levels: num_levels * float")   // each [B,h,w,9*C]
+    .Input("box_levels: num_levels * float")   // each [B,h,w,36]
+    .Input("anchors: float")                   // [A,4]
+    .Attr("num_levels: int = 5")
+    .Attr("num_classes: int = 90")
+    .Attr("image_height: float")
+    .Attr("image_width: float")
+    .Attr("max_output_size: int = 100")
+    .Attr("iou_threshold: float = 1.0")        // gaussian: 1.0; hard: nms_configs.iou_thresh
+    .Attr("score_threshold: float = 0.5")      // nms_configs.score_thresh (attacker_train.py:31)
+    .Attr("soft_nms_sigma: float = 0.25")      // gaussian: sigma / 2 (tf2/postprocess.py:196-199); hard: 0
+    .Attr("score_floor: float = 0.5")          // filter_valid_boxes(thresh=True), attacker.py:87-88
+    .Output("nms_boxes: float")                // [B,max_output_size,4], selection order, zero padded
+    .Output("nms_scores: float")               // [B,max_output_size]
+    .Output("valid_len: int32")                // [B]
+    .Output("row_splits: int32")               // [B+1]
+    .Output("ragged_boxes: float")             // [B*max_output_size,4], first row_splits[B] rows valid
+    .Output("ragged_scores: float");           // [B*max_output_size]
+
+class EotFirstPassBoxesOp : public tf::OpKernel {
+ public:
+  explicit EotFirstPassBoxesOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("num_levels", &num_levels_));
+    OP_REQUIRES_OK(c, c->GetAttr("num_classes", &num_classes_));
+    OP_REQUIRES_OK(c, c->GetAttr("image_height", &h_));
+    OP_REQUIRES_OK(c, c->GetAttr("image_width", &w_));
+    OP_REQUIRES_OK(c, c->GetAttr("max_output_size", &max_out_));
+    OP_REQUIRES_OK(c, c->GetAttr("iou_threshold", &iou_));
+    OP_REQUIRES_OK(c, c->GetAttr("score_threshold", &thr_));
+    OP_REQUIRES_OK(c, c->GetAttr("soft_nms_sigma", &sigma_));
+    OP_REQUIRES_OK(c, c->GetAttr("score_floor", &floor_));
+  }
+  void Compute(tf::OpKernelContext* ctx) override {
+    ScoreShape s{};
+    NmsShape n{};
+    const float* cls[SCORE_MAX_LEVELS];
+    const float* box[SCORE_MAX_LEVELS];
+    s.num_levels = n.num_levels = num_levels_;
+    s.num_classes = num_classes_;
+    s.batch = n.batch = ctx->input(0).dim_size(0);
+    s.anchors_per_loc = ctx->input(0).dim_size(3) / num_classes_;
+    int tot = 0;
+    for (int l = 0; l < num_levels_; ++l) {
+      const tf::Tensor& c = ctx->input(l);
+      cls[l] = c.flat<float>().data();
+      box[l] = ctx->input(num_levels_ + l).flat<float>().data();
+      s.level_locs[l] = c.dim_size(1) * c.dim_size(2);
+      n.level_anchors[l] = s.level_locs[l] * s.anchors_per_loc;
+      tot += s.level_locs[l];
+    }
+    s.total_anchors = n.total_anchors = tot * s.anchors_per_loc;
+    s.image_height = n.image_height = h_;
+    s.image_width = n.image_width = w_;
+    s.min_area = 100.0f;
+    n.max_output_size = max_out_;
+    n.max_candidates = 0;
+    n.iou_threshold = iou_; n.score_threshold = thr_; n.soft_nms_sigma = sigma_; n.score_floor = floor_;
+    const tf::Tensor& anchors = ctx->input(2 * num_levels_);
+    size_t sbytes = 0, nbytes = 0;
+    EOT_OP_OK(ctx, score_workspace_bytes(&s, &sbytes));
+    EOT_OP_OK(ctx, person_nms_workspace_bytes(&n, &nbytes));
+    tf::Tensor sws, nws, M, am, nc;
+    OP_REQUIRES_OK(ctx, ctx->allocate_temp(tf::DT_UINT8, tf::TensorShape({static_cast<tf::int64>(sbytes)}), &sws));
+    OP_REQUIRES_OK(ctx, ctx->allocate_temp(tf::DT_UINT8, tf::TensorShape({static_cast<tf::int64>(nbytes)}), &nws));
+    OP_REQUIRES_OK(ctx, ctx->allocate_temp(tf::DT_FLOAT, tf::TensorShape({s.batch}), &M));
+    OP_REQUIRES_OK(ctx, ctx->allocate_temp(tf::DT_INT32, tf::TensorShape({s.batch}), &am));
+    OP_REQUIRES_OK(ctx, ctx->allocate_temp(tf::DT_INT32, tf::TensorShape({s.batch}), &nc));
+    tf::Tensor *boxes = nullptr, *scores = nullptr, *vlen = nullptr, *splits = nullptr, *rboxes = nullptr, *rscores = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, tf::TensorShape({s.batch, max_out_, 4}), &boxes));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, tf::TensorShape({s.batch, max_out_}), &scores));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(2, tf::TensorShape({s.batch}), &vlen));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(3, tf::TensorShape({s.batch + 1}), &splits));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(4, tf::TensorShape({s.batch * max_out_, 4}), &rboxes));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(5, tf::TensorShape({s.batch * max_out_}), &rscores));
+    void* st = StreamOf(ctx);
+    EOT_OP_OK(ctx, score_max_fwd(&s, cls, box, anchors.flat<float>().data(), M.flat<float>().data(),
+                                 am.flat<tf::int32>().data(), nc.flat<tf::int32>().data(), sws.flat<tf::uint8>().data(), sbytes, st));
+    // the dense candidate scores sit in the score workspace behind the keys and the counters (ScoreLayout, csrc/score_max.cu)
+    auto align = [](size_t x) { return (x + 255) / 256 * 256; };
+    const float* cand = reinterpret_cast<const float*>(sws.flat<tf::uint8>().data() + align(align((size_t)s.batch * 8) + 2 * (size_t)s.batch * 4));
+    EOT_OP_OK(ctx, person_nms(&n, cand, box, anchors.flat<float>().data(), boxes->flat<float>().data(),
+                              scores->flat<float>().data(), vlen->flat<tf::int32>().data(), splits->flat<tf::int32>().data(),
+                              rboxes->flat<float>().data(), rscores->flat<float>().data(), nws.flat<tf::uint8>().data(), nbytes, st));
+  }
+
+ private:
+  int num_levels_, num_classes_, max_out_;
+  float h_, w_, iou_, thr_, sigma_, floor_;
+};
+REGISTER_KERNEL_BUILDER(Name("EotFirstPassBoxes").Device(tf::DEVICE_GPU), EotFirstPassBoxesOp);

@@ -54,3 +54,18 @@ class Patcher(tf.keras.layers.Layer):
         flat = boxes.flat_values
         return _apply(self._patch, self._scale, images, flat, tf.cast(boxes.row_splits, tf.int32),
                       _draw_params(tf.shape(flat)[0]), tf.concat([w, bias], axis=1))
+
+
+def first_pass_boxes(cls_outputs, box_outputs, anchors, image_hw, nms_configs):
+    """Replacement for the post-victim part of `PatchAttacker.first_pass` (attacker.py:100-116,143-170): person
+    candidates -> NonMaxSuppressionV5 -> clip_boxes -> (ragged boxes, ragged scores), one op on the GPU."""
+    gaussian = nms_configs.method == 'gaussian'
+    out = _ops.eot_first_pass_boxes(
+        cls_levels=cls_outputs, box_levels=box_outputs, anchors=anchors, image_height=float(image_hw[0]),
+        image_width=float(image_hw[1]), max_output_size=nms_configs.max_output_size,
+        iou_threshold=1.0 if gaussian else (nms_configs.iou_thresh or .5), score_threshold=nms_configs.score_thresh or 0.,
+        soft_nms_sigma=(nms_configs.sigma or .5) / 2 if gaussian else 0., score_floor=nms_configs.score_thresh or 0.)
+    n = out.row_splits[-1]
+    boxes = tf.RaggedTensor.from_row_splits(out.ragged_boxes[:n], tf.cast(out.row_splits, tf.int64))
+    scores = tf.RaggedTensor.from_row_splits(out.ragged_scores[:n], tf.cast(out.row_splits, tf.int64))
+    return boxes, scores
