@@ -173,6 +173,69 @@ def gen_adv_patch_u8():
     np.savez_compressed(os.path.join(HERE, "adv_patch_u8.npz"), n=len(cases), P=P, **out)
 
 
+def gen_patcher_ref2():
+    """A second, harder Patcher case for the oracle (CPU test only): 3 images of 96x96, 32x32 patch, scale .6 (patch sides
+    from 6 to 46 px: down- AND up-sampling), boxes that overlap each other, boxes whose window is clamped at the image
+    border (attacker.py:480-486) and one dropped by the area filter."""
+    import tf_numpy_shim as shim
+    from mladversarialobjectdetection_b200 import synth
+    from oracle import patcher, tfops
+    F = np.float32
+    attacker = shim.import_reference_attacker()
+    H = W = 96
+    P = 32
+    rng = np.random.default_rng(4242)
+    images = rng.uniform(-1, 1, (3, H, W, 3)).astype(F)
+    patch = synth.make_patch(P, seed=9)
+    boxes = [np.array([[5, 5, 80, 40], [20, 25, 90, 60], [0, 60, 30, 95], [60, 0, 95, 20]], F),        # overlapping + corners
+             np.array([[10, 10, 20, 18], [2, 3, 6, 5], [30, 30, 94, 94]], F),                            # small, filtered, huge
+             np.array([[40, 40, 95, 95], [45, 45, 90, 92]], F)]                                          # nested at the border
+    scale = F(0.6)
+    params = [np.zeros(len(b), patcher.BOX_PARAMS) for b in boxes]
+    print_wb = np.zeros((3, 6), F)
+    q = shim.QUEUE
+    q.items.clear()
+    for b in range(3):
+        zw, zb = rng.standard_normal(3).astype(F), rng.standard_normal(3).astype(F)
+        print_wb[b, :3] = zw * F(0.1) + F(0.5)
+        print_wb[b, 3:] = zb * F(0.01) + F(0.0)
+        q.push("normal", zw)
+        q.push("normal", zb)
+        plans = []
+        for j in range(len(boxes[b])):
+            params[b][j]["uy"], params[b][j]["ux"] = F(rng.random()), F(rng.random())
+            params[b][j]["scale"] = F(-1.0)
+            params[b][j]["key0"], params[b][j]["key1"] = int(rng.integers(0, 2 ** 31)), int(rng.integers(0, 2 ** 31))
+            q.push("uniform", F(params[b][j]["uy"]))
+            q.push("uniform", F(params[b][j]["ux"]))
+            plans.append(patcher.create(boxes[b][j], scale, params[b][j]["uy"], params[b][j]["ux"], 0.2, H, W))
+        for j, pl in enumerate(plans):
+            if not pl.valid:
+                continue
+            n = pl.ps * pl.ps * 3
+            words = tfops.philox4x32_10(np.arange((n + 3) // 4, dtype=np.uint32), int(params[b][j]["key0"]),
+                                        int(params[b][j]["key1"])).reshape(-1)[:n]
+            q.push("uniform", ((words & np.uint32(0x7FFFFF)) | np.uint32(0x3F800000)).view(F) - F(1.0))
+            ud, ua = F(rng.random()), F(rng.random())
+            params[b][j]["delta"] = ud * (F(0.3) - F(-0.3)) + F(-0.3)
+            q.push("uniform", ud)
+            lo, hi = F(-20.0 * np.pi / 180.0), F(20.0 * np.pi / 180.0)
+            ang = F(ua * (hi - lo) + lo)
+            params[b][j]["cos"], params[b][j]["sin"] = F(np.cos(ang)), F(np.sin(ang))
+            q.push("uniform", ua)
+    layer = attacker.Patcher(shim.Variable(patch.astype(F)), shim.Variable(scale), name="Patcher")
+    out_ref = np.asarray(layer([boxes, images]), F)
+    assert not q.items
+    out_oracle, _, states = patcher.patcher_forward(patch, images, boxes, params, print_wb, float(scale))
+    assert np.array_equal(out_ref, out_oracle), "oracle != reference Patcher on the shim (case 2)"
+    sizes = sorted(bs.plan.ps for st in states for bs in st.boxes)
+    assert sizes[0] < P < sizes[-1], sizes                                   # both resize directions are exercised
+    offsets = np.cumsum([0] + [len(b) for b in boxes]).astype(np.int32)
+    np.savez_compressed(os.path.join(HERE, "patcher_ref2.npz"), patch=patch, images=images, boxes=np.concatenate(boxes),
+                        offsets=offsets, params=np.concatenate(params).view(np.uint8), print_wb=print_wb, scale=scale,
+                        out_ref=out_ref)
+
+
 def gen_patcher_ref():
     import tf_numpy_shim as shim
     from mladversarialobjectdetection_b200 import synth
@@ -413,6 +476,7 @@ if __name__ == "__main__":
     gen_anchors_ref()
     gen_masker_ref()
     gen_patcher_ref()
+    gen_patcher_ref2()
     gen_adv_patch_u8()
     gen_map_fn()
     gen_nms_np()

@@ -218,3 +218,17 @@ def test_cuda_masker_equals_reference_masker_fixture(tag, tol):
     ops.check_workspace(ctx)
     np.testing.assert_array_equal(out.cpu().numpy(), g[f"{tag}_out"])
     np.testing.assert_array_equal(mask.cpu().numpy(), g[f"{tag}_mask"])
+
+
+def test_cuda_forward_equals_reference_patcher_fixture_harder_case():
+    """patcher_ref2 (tests/golden): overlapping boxes, border-clamped windows, down- and up-sampling, a filtered box --
+    CUDA path vs the reference's own Patcher.call run on the NumPy TF shim."""
+    g = np.load(os.path.join(GOLD, "patcher_ref2.npz"))
+    params = np.ascontiguousarray(g["params"]).view(patcher.BOX_PARAMS).reshape(-1)
+    dev = "cuda"
+    out, _, ctx = ops.apply_forward(torch.from_numpy(g["patch"]).to(dev), torch.tensor(float(g["scale"]), device=dev),
+                                    torch.from_numpy(g["images"]).to(dev), torch.from_numpy(g["boxes"]).to(dev),
+                                    torch.from_numpy(g["offsets"]).to(dev), ops.params_to_tensor(params, dev),
+                                    torch.from_numpy(g["print_wb"]).to(dev), ops.PatchGeometry())
+    ops.check_workspace(ctx)
+    np.testing.assert_array_equal(out.cpu().numpy(), g["out_ref"])

@@ -79,3 +79,17 @@ def test_oracle_equals_reference_second_and_first_pass_on_the_shim():
         np.testing.assert_array_equal(rows[b], g[f"fp_boxes{b}"])
         np.testing.assert_array_equal(row_scores[b], g[f"fp_scores{b}"])
         assert len(g[f"fp_boxes{b}"]) > 5
+
+
+def test_oracle_equals_reference_patcher_on_the_shim_harder_case():
+    """patcher_ref2: 3 images of 96x96, 32x32 patch, scale .6 -- patch sides from below to above the texture size (down-
+    and up-sampling), mutually overlapping boxes, windows clamped at the image border, one box dropped by the area filter."""
+    g = np.load(os.path.join(GOLD, "patcher_ref2.npz"))
+    params = np.ascontiguousarray(g["params"]).view(BOX_PARAMS).reshape(-1)
+    off = g["offsets"]
+    boxes = [g["boxes"][off[b]:off[b + 1]] for b in range(len(off) - 1)]
+    prm = [params[off[b]:off[b + 1]] for b in range(len(off) - 1)]
+    out, _, states = patcher.patcher_forward(g["patch"], g["images"], boxes, prm, g["print_wb"], float(g["scale"]))
+    np.testing.assert_array_equal(out, g["out_ref"])
+    sizes = sorted(bs.plan.ps for st in states for bs in st.boxes)
+    assert sizes[0] < 32 < sizes[-1] and sum(len(st.boxes) for st in states) == 8
