@@ -467,6 +467,13 @@ def gen_objective_ref():
     for b in range(B):
         out[f"sp_scores{b}"], out[f"sp_boxes{b}"] = scores_pred.rows[b], boxes_pred.rows[b]
         out[f"fp_scores{b}"], out[f"fp_boxes{b}"] = fp_scores.rows[b], fp_boxes.rows[b]
+    # the hard-NMS branch of postprocess.nms (tf2/postprocess.py:175-180) through the same reference code
+    cfg.override({"nms_configs": {"method": "hard", "iou_thresh": .5, "score_thresh": .4}})
+    hb, hs = pa.first_pass(images)
+    hrows, hscores = onms.person_boxes_after_nms(cand, b_all, anchors, (H, H), dict(cfg.nms_configs.as_dict()), thresh=True)
+    for b in range(B):
+        assert np.array_equal(hrows[b], hb.rows[b]) and np.array_equal(hscores[b], hs.rows[b])
+        out[f"hard_scores{b}"], out[f"hard_boxes{b}"] = hs.rows[b], hb.rows[b]
     np.savez_compressed(os.path.join(HERE, "objective_ref.npz"), **out)
 
 

@@ -79,6 +79,11 @@ def test_oracle_equals_reference_second_and_first_pass_on_the_shim():
         np.testing.assert_array_equal(rows[b], g[f"fp_boxes{b}"])
         np.testing.assert_array_equal(row_scores[b], g[f"fp_scores{b}"])
         assert len(g[f"fp_boxes{b}"]) > 5
+    hard = dict(method="hard", sigma=None, iou_thresh=0.5, score_thresh=0.4, max_output_size=100)
+    rows, row_scores = onms.person_boxes_after_nms(cand, b_all, anchors, (H, H), hard, thresh=True)
+    for b in range(B):                                              # hard-NMS branch of postprocess.nms
+        np.testing.assert_array_equal(rows[b], g[f"hard_boxes{b}"])
+        np.testing.assert_array_equal(row_scores[b], g[f"hard_scores{b}"])
 
 
 def test_oracle_equals_reference_patcher_on_the_shim_harder_case():
