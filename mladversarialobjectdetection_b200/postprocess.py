@@ -47,3 +47,19 @@ def person_boxes_after_nms(config, score_ctx, box_outputs: Sequence[torch.Tensor
     s = splits.numpy()
     scores = res.ragged_scores[:n].cpu().numpy()
     return boxes, [scores[s[i]:s[i + 1]] for i in range(len(s) - 1)]
+
+
+def calc_asr(scores: Sequence[np.ndarray], scores_pred: Sequence[np.ndarray], score_thresh: float = 0.5) -> float:
+    """attack success rate at a score threshold (attacker.py:238-255): 1 - (#attacked-pass boxes with score >= t) /
+    (#clean-pass boxes with score >= t), both after NMS; `scores` / `scores_pred` are the ragged per-image score lists
+    that `person_boxes_after_nms` returns for the clean and the attacked pass.  The reference counts the 4 coordinates
+    of every kept box (`tf.size(flat_values)`) and adds Keras' epsilon (1e-7) to the denominator; float32 throughout."""
+    t = np.float32(score_thresh)
+    n_first = sum(int((np.asarray(s, np.float32) >= t).sum()) for s in scores)
+    n_pred = sum(int((np.asarray(s, np.float32) >= t).sum()) for s in scores_pred)
+    return float(np.float32(1.0) - np.float32(4 * n_pred) / (np.float32(4 * n_first) + np.float32(1e-7)))
+
+
+def asr_sweep(scores, scores_pred, bins: Sequence[float]) -> np.ndarray:
+    """the threshold sweep of vis_images (attacker.py:275-277) over `PatchAttacker.bins`."""
+    return np.asarray([calc_asr(scores, scores_pred, float(b)) for b in bins], np.float32)

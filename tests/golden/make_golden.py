@@ -474,6 +474,15 @@ def gen_objective_ref():
     for b in range(B):
         assert np.array_equal(hrows[b], hb.rows[b]) and np.array_equal(hscores[b], hs.rows[b])
         out[f"hard_scores{b}"], out[f"hard_boxes{b}"] = hs.rows[b], hb.rows[b]
+    # attack success rate (attacker.py:238-255) of the reference on ragged score lists: clean pass = the hard-NMS result,
+    # "attacked" pass = the same boxes with scores scaled down, swept over PatchAttacker.bins (attacker.py:66)
+    rng = np.random.default_rng(12)
+    atk = shim.Ragged([(r * rng.uniform(0.3, 1.0, len(r))).astype(F) for r in hs.rows])
+    bins = np.arange(0.4, .805, .01, dtype="float32")
+    out["asr_bins"] = bins
+    out["asr"] = np.asarray([float(pa.calc_asr(hs, atk, hb, hb, score_thresh=float(t))) for t in bins], F)
+    for b in range(B):
+        out[f"atk_scores{b}"] = atk.rows[b]
     np.savez_compressed(os.path.join(HERE, "objective_ref.npz"), **out)
 
 

@@ -189,6 +189,10 @@ class Ragged:
     def __mul__(self, o): return self._zip(o, lambda a, b: a * b)
     def __truediv__(self, o): return self._zip(o, lambda a, b: a / b)
 
+    @property
+    def flat_values(self):
+        return np.concatenate(self.rows, axis=0) if self.rows else np.zeros((0,), F)
+
     @staticmethod
     def from_tensor(tensor, lengths):
         return Ragged([np.asarray(tensor)[i][:int(n)] for i, n in enumerate(np.asarray(lengths))])
@@ -276,6 +280,7 @@ def build_modules():
     tf.__path__ = []                                            # a package: tensorflow.compat.v1 etc. resolve to inert mocks
     tf.zeros_like = _zeros_like
     tf.Tensor = np.ndarray
+    tf.size = lambda x: np.int32(np.size(x))
     tf.convert_to_tensor = lambda x, dtype=None: np.asarray(x, dtype=dtype)
     tf.equal = _rag(np.equal)
     tf.less_equal = _rag(np.less_equal)
@@ -298,7 +303,8 @@ def build_modules():
                                      yuv_to_rgb=_yuv_to_rgb, random_flip_left_right=_random_flip(2),
                                      random_flip_up_down=_random_flip(1))
     tf.keras = types.SimpleNamespace(layers=types.SimpleNamespace(Layer=Layer), Model=Layer,
-                                     utils=types.SimpleNamespace(Sequence=object))
+                                     utils=types.SimpleNamespace(Sequence=object),
+                                     backend=types.SimpleNamespace(epsilon=lambda: 1e-7))
     tfa = types.ModuleType("tensorflow_addons")
     tfa.image = types.SimpleNamespace(rotate=_rotate)
     return tf, tfa

@@ -8,6 +8,7 @@ brightness matcher's formula order.  The leaf TF kernels underneath are the orac
 import os
 
 import numpy as np
+import pytest
 
 from oracle import patcher
 from oracle.patcher import BOX_PARAMS
@@ -98,3 +99,16 @@ def test_oracle_equals_reference_patcher_on_the_shim_harder_case():
     np.testing.assert_array_equal(out, g["out_ref"])
     sizes = sorted(bs.plan.ps for st in states for bs in st.boxes)
     assert sizes[0] < 32 < sizes[-1] and sum(len(st.boxes) for st in states) == 8
+
+
+def test_attack_success_rate_matches_reference_calc_asr():
+    """postprocess.calc_asr / asr_sweep (host metric) vs the reference's own calc_asr (attacker.py:238-255) swept over
+    PatchAttacker.bins, run on the NumPy TF shim (objective_ref.npz)."""
+    from mladversarialobjectdetection_b200 import postprocess
+    g = np.load(os.path.join(GOLD, "objective_ref.npz"))
+    B = int(g["B"])
+    first = [g[f"hard_scores{b}"] for b in range(B)]
+    attacked = [g[f"atk_scores{b}"] for b in range(B)]
+    np.testing.assert_array_equal(postprocess.asr_sweep(first, attacked, g["asr_bins"]), g["asr"])
+    assert postprocess.calc_asr(first, first, 0.5) == pytest.approx(0.0, abs=1e-6)
+    assert postprocess.calc_asr(first, [np.zeros(0, np.float32)] * B, 0.5) == 1.0
