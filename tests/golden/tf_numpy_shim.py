@@ -1,17 +1,24 @@
-"""A NumPy stand-in for the ~40 TensorFlow / TensorFlow-Addons entry points that the reference's `Patcher`
-(/root/reference/attacker.py:344-498) and `BrightnessMatcher` (/root/reference/brightness_matcher.py:14-73) call, so
-that THE REFERENCE'S OWN LAYER CODE runs verbatim in the build container (TensorFlow is not installed).
+"""A NumPy stand-in for the ~60 TensorFlow / TensorFlow-Addons entry points that the reference's hot path calls, so that
+THE REFERENCE'S OWN CODE runs verbatim in the build container (TensorFlow is not installed):
+
+  * `attacker.Patcher` (/root/reference/attacker.py:344-498) and `brightness_matcher.BrightnessMatcher`
+    (/root/reference/brightness_matcher.py:14-73)
+  * `attack_detection.Masker` (/root/reference/attack_detection.py:321-498), evaluation and training branch
+  * `PatchAttacker.first_pass / second_pass / filter_valid_boxes / _postprocessing / calc_asr`
+    (/root/reference/attacker.py:69-170,238-255) together with the vendored automl code they call, imported for real:
+    `tf2/postprocess.py` (pre_nms, nms, clip_boxes), `tf2/anchors.py`, `utils.py`, `hparams_config.py`
 
 What this pins and what it does not: the reference's Python -- control flow, the order and association of every
 arithmetic expression (each evaluated as one float32 NumPy op, as TF eager does), casts, pads, the where / clip /
-scatter sequence, the box filter, the loop over boxes and images -- is executed as written.  The LEAF kernels that
-live inside the TF / TFA wheels (ScaleAndTranslate, ImageProjectiveTransformV3, rgb_to_yuv / yuv_to_rgb, reduce_mean)
-are the oracle's restatements (oracle/tfops.py); they stay unpinned.  Random draws are served from a queue the caller
+scatter sequence, the box filters, ragged masks, the loops over boxes and images, the NMS call arguments -- is
+executed as written.  The LEAF kernels that live inside the TF / TFA wheels (ScaleAndTranslate,
+ImageProjectiveTransformV3, rgb_to_yuv / yuv_to_rgb, reduce_mean, NonMaxSuppressionV5, sigmoid / exp) are the oracle's
+restatements (oracle/tfops.py, oracle/nms.py); they stay unpinned.  Random draws are served from a queue the caller
 fills with the explicit transform seeds, mapped to the requested range the way TF's random ops do
 (u * (maxval - minval) + minval; mean + stddev * z).
 
 Only tests/golden/make_golden.py imports this module (it needs /root/reference); its outputs are committed as
-tests/golden/patcher_ref.npz.
+tests/golden/{patcher_ref,patcher_ref2,brightness_ref,masker_ref,objective_ref}.npz.
 """
 from __future__ import annotations
 
