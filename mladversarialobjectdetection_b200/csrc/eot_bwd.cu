@@ -46,16 +46,17 @@ __device__ __forceinline__ void routed_grad3(const uint8_t* __restrict__ route, 
 #endif
 __global__ void __launch_bounds__(kThreads, EOT_BWDW_MINB) k_bwd_window(EotShape s, Layout L, char* ws, const float* __restrict__ G) {
   const BoxPlan* plans = reinterpret_cast<const BoxPlan*>(ws + L.off_plans);
-  __shared__ int2 s_base[kMaxBaseSmem];
-  const int2* base = stage_base(reinterpret_cast<const int2*>(ws + L.off_base), s.total_boxes, s_base);
-  const int n_items = base[s.total_boxes].x;
+  __shared__ int s_base[kMaxBaseSmem];
+  int bstride;
+  const int* base = stage_base(reinterpret_cast<const int4*>(ws + L.off_base), kItemBwdWindow, s.total_boxes, s_base, &bstride);
+  const int n_items = base[bstride * s.total_boxes];
   const float* ubuf = reinterpret_cast<const float*>(ws + L.off_u);
   float* gubuf = reinterpret_cast<float*>(ws + L.off_gu);
   const uint8_t* routes = reinterpret_cast<const uint8_t*>(ws + L.off_route);
   const int H = s.height, W = s.width;
-  const int2* cnt = reinterpret_cast<const int2*>(ws + L.off_cnt);
+  const int4* cnt = reinterpret_cast<const int4*>(ws + L.off_cnt);
   for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-    const int2 item = find_item(base, s.total_boxes, 0, it);
+    const int2 item = find_item(base, bstride, s.total_boxes, it);
     const int j = item.x;
     const BoxPlan me = plans[j];
     const int ps = me.ps, D = me.d;
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(kThreads) k_bwd_resize(EotShape s, Layout L, c
           float a = 0.0f;
           for (int oy = rng.x; oy <= rng.y; ++oy) {
             const int kk = py - s_st[oy];
-            if (kk >= 0 && kk < span) a += s_w[oy * span + kk] * gu[oy * ps * 4 + fo];
+            if (kk >= 0 && kk < span) a += s_w[kk * ps + oy] * gu[oy * ps * 4 + fo];
           }
           tmp[r * tstride + f] = a;
         }
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(kThreads) k_bwd_resize(EotShape s, Layout L, c
         for (int ox = rng.x; ox <= rng.y; ++ox) {
           const int kk = px - s_st[ox];
           if (kk < 0 || kk >= span) continue;
-          const float w = s_w[ox * span + kk];
+          const float w = s_w[kk * ps + ox];
           const float* tp = tmp + ox * 3 + c;
 #pragma unroll
           for (int r = 0; r < kBwdChunk; ++r) a[r] += w * tp[r * tstride];
@@ -331,17 +332,18 @@ __device__ __forceinline__ void bwd_resize_passes(int P, int ps, int tcap, int p
 
 __global__ void __launch_bounds__(kThreads, EOT_BWDR_MINB) k_bwd_resize3(EotShape s, Layout L, char* ws) {
   extern __shared__ __align__(16) float smem[];
-  __shared__ int2 s_base[kMaxBaseSmem];
+  __shared__ int s_base[kMaxBaseSmem];
   __shared__ int2 s_item;
+  int bstride;
   const int P = s.patch_size, P3 = P * 3;
   const int inter_texels = max(2560, L.lmin);                      // rows * ps <= 2560 unless a single row is longer
   float4* inter = reinterpret_cast<float4*>(smem);                // [rows][ps]
   int2* s_st = reinterpret_cast<int2*>(smem + (size_t)inter_texels * 4);   // [P+1]
   float* s_wt = reinterpret_cast<float*>(s_st + (P + 1));          // [P][tstride]
-  const int2* base = stage_base(reinterpret_cast<const int2*>(ws + L.off_base), s.total_boxes, s_base);
-  const int n_items = base[s.total_boxes].y;
+  const int* base = stage_base(reinterpret_cast<const int4*>(ws + L.off_base), kItemBwdResize, s.total_boxes, s_base, &bstride);
+  const int n_items = base[bstride * s.total_boxes];
   for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-    if (threadIdx.x == 0) s_item = find_item(base, s.total_boxes, 1, it);
+    if (threadIdx.x == 0) s_item = find_item(base, bstride, s.total_boxes, it);
     __syncthreads();
     const int j = s_item.x;
     const BoxPlan* pl = reinterpret_cast<const BoxPlan*>(ws + L.off_plans) + j;

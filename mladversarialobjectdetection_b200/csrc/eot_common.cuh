@@ -36,16 +36,25 @@ namespace eot {
 #ifndef EOT_COMP_ROWS
 #define EOT_COMP_ROWS 4
 #endif
+#ifndef EOT_RESIZE_RB
+#define EOT_RESIZE_RB 2
+#endif
 #ifndef EOT_RESIZE_ROWS_CAP
 #define EOT_RESIZE_ROWS_CAP 12
 #endif
 #ifndef EOT_BWD_ROWS_CAP
 #define EOT_BWD_ROWS_CAP 32
 #endif
-constexpr int kCompRows = EOT_COMP_ROWS;  // image rows per composite work item (one CTA: a warp per row)
+constexpr int kCompRows = EOT_COMP_ROWS;  // window rows per composite work item (one warp)
 constexpr int kThreads = 256;
+// Work tickets.  One atomic counter handing out every item of a kernel is the bottleneck of warp-granular items (a
+// same-address atomic completes every ~2.3 ns on B200: 27 k items = 60 us).  Each kernel therefore owns kTicketLanes
+// counters, 256 bytes apart; counter c hands out the items c, c + kTicketLanes, c + 2 kTicketLanes, ...; a warp draws
+// from the counter (global warp index mod kTicketLanes) only.
+constexpr int kTicketSlots = 16;
+constexpr int kTicketLanes = 16;
 
-// Per-box plan written by the geometry kernel; 128 bytes.
+// Per-box plan written by the geometry kernel; 144 bytes.
 struct __align__(16) BoxPlan {
   int32_t y0, x0, ps, d;
   int32_t pad_lo, pad_hi, valid, span;
@@ -56,8 +65,11 @@ struct __align__(16) BoxPlan {
   int32_t image;
   int64_t u_off;  // float offset of this box's transformed-patch buffer
   int32_t first_box, last_box;   // CSR range of the owning image
+  float ia0, ia3;                // 1/T[0], 1/T[3] (0 when the coefficient is ~0): column range of the core per window row
+  int32_t two_tap;               // 1: the resize of this box runs from the two-tap table
+  int32_t rsv;
 };
-static_assert(sizeof(BoxPlan) == 128, "BoxPlan must stay 128 bytes");
+static_assert(sizeof(BoxPlan) == 144, "BoxPlan must stay 144 bytes");
 
 // Workspace layout (byte offsets); identical on host and device.
 struct Layout {
@@ -65,16 +77,25 @@ struct Layout {
   size_t off_ysum_patch;   // double[B]
   size_t off_gy_sum;       // double[B]   (backward: sum of dL/dY per image)
   size_t off_oor;          // int32[B]    image b holds a value outside [-1,1] (then clip(background) is not the identity)
-  size_t off_counters;     // int32[8]: 2 error flag, 5 finished geometry blocks
-  size_t off_tickets;      // int32[32]  composite band tickets
+  size_t off_counters;     // int32[8]: 2 error flag, 3 open pixels listed by the composite, 5 finished geometry blocks
+  size_t off_tickets;      // int32[kTicketSlots][kTicketLanes][64]  work tickets: slot = kernel (x image group), lane = one of
+                           //            the interleaved sub-queues (own 256-byte line each: same-address atomics serialise)
   size_t off_plans;        // BoxPlan[N]
   size_t off_starts;       // int32[N][Lmin]
-  size_t off_weights;      // float[N][wcap]
-  size_t off_match;        // float[B][P*P*3]
+  size_t off_weights;      // float[N][wcap]  tap-major: weight of tap k of output index o at [k * ps + o]
+  size_t off_tab2;         // float4[N][Lmin] two-tap boxes (up-sampling / unit scale: at most two adjacent non-zero taps
+                           //            per output index): (source index a, source index b, weight a, weight b)
+  size_t off_match;        // float4[B][P*P] matched patch per image, RGBX texels
   size_t off_u;            // float4[N][slot/4]: (ps+4)^2 texels per box = clipped (r,g,b) of the transformed patch +
                            //            inner-clip pass bits, inside a two-texel ring of the -2 pad / fill value
-  size_t off_cnt;          // int2[N]    work items of box j: (forward resize strips, backward resize strips); 0 when invalid
-  size_t off_base;         // int2[N+1]  exclusive prefix sums of off_cnt (box order == image order)
+  size_t off_cnt;          // int4[N]    work items of box j: (backward window strips, backward resize strips, forward resize
+                           //            row blocks, forward composite row blocks); 0 when invalid
+  size_t off_base;         // int4[N+1]  exclusive prefix sums of off_cnt (box order == image order)
+  size_t off_items;        // int2[N * ceil(Lmin / rb)] forward resize work items in ticket order: (box, row block)
+  size_t off_citems;       // int2[N * ceil(min(H,W) / kCompRows)] forward composite work items: (box, window row block)
+  size_t off_rowtab;       // int2[N][min(H,W)] per window row: first / last column whose sample can touch the core
+  size_t off_open;         // int2[open_cap] composite: owned pixels with an open channel inside an older box's range:
+                           //            (box, row << 16 | column << 3 | open channels)
   size_t off_inv;          // int2[N][P]  for patch index i: first/last output index whose span holds i
   size_t off_wt;           // float[N][P*tcap] transposed resize weights, row stride = the box's own max tap count:
                            //              tap k of patch index i = weight of output index st+k
@@ -92,7 +113,10 @@ struct Layout {
   int32_t tcap;            // taps per patch index in the transposed weight table
   int32_t wcap;            // floats per weight table
   int32_t lmin;            // max patch side
-  int32_t resize_rows;     // output rows per resize work item (bounded by shared memory: rows * P * 12 B)
+  int32_t resize_rows;     // output rows per backward window strip
+  int32_t rb;              // output rows per forward resize item (one warp; shared memory: rb * P * 16 B per warp)
+  int32_t cr;              // window rows per forward composite item (one warp)
+  int64_t open_cap;        // entries of the open-pixel list (overflow: the composite redoes every row the slow way)
   uint32_t p3_magic;       // ceil(2^32 / (3P)): idx / (3P) == umulhi(idx, p3_magic) for idx < 2^16
   int64_t rslot;           // bytes per route map
   int32_t use_gbox;        // per-box partial gradients fit: fully parallel resize adjoint
@@ -114,6 +138,9 @@ __host__ __device__ inline Layout make_layout(const EotShape& s) {
   L.tcap = 3 * ((lmin + s.patch_size - 1) / s.patch_size) + 3;
   int rr = 2560 / s.patch_size;              // <= 40 KB of RGBX float32 intermediate rows
   L.resize_rows = rr > EOT_RESIZE_ROWS_CAP ? EOT_RESIZE_ROWS_CAP : (rr < 1 ? 1 : rr);
+  L.rb = EOT_RESIZE_RB;
+  while (L.rb > 1 && (size_t)L.rb * s.patch_size * 16 > 12 * 1024) --L.rb;   // <= 12 KB of intermediate rows per warp
+  L.cr = EOT_COMP_ROWS;
   L.p3_magic = (uint32_t)((((uint64_t)1 << 32) + (uint64_t)(s.patch_size * 3) - 1) / (uint64_t)(s.patch_size * 3));
   const size_t PP3 = (size_t)s.patch_size * s.patch_size * 3;
   size_t o = 0;
@@ -122,14 +149,20 @@ __host__ __device__ inline Layout make_layout(const EotShape& s) {
   L.off_gy_sum = o;       o = align_up(o + B * sizeof(double), 256);
   L.off_oor = o;          o = align_up(o + B * sizeof(int32_t), 256);
   L.off_counters = o;     o = align_up(o + 8 * sizeof(int32_t), 256);
-  L.off_tickets = o;      o = align_up(o + 32 * sizeof(int32_t), 256);
+  L.off_tickets = o;      o = align_up(o + (size_t)kTicketSlots * kTicketLanes * 256, 256);
   L.off_plans = o;        o = align_up(o + N * sizeof(BoxPlan), 256);
   L.off_starts = o;       o = align_up(o + N * (size_t)lmin * sizeof(int32_t), 256);
   L.off_weights = o;      o = align_up(o + N * (size_t)L.wcap * sizeof(float), 256);
-  L.off_match = o;        o = align_up(o + B * PP3 * sizeof(float), 256);
+  L.off_tab2 = o;         o = align_up(o + N * (size_t)lmin * 16, 256);
+  L.off_match = o;        o = align_up(o + B * (size_t)s.patch_size * s.patch_size * 16, 256);
   L.off_u = o;            o = align_up(o + N * (size_t)L.slot * sizeof(float), 256);
-  L.off_cnt = o;          o = align_up(o + N * 8, 256);
-  L.off_base = o;         o = align_up(o + (N + 1) * 8, 256);
+  L.off_cnt = o;          o = align_up(o + N * 16, 256);
+  L.off_base = o;         o = align_up(o + (N + 1) * 16, 256);
+  L.off_items = o;        o = align_up(o + N * (size_t)((lmin + L.rb - 1) / L.rb) * 8, 256);
+  L.off_citems = o;       o = align_up(o + N * (size_t)((lfull + L.cr - 1) / L.cr) * 8, 256);
+  L.off_rowtab = o;       o = align_up(o + N * (size_t)lfull * 8, 256);
+  L.open_cap = (int64_t)N * lfull * 4 < ((int64_t)1 << 30) ? (int64_t)N * lfull * 4 : ((int64_t)1 << 30);
+  L.off_open = o;         o = align_up(o + (size_t)L.open_cap * 8, 256);
   L.off_inv = o;          o = align_up(o + N * (size_t)s.patch_size * 8, 256);
   L.off_wt = o;           o = align_up(o + N * (size_t)s.patch_size * L.tcap * sizeof(float), 256);
   L.off_stt = o;          o = align_up(o + N * (size_t)(s.patch_size + 1) * 8, 256);
@@ -167,6 +200,12 @@ int cuda_fail(cudaError_t e, const char* what);
 int sm_count();
 void count_launches(int n);   // kernels launched by this library since load (bench.py reports the delta)
 
+// forward window kernels (eot_resize.cu, eot_composite.cu): images [b0,b1), atomic work-ticket slot in the workspace
+int launch_resize2(const EotShape& s, const struct Layout& L, char* ws, const int32_t* offsets, int b0, int b1,
+                   int ticket_slot, cudaStream_t st);
+int launch_composite3(const EotShape& s, const struct Layout& L, char* ws, const int32_t* offsets, const float* images,
+                      float* out, float* mask, int b0, int b1, int ticket_slot, cudaStream_t st);
+
 #define EOT_CHECK_CUDA(expr)                                   \
   do {                                                         \
     cudaError_t _e = (expr);                                   \
@@ -175,6 +214,14 @@ void count_launches(int n);   // kernels launched by this library since load (be
 
 #ifdef __CUDACC__
 // ---- small device helpers ---------------------------------------------------------------------------
+// Makes a pointer opaque to the optimiser: under register pressure ptxas otherwise re-derives per-row base pointers
+// from the kernel parameters (a dozen 64-bit instructions) at every use inside the pixel loops.
+template <typename T>
+__device__ __forceinline__ T* keep_ptr(T* p) {
+  asm volatile("" : "+l"(p));
+  return p;
+}
+
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -216,21 +263,41 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t k0, uint32_
   return make_uint4(c0, c1, c2, c3);
 }
 
-// Work item i of kind `which` (0: resize strip, 1: composite row block) -> (box, index inside the box).
-// base[] holds the exclusive prefix sums of the per-box item counts, in box (== image) order.
-__device__ __forceinline__ int2 find_item(const int2* __restrict__ base, int N, int which, int i) {
-  const int* b = reinterpret_cast<const int*>(base) + which;
+// Ticket dispenser of one warp: next() returns the warp's next item index in [0, n) or a value >= n when its sub-queue
+// is exhausted (lane 0 draws, all lanes get the value).
+struct WarpTickets {
+  int* counter;
+  int sub;
+  __device__ __forceinline__ void init(char* ws, size_t off_tickets, int slot) {
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    sub = gw % kTicketLanes;
+    counter = reinterpret_cast<int*>(ws + off_tickets) + ((size_t)slot * kTicketLanes + sub) * 64;
+  }
+  // raw draw by lane 0 (other lanes: 0); combine with item() after a shuffle so that the atomic's latency can be hidden
+  __device__ __forceinline__ int draw(int lane) const { return lane == 0 ? atomicAdd(counter, 1) : 0; }
+  __device__ __forceinline__ int item(int drawn) const { return __shfl_sync(0xffffffffu, drawn, 0) * kTicketLanes + sub; }
+};
+
+// Work-item kinds of the per-box count / prefix tables (components of the int4 entries).
+enum ItemKind { kItemBwdWindow = 0, kItemBwdResize = 1, kItemResize = 2, kItemComposite = 3 };
+
+// Work item i of kind `which` -> (box, index inside the box).  base[] holds the exclusive prefix sums of the per-box
+// item counts, in box (== image) order; `stride` = ints between consecutive entries (4 in the workspace table, 1 in a
+// staged single-kind copy).
+__device__ __forceinline__ int2 find_item(const int* __restrict__ b, int stride, int N, int i) {
   int lo = 0, hi = N;                      // last j with base[j] <= i
-  while (hi - lo > 1) { const int m = (lo + hi) >> 1; if (b[2 * m] <= i) lo = m; else hi = m; }
-  return make_int2(lo, i - b[2 * lo]);
+  while (hi - lo > 1) { const int m = (lo + hi) >> 1; if (b[stride * m] <= i) lo = m; else hi = m; }
+  return make_int2(lo, i - b[stride * lo]);
 }
 
-// Copies the prefix table to shared memory when it fits (the binary search then costs no global latency).
-constexpr int kMaxBaseSmem = 1025;
-__device__ __forceinline__ const int2* stage_base(const int2* base, int N, int2* smem) {
-  if (N + 1 > kMaxBaseSmem) return base;
-  for (int i = threadIdx.x; i <= N; i += blockDim.x) smem[i] = base[i];
+// Copies one kind of the prefix table to shared memory when it fits (the binary search then costs no global latency).
+// Returns the table to search and sets *stride.
+constexpr int kMaxBaseSmem = 2049;
+__device__ __forceinline__ const int* stage_base(const int4* base, int which, int N, int* smem, int* stride) {
+  if (N + 1 > kMaxBaseSmem) { *stride = 4; return reinterpret_cast<const int*>(base) + which; }
+  for (int i = threadIdx.x; i <= N; i += blockDim.x) smem[i] = reinterpret_cast<const int*>(base)[4 * i + which];
   __syncthreads();
+  *stride = 1;
   return smem;
 }
 
@@ -276,6 +343,29 @@ struct Sampler {
 
 __device__ __forceinline__ int u_stride(int ps) { return ps + 4; }
 __device__ __forceinline__ int u_index(int ps, int ty, int tx) { return (ty + 2) * (ps + 4) + (tx + 2); }
+
+// Conservative range of window columns x in window row wy whose sample can touch the ps x ps core (affine T): outside
+// it all four taps are pad / fill and the box contributes nothing.  Half-pixel safety margins; the per-pixel core test
+// decides exactly.  Projective transforms: the whole row.
+__device__ __forceinline__ void row_core_range(const BoxPlan& pl, int wy, int* xa, int* xb) {
+  if (pl.T[6] != 0.0f || pl.T[7] != 0.0f) { *xa = 0; *xb = pl.d - 1; return; }
+  const float yf = (float)wy;
+  float lo = 0.0f, hi = (float)(pl.d - 1);
+  const float clo = (float)pl.pad_lo, chi = (float)(pl.pad_lo + pl.ps);   // core bounds in padded window coordinates
+  const float c0 = pl.T[1] * yf + pl.T[2], c1 = pl.T[4] * yf + pl.T[5];
+  {
+    const float l = clo - 1.5f - c0, h = chi + 0.5f - c0;      // need l < T0*x < h
+    if (pl.ia0 == 0.0f) { if (!(0.0f > l - 1.0f && 0.0f < h + 1.0f)) { lo = 1.0f; hi = 0.0f; } }
+    else { const float x1 = l * pl.ia0, x2 = h * pl.ia0; lo = fmaxf(lo, fminf(x1, x2) - 1.0f); hi = fminf(hi, fmaxf(x1, x2) + 1.0f); }
+  }
+  {
+    const float l = clo - 1.5f - c1, h = chi + 0.5f - c1;
+    if (pl.ia3 == 0.0f) { if (!(0.0f > l - 1.0f && 0.0f < h + 1.0f)) { lo = 1.0f; hi = 0.0f; } }
+    else { const float x1 = l * pl.ia3, x2 = h * pl.ia3; lo = fmaxf(lo, fminf(x1, x2) - 1.0f); hi = fminf(hi, fmaxf(x1, x2) + 1.0f); }
+  }
+  *xa = max((int)floorf(lo), 0);
+  *xb = min((int)ceilf(hi), pl.d - 1);
+}
 
 __device__ __forceinline__ Sampler make_sampler(const BoxPlan& pl, const float* ubuf) {
   Sampler S;

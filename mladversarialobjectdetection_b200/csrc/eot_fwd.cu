@@ -9,10 +9,9 @@
 //                       image pass  copy image -> out (128-bit I/O) while accumulating mean Y of the target
 //                                   image in float64 (the HBM-bound part)
 //   k_match           print adjust + brightness match -> matched patch per image
-//   k_resize          antialiased triangle resize (rows then columns, sequential float32
-//                     accumulation as ScaleAndTranslate) + noise + brightness delta -> u_j (RGBX texels)
-//   k_composite       gather over image tiles: projective bilinear sample of the ring-padded u_j of the
-//                     covering boxes, newest first, `< -1` mask, background select, clip, store, route bytes
+//   k_resize2         (eot_resize.cu) antialiased triangle resize + noise + brightness delta -> u_j (RGBX texels)
+//   k_composite3      (eot_composite.cu) projective bilinear sample of the ring-padded u_j, `< -1` mask,
+//                     sequential-paste resolution, clip, store, route bytes
 #include "eot_common.cuh"
 
 #include <math.h>
@@ -72,7 +71,7 @@ __device__ inline BoxPlan make_plan(const float* __restrict__ box, float shared_
                      pl.d < pl.ps || pl.ps > L.lmin;
     if (bad) {   // TF would fail in tf.pad / tensor_scatter_nd_update; we skip the box and flag it
       pl.valid = 0;
-      if (err_flag) atomicExch(err_flag, 1);
+      if (err_flag) atomicOr(err_flag, 1);
     }
   }
   const float c = p.cos_t, sn = p.sin_t;
@@ -85,6 +84,10 @@ __device__ inline BoxPlan make_plan(const float* __restrict__ box, float shared_
   pl.T[5] = (hm1 - (sn * wm1 + c * hm1)) / 2.0f;
   pl.T[6] = p.pa;
   pl.T[7] = p.pb;
+  pl.ia0 = fabsf(pl.T[0]) < 1e-6f ? 0.0f : 1.0f / pl.T[0];
+  pl.ia3 = fabsf(pl.T[3]) < 1e-6f ? 0.0f : 1.0f / pl.T[3];
+  pl.two_tap = 0;
+  pl.rsv = 0;
   {  // inverse by the adjugate in float64, rounded once (image_ops.py: _image_projective_transform_v3_grad)
     const double a = pl.T[0], b = pl.T[1], cc = pl.T[2], d = pl.T[3], e = pl.T[4], f = pl.T[5], g = pl.T[6], hh = pl.T[7];
     const double A = e - f * hh, Bm = -(d - f * g), C = d * hh - e * g;
@@ -114,12 +117,13 @@ __device__ __forceinline__ float tri_weight(int src, float sample_f, float one_o
   const float a = fabsf(kernel_pos * one_over);
   return a < 1.0f ? 1.0f - a : 0.0f;
 }
-__device__ inline void span_row(int o, const SpanCfg& c, int in_size, int* start_out, float* __restrict__ w_out) {
+// w_out: tap k at w_out[k * stride] (tap-major table: the columns pass reads it coalesced, the rows pass uniformly)
+__device__ inline void span_row(int o, const SpanCfg& c, int in_size, int* start_out, float* __restrict__ w_out, int stride) {
   const float col_f = (float)o + 0.5f;
   const float sample_f = col_f * c.inv_scale + (-c.inv_scale * 0.0f);
   if (sample_f < 0.0f || sample_f > (float)in_size) {
     *start_out = 0;
-    for (int k = 0; k < c.span; ++k) w_out[k] = 0.0f;
+    for (int k = 0; k < c.span; ++k) w_out[(size_t)k * stride] = 0.0f;
     return;
   }
   long long s0 = (long long)ceilf((sample_f - c.ks) - 0.5f);
@@ -133,7 +137,7 @@ __device__ inline void span_row(int o, const SpanCfg& c, int in_size, int* start
   const bool ok = fabsf(total) >= 1000.0f * 1.17549435e-38f;
   const float inv_total = ok ? 1.0f / total : 0.0f;
   for (int k = 0; k < c.span; ++k)
-    w_out[k] = (k < n && ok) ? tri_weight((int)s0 + k, sample_f, c.one_over) * inv_total : 0.0f;
+    w_out[(size_t)k * stride] = (k < n && ok) ? tri_weight((int)s0 + k, sample_f, c.one_over) * inv_total : 0.0f;
   *start_out = (int)s0;
 }
 
@@ -166,8 +170,9 @@ __device__ int geometry_block(const EotShape& s, const Layout& L, int j, const f
     spl = pl;
     if (ws) {
       reinterpret_cast<BoxPlan*>(ws + L.off_plans)[j] = pl;
-      reinterpret_cast<int2*>(ws + L.off_cnt)[j] =
-          pl.valid ? make_int2(fwd_strips(pl.ps, L.resize_rows), 0) : make_int2(0, 0);
+      reinterpret_cast<int4*>(ws + L.off_cnt)[j] =
+          pl.valid ? make_int4(fwd_strips(pl.ps, L.resize_rows), 0, (pl.ps + L.rb - 1) / L.rb, (pl.d + L.cr - 1) / L.cr)
+                   : make_int4(0, 0, 0, 0);
     }
     if (geom_out) {
       EotBoxGeometry g = {pl.y0, pl.x0, pl.ps, pl.d, pl.pad_lo, pl.pad_hi, pl.valid, pl.span};
@@ -181,8 +186,27 @@ __device__ int geometry_block(const EotShape& s, const Layout& L, int j, const f
   int* starts = reinterpret_cast<int*>(ws + L.off_starts) + (size_t)j * L.lmin;
   float* weights = reinterpret_cast<float*>(ws + L.off_weights) + (size_t)j * L.wcap;
   const SpanCfg cfg = span_cfg(ps, P);
-  for (int o = threadIdx.x; o < ps; o += blockDim.x) span_row(o, cfg, P, starts + o, weights + (size_t)o * cfg.span);
-  __syncthreads();                                  // starts[] of this box are complete
+  // Two-tap form: with span 3 (up-sampling / unit scale) the triangle kernel has at most two adjacent non-zero taps per
+  // output index; when that holds for every index of the box (checked, not assumed) the resize reads (a, b, wa, wb).
+  // Dropping a tap of weight 0 drops an addition of +-0: the sums are the oracle's.
+  float4* tab2 = reinterpret_cast<float4*>(ws + L.off_tab2) + (size_t)j * L.lmin;
+  bool two = cfg.span == 3;
+  for (int o = threadIdx.x; o < ps; o += blockDim.x) {
+    span_row(o, cfg, P, starts + o, weights + o, ps);
+    if (cfg.span == 3) {
+      const float w0 = weights[o], w1 = weights[ps + o], w2 = weights[2 * ps + o];
+      const int st = starts[o];
+      int ia; float wa, wb;
+      if (w2 == 0.0f) { ia = st; wa = w0; wb = w1; }
+      else if (w0 == 0.0f) { ia = st + 1; wa = w1; wb = w2; }
+      else { ia = st; wa = w0; wb = w1; two = false; }
+      const int ib = min(ia + 1, P - 1);
+      ia = min(ia, P - 1);
+      tab2[o] = make_float4(__int_as_float(ia), __int_as_float(ib), wa, wb);
+    }
+  }
+  const int all_two = __syncthreads_and(two ? 1 : 0);   // (also: starts[] of this box are complete)
+  if (threadIdx.x == 0) reinterpret_cast<BoxPlan*>(ws + L.off_plans)[j].two_tap = all_two;
   int2* inv = reinterpret_cast<int2*>(ws + L.off_inv) + (size_t)j * P;
   float* wt = reinterpret_cast<float*>(ws + L.off_wt) + (size_t)j * P * L.tcap;
   int2* stt = reinterpret_cast<int2*>(ws + L.off_stt) + (size_t)j * (P + 1);
@@ -191,7 +215,7 @@ __device__ int geometry_block(const EotShape& s, const Layout& L, int j, const f
     inv[i] = rng;
     int cnt = rng.y - rng.x + 1;
     if (cnt < 0) cnt = 0;
-    if (cnt > L.tcap) { cnt = L.tcap; if (counters) atomicExch(counters + 2, 4); }
+    if (cnt > L.tcap) { cnt = L.tcap; if (counters) atomicOr(counters + 2, 4); }
     stt[i] = make_int2(min(max(rng.x, 0), ps - 1), cnt);
     atomicMax(&s_maxcnt, cnt);
   }
@@ -207,7 +231,7 @@ __device__ int geometry_block(const EotShape& s, const Layout& L, int j, const f
       float w = 0.0f;
       if (k < cnt) {
         const int kk = i - starts[o];
-        if (kk >= 0 && kk < cfg.span) w = weights[(size_t)o * cfg.span + kk];
+        if (kk >= 0 && kk < cfg.span) w = weights[(size_t)kk * ps + o];
       }
       wt[(size_t)i * tstride + k] = w;
     }
@@ -215,7 +239,14 @@ __device__ int geometry_block(const EotShape& s, const Layout& L, int j, const f
   if (threadIdx.x == 0) {
     const int rows = bwd_strip_rows(ps);
     stt[P] = make_int2(tstride, rows);
-    reinterpret_cast<int2*>(ws + L.off_cnt)[j].y = (P + rows - 1) / rows;   // backward resize strips of this box
+    reinterpret_cast<int4*>(ws + L.off_cnt)[j].y = (P + rows - 1) / rows;   // backward resize strips of this box
+  }
+  // per window row: the columns whose sample can touch the core (the composite's segment list is cut from these)
+  int2* rowtab = reinterpret_cast<int2*>(ws + L.off_rowtab) + (size_t)j * (s.height < s.width ? s.height : s.width);
+  for (int wy = threadIdx.x; wy < spl.d; wy += blockDim.x) {
+    int xa, xb;
+    row_core_range(spl, wy, &xa, &xb);
+    rowtab[wy] = make_int2(xa, xb);
   }
   // route map of the box starts all-zero; the composite only writes the non-zero bytes
   uint4* rz = reinterpret_cast<uint4*>(ws + L.off_route + (size_t)j * L.rslot);
@@ -237,28 +268,26 @@ __device__ int geometry_block(const EotShape& s, const Layout& L, int j, const f
 }
 
 // Exclusive prefix sums of the per-box work-item counts (one CTA; N is a few hundred to a few thousand).
-__device__ void scan_block(int N, const int2* cnt, int2* base, int2* part /* [blockDim.x] shared */) {
+__device__ __forceinline__ int4 add4(int4 a, int4 b) { return make_int4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ void scan_block(int N, const int4* cnt, int4* base, int4* part /* [blockDim.x] shared */) {
   const int T = blockDim.x;
   const int per = (N + T - 1) / T;
   const int j0 = threadIdx.x * per, j1 = min(N, j0 + per);
-  int2 sum = make_int2(0, 0);
-  for (int j = j0; j < j1; ++j) { const int2 c = __ldcg(cnt + j); sum.x += c.x; sum.y += c.y; }
+  int4 sum = make_int4(0, 0, 0, 0);
+  for (int j = j0; j < j1; ++j) sum = add4(sum, __ldcg(cnt + j));
   part[threadIdx.x] = sum;
   __syncthreads();
   for (int d = 1; d < T; d <<= 1) {
-    int2 v = make_int2(0, 0);
+    int4 v = make_int4(0, 0, 0, 0);
     if ((int)threadIdx.x >= d) v = part[threadIdx.x - d];
     __syncthreads();
-    part[threadIdx.x].x += v.x;
-    part[threadIdx.x].y += v.y;
+    part[threadIdx.x] = add4(part[threadIdx.x], v);
     __syncthreads();
   }
-  int2 run = threadIdx.x ? part[threadIdx.x - 1] : make_int2(0, 0);
+  int4 run = threadIdx.x ? part[threadIdx.x - 1] : make_int4(0, 0, 0, 0);
   for (int j = j0; j < j1; ++j) {
     base[j] = run;
-    const int2 c = __ldcg(cnt + j);
-    run.x += c.x;
-    run.y += c.y;
+    run = add4(run, __ldcg(cnt + j));
   }
   if ((int)threadIdx.x == T - 1) base[N] = part[T - 1];
   __syncthreads();
@@ -389,7 +418,7 @@ __global__ void __launch_bounds__(kThreads) k_prepass(EotShape s, Layout L, cons
   int blk = blockIdx.x;
   if (blk < n_geom) {
     __shared__ int s_last;
-    __shared__ int2 s_part[kThreads];
+    __shared__ int4 s_part[kThreads];
     geometry_block(s, L, blk, boxes, offsets, params, scale, ws, nullptr);
     __threadfence();
     __syncthreads();
@@ -398,7 +427,16 @@ __global__ void __launch_bounds__(kThreads) k_prepass(EotShape s, Layout L, cons
     __syncthreads();
     if (s_last) {                                        // last geometry block: prefix sums of the work-item counts
       __threadfence();
-      scan_block(n_geom, reinterpret_cast<const int2*>(ws + L.off_cnt), reinterpret_cast<int2*>(ws + L.off_base), s_part);
+      const int4* cnt = reinterpret_cast<const int4*>(ws + L.off_cnt);
+      int4* base = reinterpret_cast<int4*>(ws + L.off_base);
+      scan_block(n_geom, cnt, base, s_part);
+      int2* items = reinterpret_cast<int2*>(ws + L.off_items);    // forward resize / composite items in ticket order
+      int2* citems = reinterpret_cast<int2*>(ws + L.off_citems);
+      for (int j = threadIdx.x; j < n_geom; j += blockDim.x) {
+        const int4 n = __ldcg(cnt + j), at = base[j];
+        for (int i = 0; i < n.z; ++i) items[at.z + i] = make_int2(j, i);
+        for (int i = 0; i < n.w; ++i) citems[at.w + i] = make_int2(j, i);
+      }
     }
     return;
   }
@@ -424,9 +462,11 @@ __global__ void __launch_bounds__(kThreads) k_prepass(EotShape s, Layout L, cons
 __device__ __forceinline__ void match_block(const EotShape& s, const Layout& L, const float* __restrict__ patch,
                                             const float* __restrict__ print_wb, char* ws, int b, int part, int nparts);
 
+// blocks [0, nb * pchunks): match the patch to image b0 + blk / pchunks (needs the finished pre-pass: mean luma)
 __global__ void __launch_bounds__(kThreads) k_match(EotShape s, Layout L, const float* __restrict__ patch,
-                                                    const float* __restrict__ print_wb, char* ws, int b0) {
-  match_block(s, L, patch, print_wb, ws, b0 + blockIdx.y, blockIdx.x, gridDim.x);
+                                                    const float* __restrict__ print_wb, char* ws, int b0, int pchunks) {
+  const int blk = blockIdx.x;
+  match_block(s, L, patch, print_wb, ws, b0 + blk / pchunks, blk % pchunks, pchunks);
 }
 
 __device__ __forceinline__ void match_block(const EotShape& s, const Layout& L, const float* __restrict__ patch,
@@ -438,7 +478,7 @@ __device__ __forceinline__ void match_block(const EotShape& s, const Layout& L, 
   const float mu_s = (float)(ysum_patch[b] / (double)((size_t)P * P));
   const float* wb = print_wb + (size_t)b * 6;
   const float* base = patch + (s.num_patches > 1 ? (int64_t)b * s.patch_stride_n : 0);
-  float* m = reinterpret_cast<float*>(ws + L.off_match) + (size_t)b * P * P * 3;
+  float4* m = reinterpret_cast<float4*>(ws + L.off_match) + (size_t)b * P * P;
   for (int t = part * blockDim.x + threadIdx.x; t < P * P; t += nparts * blockDim.x) {
     const int py = t / P, px = t - py * P;
     const float* p = base + (int64_t)py * s.patch_stride_y + (int64_t)px * s.patch_stride_x;
@@ -448,9 +488,8 @@ __device__ __forceinline__ void match_block(const EotShape& s, const Layout& L, 
     const float r = (yp * 1.0f + y.u * EOT_I10) + y.v * EOT_I20;
     const float g = (yp * 1.0f + y.u * EOT_I11) + y.v * EOT_I21;
     const float bl = (yp * 1.0f + y.u * EOT_I12) + y.v * EOT_I22;
-    m[(size_t)t * 3 + 0] = clampf(r, 0.0f, 1.0f) * EOT_C255_127 - 1.0f;
-    m[(size_t)t * 3 + 1] = clampf(g, 0.0f, 1.0f) * EOT_C255_127 - 1.0f;
-    m[(size_t)t * 3 + 2] = clampf(bl, 0.0f, 1.0f) * EOT_C255_127 - 1.0f;
+    m[t] = make_float4(clampf(r, 0.0f, 1.0f) * EOT_C255_127 - 1.0f, clampf(g, 0.0f, 1.0f) * EOT_C255_127 - 1.0f,
+                       clampf(bl, 0.0f, 1.0f) * EOT_C255_127 - 1.0f, 0.0f);
   }
 }
 
@@ -483,430 +522,6 @@ __global__ void __launch_bounds__(kThreads) k_bm_apply(const float* __restrict__
     out[i * 3] = clampf(r, 0.0f, 1.0f) * EOT_C255_127 - 1.0f;
     out[i * 3 + 1] = clampf(g, 0.0f, 1.0f) * EOT_C255_127 - 1.0f;
     out[i * 3 + 2] = clampf(b, 0.0f, 1.0f) * EOT_C255_127 - 1.0f;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// resize + noise + delta + clip for one strip of L.resize_rows output rows of one box
-// (attacker.py:425-428; ScaleAndTranslate GatherRows then GatherColumns).
-// The box's span table is staged in shared memory first (no dependent global loads in the loops).
-// Rows pass: a lane owns four texels (12 floats = 3 x 128-bit loads per tap) of a source row and writes
-// them as RGBX texels into the shared intermediate.  Columns pass: a lane owns a quad of 4 consecutive
-// output texels = 12 elements = exactly 3 Philox groups; one 128-bit shared load per tap.  Accumulation
-// order == the oracle's.  Output texel: (clip r, clip g, clip b, inner-clip pass bits).
-// ------------------------------------------------------------------------------------------------
-__host__ __device__ inline size_t resize_smem_bytes(const EotShape& s, const Layout& L) {
-  return ((size_t)L.resize_rows * s.patch_size * 4 + (size_t)L.wcap + (size_t)L.lmin) * sizeof(float);
-}
-
-// SPAN > 0: compile-time tap count (3 = up-sampling / unit scale, 5 and 7 = moderate down-sampling), every tap
-// loop fully unrolled; weights past the true span are stored as 0 and the clamped source index is finite, so the
-// padded taps add +0 -- the same sums as the oracle's.  SPAN == 0: run-time span (any scale).
-template <int SPAN>
-__device__ __forceinline__ void resize_passes(const EotShape& s, int P, int ps, int span, int oy0, int rows,
-                                              const float* m, const int* s_st, const float* s_w, float4* inter,
-                                              float4* u4, float delta, uint32_t key0, uint32_t key1) {
-  const int P3 = P * 3;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  constexpr int NT = SPAN > 0 ? SPAN : 1;
-  // ---- rows pass ----
-  if ((P & 3) == 0) {
-    const int nq = P >> 2;                                    // texel quads per source row
-    // (row, quad) pairs flattened over the CTA (a warp per row would idle 7 lanes of 32 at P = 100)
-    for (int idx = threadIdx.x; idx < rows * nq; idx += blockDim.x) {
-      const int r = idx / nq;
-      const int oy = oy0 + r;
-      const int st = s_st[oy];
-      const float* w = s_w + oy * (SPAN > 0 ? SPAN : span);
-      const int nk = SPAN > 0 ? SPAN : min(span, P - st);
-      {
-        const int tq = idx - r * nq;
-        float acc[12];
-#pragma unroll
-        for (int i = 0; i < 12; ++i) acc[i] = 0.0f;
-        if (SPAN > 0) {
-          float4 v[NT][3];
-#pragma unroll
-          for (int k = 0; k < NT; ++k) {
-            const float4* mp = reinterpret_cast<const float4*>(m + (size_t)min(st + k, P - 1) * P3) + 3 * tq;
-            v[k][0] = mp[0]; v[k][1] = mp[1]; v[k][2] = mp[2];
-          }
-#pragma unroll
-          for (int k = 0; k < NT; ++k) {
-            const float wk = w[k];
-            const float x[12] = {v[k][0].x, v[k][0].y, v[k][0].z, v[k][0].w, v[k][1].x, v[k][1].y, v[k][1].z, v[k][1].w,
-                                 v[k][2].x, v[k][2].y, v[k][2].z, v[k][2].w};
-#pragma unroll
-            for (int i = 0; i < 12; ++i) acc[i] = acc[i] + wk * x[i];
-          }
-        } else {
-          for (int k = 0; k < nk; ++k) {
-            const float4* mp = reinterpret_cast<const float4*>(m + (size_t)(st + k) * P3) + 3 * tq;
-            const float4 a = mp[0], b = mp[1], c = mp[2];
-            const float wk = w[k];
-            const float x[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-#pragma unroll
-            for (int i = 0; i < 12; ++i) acc[i] = acc[i] + wk * x[i];
-          }
-        }
-        float4* o = inter + r * P + 4 * tq;
-        o[0] = make_float4(acc[0], acc[1], acc[2], 0.0f);
-        o[1] = make_float4(acc[3], acc[4], acc[5], 0.0f);
-        o[2] = make_float4(acc[6], acc[7], acc[8], 0.0f);
-        o[3] = make_float4(acc[9], acc[10], acc[11], 0.0f);
-      }
-    }
-  } else {                                                    // any P: one lane per texel, scalar loads
-    for (int r = warp; r < rows; r += nwarps) {
-      const int oy = oy0 + r;
-      const int st = s_st[oy];
-      const float* w = s_w + oy * (SPAN > 0 ? SPAN : span);
-      const int nk = SPAN > 0 ? SPAN : min(span, P - st);
-      for (int x = lane; x < P; x += 32) {
-        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
-        for (int k = 0; k < nk; ++k) {
-          const float* mp = m + (size_t)min(st + k, P - 1) * P3 + x * 3;
-          const float wk = w[k];
-          a0 = a0 + wk * mp[0];
-          a1 = a1 + wk * mp[1];
-          a2 = a2 + wk * mp[2];
-        }
-        inter[r * P + x] = make_float4(a0, a1, a2, 0.0f);
-      }
-    }
-  }
-  __syncthreads();
-  // ---- columns pass + noise + delta + clip ----
-  const int S = u_stride(ps);
-  const int p_begin = oy0 * ps, p_end = (oy0 + rows) * ps;   // flat texel range of the strip
-  for (int q = (p_begin >> 2) + threadIdx.x; q <= ((p_end - 1) >> 2); q += blockDim.x) {
-    uint32_t words[12];
-#pragma unroll
-    for (int g = 0; g < 3; ++g) {
-      const uint4 rnd = philox4x32_10((uint32_t)(3 * q + g), key0, key1);
-      words[4 * g] = rnd.x; words[4 * g + 1] = rnd.y; words[4 * g + 2] = rnd.z; words[4 * g + 3] = rnd.w;
-    }
-    int p = 4 * q;
-    int oy = p / ps, ox = p - oy * ps;
-#pragma unroll
-    for (int t = 0; t < 4; ++t, ++p) {
-      if (p >= p_begin && p < p_end) {
-        const int st = s_st[ox];
-        const float4* irow = inter + (oy - oy0) * P;
-        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
-        if (SPAN > 0) {
-          const float* w = s_w + ox * SPAN;
-#pragma unroll
-          for (int k = 0; k < NT; ++k) {
-            const float wk = w[k];
-            const float4 v = irow[min(st + k, P - 1)];
-            a0 = a0 + wk * v.x;
-            a1 = a1 + wk * v.y;
-            a2 = a2 + wk * v.z;
-          }
-        } else {
-          const float* w = s_w + ox * span;
-          const int nk = min(span, P - st);
-          for (int k = 0; k < nk; ++k) {
-            const float wk = w[k];
-            const float4 v = irow[st + k];
-            a0 = a0 + wk * v.x;
-            a1 = a1 + wk * v.y;
-            a2 = a2 + wk * v.z;
-          }
-        }
-        const float v0 = (a0 + noise_from_word(words[3 * t], s.noise_amp)) + delta;
-        const float v1 = (a1 + noise_from_word(words[3 * t + 1], s.noise_amp)) + delta;
-        const float v2 = (a2 + noise_from_word(words[3 * t + 2], s.noise_amp)) + delta;
-        const unsigned bits = (unsigned)(v0 >= -1.0f && v0 <= 1.0f) | ((unsigned)(v1 >= -1.0f && v1 <= 1.0f) << 1) |
-                              ((unsigned)(v2 >= -1.0f && v2 <= 1.0f) << 2);
-        u4[(oy + 2) * S + ox + 2] =
-            make_float4(clampf(v0, -1.0f, 1.0f), clampf(v1, -1.0f, 1.0f), clampf(v2, -1.0f, 1.0f), __uint_as_float(bits));
-      }
-      if (++ox == ps) { ox = 0; ++oy; }
-    }
-  }
-}
-
-__device__ __forceinline__ void resize_item(const EotShape& s, const Layout& L, char* ws, int2 item, float* smem) {
-  const int P = s.patch_size, P3 = P * 3;
-  float4* inter = reinterpret_cast<float4*>(smem);           // [resize_rows][P] RGBX
-  float* s_w = smem + (size_t)L.resize_rows * P * 4;         // [ps][span]
-  int* s_st = reinterpret_cast<int*>(s_w + L.wcap);          // [ps]
-  const BoxPlan* pl = reinterpret_cast<const BoxPlan*>(ws + L.off_plans) + item.x;
-  const int j = item.x;
-  const int ps = pl->ps, span = pl->span;
-  const float delta = pl->delta;
-  const uint32_t key0 = pl->key0, key1 = pl->key1;
-  const int RR = strip_rows(ps, reinterpret_cast<const int2*>(ws + L.off_cnt)[j].x);
-  const int oy0 = item.y * RR;
-  const int rows = min(RR, ps - oy0);
-  const float* m = reinterpret_cast<const float*>(ws + L.off_match) + (size_t)pl->image * P * P3;
-  const int* starts = reinterpret_cast<const int*>(ws + L.off_starts) + (size_t)j * L.lmin;
-  const float* wts = reinterpret_cast<const float*>(ws + L.off_weights) + (size_t)j * L.wcap;
-  float4* u4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(ws + L.off_u) + pl->u_off);
-  for (int i = threadIdx.x; i < ps; i += blockDim.x) s_st[i] = starts[i];
-  for (int i = threadIdx.x; i < ps * span; i += blockDim.x) s_w[i] = wts[i];
-  __syncthreads();
-  if (span == 3) resize_passes<3>(s, P, ps, span, oy0, rows, m, s_st, s_w, inter, u4, delta, key0, key1);
-  else if (span == 5) resize_passes<5>(s, P, ps, span, oy0, rows, m, s_st, s_w, inter, u4, delta, key0, key1);
-  else if (span == 7) resize_passes<7>(s, P, ps, span, oy0, rows, m, s_st, s_w, inter, u4, delta, key0, key1);
-  else resize_passes<0>(s, P, ps, span, oy0, rows, m, s_st, s_w, inter, u4, delta, key0, key1);
-}
-
-#ifndef EOT_RESIZE_MINB
-#define EOT_RESIZE_MINB 4
-#endif
-#ifndef EOT_RESIZE_THREADS
-#define EOT_RESIZE_THREADS 256
-#endif
-__global__ void __launch_bounds__(EOT_RESIZE_THREADS, EOT_RESIZE_MINB) k_resize(EotShape s, Layout L, char* ws, const int32_t* __restrict__ offsets,
-                                                        int b0, int b1) {
-  extern __shared__ __align__(16) float resize_smem[];
-  __shared__ int2 s_base[kMaxBaseSmem];
-  const int2* base = stage_base(reinterpret_cast<const int2*>(ws + L.off_base), s.total_boxes, s_base);
-  const int lo = base[offsets[b0]].x, hi = base[offsets[b1]].x;
-  __shared__ int2 s_item;
-  for (int it = lo + blockIdx.x; it < hi; it += gridDim.x) {
-    if (threadIdx.x == 0) s_item = find_item(base, s.total_boxes, 0, it);
-    __syncthreads();
-    resize_item(s, L, ws, s_item, resize_smem);
-    __syncthreads();
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// composite (attacker.py:436-444) in gather form over IMAGE tiles.
-//
-// Sequential-paste semantics: an element's final value is clip(R_j) of the LAST box j (in paste order)
-// covering it with R_j >= -1, else clip(original); pixels outside every window are untouched.  One work
-// item = a band of kCompRows rows of one image; the boxes whose windows meet the band are staged in shared
-// memory once; a warp owns a row and sweeps it in 32-pixel tiles, one lane per pixel (sampling coordinates
-// shared by the three channels).  Per tile the candidate boxes are visited newest first, warp-uniformly;
-// a box is sampled only where the pixel is inside its window, still misses a channel, and at least one of
-// the four taps can touch the ps x ps core (everything else blends to -2 exactly as the padded image
-// would).  Every output pixel is written once, by one thread: no ordering between work items, no waits.
-//
-// Each pixel leaves a route byte in the map of every box that provided one of its channels (bit c: channel
-// c of the output came from this box and passes the outer clip): the backward's TensorScatterUpdate /
-// SelectV2 / clip routing without re-sampling.
-// ------------------------------------------------------------------------------------------------
-#ifndef EOT_COMP_THREADS
-#define EOT_COMP_THREADS 128
-#endif
-constexpr int kCompThreads = EOT_COMP_THREADS;   // threads per composite CTA: one warp per band row
-constexpr int kMaxBandBoxes = 32;   // boxes of one image whose windows meet one band (more: flagged, first 32 handled)
-
-struct BandBox {
-  float t0, t1, t2, t3, t4, t5, t6, t7;
-  float lo2, hi;              // clamp range of the floor coordinates
-  float ia0, ia3;             // 1/t0, 1/t3 (0 when the coefficient is ~0): column range of the core per row
-  int org, S;
-  int y0, x0, d, j;
-  const float4* u;
-  uint8_t* route;
-};
-
-struct CompositeSmem {
-  BandBox box[kMaxBandBoxes];
-  int n;
-};
-
-// Conservative range of window columns x in window row y whose sample can touch the ps x ps core (affine T):
-// outside it all four taps are pad/fill and the box contributes nothing.
-__device__ __forceinline__ void core_range(const BandBox& bx, float yf, int* xa, int* xb) {
-  float lo = 0.0f, hi = (float)(bx.d - 1);
-  const float clo = bx.lo2 + 2.0f, chi = bx.hi;               // core bounds in padded coordinates
-  const float c0 = bx.t1 * yf + bx.t2, c1 = bx.t4 * yf + bx.t5;
-  {
-    const float l = clo - 1.5f - c0, h = chi + 0.5f - c0;      // need l < t0*x < h (half-pixel safety margin)
-    if (bx.ia0 == 0.0f) { if (!(0.0f > l - 1.0f && 0.0f < h + 1.0f)) { lo = 1.0f; hi = 0.0f; } }
-    else { const float x1 = l * bx.ia0, x2 = h * bx.ia0; lo = fmaxf(lo, fminf(x1, x2) - 1.0f); hi = fminf(hi, fmaxf(x1, x2) + 1.0f); }
-  }
-  {
-    const float l = clo - 1.5f - c1, h = chi + 0.5f - c1;
-    if (bx.ia3 == 0.0f) { if (!(0.0f > l - 1.0f && 0.0f < h + 1.0f)) { lo = 1.0f; hi = 0.0f; } }
-    else { const float x1 = l * bx.ia3, x2 = h * bx.ia3; lo = fmaxf(lo, fminf(x1, x2) - 1.0f); hi = fminf(hi, fmaxf(x1, x2) + 1.0f); }
-  }
-  *xa = (int)floorf(lo);
-  *xb = (int)ceilf(hi);
-}
-
-__device__ __forceinline__ void composite_band(const EotShape& s, const Layout& L, char* ws,
-                                               const float* __restrict__ images, float* out, float* mask, int b, int band,
-                                               const int32_t* __restrict__ offsets, CompositeSmem& sm) {
-  const BoxPlan* plans = reinterpret_cast<const BoxPlan*>(ws + L.off_plans);
-  const int H = s.height, W = s.width;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ya = band * kCompRows, yb = min(H, ya + kCompRows);
-  if (warp == 0) {                                              // stage the boxes meeting the band, in paste order
-    const float* ubuf = reinterpret_cast<const float*>(ws + L.off_u);
-    uint8_t* routes = reinterpret_cast<uint8_t*>(ws + L.off_route);
-    const int first = offsets[b], last = offsets[b + 1];
-    int n = 0;
-    for (int q0 = first; q0 < last; q0 += 32) {
-      const int q = q0 + lane;
-      bool hit = false;
-      if (q < last) {
-        const BoxPlan* o = plans + q;
-        hit = o->valid && o->y0 < yb && o->y0 + o->d > ya;
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, hit);
-      const int pos = n + __popc(m & ((1u << lane) - 1u));
-      if (hit && pos < kMaxBandBoxes) {
-        const BoxPlan* o = plans + q;
-        BandBox& bx = sm.box[pos];
-        bx.t0 = o->T[0]; bx.t1 = o->T[1]; bx.t2 = o->T[2]; bx.t3 = o->T[3];
-        bx.t4 = o->T[4]; bx.t5 = o->T[5]; bx.t6 = o->T[6]; bx.t7 = o->T[7];
-        bx.lo2 = (float)(o->pad_lo - 2);
-        bx.hi = (float)(o->pad_lo + o->ps);
-        bx.ia0 = fabsf(o->T[0]) < 1e-6f ? 0.0f : 1.0f / o->T[0];
-        bx.ia3 = fabsf(o->T[3]) < 1e-6f ? 0.0f : 1.0f / o->T[3];
-        bx.org = o->pad_lo - 2;
-        bx.S = o->ps + 4;
-        bx.y0 = o->y0; bx.x0 = o->x0; bx.d = o->d; bx.j = q;
-        bx.u = reinterpret_cast<const float4*>(ubuf + o->u_off);
-        bx.route = routes + (size_t)q * L.rslot;
-      }
-      n += __popc(m);
-    }
-    if (n > kMaxBandBoxes) {
-      if (lane == 0) atomicExch(reinterpret_cast<int*>(ws + L.off_counters) + 2, 2);
-      n = kMaxBandBoxes;
-    }
-    if (lane == 0) sm.n = n;
-  }
-  __syncthreads();
-  const int n = sm.n;
-  if (n == 0) return;
-  const bool oor = reinterpret_cast<const int*>(ws + L.off_oor)[b] != 0;
-  // with a background clip that is not the identity, or the Masker's mask, every pixel inside a window is written
-  const bool all_px = oor || mask != nullptr;
-  const size_t img_off = (size_t)b * H * W * 3;
-  const float* img = images + img_off;
-  float* o_img = out + img_off;
-  float* m_img = mask ? mask + img_off : nullptr;
-  for (int gy = ya + warp; gy < yb; gy += kCompThreads / 32) {
-    // lane i: the column range of this row in which box i can matter (its whole window when every window pixel is
-    // written or T is projective, else the conservative range of the rotated core)
-    int rx0 = 1, rx1 = 0;
-    if (lane < n) {
-      const BandBox& bx = sm.box[lane];
-      if (gy >= bx.y0 && gy < bx.y0 + bx.d) {
-        int xa = 0, xb = bx.d - 1;
-        if (!all_px && bx.t6 == 0.0f && bx.t7 == 0.0f) {
-          core_range(bx, (float)(gy - bx.y0), &xa, &xb);
-          xa = max(xa, 0);
-          xb = min(xb, bx.d - 1);
-        }
-        rx0 = bx.x0 + xa;
-        rx1 = bx.x0 + xb;
-      }
-    }
-    if (!__any_sync(0xffffffffu, rx0 <= rx1)) continue;
-    int xlo = rx0 <= rx1 ? rx0 : W, xhi = rx0 <= rx1 ? rx1 : -1;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      xlo = min(xlo, __shfl_xor_sync(0xffffffffu, xlo, o));
-      xhi = max(xhi, __shfl_xor_sync(0xffffffffu, xhi, o));
-    }
-    const int row_off = gy * W * 3;
-    // the box whose constants sit in registers (tiles of one row mostly meet the same single box)
-    int cur = -1;
-    float t0 = 0.f, t3 = 0.f, c0 = 0.f, c1 = 0.f, t6 = 0.f, c2 = 0.f, lo2 = 0.f, hi = 0.f;
-    int org = 0, S = 0, bx0 = 0, bd = 0;
-    const float4* bu = nullptr;
-    uint8_t* brow = nullptr;
-    bool proj_on = false;
-    for (int xs = xlo & ~31; xs <= xhi; xs += 32) {
-      const int gx = xs + lane;
-      unsigned rest = __ballot_sync(0xffffffffu, rx0 <= rx1 && rx0 <= xs + 31 && rx1 >= xs);
-      if (!rest) continue;
-      unsigned found = 0;
-      bool in_any = false;
-      float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f;
-      while (rest) {                                            // newest paste first (warp-uniform loop)
-        const int i = 31 - __clz(rest);
-        rest &= ~(1u << i);
-        if (i != cur) {
-          const BandBox& bx = sm.box[i];
-          const float yf = (float)(gy - bx.y0);
-          cur = i;
-          t0 = bx.t0; t3 = bx.t3; c0 = bx.t1 * yf; c1 = bx.t4 * yf; c2 = bx.t7 * yf; t6 = bx.t6;
-          proj_on = bx.t6 != 0.0f || bx.t7 != 0.0f;
-          lo2 = bx.lo2; hi = bx.hi; org = bx.org; S = bx.S; bx0 = bx.x0; bd = bx.d;
-          bu = bx.u;
-          brow = bx.route + (gy - bx.y0) * bx.d;
-        }
-        const BandBox& bxs = sm.box[i];
-        const int x = gx - bx0;
-        const bool inwin = x >= 0 && x < bd;
-        in_any = in_any || inwin;
-        const float xf = (float)x;
-        float ix = (t0 * xf + c0) + bxs.t2;
-        float iy = (t3 * xf + c1) + bxs.t5;
-        bool degenerate = false;
-        if (proj_on) {
-          const float proj = (t6 * xf + c2) + 1.0f;
-          degenerate = proj == 0.0f;
-          ix = ix / proj;
-          iy = iy / proj;
-        }
-        const float x0f = floorf(ix), y0f = floorf(iy);
-        // at least one tap inside the core <=> floor coordinate in [pad_lo - 1, pad_lo + ps - 1] on both axes
-        const bool core = x0f > lo2 && x0f < hi && y0f > lo2 && y0f < hi;
-        const bool take = inwin && found != 7u && core && !degenerate;
-        if (!__any_sync(0xffffffffu, take)) continue;
-        const float wx1 = (x0f + 1.0f) - ix, wx0 = ix - x0f, wy1 = (y0f + 1.0f) - iy, wy0 = iy - y0f;
-        const int xi = (int)fminf(fmaxf(x0f, lo2), hi) - org;
-        const int yi = (int)fminf(fmaxf(y0f, lo2), hi) - org;
-        const float4* p = bu + (yi * S + xi);
-        float R[3];
-        blend3(p[0], p[1], p[S], p[S + 1], wx1, wx0, wy1, wy0, R);
-        if (take) {
-          unsigned bits = 0;
-          if (!(found & 1u) && !(R[0] < -1.0f)) { v0 = R[0]; found |= 1u; bits |= (unsigned)(R[0] <= 1.0f); }
-          if (!(found & 2u) && !(R[1] < -1.0f)) { v1 = R[1]; found |= 2u; bits |= (unsigned)(R[1] <= 1.0f) << 1; }
-          if (!(found & 4u) && !(R[2] < -1.0f)) { v2 = R[2]; found |= 4u; bits |= (unsigned)(R[2] <= 1.0f) << 2; }
-          if (bits) brow[x] = (uint8_t)bits;
-        }
-      }
-      if (found || (in_any && all_px)) {
-        const int e = row_off + gx * 3;
-        float b0 = 0.0f, b1 = 0.0f, b2 = 0.0f;
-        if (found != 7u || m_img) { b0 = __ldg(img + e); b1 = __ldg(img + e + 1); b2 = __ldg(img + e + 2); }
-        const float o0 = clampf((found & 1u) ? v0 : b0, -1.0f, 1.0f);
-        const float o1 = clampf((found & 2u) ? v1 : b1, -1.0f, 1.0f);
-        const float o2 = clampf((found & 4u) ? v2 : b2, -1.0f, 1.0f);
-        o_img[e] = o0; o_img[e + 1] = o1; o_img[e + 2] = o2;
-        if (m_img) {                                            // Masker: mask = original - pasted (attack_detection.py:429-430)
-          m_img[e] = b0 - o0; m_img[e + 1] = b1 - o1; m_img[e + 2] = b2 - o2;
-        }
-      }
-    }
-  }
-}
-
-// Bands are handed out by an atomic ticket (their cost varies from nothing to several overlapping windows).
-#ifndef EOT_COMP_MINB
-#define EOT_COMP_MINB (1024 / EOT_COMP_THREADS)
-#endif
-__global__ void __launch_bounds__(kCompThreads, EOT_COMP_MINB) k_composite(EotShape s, Layout L, char* ws,
-                                                        const float* __restrict__ images, float* out, float* mask,
-                                                        const int32_t* __restrict__ offsets, int b0, int b1, int group) {
-  __shared__ CompositeSmem sm;
-  __shared__ int s_it;
-  const int bands = (s.height + kCompRows - 1) / kCompRows;
-  const int total = (b1 - b0) * bands;
-  int* ticket = reinterpret_cast<int*>(ws + L.off_tickets) + group;
-  for (;;) {
-    if (threadIdx.x == 0) s_it = atomicAdd(ticket, 1);
-    __syncthreads();
-    const int it = s_it;
-    if (it >= total) break;
-    const int b = b0 + it / bands;
-    composite_band(s, L, ws, images, out, mask, b, it - (it / bands) * bands, offsets, sm);
-    __syncthreads();
   }
 }
 
@@ -973,7 +588,6 @@ static int launch_forward(const EotShape& s, const Layout& L, const float* patch
   const int pchunks = max(1, min((P * P + kThreads * 4 - 1) / (kThreads * 4), 64));
   const int cpi = (HW + kPassPixPerBlock - 1) / kPassPixPerBlock;
   const bool vec = (HW % 4 == 0) && (((uintptr_t)images | (uintptr_t)out_images | (uintptr_t)(mask ? mask : out_images)) & 15) == 0;
-  const int nsm = sm_count();
   const long long nblocks = (long long)N + (long long)B * pchunks + (long long)B * cpi;
   if (nblocks >= (1ll << 31)) { set_error("eot_apply_fwd: grid too large"); return EOT_ERR_BAD_SHAPE; }
   if (vec)
@@ -984,12 +598,10 @@ static int launch_forward(const EotShape& s, const Layout& L, const float* patch
                                                              out_images, mask, ws, N, B, pchunks, cpi, 0);
   count_launches(1);
   if (N > 0) {
-    const size_t smem = resize_smem_bytes(s, L);
-    if (smem > 32 * 1024) EOT_CHECK_CUDA(cudaFuncSetAttribute(k_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // static + dynamic may pass 48 KB
-    k_match<<<dim3(pchunks, B), kThreads, 0, st>>>(s, L, patch, print_wb, ws, 0);
-    k_resize<<<nsm * EOT_RESIZE_MINB, EOT_RESIZE_THREADS, smem, st>>>(s, L, ws, box_offsets, 0, B);
-    k_composite<<<nsm * EOT_COMP_MINB, kCompThreads, 0, st>>>(s, L, ws, images, out_images, mask, box_offsets, 0, B, 0);
-    count_launches(3);
+    k_match<<<B * pchunks, kThreads, 0, st>>>(s, L, patch, print_wb, ws, 0, pchunks);
+    count_launches(1);
+    if (int rc = launch_resize2(s, L, ws, box_offsets, 0, B, 0, st)) return rc;
+    if (int rc = launch_composite3(s, L, ws, box_offsets, images, out_images, mask, 0, B, 1, st)) return rc;
   }
   EOT_CHECK_CUDA(cudaPeekAtLastError());
   return EOT_OK;
@@ -1036,6 +648,7 @@ extern "C" int eot_check_workspace(const EotShape* shape, const void* workspace,
   EOT_CHECK_CUDA(cudaMemcpyAsync(&flag, static_cast<const char*>(workspace) + L.off_counters + 2 * sizeof(int), sizeof(int),
                                  cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   EOT_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  if (flag & 4) { set_error("internal: the transposed resize-weight table overflowed its tap capacity"); return EOT_ERR_GEOMETRY; }
   if (flag) { set_error("a patch window did not fit the image (the reference would fail in tf.pad / scatter)"); return EOT_ERR_GEOMETRY; }
   return EOT_OK;
 }
