@@ -4,6 +4,7 @@
 #include <atomic>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace eot {
 
@@ -29,6 +30,41 @@ int sm_count() {
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
   return n;
+}
+
+static bool stage_times_enabled() {
+  static const bool on = [] { const char* e = getenv("EOT_KERNEL_TIMES"); return e && e[0] == '1'; }();
+  return on;
+}
+
+StageTimer::StageTimer(cudaStream_t stream, const char* w) : on(false), st(stream), what(w), n(0) {
+  if (!stage_times_enabled()) return;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
+  on = true;
+  mark("start");
+}
+
+void StageTimer::mark(const char* stage) {
+  if (!on || n >= 16) return;
+  cudaEventCreate(&ev[n]);
+  cudaEventRecord(ev[n], st);
+  names[n++] = stage;
+}
+
+StageTimer::~StageTimer() {
+  if (!on) return;
+  cudaStreamSynchronize(st);
+  float total = 0.0f;
+  cudaEventElapsedTime(&total, ev[0], ev[n - 1]);
+  fprintf(stderr, "[eot] %s: %.1f us =", what, total * 1e3f);
+  for (int i = 1; i < n; ++i) {
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+    fprintf(stderr, " %s %.1f", names[i], ms * 1e3f);
+  }
+  fprintf(stderr, "\n");
+  for (int i = 0; i < n; ++i) cudaEventDestroy(ev[i]);
 }
 
 }  // namespace eot

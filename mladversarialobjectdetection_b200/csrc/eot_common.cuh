@@ -34,7 +34,7 @@ namespace eot {
 #define EOT_SQRT2 1.41421354f                   // float32(2. ** .5), attacker.py:470
 
 #ifndef EOT_COMP_ROWS
-#define EOT_COMP_ROWS 4
+#define EOT_COMP_ROWS 2
 #endif
 #ifndef EOT_RESIZE_RB
 #define EOT_RESIZE_RB 2
@@ -77,7 +77,9 @@ struct Layout {
   size_t off_ysum_patch;   // double[B]
   size_t off_gy_sum;       // double[B]   (backward: sum of dL/dY per image)
   size_t off_oor;          // int32[B]    image b holds a value outside [-1,1] (then clip(background) is not the identity)
-  size_t off_counters;     // int32[8]: 2 error flag, 3 open pixels listed by the composite, 5 finished geometry blocks
+  size_t off_counters;     // int32[32]: 2 error flag, 5 finished geometry blocks, 6 an image needs the composite's general
+                           //            path (out-of-range values or more than 32 boxes), 8 + g open pixels listed by the composite
+                           //            of image group g
   size_t off_tickets;      // int32[kTicketSlots][kTicketLanes][64]  work tickets: slot = kernel (x image group), lane = one of
                            //            the interleaved sub-queues (own 256-byte line each: same-address atomics serialise)
   size_t off_plans;        // BoxPlan[N]
@@ -148,7 +150,7 @@ __host__ __device__ inline Layout make_layout(const EotShape& s) {
   L.off_ysum_patch = o;   o = align_up(o + B * sizeof(double), 256);
   L.off_gy_sum = o;       o = align_up(o + B * sizeof(double), 256);
   L.off_oor = o;          o = align_up(o + B * sizeof(int32_t), 256);
-  L.off_counters = o;     o = align_up(o + 8 * sizeof(int32_t), 256);
+  L.off_counters = o;     o = align_up(o + 32 * sizeof(int32_t), 256);
   L.off_tickets = o;      o = align_up(o + (size_t)kTicketSlots * kTicketLanes * 256, 256);
   L.off_plans = o;        o = align_up(o + N * sizeof(BoxPlan), 256);
   L.off_starts = o;       o = align_up(o + N * (size_t)lmin * sizeof(int32_t), 256);
@@ -203,8 +205,24 @@ void count_launches(int n);   // kernels launched by this library since load (be
 // forward window kernels (eot_resize.cu, eot_composite.cu): images [b0,b1), atomic work-ticket slot in the workspace
 int launch_resize2(const EotShape& s, const struct Layout& L, char* ws, const int32_t* offsets, int b0, int b1,
                    int ticket_slot, cudaStream_t st);
+constexpr int kMaxGroups = 8;   // image groups of one forward call (own work tickets and open-pixel list each)
 int launch_composite3(const EotShape& s, const struct Layout& L, char* ws, const int32_t* offsets, const float* images,
-                      float* out, float* mask, int b0, int b1, int ticket_slot, cudaStream_t st);
+                      float* out, float* mask, int b0, int b1, int group, int ngroups, cudaStream_t st);
+
+// Debug aid, off unless the environment holds EOT_KERNEL_TIMES=1: CUDA events between the stages of one call; the
+// destructor synchronises the stream and prints the stage times to stderr (warm caches, real launch gaps -- what the
+// ncu launch list cannot show).  Never active in a captured stream.
+struct StageTimer {
+  StageTimer(cudaStream_t st, const char* what);
+  ~StageTimer();
+  void mark(const char* stage);
+  bool on;
+  cudaStream_t st;
+  const char* what;
+  int n;
+  cudaEvent_t ev[16];
+  const char* names[16];
+};
 
 #define EOT_CHECK_CUDA(expr)                                   \
   do {                                                         \

@@ -15,6 +15,7 @@
 #include "eot_common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace eot {
 
@@ -464,9 +465,15 @@ __device__ __forceinline__ void match_block(const EotShape& s, const Layout& L, 
 
 // blocks [0, nb * pchunks): match the patch to image b0 + blk / pchunks (needs the finished pre-pass: mean luma)
 __global__ void __launch_bounds__(kThreads) k_match(EotShape s, Layout L, const float* __restrict__ patch,
-                                                    const float* __restrict__ print_wb, char* ws, int b0, int pchunks) {
+                                                    const float* __restrict__ print_wb, const int32_t* __restrict__ offsets,
+                                                    char* ws, int b0, int pchunks) {
   const int blk = blockIdx.x;
-  match_block(s, L, patch, print_wb, ws, b0 + blk / pchunks, blk % pchunks, pchunks);
+  const int b = b0 + blk / pchunks;
+  // images the composite's common path does not take (values outside [-1,1], more than 32 boxes): tell its second kernel
+  if (blk % pchunks == 0 && threadIdx.x == 0 &&
+      (reinterpret_cast<const int*>(ws + L.off_oor)[b] != 0 || offsets[b + 1] - offsets[b] > 32))
+    atomicOr(reinterpret_cast<int*>(ws + L.off_counters) + 6, 1);
+  match_block(s, L, patch, print_wb, ws, b, blk % pchunks, pchunks);
 }
 
 __device__ __forceinline__ void match_block(const EotShape& s, const Layout& L, const float* __restrict__ patch,
@@ -578,30 +585,93 @@ extern "C" int eot_box_geometry(const EotShape* shape, const float* boxes, const
 
 namespace eot {
 
-// Enqueues the whole forward on `st`: memset of the small accumulators, the pre-pass (geometry + patch statistics +
-// image pass in one launch), then match -> resize -> composite.
+// Auxiliary stream + events of the calling host thread for the current device (created on first use, kept for the life
+// of the thread): the window kernels of image group g run there while the caller's stream copies group g + 1.  Nothing
+// but these handles is cached; every call forks from and joins back into the caller's stream, so the call remains
+// asynchronous on that stream and can be captured into a CUDA graph (the fork / join become graph edges).
+struct AuxStream {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t pre[kMaxGroups] = {};
+  cudaEvent_t done = nullptr;
+};
+static int aux_stream(AuxStream** out) {
+  static thread_local AuxStream aux[8];
+  int dev = 0;
+  EOT_CHECK_CUDA(cudaGetDevice(&dev));
+  AuxStream* a = nullptr;
+  for (auto& e : aux)
+    if (e.device == dev || e.device < 0) { a = &e; break; }
+  if (!a) { set_error("eot_apply_fwd: more than 8 devices used by one host thread"); return EOT_ERR_CUDA; }
+  if (a->device < 0) {
+    EOT_CHECK_CUDA(cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking));
+    for (auto& e : a->pre) EOT_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    EOT_CHECK_CUDA(cudaEventCreateWithFlags(&a->done, cudaEventDisableTiming));
+    a->device = dev;
+  }
+  *out = a;
+  return EOT_OK;
+}
+
+static int forward_groups(int B, int N) {
+  static const int forced = [] { const char* e = getenv("EOT_FWD_GROUPS"); return e ? atoi(e) : 0; }();
+  // default 1: measured on B200 (profiles/r02_forward.md), the persistent window kernels take every register of an SM,
+  // so the image pass of the next group cannot co-reside and each extra group only adds launches (+40..50 us per group
+  // under graph replay).  EOT_FWD_GROUPS keeps the A/B reproducible.
+  int g = forced > 0 ? forced : 1;
+  if (N == 0) g = 1;
+  return g < 1 ? 1 : (g > kMaxGroups ? kMaxGroups : (g > B ? B : g));
+}
+
+// Enqueues the whole forward: memset of the small accumulators, then per image group the pre-pass (image pass; the
+// first one also carries the geometry and patch-statistics roles) on the caller's stream and match -> resize ->
+// composite on the auxiliary stream, so that the HBM-bound image pass of group g + 1 overlaps the L2-resident,
+// instruction-bound window work of group g.
 static int launch_forward(const EotShape& s, const Layout& L, const float* patch, const float* scale, const float* images,
                           const float* boxes, const int32_t* box_offsets, const EotBoxParams* params,
                           const float* print_wb, float* out_images, float* mask, char* ws, cudaStream_t st) {
   const int B = s.batch, P = s.patch_size, HW = s.height * s.width, N = s.total_boxes;
+  StageTimer timer(st, "eot_apply_fwd");
   EOT_CHECK_CUDA(cudaMemsetAsync(ws + L.off_ysum_img, 0, L.off_plans - L.off_ysum_img, st));
   const int pchunks = max(1, min((P * P + kThreads * 4 - 1) / (kThreads * 4), 64));
   const int cpi = (HW + kPassPixPerBlock - 1) / kPassPixPerBlock;
   const bool vec = (HW % 4 == 0) && (((uintptr_t)images | (uintptr_t)out_images | (uintptr_t)(mask ? mask : out_images)) & 15) == 0;
-  const long long nblocks = (long long)N + (long long)B * pchunks + (long long)B * cpi;
-  if (nblocks >= (1ll << 31)) { set_error("eot_apply_fwd: grid too large"); return EOT_ERR_BAD_SHAPE; }
-  if (vec)
-    k_prepass<true><<<(unsigned)nblocks, kThreads, 0, st>>>(s, L, patch, print_wb, boxes, box_offsets, params, scale, images,
-                                                            out_images, mask, ws, N, B, pchunks, cpi, 0);
-  else
-    k_prepass<false><<<(unsigned)nblocks, kThreads, 0, st>>>(s, L, patch, print_wb, boxes, box_offsets, params, scale, images,
-                                                             out_images, mask, ws, N, B, pchunks, cpi, 0);
-  count_launches(1);
-  if (N > 0) {
-    k_match<<<B * pchunks, kThreads, 0, st>>>(s, L, patch, print_wb, ws, 0, pchunks);
+  const int G = forward_groups(B, N);
+  AuxStream* aux = nullptr;
+  if (G > 1)
+    if (int rc = aux_stream(&aux)) return rc;
+  for (int g = 0; g < G; ++g) {
+    const int b0 = (int)((long long)B * g / G), b1 = (int)((long long)B * (g + 1) / G);
+    const int n_geom = g == 0 ? N : 0, n_stat = g == 0 ? B : 0;
+    const long long nblocks = (long long)n_geom + (long long)n_stat * pchunks + (long long)(b1 - b0) * cpi;
+    if (nblocks >= (1ll << 31)) { set_error("eot_apply_fwd: grid too large"); return EOT_ERR_BAD_SHAPE; }
+    if (vec)
+      k_prepass<true><<<(unsigned)nblocks, kThreads, 0, st>>>(s, L, patch, print_wb, boxes, box_offsets, params, scale, images,
+                                                              out_images, mask, ws, n_geom, n_stat, pchunks, cpi, b0);
+    else
+      k_prepass<false><<<(unsigned)nblocks, kThreads, 0, st>>>(s, L, patch, print_wb, boxes, box_offsets, params, scale, images,
+                                                               out_images, mask, ws, n_geom, n_stat, pchunks, cpi, b0);
     count_launches(1);
-    if (int rc = launch_resize2(s, L, ws, box_offsets, 0, B, 0, st)) return rc;
-    if (int rc = launch_composite3(s, L, ws, box_offsets, images, out_images, mask, 0, B, 1, st)) return rc;
+    if (G == 1) timer.mark("prepass");
+    if (N == 0) continue;
+    cudaStream_t sw = st;
+    if (G > 1) {
+      EOT_CHECK_CUDA(cudaEventRecord(aux->pre[g], st));
+      EOT_CHECK_CUDA(cudaStreamWaitEvent(aux->stream, aux->pre[g], 0));
+      sw = aux->stream;
+    }
+    k_match<<<(b1 - b0) * pchunks, kThreads, 0, sw>>>(s, L, patch, print_wb, box_offsets, ws, b0, pchunks);
+    count_launches(1);
+    if (G == 1) timer.mark("match");
+    if (int rc = launch_resize2(s, L, ws, box_offsets, b0, b1, 2 * g, sw)) return rc;
+    if (G == 1) timer.mark("resize");
+    if (int rc = launch_composite3(s, L, ws, box_offsets, images, out_images, mask, b0, b1, g, G, sw)) return rc;
+    if (G == 1) timer.mark("composite");
+  }
+  if (G > 1 && N > 0) {
+    EOT_CHECK_CUDA(cudaEventRecord(aux->done, aux->stream));
+    EOT_CHECK_CUDA(cudaStreamWaitEvent(st, aux->done, 0));
+    timer.mark("all");
   }
   EOT_CHECK_CUDA(cudaPeekAtLastError());
   return EOT_OK;

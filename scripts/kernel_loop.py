@@ -22,6 +22,7 @@ ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--what", default="fwd,bwd,score")
 ap.add_argument("--max-boxes", type=int, default=8)
 ap.add_argument("--time", action="store_true")
+ap.add_argument("--graph", action="store_true", help="time replays of a CUDA graph of the call(s) instead of eager launches")
 args = ap.parse_args()
 B, H, P = args.batch, args.image, args.patch
 dev = "cuda"
@@ -71,9 +72,16 @@ if args.time:
         what_saved, what = what, [name]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         one(); torch.cuda.synchronize()
+        run = one
+        if args.graph:
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                one()
+            run = gr.replay
+            run(); torch.cuda.synchronize()
         e0.record()
         for _ in range(args.iters):
-            one()
+            run()
         e1.record(); torch.cuda.synchronize()
         print(f"{name}: {e0.elapsed_time(e1) / args.iters * 1e3:.1f} us per call")
         what = what_saved
