@@ -54,7 +54,8 @@ typedef struct EotShape {
   int32_t height, width;  /* H, W                                                                  */
   int32_t patch_size;     /* P: patch texture is [P,P,3]                                           */
   int32_t num_patches;    /* 1: one shared patch (Patcher); B: one texture per image (Masker train) */
-  int32_t total_boxes;    /* N = box_offsets[B]                                                    */
+  int32_t total_boxes;    /* N: box capacity of the call, >= box_offsets[B] (the count in use is read on the
+                           * device: a caller whose boxes come out of a kernel needs no host read)      */
   uint32_t flags;         /* EOT_FLAG_*                                                            */
   float tolerance;        /* centre jitter fraction: .2 Patcher (attacker.py:465), .5/0 Masker     */
   float noise_amp;        /* .01 Patcher (attacker.py:426), .1 Masker (attack_detection.py:411)    */
@@ -70,6 +71,17 @@ typedef struct EotBoxGeometry {
   int32_t y0, x0, ps, d, pad_lo, pad_hi, valid, span;
 } EotBoxGeometry;
 
+/* What the transform draw needs (eot_draw_transforms): the reference's distributions with its constants as
+ * defaults -- max_angle 20 deg (attacker.py:436), max_delta .3 (:427), perspective 0 (no projective row),
+ * scale_lo < 0: shared trainable scale; Masker training: scale ~ U(.3,.5), i.e. (.3, .2) (attack_detection.py:453). */
+typedef struct EotDrawConfig {
+  int64_t seed, step;      /* layer seed and call counter: the hash key                                  */
+  int64_t first_image;     /* global index of this rank's first image (data-parallel sharding)           */
+  float max_angle, max_delta, perspective;
+  float scale_lo, scale_span; /* scale ~ scale_lo + U[0,1) * scale_span                                */
+  float rsv;
+} EotDrawConfig;
+
 const char* eot_last_error(void);
 int eot_version(void);
 /* Number of CUDA kernels this library has launched since it was loaded (all threads). */
@@ -83,6 +95,14 @@ int eot_workspace_bytes(const EotShape* shape, size_t* bytes);
 int eot_box_geometry(const EotShape* shape, const float* boxes, const int32_t* box_offsets,
                      const EotBoxParams* params, const float* scale, EotBoxGeometry* geometry_out,
                      void* stream);
+
+/* Everything `Patcher` / `Masker` draw from TF's RNG inside the graph (attacker.py:370-371, 426-427, 436, 473-474;
+ * attack_detection.py:350-351, 411, 421, 451-453), as one launch: params_out[box_capacity] (slots past
+ * box_offsets[B] zero-filled) and print_wb_out[B,6].  Counter-based on (seed, step, global image, box in image):
+ * a sharded batch draws what the single-GPU batch draws. */
+int eot_draw_transforms(const EotDrawConfig* cfg, int32_t batch, int32_t box_capacity,
+                        const int32_t* box_offsets, EotBoxParams* params_out, float* print_wb_out,
+                        void* stream);
 
 /* `Patcher.call` (attacker.py:490-498) / `Masker.call` (attack_detection.py:478-498):
  * out_images[B,H,W,3] = images with every valid box patched in order; out_masks (optional,

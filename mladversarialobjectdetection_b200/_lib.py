@@ -16,7 +16,7 @@ SCORE_MAX_LEVELS = 8
 
 # every symbol include/eotpatch.h declares (tests check the export list against the header)
 SYMBOLS = ["eot_last_error", "eot_version", "eot_launch_count", "eot_workspace_bytes", "eot_box_geometry", "eot_apply_fwd",
-           "eot_apply_bwd", "eot_brightness_match", "eot_check_workspace", "score_workspace_bytes", "score_max_fwd", "score_max_bwd",
+           "eot_apply_bwd", "eot_draw_transforms", "eot_brightness_match", "eot_check_workspace", "score_workspace_bytes", "score_max_fwd", "score_max_bwd",
            "person_nms_workspace_bytes", "person_nms", "eot_letterbox_normalize", "eot_channel_sums",
            "eot_augment_batch", "adv_u8_box_geometry", "adv_u8_print_patch", "adv_u8_workspace_bytes", "adv_u8_add_patches",
            "patch_tv_grad", "adam_clip_update", "nhwc_bias_act_fwd", "nhwc_bias_silu_bwd",
@@ -30,6 +30,12 @@ class EotShape(ctypes.Structure):
                 ("min_patch_area", ctypes.c_float), ("max_scale", ctypes.c_float),
                 ("patch_stride_n", ctypes.c_int64), ("patch_stride_y", ctypes.c_int64),
                 ("patch_stride_x", ctypes.c_int64)]
+
+
+class EotDrawConfig(ctypes.Structure):
+    _fields_ = [("seed", ctypes.c_int64), ("step", ctypes.c_int64), ("first_image", ctypes.c_int64),
+                ("max_angle", ctypes.c_float), ("max_delta", ctypes.c_float), ("perspective", ctypes.c_float),
+                ("scale_lo", ctypes.c_float), ("scale_span", ctypes.c_float), ("rsv", ctypes.c_float)]
 
 
 class ScoreShape(ctypes.Structure):
@@ -62,6 +68,7 @@ def _declare(lib):
     lib.eot_box_geometry.argtypes = [ctypes.POINTER(EotShape), vp, vp, vp, vp, vp, vp]
     lib.eot_apply_fwd.argtypes = [ctypes.POINTER(EotShape), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.eot_apply_bwd.argtypes = [ctypes.POINTER(EotShape), vp, vp, vp, vp, sz, vp, ctypes.c_int, vp]
+    lib.eot_draw_transforms.argtypes = [ctypes.POINTER(EotDrawConfig), i32, i32, vp, vp, vp, vp]
     lib.eot_brightness_match.argtypes = [vp, i64, vp, i64, vp, vp, sz, vp]
     lib.eot_check_workspace.argtypes = [ctypes.POINTER(EotShape), vp, vp]
     lib.score_workspace_bytes.argtypes = [ctypes.POINTER(ScoreShape), ctypes.POINTER(sz)]

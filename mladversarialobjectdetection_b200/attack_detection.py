@@ -26,7 +26,7 @@ class Masker:
         self.name = name
         self.is_training = False
         self.sampler = TransformSampler(seed)
-        self.first_image = 0
+        self.first_image = None       # None: rank * local batch under torch.distributed, else 0 (see attacker.resolve_first_image)
         self._step = 0
         self._workspace = None
 
@@ -62,11 +62,12 @@ class Masker:
             patch = self._patch
             scale_range = None
         if transforms is None:
-            params = self.sampler.box_params(self._step, self.first_image, boxes.row_splits, n, scale_range=scale_range)
-            print_wb = self.sampler.print_wb(self._step, self.first_image, images.shape[0], images.device)
+            from .attacker import resolve_first_image
+            params, print_wb = self.sampler.draw(self._step, resolve_first_image(self.first_image, images.shape[0]),
+                                                 boxes.row_splits, n, scale_range=scale_range)
+            self._step += 1           # (like Patcher: explicit transforms replay a draw, they do not consume one)
         else:
             params, print_wb = transforms
-        self._step += 1
         out, mask, ctx = ops.apply_forward(patch, self._scale, images, boxes.values, boxes.row_splits, params, print_wb,
                                            geom, want_mask=True, workspace=self._workspace)
         self._workspace = ctx.workspace

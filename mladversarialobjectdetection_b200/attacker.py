@@ -25,6 +25,15 @@ from .ragged import RaggedBoxes
 from .sampler import TransformSampler
 
 
+def resolve_first_image(first_image: Optional[int], local_batch: int) -> int:
+    """Global index of this rank's first image: explicit, else rank * local batch (even data-parallel shards)."""
+    if first_image is not None:
+        return int(first_image)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        return torch.distributed.get_rank() * int(local_batch)
+    return 0
+
+
 class Patcher:
     """apply patch to persons in an image (reference: attacker.py:344)."""
 
@@ -36,7 +45,9 @@ class Patcher:
         self.name = name
         self.geometry = ops.PatchGeometry(tolerance=0.2, noise_amp=0.01, min_patch_area=float(min_patch_area))
         self.sampler = TransformSampler(seed, perspective=perspective)
-        self.first_image = 0          # global index of this rank's first image (data-parallel sharding)
+        # global index of this rank's first image (data-parallel sharding: the draws hash the GLOBAL image index).
+        # None: rank * local batch when torch.distributed is initialised (even shards), else 0; set it for uneven shards.
+        self.first_image: Optional[int] = None
         self._step = 0
         self._workspace = None
         self.last_context: Optional[ops.ApplyContext] = None
@@ -52,10 +63,10 @@ class Patcher:
         boxes, images = inputs
         if not isinstance(boxes, RaggedBoxes):
             boxes = RaggedBoxes.from_rows(boxes, images.device)
-        n = int(boxes.values.shape[0])
+        n = int(boxes.values.shape[0])              # box capacity; the count in use is row_splits[-1], read on the device
         if transforms is None:
-            params = self.sampler.box_params(self._step, self.first_image, boxes.row_splits, n)
-            print_wb = self.sampler.print_wb(self._step, self.first_image, images.shape[0], images.device)
+            params, print_wb = self.sampler.draw(self._step, resolve_first_image(self.first_image, images.shape[0]),
+                                                 boxes.row_splits, n)
             self._step += 1
         else:
             params, print_wb = transforms
@@ -77,7 +88,7 @@ class PatchAttacker:
 
     def __init__(self, model, initial_patch=None, config_override=None, visualize_freq=200, *,
                  patch_size: int = 640, device=None, seed: int = 0, process_group=None, perspective: float = 0.0,
-                 cuda_graphs: bool = False):
+                 cuda_graphs: bool = False, always_first_pass: bool = False, box_capacity: Optional[int] = None):
         self.model = model
         self.config = model.config
         if config_override:
@@ -104,11 +115,18 @@ class PatchAttacker:
         self._adam_m = torch.zeros(n, dtype=torch.float32, device=self.device)
         self._adam_v = torch.zeros(n, dtype=torch.float32, device=self.device)
         self._anchors = None
+        self._packed = None
         self.metrics = {}
         # CUDA graphs of the two fixed-shape victim passes (clean forward + score; attacked forward + score +
         # objective gradient + victim backward): the ~2000 framework launches of a step become two replays.
         # The patcher itself stays outside (its box count changes from step to step).
         self.cuda_graphs = bool(cuda_graphs)
+        # run the clean victim pass + NMS even when `boxes` are supplied (synthetic benchmarks that must pay for it)
+        self.always_first_pass = bool(always_first_pass)
+        # None: the first pass reads its box count back (exact-size launches).  An int: no host read at all -- the ragged
+        # NMS output is handed to the patcher at this capacity (total boxes per batch) and the count stays on the
+        # device; surplus boxes are dropped and flagged (ops.check_workspace / `boxes_dropped`).
+        self.box_capacity = box_capacity
         self._graphs = None
         self.graph_launches = 0           # libeotpatch kernels launched through CUDA-graph replays (see _build_graphs)
 
@@ -141,12 +159,12 @@ class PatchAttacker:
         return cls_outputs, box_outputs, M, argmax, ncand, ctx
 
     def first_pass(self, images: torch.Tensor):
-        """clean pass through the victim (attacker.py:91-116).  Returns (boxes RaggedBoxes, scores list)."""
+        """clean pass through the victim (attacker.py:91-116).  Returns (boxes RaggedBoxes, scores list | None)."""
         from . import postprocess
         with torch.no_grad():
             cls_outputs, box_outputs, _, _, _, ctx = self._score(images)
             return postprocess.person_boxes_after_nms(self.config, ctx, box_outputs, self._anchor_table(images),
-                                                      images.shape[1:3], thresh=True)
+                                                      images.shape[1:3], thresh=True, box_capacity=self.box_capacity)
 
     def second_pass(self, images: torch.Tensor):
         """pass after addition of patches (attacker.py:118-141): per-image max candidate score + context."""
@@ -204,13 +222,14 @@ class PatchAttacker:
             g["g1"].replay()
             self.graph_launches += g["launches"][0]
             det_boxes, _ = postprocess.person_boxes_after_nms(self.config, g["clean_ctx"], g["clean_box"],
-                                                              self._anchor_table(images), images.shape[1:3], thresh=True)
+                                                              self._anchor_table(images), images.shape[1:3], thresh=True,
+                                                              box_capacity=self.box_capacity)
             if boxes is None:
                 boxes = det_boxes
         self._patcher([boxes, images], transforms=transforms, out=g["patched"].detach())
         g["g2"].replay()
         self.graph_launches += g["launches"][1]
-        grad_patch = self._patcher.backward(g["grad"])
+        grad_patch = self._patcher.backward(g["grad"], grad_patch=self._grad_view())
         self._last = dict(max_scores=g["M"], data_loss=g["data_loss"], dscale=g["dscale"], ncand=g["ncand"])
         return [g["dscale"], grad_patch]
 
@@ -232,21 +251,24 @@ class PatchAttacker:
         cls_outputs, M, argmax, ncand, sctx = self.second_pass(patched)
         dcls, dscale, data_loss = ops.score_max_backward(sctx, self._scale_regressor)
         torch.autograd.backward(cls_outputs, dcls)                       # victim backward on the framework path
-        grad_patch = self._patcher.backward(patched.grad)
+        grad_patch = self._patcher.backward(patched.grad, grad_patch=self._grad_view())
         self._last = dict(max_scores=M, data_loss=data_loss, dscale=dscale, ncand=ncand)
         return [dscale, grad_patch]
 
-    always_first_pass = True
-
     # -- steps -------------------------------------------------------------------------------------
+    def _grad_view(self) -> torch.Tensor:
+        """dL/dpatch is written straight into the head of the packed all-reduce buffer [dpatch | dscale | loss | sum M | sum M^2]."""
+        n = self._patch.numel()
+        if self._packed is None:
+            self._packed = torch.empty(n + 4, dtype=torch.float32, device=self.device)
+        return self._packed[:n].view_as(self._patch)
+
     def _pack(self, dscale, grad_patch, M):
-        n = grad_patch.numel()
-        buf = torch.empty(n + 4, dtype=torch.float32, device=self.device)
-        buf[:n] = grad_patch.reshape(-1)
-        buf[n] = dscale
-        buf[n + 1] = self._last["data_loss"]
-        buf[n + 2] = M.sum()
-        buf[n + 3] = (M * M).sum()
+        n = self._patch.numel()
+        buf = self._packed
+        if grad_patch.data_ptr() != buf.data_ptr():
+            buf[:n] = grad_patch.reshape(-1)
+        buf[n:] = torch.stack([dscale.reshape(()), self._last["data_loss"].reshape(()), M.sum(), torch.dot(M, M)])
         return buf
 
     def train_step(self, inputs, boxes: Optional[RaggedBoxes] = None, transforms=None, global_batch: Optional[int] = None):

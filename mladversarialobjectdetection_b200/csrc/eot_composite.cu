@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, EOT_COMP_MINB) k_composite3(EotShape
   int2* open_list = reinterpret_cast<int2*>(ws + L.off_open) + (size_t)group * open_cap;
   const int W = s.width, lfull = s.height < s.width ? s.height : s.width;
   const size_t img_elems = (size_t)s.height * s.width * 3;
-  const int lo = base[offsets[b0]].w, hi = base[offsets[b1]].w;
+  const int lo = base[min(offsets[b0], s.total_boxes)].w, hi = base[min(offsets[b1], s.total_boxes)].w;
   WarpTickets tk;
   tk.init(ws, L.off_tickets, 2 * group + 1);
   int it = lo + tk.item(tk.draw(lane));
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(kThreads) k_composite_rest(EotShape s, Layout 
   }
   // whole rows of the items outside the common case (k_match flags their presence)
   if (!overflow && reinterpret_cast<const int*>(ws + L.off_counters)[6] == 0) return;
-  const int lo = base[offsets[b0]].w, hi = base[offsets[b1]].w;
+  const int lo = base[min(offsets[b0], s.total_boxes)].w, hi = base[min(offsets[b1], s.total_boxes)].w;
   const int nw = (gridDim.x * blockDim.x) >> 5;
   for (int it = lo + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); it < hi; it += nw) {
     const int2 item = citems[it];

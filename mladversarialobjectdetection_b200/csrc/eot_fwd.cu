@@ -163,10 +163,24 @@ __device__ int geometry_block(const EotShape& s, const Layout& L, int j, const f
   int* counters = ws ? reinterpret_cast<int*>(ws + L.off_counters) : nullptr;
   if (threadIdx.x == 0) {
     s_maxcnt = 0;
+    // total_boxes is a CAPACITY: the boxes in use are [0, box_offsets[B]) (read here, on the device, so that a caller
+    // whose box count comes out of a kernel -- the first pass' NMS -- needs no host read); the slots past them are
+    // invalid boxes without work.  More boxes than the capacity: flagged (eot_check_workspace), the surplus is dropped.
+    const int n_used = offsets[s.batch];
+    if (n_used > s.total_boxes && counters) atomicOr(counters + 2, 8);
     int a = 0, b = s.batch;                       // image of box j: last b with offsets[b] <= j
     while (a < b) { const int m = (a + b) >> 1; if (offsets[m + 1] <= j) a = m + 1; else b = m; }
-    BoxPlan pl = make_plan(boxes + (size_t)j * 4, *scale, params[j], s, a, offsets[a], offsets[a + 1],
-                           (int64_t)j * L.slot, counters ? counters + 2 : nullptr);
+    const bool used = j < n_used && a < s.batch;
+    if (!used) a = s.batch - 1;
+    EotBoxParams prm = {};
+    float bx[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (used) {
+      prm = params[j];
+      for (int k = 0; k < 4; ++k) bx[k] = boxes[(size_t)j * 4 + k];
+    }
+    BoxPlan pl = make_plan(bx, *scale, prm, s, a, offsets[a], min(offsets[a + 1], s.total_boxes), (int64_t)j * L.slot,
+                           used && counters ? counters + 2 : nullptr);
+    if (!used) pl.valid = 0;
     if (pl.valid) pl.span = span_cfg(pl.ps, s.patch_size).span;
     spl = pl;
     if (ws) {
@@ -447,7 +461,7 @@ __global__ void __launch_bounds__(kThreads) k_prepass(EotShape s, Layout L, cons
     patch_stats_block(s, b, blk - b * pchunks, pchunks, patch, print_wb, reinterpret_cast<double*>(ws + L.off_ysum_patch), red);
     if (blk == 0 && threadIdx.x == 0) {                  // CSR copy for the backward
       int32_t* off_copy = reinterpret_cast<int32_t*>(ws + L.off_offsets);
-      for (int i = 0; i <= s.batch; ++i) off_copy[i] = offsets[i];
+      for (int i = 0; i <= s.batch; ++i) off_copy[i] = min(offsets[i], s.total_boxes);
     }
     return;
   }
@@ -718,6 +732,7 @@ extern "C" int eot_check_workspace(const EotShape* shape, const void* workspace,
   EOT_CHECK_CUDA(cudaMemcpyAsync(&flag, static_cast<const char*>(workspace) + L.off_counters + 2 * sizeof(int), sizeof(int),
                                  cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   EOT_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  if (flag & 8) { set_error("box_offsets[B] exceeds shape.total_boxes (the box capacity of the call): the surplus boxes were dropped"); return EOT_ERR_GEOMETRY; }
   if (flag & 4) { set_error("internal: the transposed resize-weight table overflowed its tap capacity"); return EOT_ERR_GEOMETRY; }
   if (flag) { set_error("a patch window did not fit the image (the reference would fail in tf.pad / scatter)"); return EOT_ERR_GEOMETRY; }
   return EOT_OK;

@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(kThreads, EOT_RESIZE_MINB) k_resize2(EotShape 
   float4* inter = reinterpret_cast<float4*>(resize_smem + (size_t)warp * per_warp);
   uint32_t* words = reinterpret_cast<uint32_t*>(resize_smem + (size_t)warp * per_warp + (size_t)L.rb * s.patch_size * 16);
   const int4* base = reinterpret_cast<const int4*>(ws + L.off_base);
-  const int lo = base[offsets[b0]].z, hi = base[offsets[b1]].z;
+  const int lo = base[min(offsets[b0], s.total_boxes)].z, hi = base[min(offsets[b1], s.total_boxes)].z;
   WarpTickets tk;
   tk.init(ws, L.off_tickets, ticket_slot);
   const int2* items = reinterpret_cast<const int2*>(ws + L.off_items);

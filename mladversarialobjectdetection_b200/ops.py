@@ -5,6 +5,7 @@ hot path runs in libeotpatch.so.  Everything raises if the input is not on a CUD
 from __future__ import annotations
 
 import ctypes
+import math
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple
 
@@ -159,6 +160,29 @@ def apply_backward(ctx: ApplyContext, grad_images: torch.Tensor, *, grad_patch: 
                                          _ptr(ctx.workspace), ctypes.c_size_t(ctx.workspace.numel()),
                                          _ptr(grad_patch), int(bool(accumulate)), _stream()), "eot_apply_bwd")
     return grad_patch
+
+
+def draw_transforms(seed: int, step: int, first_image: int, offsets: torch.Tensor, box_capacity: int, *,
+                    max_angle: float = 20.0 * math.pi / 180.0, max_delta: float = 0.3, perspective: float = 0.0,
+                    scale_range: Optional[Tuple[float, float]] = None):
+    """Everything `Patcher` / `Masker` draw from TF's RNG, in one launch (eot_draw_transforms): returns
+    (params uint8 [box_capacity,48], print_wb float32 [B,6]).  offsets: int32 [B+1] on the device."""
+    _need_cuda(offsets)
+    if offsets.dtype != torch.int32:
+        raise ValueError("offsets must be int32 [B+1]")
+    B = offsets.numel() - 1
+    cfg = _lib.EotDrawConfig()
+    cfg.seed, cfg.step, cfg.first_image = int(seed), int(step), int(first_image)
+    cfg.max_angle, cfg.max_delta, cfg.perspective = float(max_angle), float(max_delta), float(perspective)
+    if scale_range is None:
+        cfg.scale_lo, cfg.scale_span = -1.0, 0.0
+    else:
+        cfg.scale_lo, cfg.scale_span = float(scale_range[0]), float(scale_range[1] - scale_range[0])
+    params = torch.empty((box_capacity, 48), dtype=torch.uint8, device=offsets.device)
+    print_wb = torch.empty((B, 6), dtype=torch.float32, device=offsets.device)
+    _lib.check(_lib.load().eot_draw_transforms(ctypes.byref(cfg), B, int(box_capacity), _ptr(offsets), _ptr(params),
+                                               _ptr(print_wb), _stream()), "eot_draw_transforms")
+    return params, print_wb
 
 
 def brightness_match(src: torch.Tensor, tgt: torch.Tensor) -> torch.Tensor:

@@ -30,15 +30,23 @@ def nms_settings(nms_configs: dict):
 
 
 def person_boxes_after_nms(config, score_ctx, box_outputs: Sequence[torch.Tensor], anchors: torch.Tensor,
-                           image_hw, thresh: bool = True, max_candidates: int = 0) -> Tuple[RaggedBoxes, List[np.ndarray]]:
+                           image_hw, thresh: bool = True, max_candidates: int = 0, box_capacity=None):
     """attacker.py:104-116: candidates (person & valid, from the score kernel) [>= score_thresh] -> NMS ->
-    clip -> ragged boxes / scores.  One small device->host read (row_splits) because the result is ragged."""
+    clip -> ragged boxes / scores.
+
+    box_capacity None: one small device->host read (row_splits) sizes the ragged result exactly and the per-image
+    score lists are returned (metrics / ASR).  box_capacity = n: NO host read -- the boxes come back at that capacity
+    (the kernels downstream read the count in use, row_splits[-1], on the device) and the scores stay on the device
+    (second return value: the NmsResult)."""
     sigma, iou_thresh, nms_score_thresh = nms_settings(config.nms_configs)
     floor = float(config.nms_configs["score_thresh"]) if thresh else 0.0
     res = ops.person_nms(ops.score_candidate_view(score_ctx), box_outputs, anchors, image_hw,
                          max_output_size=int(config.nms_configs["max_output_size"]), iou_threshold=float(iou_thresh),
                          score_threshold=max(float(nms_score_thresh), 0.0), soft_nms_sigma=float(sigma),
                          score_floor=max(floor, 0.0), max_candidates=max_candidates)
+    if box_capacity is not None:
+        cap = min(int(box_capacity), int(res.ragged_boxes.shape[0]))
+        return RaggedBoxes(res.ragged_boxes[:cap], res.row_splits), res
     splits = res.row_splits.cpu()                                             # the one host sync
     n = int(splits[-1])
     if n < 0:

@@ -1,9 +1,12 @@
-"""Device-side draw of the transform seeds the reference takes from TF's RNG inside `Patcher`
+"""Draw of the transform seeds the reference takes from TF's RNG inside `Patcher`
 (attacker.py:370-371, 426-427, 436, 473-474; Masker: attack_detection.py:350-351, 411, 421, 451-453).
 
 Counter-based: every number is a hash of (seed, step, GLOBAL image index, box index in image, slot), so a
 batch sharded over G ranks draws exactly what the single-GPU batch draws, with no host sync and no state.
-Plumbing only (a handful of tiny torch ops per step); the arithmetic of the hot path is in libeotpatch.
+
+On the device the whole draw is ONE kernel of libeotpatch (`eot_draw_transforms`, csrc/eot_draw.cu): `draw`.
+`box_params` / `print_wb` below are the same arithmetic in torch ops -- the definition the kernel is tested
+against, and what the CPU-only (gloo) tests of the sharding logic use; CUDA callers are routed to the kernel.
 """
 from __future__ import annotations
 
@@ -41,6 +44,14 @@ class TransformSampler:
         self.max_angle = max_angle
         self.max_delta = max_delta
         self.perspective = perspective
+
+    def draw(self, step: int, first_image: int, offsets: torch.Tensor, box_capacity: int,
+             scale_range: Optional[Tuple[float, float]] = None):
+        """(params uint8 [box_capacity,48], print_wb [B,6]) in one kernel launch; the box count in use is read on the
+        device (offsets[B]), slots past it are zero."""
+        from . import ops
+        return ops.draw_transforms(self.seed, step, first_image, offsets, box_capacity, max_angle=self.max_angle,
+                                   max_delta=self.max_delta, perspective=self.perspective, scale_range=scale_range)
 
     def _base(self, step: int, idx: torch.Tensor, slot: int) -> torch.Tensor:
         k = torch.full_like(idx, (self.seed * 1000003 + step) & 0x7FFFFFFFFFFFFFFF)
