@@ -76,6 +76,7 @@ struct Layout {
   size_t off_ysum_img;     // double[B]
   size_t off_ysum_patch;   // double[B]
   size_t off_gy_sum;       // double[B]   (backward: sum of dL/dY per image)
+  size_t off_bwd_cnt;      // int32[1 + ceil(P*P/256)] backward: work ticket, finished image groups per texel chunk
   size_t off_oor;          // int32[B]    image b holds a value outside [-1,1] (then clip(background) is not the identity)
   size_t off_counters;     // int32[32]: 2 error flag, 5 finished geometry blocks, 6 an image needs the composite's general
                            //            path (out-of-range values or more than 32 boxes), 8 + g open pixels listed by the composite
@@ -109,6 +110,7 @@ struct Layout {
   size_t off_gp_part;      // float[16][P*P*3] backward: partial dL/dpatch per image group
   size_t off_gbox;         // float[N][P*P*3]  backward: dL/d(matched patch) per box (0 bytes when it would exceed gbox_cap)
   size_t off_offsets;      // int32[B+1] copy of the CSR row splits (the backward has no other source)
+  size_t off_order;        // int32[B]   images by decreasing window work (the backward starts the heavy images first)
   size_t total;
   int64_t slot;            // floats per u slot (4 per texel)
   int64_t gslot;           // floats per g_u slot (RGBX: 4 per texel)
@@ -149,6 +151,7 @@ __host__ __device__ inline Layout make_layout(const EotShape& s) {
   L.off_ysum_img = o;     o = align_up(o + B * sizeof(double), 256);
   L.off_ysum_patch = o;   o = align_up(o + B * sizeof(double), 256);
   L.off_gy_sum = o;       o = align_up(o + B * sizeof(double), 256);
+  L.off_bwd_cnt = o;      o = align_up(o + (1 + ((size_t)s.patch_size * s.patch_size + 255) / 256) * sizeof(int32_t), 256);
   L.off_oor = o;          o = align_up(o + B * sizeof(int32_t), 256);
   L.off_counters = o;     o = align_up(o + 32 * sizeof(int32_t), 256);
   L.off_tickets = o;      o = align_up(o + (size_t)kTicketSlots * kTicketLanes * 256, 256);
@@ -171,11 +174,12 @@ __host__ __device__ inline Layout make_layout(const EotShape& s) {
   L.rslot = (int64_t)align_up((size_t)lfull * lfull, 32);
   L.off_route = o;        o = align_up(o + N * (size_t)L.rslot, 256);
   L.off_gm = o;           o = align_up(o + B * PP3 * sizeof(float), 256);
-  L.off_gu = o;           o = align_up(o + N * (size_t)L.gslot * sizeof(float), 256);
+  L.off_gu = o;           // (the backward keeps dL/d(u) in shared memory)
   L.off_gp_part = o;      o = align_up(o + 16 * PP3 * sizeof(float), 256);
   L.use_gbox = (N * PP3 * sizeof(float) <= ((size_t)1 << 30) && !(s.flags & EOT_FLAG_SERIAL_ADJOINT)) ? 1 : 0;
-  L.off_gbox = o;         o = align_up(o + (L.use_gbox ? N * PP3 * sizeof(float) : 0), 256);
+  L.off_gbox = o;         // (the backward accumulates per image in shared memory: no per-box partials)
   L.off_offsets = o;      o = align_up(o + (B + 1) * sizeof(int32_t), 256);
+  L.off_order = o;        o = align_up(o + B * sizeof(int32_t), 256);
   L.total = o;
   return L;
 }

@@ -445,6 +445,28 @@ __global__ void __launch_bounds__(kThreads) k_prepass(EotShape s, Layout L, cons
       const int4* cnt = reinterpret_cast<const int4*>(ws + L.off_cnt);
       int4* base = reinterpret_cast<int4*>(ws + L.off_base);
       scan_block(n_geom, cnt, base, s_part);
+      // images by decreasing window work (sum of ps^2 over their valid boxes; ties by index): the backward's per-image
+      // items are handed out heaviest first
+      {
+        const BoxPlan* pls = reinterpret_cast<const BoxPlan*>(ws + L.off_plans);
+        int* order = reinterpret_cast<int*>(ws + L.off_order);
+        const int B = s.batch;
+        if (B <= 2048) {
+          for (int b = threadIdx.x; b < B; b += blockDim.x) {
+            long long mine = 0;
+            for (int j = min(offsets[b], n_geom); j < min(offsets[b + 1], n_geom); ++j) mine += pls[j].valid ? (long long)pls[j].ps * pls[j].ps : 0;
+            int rank = 0;
+            for (int o2 = 0; o2 < B; ++o2) {
+              long long c = 0;
+              for (int j = min(offsets[o2], n_geom); j < min(offsets[o2 + 1], n_geom); ++j) c += pls[j].valid ? (long long)pls[j].ps * pls[j].ps : 0;
+              rank += (c > mine || (c == mine && o2 < b)) ? 1 : 0;
+            }
+            order[rank] = b;
+          }
+        } else {
+          for (int b = threadIdx.x; b < B; b += blockDim.x) order[b] = b;
+        }
+      }
       int2* items = reinterpret_cast<int2*>(ws + L.off_items);    // forward resize / composite items in ticket order
       int2* citems = reinterpret_cast<int2*>(ws + L.off_citems);
       for (int j = threadIdx.x; j < n_geom; j += blockDim.x) {
