@@ -234,8 +234,9 @@ int eot_augment_batch(const float* images, float* out, int32_t batch, int32_t he
  * uint8 inference-time patcher: GPU twin of `adv_patch.AdversarialPatch` (adv_patch.py:40-201).
  * Frames and patches are uint8 [h,w,3] RGB on the device; results are bit-identical to the
  * reference's NumPy + OpenCV code (8-bit fixed-point colour conversion, INTER_LINEAR letter-box,
- * INTER_AREA patch down-sampling).  The INTER_CUBIC branch (a box that needs the patch larger
- * than its texture) is not provided: EOT_ERR_BAD_SHAPE.
+ * INTER_AREA patch down-sampling, INTER_CUBIC patch up-sampling as OpenCV's own 8-bit kernel computes
+ * it -- pip wheels run that one call through Intel IPP, which differs by one grey level on ~4 % of
+ * the elements).
  * ------------------------------------------------------------------------------------------ */
 /* `_create` (adv_patch.py:61-92) for n boxes; HOST in, HOST out: placements[n,4] =
  * (ymin_patch, xmin_patch, patch_h, patch_w).  No GPU work (sizes the noise buffer). */

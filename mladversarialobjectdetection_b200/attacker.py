@@ -1,9 +1,9 @@
 """Host-side mirror of the reference's `attacker.py` for the hot path: `Patcher` (attacker.py:344-498) and
-`PatchAttacker` call / train_step / test_step / save_weights (attacker.py:24-342).
+`PatchAttacker` call / train_step / test_step / fit / save_weights (attacker.py:24-342).
 
-Same class names, constructor arguments and call signatures as the reference, so a script written against
-`attacker.PatchAttacker` keeps working; tensors are torch CUDA tensors (device memory + streams are the only
-thing torch provides here) and every per-pixel / per-anchor operation runs in libeotpatch.so:
+Same class names, constructor arguments, call signatures and metric names as the reference; what differs from the
+Keras surface is listed in INTEGRATION.md ("API differences").  Tensors are torch CUDA tensors (device memory +
+streams are the only thing torch provides here) and every per-pixel / per-anchor operation runs in libeotpatch.so:
 
     images' = Patcher([boxes, images])          -> eot_apply_fwd
     second_pass + max_scores + loss             -> victim forward (framework convs) + score_max_fwd
@@ -238,15 +238,26 @@ class PatchAttacker:
         (max_scores, argmax_anchor).  `boxes` overrides the first pass' detections (synthetic benchmarks)."""
         if training and self.cuda_graphs:
             return self._call_graphed(images, boxes, transforms)
-        det_boxes, _ = self.first_pass(images) if boxes is None or self.always_first_pass else (None, None)
+        det_boxes, det_scores = self.first_pass(images) if boxes is None or self.always_first_pass else (None, None)
+        if not isinstance(det_scores, list):
+            det_scores = None                                           # sync-free first pass: scores stay on the device
         if boxes is None:
             boxes = det_boxes
         patched = self._patcher([boxes, images], transforms=transforms)
         if not training:
+            # validation (attacker.py:318-326 -> call(training=False)): metrics of the same loss, and the reference's
+            # return value: the second pass' person boxes / scores after NMS (attacker.py:204, 219)
+            from . import postprocess
             with torch.no_grad():
-                _, M, argmax, _, _ = self.second_pass(patched)
-            self._record_metrics(M, None, None)
-            return M, argmax
+                cls_outputs, box_outputs, M, argmax, ncand, sctx = self._score(patched)
+                self._record_eval_metrics(M)
+                boxes_pred, scores_pred = postprocess.person_boxes_after_nms(
+                    self.config, sctx, box_outputs, self._anchor_table(patched), patched.shape[1:3], thresh=False)
+            self._last = dict(max_scores=M, argmax=argmax, ncand=ncand, first_pass_scores=det_scores, boxes=boxes)
+            if det_scores is not None:
+                asr = postprocess.calc_asr(det_scores, scores_pred)
+                self.metrics.update(asr=asr, asr_to_scale=asr / max(float(self._scale_regressor), 1e-12))
+            return boxes_pred, scores_pred
         patched.requires_grad_(True)
         cls_outputs, M, argmax, ncand, sctx = self.second_pass(patched)
         dcls, dscale, data_loss = ops.score_max_backward(sctx, self._scale_regressor)
@@ -254,6 +265,9 @@ class PatchAttacker:
         grad_patch = self._patcher.backward(patched.grad, grad_patch=self._grad_view())
         self._last = dict(max_scores=M, data_loss=data_loss, dscale=dscale, ncand=ncand)
         return [dscale, grad_patch]
+
+    def __call__(self, images, *, training=True, **kw):
+        return self.call(images, training=training, **kw)
 
     # -- steps -------------------------------------------------------------------------------------
     def _grad_view(self) -> torch.Tensor:
@@ -304,15 +318,59 @@ class PatchAttacker:
         return self.metrics
 
     def _record_metrics(self, M, buf, tv, B=None):
-        """add_metric calls of attacker.py:196-201 (device scalars; nothing is synchronised here)."""
-        if buf is not None:
-            n = self._patch.numel()
-            data_loss, s1, s2 = buf[n + 1], buf[n + 2], buf[n + 3]
-            mean = s1 / B
-            self.metrics = dict(loss=data_loss + 1e-5 * tv, scale=self._scale_regressor, tv_loss=tv,
-                                mean_max_score=mean, std_max_score=torch.sqrt(torch.clamp(s2 / B - mean * mean, min=0.0)))
-        elif M is not None:
-            self.metrics = dict(mean_max_score=M.mean(), std_max_score=M.std(unbiased=False), scale=self._scale_regressor)
+        """add_metric calls of attacker.py:196-201 (device scalars; nothing is synchronised here).  `asr` / `asr_to_scale`
+        need both passes' NMS results on the host and are recorded by the validation path only."""
+        n = self._patch.numel()
+        data_loss, s1, s2 = buf[n + 1], buf[n + 2], buf[n + 3]
+        mean = s1 / B
+        sc = self._scale_regressor
+        self.metrics = dict(loss=data_loss + 1e-5 * tv, scale=sc, tv_loss=tv,
+                            scale_loss=s2 - 2.0 * sc * s1 + B * sc * sc,       # sum_b (M_b - scale)^2 (attacker.py:191,198)
+                            mean_max_score=mean, std_max_score=torch.sqrt(torch.clamp(s2 / B - mean * mean, min=0.0)))
+
+    def _record_eval_metrics(self, M):
+        """the same metrics for a validation batch (attacker.py:190-201 run with training=False)."""
+        sc = self._scale_regressor
+        scale_losses = (M - sc) ** 2
+        tv = ops.tv_value(self._patch)
+        self.metrics = dict(loss=(M * M + scale_losses).sum() + 1e-5 * tv, scale=sc, scale_loss=scale_losses.sum(), tv_loss=tv,
+                            mean_max_score=M.mean(), std_max_score=M.std(unbiased=False))
+
+    def fit(self, train_data, validation_data=None, epochs: int = 1, steps_per_epoch: Optional[int] = None,
+            validation_steps: Optional[int] = None, save_dir: Optional[str] = None,
+            save_file: str = "patch_{epoch:02d}_{val_asr_to_scale:.4f}", verbose: bool = True):
+        """The loop `attacker_train.py:52-65` drives through Keras' Model.fit + ModelCheckpoint(save_weights_only=True,
+        save_freq='epoch'): per epoch `steps_per_epoch` train steps, `validation_steps` validation steps, epoch means
+        of the metrics (validation ones prefixed `val_`), one `save_weights` under `save_dir / save_file` (same name
+        template).  Batches are [B,H,W,3] float32 CUDA tensors (or anything `torch.as_tensor` takes); Keras callback
+        objects are not interpreted.  Returns the history as a list of dicts."""
+        def mean_metrics(acc, count, prefix=""):
+            return {prefix + k: float(v) / max(count, 1) for k, v in acc.items()}
+
+        def run(data, steps, step_fn):
+            acc, count = {}, 0
+            for i, batch in enumerate(data):
+                if steps is not None and i >= steps:
+                    break
+                x = torch.as_tensor(batch[0] if isinstance(batch, (tuple, list)) else batch, dtype=torch.float32, device=self.device)
+                for k, v in step_fn(x).items():
+                    acc[k] = acc.get(k, 0.0) + float(v)
+                count += 1
+            return acc, count
+
+        history = []
+        for epoch in range(1, epochs + 1):
+            logs = mean_metrics(*run(train_data, steps_per_epoch, self.train_step))
+            if validation_data is not None:
+                logs.update(mean_metrics(*run(validation_data, validation_steps, self.test_step), prefix="val_"))
+            logs["epoch"] = epoch
+            if save_dir is not None:
+                fmt = {"val_asr_to_scale": float("nan"), "val_loss": float("nan"), **logs}
+                self.save_weights(os.path.join(save_dir, save_file.format(**fmt)))
+            if verbose:
+                print("epoch %d: " % epoch + ", ".join(f"{k}={v:.4f}" for k, v in logs.items() if k != "epoch"))
+            history.append(logs)
+        return history
 
     def save_weights(self, dirpath, **kwargs):
         """save patch and current scale to disk (attacker.py:328-341): scale.txt, patch.png, patch.tiff."""

@@ -14,7 +14,9 @@
 //
 // Integer and float32 arithmetic is evaluated exactly as OpenCV's scalar code does (this TU is built with -fmad=false);
 // results are bit-identical to the reference run with opencv-python 4.13 (tests/golden/adv_patch_u8.npz).
-// Not provided: the INTER_CUBIC branch (patch up-sampling, adv_patch.py:158-160) -> EOT_ERR_BAD_SHAPE.
+// The INTER_CUBIC branch (patch up-sampling, adv_patch.py:158-160) follows OpenCV's own 8-bit bicubic kernel bit for
+// bit; pip wheels route that call through Intel IPP, whose closed-source evaluation differs by one grey level on ~4 % of
+// the elements (see oracle/adv_patch_u8.py).
 #include "eot_common.cuh"
 
 #include <math.h>
@@ -155,7 +157,27 @@ __device__ __forceinline__ void hsum3(const uint8_t* __restrict__ row, const Are
   }
 }
 
-// mode 0: no resize (patch side == target), 1: integer box sums (ix x iy cells), 2: general area tables
+// cv2.resize INTER_CUBIC on 8-bit data (resize.cpp, OpenCV's own kernel): source offset and 11-bit taps of a
+// destination index (interpolateCubic, A = -0.75, float32; saturate_cast<short> = round half to even).
+struct CubicTaps { int s; int a[4]; };
+__device__ __forceinline__ CubicTaps cubic_taps(int d, double scale) {
+  CubicTaps t;
+  const float f = (float)(((double)d + 0.5) * scale - 0.5);
+  const float fl = floorf(f);
+  t.s = (int)fl;
+  const float x = f - fl, A = -0.75f;
+  const float c0 = ((A * (x + 1.0f) - 5.0f * A) * (x + 1.0f) + 8.0f * A) * (x + 1.0f) - 4.0f * A;
+  const float c1 = ((A + 2.0f) * x - (A + 3.0f)) * x * x + 1.0f;
+  const float y = 1.0f - x;
+  const float c2 = ((A + 2.0f) * y - (A + 3.0f)) * y * y + 1.0f;
+  const float c3 = 1.0f - c0 - c1 - c2;
+  t.a[0] = __float2int_rn(c0 * 2048.0f); t.a[1] = __float2int_rn(c1 * 2048.0f);
+  t.a[2] = __float2int_rn(c2 * 2048.0f); t.a[3] = __float2int_rn(c3 * 2048.0f);
+  return t;
+}
+
+// mode 0: no resize (patch side == target), 1: integer box sums (ix x iy cells), 2: general area tables,
+// 3: INTER_CUBIC up-sampling (adv_patch.py:158-160)
 __global__ void __launch_bounds__(kThreads) k_adv_area_paste(const uint8_t* __restrict__ matched, int src_h, int src_w,
                                                              int ph, int pw, int mode, int ix, int iy, double scale_y,
                                                              double scale_x, const double* __restrict__ noise,
@@ -178,6 +200,40 @@ __global__ void __launch_bounds__(kThreads) k_adv_area_paste(const uint8_t* __re
         const float sc = 1.0f / (float)(ix * iy);
 #pragma unroll
         for (int c = 0; c < 3; ++c) v[c] = sat_u8(__float2int_rn((float)s[c] * sc));
+      }
+    } else if (mode == 3) {
+      // HResizeCubic (int32, replicated borders) of the four source rows, then VResizeCubic: the vectorised part of the
+      // row (8 elements per step in the baseline build) in float32 without fused multiply-adds, its tail with the
+      // 22-bit rounding shift
+      const CubicTaps tx = cubic_taps(dx, scale_x), ty = cubic_taps(dy, scale_y);
+      int hrow[4][3];
+#pragma unroll
+      for (int ky = 0; ky < 4; ++ky) {
+        const int sy = min(max(ty.s - 1 + ky, 0), src_h - 1);
+        hrow[ky][0] = hrow[ky][1] = hrow[ky][2] = 0;
+#pragma unroll
+        for (int kx = 0; kx < 4; ++kx) {
+          const int sx = min(max(tx.s - 1 + kx, 0), src_w - 1);
+          const uint8_t* q = matched + ((size_t)sy * src_w + sx) * 3;
+          hrow[ky][0] += (int)q[0] * tx.a[kx]; hrow[ky][1] += (int)q[1] * tx.a[kx]; hrow[ky][2] += (int)q[2] * tx.a[kx];
+        }
+      }
+      const int nvec = (pw * 3 / 8) * 8;
+      const float sc = 1.0f / (2048.0f * 2048.0f);
+      const float b0 = (float)ty.a[0] * sc, b1 = (float)ty.a[1] * sc, b2 = (float)ty.a[2] * sc, b3 = (float)ty.a[3] * sc;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (dx * 3 + c < nvec) {
+          float t = (float)hrow[3][c] * b3;
+          t = (float)hrow[2][c] * b2 + t;
+          t = (float)hrow[1][c] * b1 + t;
+          t = (float)hrow[0][c] * b0 + t;
+          v[c] = sat_u8(__float2int_rn(t));
+        } else {
+          const long long acc = (long long)hrow[0][c] * ty.a[0] + (long long)hrow[1][c] * ty.a[1] +
+                                (long long)hrow[2][c] * ty.a[2] + (long long)hrow[3][c] * ty.a[3];
+          v[c] = sat_u8((int)((acc + (1ll << 21)) >> 22));
+        }
       }
     } else {
       const AreaTaps tx = area_taps(dx, scale_x, src_w), ty = area_taps(dy, scale_y, src_h);
@@ -307,7 +363,6 @@ extern "C" int adv_u8_add_patches(uint8_t* frame, int32_t frame_h, int32_t frame
     int32_t pl[4];
     create_host(frame_h, frame_w, boxes + (size_t)i * 4, scale, pl);
     if (pl[2] <= 0 || pl[3] <= 0) { set_error("adv_u8_add_patches: box %d gives an empty patch (cv2.resize would fail)", i); return EOT_ERR_BAD_SHAPE; }
-    if (pl[2] > patch_h) { set_error("adv_u8_add_patches: box %d needs a %d px patch from a %d px texture: INTER_CUBIC up-sampling is not provided", i, pl[2], patch_h); return EOT_ERR_BAD_SHAPE; }
     if (pl[0] < 0 || pl[1] < 0 || pl[0] + pl[2] > frame_h || pl[1] + pl[3] > frame_w) { set_error("adv_u8_add_patches: box %d does not fit the frame", i); return EOT_ERR_BAD_SHAPE; }
     // resize() compares the heights only (adv_patch.py:154-160): equal height + different width would fail in the paste
     if (pl[2] == patch_h && pl[3] != patch_w) { set_error("adv_u8_add_patches: box %d: patch height matches the texture but the width does not", i); return EOT_ERR_BAD_SHAPE; }
@@ -327,6 +382,8 @@ extern "C" int adv_u8_add_patches(uint8_t* frame, int32_t frame_h, int32_t frame
     const double sc_x = (double)patch_w / (double)pw, sc_y = (double)patch_h / (double)ph;
     if (patch_h == ph) {
       mode = 0;                                                      // same height: no resize (validated above)
+    } else if (patch_h < ph) {
+      mode = 3;                                                      // bicubic up-sampling (adv_patch.py:158-160)
     } else {
       ix = (int)lrint(sc_x); iy = (int)lrint(sc_y);
       if (fabs(sc_x - ix) < 2.220446049250313e-16 && fabs(sc_y - iy) < 2.220446049250313e-16) mode = 1;

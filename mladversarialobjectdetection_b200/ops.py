@@ -110,6 +110,7 @@ class ApplyContext:
     workspace: torch.Tensor
     patch: torch.Tensor
     print_wb: torch.Tensor
+    generation: int = 0          # forward calls this workspace has served: a later forward invalidates the context
 
 
 def apply_forward(patch: torch.Tensor, scale: torch.Tensor, images: torch.Tensor, boxes: torch.Tensor,
@@ -141,7 +142,11 @@ def apply_forward(patch: torch.Tensor, scale: torch.Tensor, images: torch.Tensor
                                          _ptr(offsets), _ptr(params), _ptr(print_wb), _ptr(out), _ptr(mask),
                                          _ptr(workspace), ctypes.c_size_t(workspace.numel()), _stream()),
                "eot_apply_fwd")
-    return out, mask, ApplyContext(shape, workspace, patch, print_wb)
+    gen = getattr(workspace, "_eot_generation", 0) + 1
+    workspace._eot_generation = gen
+    if patch.dim() == 3 and not patch.is_contiguous():
+        patch = patch.contiguous()                     # the backward reads the shared patch densely: keep that copy
+    return out, mask, ApplyContext(shape, workspace, patch, print_wb, gen)
 
 
 def apply_backward(ctx: ApplyContext, grad_images: torch.Tensor, *, grad_patch: Optional[torch.Tensor] = None,
@@ -150,6 +155,9 @@ def apply_backward(ctx: ApplyContext, grad_images: torch.Tensor, *, grad_patch: 
     _need_cuda(grad_images)
     if ctx.shape.num_patches != 1:
         raise ValueError("the backward exists for the shared adversarial patch only (Masker carries no gradient)")
+    if getattr(ctx.workspace, "_eot_generation", ctx.generation) != ctx.generation:
+        raise RuntimeError("this ApplyContext is stale: its workspace has served a later eot_apply_fwd call "
+                           "(give the call whose gradient is needed its own workspace)")
     grad_images = _f32c(grad_images, "grad_images")
     P = ctx.shape.patch_size
     if grad_patch is None:
@@ -470,6 +478,12 @@ def tv_grad_(patch: torch.Tensor, grad_patch: torch.Tensor, weight: float = 1e-5
     _lib.check(_lib.load().patch_tv_grad(_ptr(_f32c(patch, "patch")), patch.shape[0], ctypes.c_float(weight),
                                          _ptr(grad_patch), _ptr(tv), _stream()), "patch_tv_grad")
     return tv
+
+
+def tv_value(patch: torch.Tensor) -> torch.Tensor:
+    """tf.image.total_variation(patch) as a device scalar (validation metrics; the gradient is not touched)."""
+    scratch = torch.zeros_like(patch)
+    return tv_grad_(patch, scratch, 0.0, want_tv=True)
 
 
 def adam_clip_(var: torch.Tensor, m: torch.Tensor, v: torch.Tensor, grad: torch.Tensor, step: int, *, lr: float,

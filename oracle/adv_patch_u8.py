@@ -12,9 +12,14 @@ PINNED, bit for bit:
     through both resizes (tests/test_oracle_adv_patch_u8.py);
   * against the reference's own `AdversarialPatch.add_adv_to_img` run in the build container on seeded frames
     (fixtures tests/golden/adv_patch_u8.npz, generator tests/golden/make_golden.py).
-NOT restated: the INTER_CUBIC branch of `resize` (patch up-sampling, adv_patch.py:158-160) -- the wheel's bicubic
-8-bit path is not reproduced by OpenCV's documented fixed-point formula (4.6 % of elements differ by 1); the
-restatement and the CUDA twin raise for it.
+INTER_CUBIC (patch up-sampling, adv_patch.py:158-160): `resize_cubic_u8` restates OpenCV's own 8-bit bicubic
+(resize.cpp: interpolateCubic with A = -0.75, coefficients quantised to 11 bits, integer horizontal pass, vertical pass
+in float32 for the vectorised part of a row and with the 22-bit rounding shift for its tail) and is bit-identical to cv2.resize of the installed OpenCV 4.13 with IPP switched off.
+The pip wheels (the reference pins opencv-python 4.5.5.64) route this one call through Intel IPP's closed-source
+ippiResizeCubic, whose output differs from OpenCV's own kernel by one grey level on about 4 % of the elements and is a
+float evaluation nobody can restate bit for bit (the closest open formulation found here -- float32 separable, double
+coordinates -- still misses ~1e-5 of the elements); the pinned target is therefore OpenCV's kernel, and the IPP build is
+reproduced to within one grey level (tests/test_oracle_adv_patch_u8.py states both).
 """
 from __future__ import annotations
 
@@ -137,6 +142,54 @@ def resize_linear_u8(img: np.ndarray, dw: int, dh: int) -> np.ndarray:
 
 
 # ---- adv_patch.AdversarialPatch -----------------------------------------------------------------------------
+def _cubic_tab(dsize: int, ssize: int):
+    """resize.cpp (INTER_CUBIC): source offset and the four 11-bit fixed-point taps of every destination index."""
+    scale = ssize / dsize
+    ofs = np.zeros(dsize, np.int64)
+    taps = np.zeros((dsize, 4), np.int64)
+    A = np.float32(-0.75)
+    one = np.float32(1.0)
+    for d in range(dsize):
+        f = np.float32((d + 0.5) * scale - 0.5)
+        s0 = int(np.floor(f))
+        x = np.float32(f - np.float32(s0))
+        c0 = ((A * (x + one) - np.float32(5) * A) * (x + one) + np.float32(8) * A) * (x + one) - np.float32(4) * A   # interpolateCubic
+        c1 = ((A + np.float32(2)) * x - (A + np.float32(3))) * x * x + one
+        y = one - x
+        c2 = ((A + np.float32(2)) * y - (A + np.float32(3))) * y * y + one
+        c3 = one - c0 - c1 - c2
+        taps[d] = np.rint(np.array([c0, c1, c2, c3], np.float32) * np.float32(2048)).astype(np.int64)     # saturate_cast<short>
+        ofs[d] = s0
+    return ofs, taps
+
+
+def resize_cubic_u8(img: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    """cv2.resize(img, (dw, dh), interpolation=cv2.INTER_CUBIC) on 8-bit data, OpenCV's own kernel (no IPP): taps at
+    offsets -1..2 with replicated borders, HResizeCubic in int32, VResizeCubic with FixedPtCast<int, uchar, 22>."""
+    sh, sw, _ = img.shape
+    xo, xa = _cubic_tab(dw, sw)
+    yo, ya = _cubic_tab(dh, sh)
+    S = img.astype(np.int64)
+    xi = np.clip(xo[:, None] + np.arange(-1, 3)[None, :], 0, sw - 1)
+    yi = np.clip(yo[:, None] + np.arange(-1, 3)[None, :], 0, sh - 1)
+    H = (S[:, xi, :] * xa[None, :, :, None]).sum(2)                               # [sh, dw, 3]
+    rows = H[yi, :, :].reshape(dh, 4, dw * 3)                                     # the four source rows of every output row
+    V = (rows * ya[:, :, None]).sum(1)
+    out = np.clip((V + (1 << 21)) >> 22, 0, 255).astype(np.uint8)                 # scalar tail: FixedPtCast<int, uchar, 22>
+    # VResizeCubicVec_32s8u (128-bit universal intrinsics of the baseline build: eight elements per step, no fused
+    # multiply-add): float32 evaluation S3*b3, then S2*b2 + t, S1*b1 + t, S0*b0 + t with b_k = beta_k / 2^22,
+    # round half to even.  Differs from the integer rounding on ~1e-5 of the elements.
+    nvec = (dw * 3 // 8) * 8
+    if nvec:
+        f = rows[:, :, :nvec].astype(np.float32)
+        bf = (ya.astype(np.float32) * np.float32(1.0 / (2048 * 2048)))[:, :, None]
+        t = f[:, 3] * bf[:, 3]
+        for k in (2, 1, 0):
+            t = f[:, k] * bf[:, k] + t
+        out[:, :nvec] = np.clip(np.rint(t), 0, 255).astype(np.uint8)
+    return out.reshape(dh, dw, 3)
+
+
 def print_patch(patch_u8: np.ndarray) -> np.ndarray:
     """adv_patch.py:40-59: deterministic print adjust, float64, truncating cast."""
     p = patch_u8 - 127.0
@@ -185,7 +238,7 @@ def transformed_patch(frame: np.ndarray, patch_printed: np.ndarray, output_size,
     if h > ph:
         patch = resize_area_u8(patch, pw, ph)
     elif h < ph:
-        raise NotImplementedError("INTER_CUBIC up-sampling of the patch is not restated (see the module docstring)")
+        patch = resize_cubic_u8(patch, pw, ph)
     p = patch - 127.0
     p /= 128.0
     p = np.clip(p + noise, -1.0, 1.0)

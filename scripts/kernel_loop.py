@@ -52,9 +52,9 @@ state = {}
 def one():
     res = {}
     if "fwd" in what:
-        ops.apply_forward(patch, scale, images, boxes, offsets, params, wb, geo, out=out, workspace=ctx.workspace)
+        state["ctx"] = ops.apply_forward(patch, scale, images, boxes, offsets, params, wb, geo, out=out, workspace=ctx.workspace)[2]
     if "bwd" in what:
-        ops.apply_backward(ctx, G, grad_patch=gp)
+        ops.apply_backward(state.get("ctx", ctx), G, grad_patch=gp)
     if "score" in what or "scoref" in what:
         r = ops.score_max_forward(cls, box, anc, (H, H))
         state["sctx"] = r[3]

@@ -10,3 +10,19 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    """A plain `pytest` on a box without CUDA (or without the built library) skips the gpu tests instead of failing them.
+    The product itself never falls back: with a GPU present a missing libeotpatch.so is an error, not a skip."""
+    try:
+        import torch
+        have_gpu = torch.cuda.is_available()
+    except Exception:
+        have_gpu = False
+    if have_gpu:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device on this host")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)

@@ -148,8 +148,13 @@ def gen_adv_patch_u8():
     cases = [((96, 96), [(10, 20, 90, 60), (30, 50, 70, 95)], 0.5),          # frame == output size
              ((72, 96), [(5, 5, 60, 40), (20, 40, 71, 90), (0, 0, 30, 30)], 0.5),
              ((192, 192), [(0, 40, 192, 120), (60, 60, 180, 150)], 0.5),      # exact 2x rescale; first box: patch side == P
-             ((150, 211), [(20, 30, 140, 100), (40, 100, 120, 200), (100, 10, 149, 60)], 0.4)]
+             ((150, 211), [(20, 30, 140, 100), (40, 100, 120, 200), (100, 10, 149, 60)], 0.4),
+             # boxes whose patch side exceeds the 96 px texture: the INTER_CUBIC branch (adv_patch.py:158-160); this case
+             # runs with IPP switched off -- OpenCV's own bicubic kernel, see oracle/adv_patch_u8.py
+             ((400, 420), [(10, 20, 390, 200), (30, 150, 330, 400), (100, 100, 200, 160)], 0.5)]
+    import cv2
     for k, (hw, boxes, scale) in enumerate(cases):
+        cv2.ipp.setUseIPP(k != 4)
         np.random.seed(100 + k)
         raw = (np.random.rand(P, P, 3) * 255).astype("uint8")               # what __init__ draws for patch_file=None
         np.random.seed(100 + k)
@@ -170,6 +175,7 @@ def gen_adv_patch_u8():
         out[f"result{k}"] = res
         for i, nz in enumerate(noises):
             out[f"noise{k}_{i}"] = nz
+    cv2.ipp.setUseIPP(True)
     np.savez_compressed(os.path.join(HERE, "adv_patch_u8.npz"), n=len(cases), P=P, **out)
 
 

@@ -31,10 +31,66 @@ def test_library_exports_every_declared_symbol():
     assert lib.eot_last_error() is not None
 
 
-def test_struct_sizes_match_header_layout():
-    # EotShape: 7 x int32/uint32 + 4 x float + pad + 3 x int64 ; EotBoxParams 48 B ; ScoreShape
-    assert ctypes.sizeof(_lib.EotShape) == 72
-    assert ctypes.sizeof(_lib.ScoreShape) == 4 * 4 + 4 * 8 + 4 + 3 * 4
+C_LAYOUT_PROBE = r"""
+#include <stddef.h>
+#include <stdio.h>
+#include "eotpatch.h"
+#define S(T) printf("sizeof %s %zu\n", #T, sizeof(T))
+#define O(T, f) printf("offsetof %s.%s %zu\n", #T, #f, offsetof(T, f))
+int main(void) {
+  S(EotShape); O(EotShape, batch); O(EotShape, height); O(EotShape, width); O(EotShape, patch_size); O(EotShape, num_patches);
+  O(EotShape, total_boxes); O(EotShape, flags); O(EotShape, tolerance); O(EotShape, noise_amp); O(EotShape, min_patch_area);
+  O(EotShape, max_scale); O(EotShape, patch_stride_n); O(EotShape, patch_stride_y); O(EotShape, patch_stride_x);
+  S(EotBoxParams); O(EotBoxParams, uy); O(EotBoxParams, delta); O(EotBoxParams, cos_t); O(EotBoxParams, pa); O(EotBoxParams, scale);
+  O(EotBoxParams, key0); O(EotBoxParams, key1);
+  S(EotBoxGeometry); O(EotBoxGeometry, span);
+  S(EotDrawConfig); O(EotDrawConfig, seed); O(EotDrawConfig, step); O(EotDrawConfig, first_image); O(EotDrawConfig, max_angle);
+  O(EotDrawConfig, max_delta); O(EotDrawConfig, perspective); O(EotDrawConfig, scale_lo); O(EotDrawConfig, scale_span);
+  S(ScoreShape); O(ScoreShape, level_locs); O(ScoreShape, total_anchors); O(ScoreShape, image_height); O(ScoreShape, min_area);
+  S(NmsShape); O(NmsShape, max_candidates); O(NmsShape, level_anchors); O(NmsShape, iou_threshold); O(NmsShape, image_width);
+  return 0;
+}
+"""
+
+
+def test_struct_layouts_match_a_c_compiler(tmp_path):
+    """include/eotpatch.h compiled as C11 by gcc: sizeof / offsetof of every struct that crosses the boundary against the
+    ctypes mirrors in _lib.py and the structured dtype the Python side packs EotBoxParams with."""
+    import shutil
+    import subprocess
+    import numpy as np
+    from mladversarialobjectdetection_b200 import synth
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "probe.c"
+    src.write_text(C_LAYOUT_PROBE)
+    exe = tmp_path / "probe"
+    subprocess.run([gcc, "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    mirrors = {"EotShape": _lib.EotShape, "EotDrawConfig": _lib.EotDrawConfig, "ScoreShape": _lib.ScoreShape, "NmsShape": _lib.NmsShape}
+    checked = 0
+    for line in out.splitlines():
+        kind, name, value = line.split()
+        value = int(value)
+        if kind == "sizeof":
+            if name in mirrors:
+                assert ctypes.sizeof(mirrors[name]) == value, line
+            elif name == "EotBoxParams":
+                assert synth.BOX_PARAMS.itemsize == value == 48, line
+            elif name == "EotBoxGeometry":
+                assert value == 32, line                    # ops.box_geometry reads int32 [N,8]
+        else:
+            struct, field = name.split(".")
+            if struct in mirrors:
+                assert getattr(mirrors[struct], field).offset == value, line
+            elif struct == "EotBoxParams":
+                np_name = {"cos_t": "cos"}.get(field, field)
+                assert synth.BOX_PARAMS.fields[np_name][1] == value, line
+            elif struct == "EotBoxGeometry":
+                assert value == 28, line
+        checked += 1
+    assert checked >= 40
 
 
 def test_workspace_bytes_and_shape_validation_without_gpu():
@@ -82,3 +138,23 @@ def test_new_entry_points_validate_shapes_without_gpu():
     assert lib.eot_channel_sums(None, 1, 4, 4, None, None) == 1
     assert lib.nhwc_bias_act_fwd(None, None, None, 4, 4, 1, None) == 1
     assert ctypes.sizeof(_lib.NmsShape) == 5 * 4 + 8 * 4 + 6 * 4
+
+
+def test_patch_tiff_is_read_back_by_an_independent_codec(tmp_path):
+    """patch.tiff written by patch_io (attacker.py:341: tifffile.imwrite of the float32 patch) read back with OpenCV's
+    libtiff (tifffile itself is not installed here); the reference reads it with tifffile.imread
+    (attack_detection.py:57), which takes any baseline float32 TIFF."""
+    import numpy as np
+    cv2 = pytest.importorskip("cv2")
+    from mladversarialobjectdetection_b200 import patch_io
+    patch = np.random.default_rng(4).uniform(-1, 1, (37, 53, 3)).astype(np.float32)
+    path = str(tmp_path / "patch.tiff")
+    patch_io.write_tiff_f32(path, patch)
+    back = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    assert back is not None and back.dtype == np.float32 and back.shape == patch.shape
+    np.testing.assert_array_equal(back[..., ::-1], patch)           # OpenCV hands colour images back as BGR
+    np.testing.assert_array_equal(patch_io.read_tiff_f32(path), patch)
+    patch_io.save_weights(str(tmp_path / "w"), patch, 0.4, (123.675, 116.28, 103.53), (58.395, 57.12, 57.375))
+    p2, s2 = patch_io.load_weights(str(tmp_path / "w"))
+    np.testing.assert_array_equal(p2, patch)
+    assert abs(s2 - 0.4) < 1e-7

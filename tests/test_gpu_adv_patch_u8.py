@@ -59,12 +59,28 @@ def test_device_frame_in_device_frame_out_and_no_boxes():
     assert changed[y:y + ph, x:x + pw].float().mean() > 0.9 and not changed[:y].any() and not changed[:, :x].any()
 
 
-def test_unsupported_and_invalid_boxes_raise_before_any_launch():
+def test_bicubic_upsampling_branch_against_oracle():
+    """boxes that need the patch larger than its texture (adv_patch.py:158-160, INTER_CUBIC), mixed with down-sampled
+    ones; also pinned by the last case of the reference fixture above."""
+    rng = np.random.default_rng(33)
+    for P, hw in [(32, (200, 240)), (100, (512, 512)), (48, (301, 277))]:
+        raw = rng.integers(0, 256, size=(P, P, 3), dtype=np.uint8)
+        frame = rng.integers(0, 256, size=hw + (3,), dtype=np.uint8)
+        H, W = hw
+        boxes = [(0, 0, 0.95 * H, 0.5 * W), (0.1 * H, 0.3 * W, 0.9 * H, 0.9 * W), (5, 5, 5 + P, 5 + 0.5 * P)]
+        ap = AdversarialPatch(scale=0.5, h=P, w=P, patch=raw)
+        pl = ap.placements(H, W, boxes)
+        assert any(int(p[2]) > P for p in pl) and any(int(p[2]) < P for p in pl)
+        noises = [rng.uniform(-0.01, 0.01, size=(int(p[2]), int(p[3]), 3)) for p in pl]
+        got = ap.add_adv_to_img(frame, boxes, noise=noises)
+        want = o.add_adv_to_img(frame, boxes, o.print_patch(raw), (P, P), 0.5, noises)
+        np.testing.assert_array_equal(got, want)
+
+
+def test_invalid_boxes_raise_before_any_launch():
     raw = np.zeros((32, 32, 3), np.uint8)
     ap = AdversarialPatch(scale=0.5, h=32, w=32, patch=raw)
     frame = np.zeros((200, 200, 3), np.uint8)
-    with pytest.raises(RuntimeError, match="INTER_CUBIC"):
-        ap.add_adv_to_img(frame, [(0, 0, 200, 100)])                   # needs a 100 px patch from a 32 px texture
     with pytest.raises(RuntimeError, match="empty patch"):
         ap.add_adv_to_img(frame, [(5, 5, 6, 6)])
 

@@ -269,3 +269,34 @@ def test_fused_bifpn_fusion_matches_torch_ops():
                 torch.testing.assert_close(xa[i].grad, xb[i].grad, rtol=1e-4, atol=1e-6)
         with torch.no_grad():
             torch.testing.assert_close(victim.fuse_silu(xs, w), ob, rtol=1e-5, atol=1e-6)
+
+
+def test_fit_loop_validation_return_values_and_checkpoint(tmp_path):
+    """the Keras-facing surface attacker_train.py drives: fit() -> train_step / test_step, epoch means, the
+    ModelCheckpoint-style save under `patch_{epoch:02d}_{val_asr_to_scale:.4f}`; call(training=False) returns the second
+    pass' (boxes, scores) as the reference does (attacker.py:219) and records the reference's metric names."""
+    import os
+    from mladversarialobjectdetection_b200 import patch_io
+    H, P, B = 128, 24, 2
+    torch.manual_seed(0)
+    model = victim.get_victim_model("efficientdet-d0", device="cuda", image_size=H)
+    att = PatchAttacker(model, patch_size=P, device="cuda", seed=2)
+    att.compile(learning_rate=1e-2)
+    bt = synth.make_batch(B, H, H, seed=5, max_boxes=2)
+    images = torch.from_numpy(bt.images).cuda()
+    hist = att.fit([images, images], validation_data=[images], epochs=2, steps_per_epoch=2, validation_steps=1,
+                   save_dir=str(tmp_path), verbose=False)
+    assert len(hist) == 2
+    for k in ("loss", "scale", "scale_loss", "tv_loss", "mean_max_score", "std_max_score", "val_loss", "val_scale_loss",
+              "val_tv_loss", "val_asr", "val_asr_to_scale"):
+        assert k in hist[-1], k
+    saved = sorted(os.listdir(tmp_path))
+    assert len(saved) == 2 and saved[0].startswith("patch_01_") and saved[1].startswith("patch_02_")
+    p2, s2 = patch_io.load_weights(os.path.join(str(tmp_path), saved[1]))
+    np.testing.assert_array_equal(p2, att._patch.cpu().numpy())
+    boxes_pred, scores_pred = att(images, training=False)
+    assert boxes_pred.nrows() == B and len(scores_pred) == B
+    # validation loss = sum(M^2 + (M - scale)^2) + 1e-5 TV, from the same pieces the training step reports
+    m = att.metrics
+    assert abs(float(m["loss"]) - (float(m["scale_loss"]) + B * (float(m["mean_max_score"]) ** 2 + float(m["std_max_score"]) ** 2)
+                                   + 1e-5 * float(m["tv_loss"]))) < 1e-4 * max(1.0, float(m["loss"]))

@@ -29,7 +29,7 @@ def test_print_patch_and_full_paste_match_reference_fixtures():
         np.testing.assert_array_equal(got, c["result"])
         assert (got != c["frame"]).any()
         n += 1
-    assert n == 4
+    assert n == 5          # the last case takes the INTER_CUBIC branch (boxes longer than twice the texture side)
 
 
 def test_create_matches_reference_create_fixture():
@@ -60,7 +60,23 @@ def test_resizes_against_cv2():
     np.testing.assert_array_equal(o.resize_linear_u8(im, 64, 32), cv2.resize(im, (64, 32)))   # exact 2x
 
 
-def test_upsampling_branch_is_refused():
-    frame = np.zeros((64, 64, 3), np.uint8)
-    with pytest.raises(NotImplementedError):
-        o.transformed_patch(frame, np.zeros((8, 8, 3), np.uint8), (8, 8), 16, 16, np.zeros((16, 16, 3)))
+def test_bicubic_upsampling_against_cv2():
+    """INTER_CUBIC on 8-bit data: bit-identical to OpenCV's own kernel (IPP off); the IPP build of the same call (what a
+    pip wheel runs by default) is a closed-source float evaluation that differs by at most one grey level."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(13)
+    had = cv2.ipp.useIPP()
+    try:
+        for _ in range(12):
+            sh, sw = (int(v) for v in rng.integers(8, 120, 2))
+            dh, dw = sh + int(rng.integers(1, 200)), sw + int(rng.integers(1, 200))
+            im = rng.integers(0, 256, size=(sh, sw, 3), dtype=np.uint8)
+            got = o.resize_cubic_u8(im, dw, dh)
+            cv2.ipp.setUseIPP(False)
+            np.testing.assert_array_equal(got, cv2.resize(im, (dw, dh), interpolation=cv2.INTER_CUBIC))
+            if had:
+                cv2.ipp.setUseIPP(True)
+                ipp = cv2.resize(im, (dw, dh), interpolation=cv2.INTER_CUBIC)
+                assert np.abs(got.astype(int) - ipp.astype(int)).max() <= 1
+    finally:
+        cv2.ipp.setUseIPP(had)
