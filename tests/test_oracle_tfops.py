@@ -98,3 +98,86 @@ def test_total_variation_gradient_numeric():
         xm = x.copy(); xm[idx] -= eps
         num = (tfops.total_variation(xp)[0] - tfops.total_variation(xm)[0]) / (2 * eps)
         assert abs(num - g[idx]) < 2e-2
+
+
+# ---- known answers derived by hand from the published TF / TFA algorithms (no TensorFlow needed) -------------------------
+def test_scale_and_translate_known_answers_4_to_2_and_3_to_5():
+    """tensorflow/core/kernels/image/scale_and_translate_op.cc, ComputeSpansCore with the triangle kernel, antialias=True.
+    4 -> 2: kernel scale 2, sample positions 1.0 and 3.0, taps |(k + .5 - s) / 2| -> weights (3,3,1)/7 at 0..2 and
+    (1,3,3)/7 at 1..3.   3 -> 5: kernel scale 1 (up-sampling), sample positions .3 .9 1.5 2.1 2.7 -> plain bilinear taps."""
+    starts, w, n = tfops.compute_spans(2, 4)
+    assert n == 4 and list(starts) == [0, 1]
+    np.testing.assert_allclose(w[0, :3], np.array([3, 3, 1], F) / F(7), rtol=0, atol=1e-7)
+    np.testing.assert_allclose(w[1, :3], np.array([1, 3, 3], F) / F(7), rtol=0, atol=1e-7)
+    assert w[0, 3] == 0 and w[1, 3] == 0
+    ramp = np.arange(4, dtype=F)
+    x = np.broadcast_to(ramp[:, None, None], (4, 4, 3)).copy()
+    np.testing.assert_allclose(tfops.aa_resize(x, 2, 2)[:, 0, 0], [5 / 7, 16 / 7], rtol=5e-7)       # float32 accumulation
+    starts, w, n = tfops.compute_spans(5, 3)
+    assert n == 3
+    x3 = np.array([1.0, 10.0, 100.0], F)
+    col = np.broadcast_to(x3[:, None, None], (3, 3, 3)).copy()
+    got = tfops.aa_resize(col, 5, 5)[:, 0, 0]
+    want = [1.0, 0.6 * 1 + 0.4 * 10, 10.0, 0.4 * 10 + 0.6 * 100, 100.0]
+    np.testing.assert_allclose(got, want, rtol=3e-7)
+
+
+def test_projective_transform_known_answer_90_degrees_on_a_ramp():
+    """tfa.image.rotate(+90 deg) = ImageProjectiveTransformV3 with angles_to_projective_transforms: for a 3x3 image
+    x_offset = ((W-1) - (cos (W-1) - sin (H-1))) / 2 = 2, y_offset = 0, so output(y, x) = input(row x, column 2 - y)."""
+    img = np.arange(9, dtype=F).reshape(3, 3, 1)
+    T = tfops.rotation_transform(F(0.0), F(1.0), 3)
+    np.testing.assert_allclose(T, [0, -1, 2, 1, 0, 0, 0, 0], atol=0)
+    out = tfops.projective_bilinear(img, T, -2.0)[..., 0]
+    np.testing.assert_array_equal(out, np.array([[2, 5, 8], [1, 4, 7], [0, 3, 6]], F))
+    # a half-pixel shift: bilinear blend with the fill value outside (CONSTANT fill mode)
+    Tshift = np.array([1, 0, 0.5, 0, 1, 0, 0, 0], F)
+    out = tfops.projective_bilinear(img, Tshift, -2.0)[..., 0]
+    np.testing.assert_array_equal(out[0], np.array([0.5, 1.5, 0.5 * 2 + 0.5 * -2.0], F))
+
+
+def test_projective_gradient_is_the_inverse_warp_with_zero_fill():
+    """tensorflow/python/ops/image_ops.py, _image_projective_transform_v3_grad: the registered gradient of the op is the
+    op itself applied to the incoming gradient with the INVERTED transform and fill 0 (not the scatter adjoint)."""
+    D = 23
+    rng = np.random.default_rng(6)
+    T = tfops.rotation_transform(F(np.cos(0.3)), F(np.sin(0.3)), D, F(1e-4), F(-2e-4))
+    for g in (np.eye(D, dtype=F)[:, :, None].repeat(3, 2), rng.normal(size=(D, D, 3)).astype(F)):
+        got = tfops.projective_bilinear_grad(g, T)
+        want = tfops.projective_bilinear(g, tfops.invert_transform(T), 0.0)
+        np.testing.assert_array_equal(got, want)
+    delta = np.zeros((D, D, 3), F)
+    delta[11, 7] = 1.0
+    back = tfops.projective_bilinear_grad(delta, T)
+    assert back.sum() > 0 and (back > 0).sum() <= 4 * 3          # one delta spreads over at most four taps
+
+
+def test_patcher_chain_gradient_against_finite_differences_without_rotation():
+    """Everything in the backward chain except the rotate gradient (whose definition is pinned above): with angle 0 the
+    warp is the identity sampling, so d(sum G * out)/d(patch) from the oracle's restated chain must agree with central
+    differences of the oracle's forward (resize adjoint, noise / delta pass-through, inner and outer clips away from
+    their kinks, print adjust, brightness-match mean term)."""
+    from mladversarialobjectdetection_b200 import synth
+    from oracle import patcher
+    H, P = 96, 20
+    bt = synth.make_batch(2, H, H, seed=41, max_boxes=2, min_boxes=2)
+    bt.params["cos"], bt.params["sin"] = F(1.0), F(0.0)
+    bt.params["delta"] = F(0.05)
+    bt.images *= F(0.5)
+    patch = (synth.make_patch(P, seed=41) * F(0.5)).astype(F)         # away from the clip limits
+    bx, pr = bt.ragged()
+    G = np.random.default_rng(42).normal(size=bt.images.shape).astype(F)
+
+    def loss(p):
+        out, _, _ = patcher.patcher_forward(p.astype(F), bt.images, bx, pr, bt.print_wb, 0.5)
+        return float((out.astype(np.float64) * G).sum())
+
+    _, _, states = patcher.patcher_forward(patch, bt.images, bx, pr, bt.print_wb, 0.5)
+    g = patcher.patcher_backward(G, patch, bt.print_wb, states, dtype=np.float64)
+    rng = np.random.default_rng(43)
+    eps = 2e-2
+    for _ in range(4):
+        d = rng.normal(size=patch.shape).astype(F)
+        num = (loss(patch + F(eps) * d) - loss(patch - F(eps) * d)) / (2 * eps)
+        ana = float((g * d).sum())
+        assert abs(num - ana) <= 2e-2 * max(1.0, abs(ana)), (num, ana)
