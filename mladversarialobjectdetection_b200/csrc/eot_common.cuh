@@ -366,15 +366,39 @@ struct Sampler {
 __device__ __forceinline__ int u_stride(int ps) { return ps + 4; }
 __device__ __forceinline__ int u_index(int ps, int ty, int tx) { return (ty + 2) * (ps + 4) + (tx + 2); }
 
-// Conservative range of window columns x in window row wy whose sample can touch the ps x ps core (affine T): outside
-// it all four taps are pad / fill and the box contributes nothing.  Half-pixel safety margins; the per-pixel core test
-// decides exactly.  Projective transforms: the whole row.
+// Conservative range of window columns x in window row wy whose sample can touch the ps x ps core: outside it all four
+// taps are pad / fill and the box contributes nothing.  Safety margins of a pixel and more; the per-pixel core test
+// decides exactly.  Affine T: l < T0 x + c0 < h and l < T3 x + c1 < h.  Projective T (denominator D(x) = T6 x + q positive
+// over the row, else the whole row): (T0 x + c0) / D(x) > L  <=>  (T0 - L T6) x > L q - c0, a half-line per bound.
+__device__ __forceinline__ void half_line(float a, float b, bool greater, float* lo, float* hi) {
+  // a * x > b (greater) or a * x < b, intersected into [lo, hi] with a one-pixel margin
+  if (fabsf(a) < 1e-6f) {
+    const bool holds = greater ? (0.0f > b - 1.0f) : (0.0f < b + 1.0f);   // a ~ 0: a * x ~ 0 for every column of the row
+    if (!holds) { *lo = 1.0f; *hi = 0.0f; }
+    return;
+  }
+  const float x0 = b / a;
+  if ((a > 0.0f) == greater) *lo = fmaxf(*lo, x0 - 1.0f);
+  else *hi = fminf(*hi, x0 + 1.0f);
+}
 __device__ __forceinline__ void row_core_range(const BoxPlan& pl, int wy, int* xa, int* xb) {
-  if (pl.T[6] != 0.0f || pl.T[7] != 0.0f) { *xa = 0; *xb = pl.d - 1; return; }
   const float yf = (float)wy;
   float lo = 0.0f, hi = (float)(pl.d - 1);
   const float clo = (float)pl.pad_lo, chi = (float)(pl.pad_lo + pl.ps);   // core bounds in padded window coordinates
   const float c0 = pl.T[1] * yf + pl.T[2], c1 = pl.T[4] * yf + pl.T[5];
+  if (pl.T[6] != 0.0f || pl.T[7] != 0.0f) {
+    const float q = pl.T[7] * yf + 1.0f;
+    const float d0 = q, d1 = pl.T[6] * hi + q;
+    if (!(d0 > 0.05f && d1 > 0.05f)) { *xa = 0; *xb = pl.d - 1; return; }   // denominator near / through zero: whole row
+    const float L = clo - 2.0f, U = chi + 1.0f;                    // half a pixel more slack than the affine bounds
+    half_line(pl.T[0] - L * pl.T[6], L * q - c0, true, &lo, &hi);
+    half_line(pl.T[0] - U * pl.T[6], U * q - c0, false, &lo, &hi);
+    half_line(pl.T[3] - L * pl.T[6], L * q - c1, true, &lo, &hi);
+    half_line(pl.T[3] - U * pl.T[6], U * q - c1, false, &lo, &hi);
+    *xa = max((int)floorf(lo) - 1, 0);
+    *xb = min((int)ceilf(hi) + 1, pl.d - 1);
+    return;
+  }
   {
     const float l = clo - 1.5f - c0, h = chi + 0.5f - c0;      // need l < T0*x < h
     if (pl.ia0 == 0.0f) { if (!(0.0f > l - 1.0f && 0.0f < h + 1.0f)) { lo = 1.0f; hi = 0.0f; } }

@@ -282,6 +282,8 @@ __device__ int geometry_block(const EotShape& s, const Layout& L, int j, const f
   return image;
 }
 
+constexpr int kMaxOrderedImages = 2048;   // batches beyond this keep the identity order (the ranking is quadratic in one CTA)
+
 // Exclusive prefix sums of the per-box work-item counts (one CTA; N is a few hundred to a few thousand).
 __device__ __forceinline__ int4 add4(int4 a, int4 b) { return make_int4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ void scan_block(int N, const int4* cnt, int4* base, int4* part /* [blockDim.x] shared */) {
@@ -451,16 +453,19 @@ __global__ void __launch_bounds__(kThreads) k_prepass(EotShape s, Layout L, cons
         const BoxPlan* pls = reinterpret_cast<const BoxPlan*>(ws + L.off_plans);
         int* order = reinterpret_cast<int*>(ws + L.off_order);
         const int B = s.batch;
-        if (B <= 2048) {
+        __shared__ unsigned s_cost[kMaxOrderedImages];
+        if (B <= kMaxOrderedImages) {
           for (int b = threadIdx.x; b < B; b += blockDim.x) {
-            long long mine = 0;
-            for (int j = min(offsets[b], n_geom); j < min(offsets[b + 1], n_geom); ++j) mine += pls[j].valid ? (long long)pls[j].ps * pls[j].ps : 0;
+            unsigned c = 0;
+            for (int j = min(offsets[b], n_geom); j < min(offsets[b + 1], n_geom); ++j)
+              c += pls[j].valid ? min((unsigned)pls[j].ps * (unsigned)pls[j].ps, 1u << 22) : 0u;
+            s_cost[b] = c;
+          }
+          __syncthreads();
+          for (int b = threadIdx.x; b < B; b += blockDim.x) {
+            const unsigned mine = s_cost[b];
             int rank = 0;
-            for (int o2 = 0; o2 < B; ++o2) {
-              long long c = 0;
-              for (int j = min(offsets[o2], n_geom); j < min(offsets[o2 + 1], n_geom); ++j) c += pls[j].valid ? (long long)pls[j].ps * pls[j].ps : 0;
-              rank += (c > mine || (c == mine && o2 < b)) ? 1 : 0;
-            }
+            for (int o2 = 0; o2 < B; ++o2) rank += (s_cost[o2] > mine || (s_cost[o2] == mine && o2 < b)) ? 1 : 0;
             order[rank] = b;
           }
         } else {

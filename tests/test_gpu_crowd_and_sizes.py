@@ -106,3 +106,60 @@ def test_draw_kernel_equals_the_torch_definition():
         assert torch.equal(got[:n, 8:10].view(torch.int32), ref[:, 8:10].view(torch.int32))   # Philox keys
         assert torch.allclose(got[:n, 3:5], ref[:, 3:5], rtol=0, atol=2e-7)                      # cos / sin (libdevice)
         assert torch.allclose(wb, s.print_wb(5, 40, 7, "cuda"), rtol=0, atol=2e-7)
+
+
+def test_no_writes_outside_the_callers_buffers():
+    """compute-sanitizer is closed on this GPU pool, so out-of-bounds writes are hunted with red zones of our own: every
+    buffer the C ABI writes (workspace, out images, masks, gradient) sits between canary blocks inside a larger
+    allocation, at odd sizes, and the canaries must survive a forward + backward (crowd, projective rows, out-of-range
+    image, mask output)."""
+    import ctypes
+    from mladversarialobjectdetection_b200 import _lib
+
+    def guarded(nbytes, align=256, pad=4096):
+        raw = torch.full((nbytes + 2 * pad + align,), 0xA5, dtype=torch.uint8, device="cuda")
+        off = pad + (-(raw.data_ptr() + pad)) % align
+        return raw, off, raw[off:off + nbytes]
+
+    def canaries_intact(raw, off, nbytes):
+        return bool((raw[:off] == 0xA5).all()) and bool((raw[off + nbytes:] == 0xA5).all())
+
+    for want_mask, persp, H, P, nb in [(False, 0.0, 150, 37, 9), (True, 3e-4, 131, 20, 5), (False, 2e-4, 97, 64, 40)]:
+        bt = synth.make_batch(3, H, H, seed=H, max_boxes=nb, min_boxes=max(1, nb // 2), perspective=persp)
+        bt.images[1] *= F(1.4)
+        d = to_device(bt)
+        patch = torch.from_numpy(synth.make_patch(P, seed=1)).cuda()
+        sc = torch.tensor(0.45, device="cuda")
+        geom = ops.PatchGeometry()
+        shape = ops._shape(d["images"], patch, int(bt.boxes.shape[0]), geom, want_mask)
+        need = ops.workspace_bytes(shape)
+        ws_raw, ws_off, ws = guarded(need)
+        nimg = d["images"].numel() * 4
+        out_raw, out_off, out_b = guarded(nimg, align=16)
+        out = out_b.view(torch.float32).view_as(d["images"])
+        lib = _lib.load()
+        mask_raw = mask_off = None
+        mask = None
+        if want_mask:
+            mask_raw, mask_off, mask_b = guarded(nimg, align=16)
+            mask = mask_b.view(torch.float32).view_as(d["images"])
+        _lib.check(lib.eot_apply_fwd(ctypes.byref(shape), ops._ptr(patch), ops._ptr(sc), ops._ptr(d["images"]), ops._ptr(d["boxes"]),
+                                     ops._ptr(d["offsets"]), ops._ptr(d["params"]), ops._ptr(d["print_wb"]), ops._ptr(out),
+                                     ops._ptr(mask), ops._ptr(ws), ctypes.c_size_t(need), ops._stream()), "eot_apply_fwd")
+        gp_raw, gp_off, gp_b = guarded(P * P * 3 * 4, align=16)
+        if not want_mask:
+            G = torch.randn_like(out)
+            _lib.check(lib.eot_apply_bwd(ctypes.byref(shape), ops._ptr(patch), ops._ptr(d["print_wb"]), ops._ptr(G), ops._ptr(ws),
+                                         ctypes.c_size_t(need), ops._ptr(gp_b), 0, ops._stream()), "eot_apply_bwd")
+        torch.cuda.synchronize()
+        assert canaries_intact(ws_raw, ws_off, need), "write outside the workspace"
+        assert canaries_intact(out_raw, out_off, nimg), "write outside out_images"
+        assert canaries_intact(gp_raw, gp_off, P * P * 3 * 4), "write outside grad_patch"
+        if want_mask:
+            assert canaries_intact(mask_raw, mask_off, nimg), "write outside out_masks"
+        # and the guarded run computes what the ordinary call computes
+        ref_out, ref_mask, _ = ops.apply_forward(patch, sc, d["images"], d["boxes"], d["offsets"], d["params"], d["print_wb"], geom,
+                                                 want_mask=want_mask)
+        assert torch.equal(out, ref_out)
+        if want_mask:
+            assert torch.equal(mask, ref_mask)
