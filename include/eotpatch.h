@@ -271,6 +271,15 @@ int adam_clip_update(float* var, float* m, float* v, const float* grad, int64_t 
                      float beta1, float beta2, float eps, int64_t step, float lo, float hi,
                      void* stream);
 
+/* Scalars of the step around the data-parallel exchange (attacker.py:190-201, 217): out4 = [dL/dscale, data loss,
+ * sum_b M_b, sum_b M_b^2] -- the tail of the packed buffer [dL/dpatch | out4] that is sum-all-reduced. */
+int attack_pack_scalars(const float* max_scores, int32_t batch, const float* dscale, const float* data_loss,
+                        float* out4, void* stream);
+/* out6 = [loss, scale_loss, mean_max_score, std_max_score, tv_loss, scale] from the (reduced) tail, TV(patch) and the
+ * scale variable: the add_metric values of attacker.py:196-201 as device scalars. */
+int attack_step_metrics(const float* tail4, const float* tv, const float* scale, float global_batch, float tv_weight,
+                        float* out6, void* stream);
+
 /* --------------------------------------------------------------------------------------------
  * Epilogue helpers of the torch stand-in of the victim (victim.py) -- not a reference interface:
  * the convolutions stay on the framework's cuDNN path; the per-channel bias add and the SiLU that

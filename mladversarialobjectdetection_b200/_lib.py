@@ -19,7 +19,7 @@ SYMBOLS = ["eot_last_error", "eot_version", "eot_launch_count", "eot_workspace_b
            "eot_apply_bwd", "eot_draw_transforms", "eot_brightness_match", "eot_check_workspace", "score_workspace_bytes", "score_max_fwd", "score_max_bwd",
            "person_nms_workspace_bytes", "person_nms", "eot_letterbox_normalize", "eot_channel_sums",
            "eot_augment_batch", "adv_u8_box_geometry", "adv_u8_print_patch", "adv_u8_workspace_bytes", "adv_u8_add_patches",
-           "patch_tv_grad", "adam_clip_update", "nhwc_bias_act_fwd", "nhwc_bias_silu_bwd",
+           "patch_tv_grad", "adam_clip_update", "attack_pack_scalars", "attack_step_metrics", "nhwc_bias_act_fwd", "nhwc_bias_silu_bwd",
            "nhwc_channel_scale", "nhwc_channel_dot", "nhwc_fuse_silu_fwd", "nhwc_fuse_silu_bwd"]
 
 
@@ -95,6 +95,8 @@ def _declare(lib):
     lib.nhwc_fuse_silu_fwd.argtypes = [ctypes.POINTER(vp), i32, vp, vp, i64, vp]
     lib.nhwc_fuse_silu_bwd.argtypes = [ctypes.POINTER(vp), i32, vp, vp, ctypes.POINTER(vp), i64, vp]
     lib.patch_tv_grad.argtypes = [vp, i32, f32, vp, vp, vp]
+    lib.attack_pack_scalars.argtypes = [vp, i32, vp, vp, vp, vp]
+    lib.attack_step_metrics.argtypes = [vp, vp, vp, f32, f32, vp, vp]
     lib.adam_clip_update.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i64, f32, f32, vp]
     for name in SYMBOLS:
         if name not in ("eot_last_error", "eot_launch_count"):

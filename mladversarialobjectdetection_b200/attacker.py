@@ -282,7 +282,7 @@ class PatchAttacker:
         buf = self._packed
         if grad_patch.data_ptr() != buf.data_ptr():
             buf[:n] = grad_patch.reshape(-1)
-        buf[n:] = torch.stack([dscale.reshape(()), self._last["data_loss"].reshape(()), M.sum(), torch.dot(M, M)])
+        ops.pack_scalars_(buf[n:], M, dscale, self._last["data_loss"])
         return buf
 
     def train_step(self, inputs, boxes: Optional[RaggedBoxes] = None, transforms=None, global_batch: Optional[int] = None):
@@ -299,8 +299,8 @@ class PatchAttacker:
         n = self._patch.numel()
         g_patch = buf[:n].view_as(self._patch)
         tv = ops.tv_grad_(self._patch, g_patch, 1e-5)                   # + 1e-5 * d TV/d patch, once (attacker.py:192-193)
-        self._apply_gradients(buf[n:n + 1], g_patch)
-        self._record_metrics(None, buf, tv, B)
+        self._record_metrics(None, buf, tv, B)                          # as the reference: metrics of the step's own variables,
+        self._apply_gradients(buf[n:n + 1], g_patch)                    # recorded before apply_gradients (attacker.py:196-201, 315)
         return self.metrics
 
     def _apply_gradients(self, g_scale: torch.Tensor, g_patch: torch.Tensor):
@@ -321,12 +321,8 @@ class PatchAttacker:
         """add_metric calls of attacker.py:196-201 (device scalars; nothing is synchronised here).  `asr` / `asr_to_scale`
         need both passes' NMS results on the host and are recorded by the validation path only."""
         n = self._patch.numel()
-        data_loss, s1, s2 = buf[n + 1], buf[n + 2], buf[n + 3]
-        mean = s1 / B
-        sc = self._scale_regressor
-        self.metrics = dict(loss=data_loss + 1e-5 * tv, scale=sc, tv_loss=tv,
-                            scale_loss=s2 - 2.0 * sc * s1 + B * sc * sc,       # sum_b (M_b - scale)^2 (attacker.py:191,198)
-                            mean_max_score=mean, std_max_score=torch.sqrt(torch.clamp(s2 / B - mean * mean, min=0.0)))
+        m = ops.step_metrics(buf[n:], tv, self._scale_regressor, B)             # one launch; the dict holds views of it
+        self.metrics = dict(loss=m[0], scale_loss=m[1], mean_max_score=m[2], std_max_score=m[3], tv_loss=m[4], scale=m[5])
 
     def _record_eval_metrics(self, M):
         """the same metrics for a validation batch (attacker.py:190-201 run with training=False)."""

@@ -45,9 +45,55 @@ __global__ void __launch_bounds__(kThreads) k_adam_clip(float* var, float* m, fl
   }
 }
 
+// tail of the packed all-reduce buffer: [dL/dscale, data loss, sum_b M_b, sum_b M_b^2] (attacker.py:190-201 needs the last two
+// for the mean / std metrics of the GLOBAL batch)
+__global__ void __launch_bounds__(kThreads) k_pack_scalars(const float* __restrict__ M, int batch, const float* __restrict__ dscale,
+                                                           const float* __restrict__ data_loss, float* out4) {
+  __shared__ double red[32];
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = threadIdx.x; i < batch; i += blockDim.x) { const double m = (double)M[i]; s1 += m; s2 += m * m; }
+  s1 = block_sum(s1, red);
+  s2 = block_sum(s2, red);
+  if (threadIdx.x == 0) { out4[0] = *dscale; out4[1] = *data_loss; out4[2] = (float)s1; out4[3] = (float)s2; }
+}
+
+// add_metric values of attacker.py:196-201 from the (all-reduced) tail: loss, scale_loss, mean / std of the max scores
+__global__ void k_step_metrics(const float* __restrict__ tail4, const float* __restrict__ tv, const float* __restrict__ scale,
+                               float global_batch, float tv_weight, float* out6) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float s1 = tail4[2], s2 = tail4[3], sc = *scale, B = global_batch;
+  const float mean = s1 / B;
+  out6[0] = tail4[1] + tv_weight * *tv;                           // loss = sum(M^2 + (M - scale)^2) + 1e-5 TV
+  out6[1] = s2 - 2.0f * sc * s1 + B * sc * sc;                     // scale_loss = sum (M - scale)^2
+  out6[2] = mean;
+  out6[3] = sqrtf(fmaxf(s2 / B - mean * mean, 0.0f));
+  out6[4] = *tv;
+  out6[5] = sc;
+}
+
 }  // namespace eot
 
 using namespace eot;
+
+extern "C" int attack_pack_scalars(const float* max_scores, int32_t batch, const float* dscale, const float* data_loss,
+                                   float* out4, void* stream) {
+  if (!max_scores || !dscale || !data_loss || !out4) { set_error("attack_pack_scalars: NULL pointer"); return EOT_ERR_NULL_POINTER; }
+  if (batch <= 0) { set_error("attack_pack_scalars: bad batch %d", batch); return EOT_ERR_BAD_SHAPE; }
+  k_pack_scalars<<<1, kThreads, 0, (cudaStream_t)stream>>>(max_scores, batch, dscale, data_loss, out4);
+  count_launches(1);
+  EOT_CHECK_CUDA(cudaPeekAtLastError());
+  return EOT_OK;
+}
+
+extern "C" int attack_step_metrics(const float* tail4, const float* tv, const float* scale, float global_batch, float tv_weight,
+                                   float* out6, void* stream) {
+  if (!tail4 || !tv || !scale || !out6) { set_error("attack_step_metrics: NULL pointer"); return EOT_ERR_NULL_POINTER; }
+  if (!(global_batch > 0.0f)) { set_error("attack_step_metrics: bad batch"); return EOT_ERR_BAD_SHAPE; }
+  k_step_metrics<<<1, 32, 0, (cudaStream_t)stream>>>(tail4, tv, scale, global_batch, tv_weight, out6);
+  count_launches(1);
+  EOT_CHECK_CUDA(cudaPeekAtLastError());
+  return EOT_OK;
+}
 
 extern "C" int patch_tv_grad(const float* patch, int32_t patch_size, float weight, float* grad_patch, float* tv_out,
                              void* stream) {

@@ -480,6 +480,22 @@ def tv_grad_(patch: torch.Tensor, grad_patch: torch.Tensor, weight: float = 1e-5
     return tv
 
 
+def pack_scalars_(out4: torch.Tensor, max_scores: torch.Tensor, dscale: torch.Tensor, data_loss: torch.Tensor) -> None:
+    """out4 <- [dL/dscale, data loss, sum M, sum M^2] (one launch; the tail of the packed all-reduce buffer)."""
+    _need_cuda(out4, max_scores, dscale, data_loss)
+    _lib.check(_lib.load().attack_pack_scalars(_ptr(_f32c(max_scores, "max_scores")), int(max_scores.numel()), _ptr(dscale),
+                                               _ptr(data_loss), _ptr(out4), _stream()), "attack_pack_scalars")
+
+
+def step_metrics(tail4: torch.Tensor, tv: torch.Tensor, scale: torch.Tensor, global_batch: int, tv_weight: float = 1e-5):
+    """[loss, scale_loss, mean_max_score, std_max_score, tv_loss, scale] as one float32 [6] device tensor (one launch)."""
+    _need_cuda(tail4, tv, scale)
+    out = torch.empty(6, dtype=torch.float32, device=tail4.device)
+    _lib.check(_lib.load().attack_step_metrics(_ptr(tail4), _ptr(tv), _ptr(scale), ctypes.c_float(float(global_batch)),
+                                               ctypes.c_float(tv_weight), _ptr(out), _stream()), "attack_step_metrics")
+    return out
+
+
 def tv_value(patch: torch.Tensor) -> torch.Tensor:
     """tf.image.total_variation(patch) as a device scalar (validation metrics; the gradient is not touched)."""
     scratch = torch.zeros_like(patch)
