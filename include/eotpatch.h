@@ -46,8 +46,8 @@ typedef struct EotBoxParams {
 } EotBoxParams;
 
 #define EOT_FLAG_MASK_OUTPUT 1u /* Masker: also write mask = original - pasted (attack_detection.py:429-430) */
-#define EOT_FLAG_SERIAL_ADJOINT 2u /* backward: per-image serial resize adjoint (no per-box partial buffer; the
-                                     default when that buffer would exceed 1 GiB) */
+#define EOT_FLAG_SERIAL_ADJOINT 2u /* accepted for compatibility: the backward always accumulates per image in shared
+                                     memory (no per-box partial buffers) since version 101 */
 
 typedef struct EotShape {
   int32_t batch;          /* B images held by this rank                                            */

@@ -70,5 +70,5 @@ StageTimer::~StageTimer() {
 }  // namespace eot
 
 extern "C" const char* eot_last_error(void) { return eot::g_err; }
-extern "C" int eot_version(void) { return 100; }
+extern "C" int eot_version(void) { return 101; }
 extern "C" uint64_t eot_launch_count(void) { return eot::g_launches.load(std::memory_order_relaxed); }
