@@ -262,7 +262,7 @@ __device__ __forceinline__ void composite_row_main(const SegBox& me, const BoxPl
                                                    const int2* __restrict__ rowtab, uint8_t* route_j, int lfull, int W, int j,
                                                    int wy, bool cand, bool others, int first, int last,
                                                    const float* __restrict__ img, float* o_img, float* m_img, int* open_count,
-                                                   int2* open_list, int open_cap, int lane) {
+                                                   int2* open_list, int open_cap, float one, int lane) {
   const int2 sp = __ldg(rowtab + (size_t)j * lfull + wy);
   if (sp.x > sp.y) return;
   const int S = me.S;
@@ -310,7 +310,11 @@ __device__ __forceinline__ void composite_row_main(const SegBox& me, const BoxPl
         const float ix = pc.ix, iy = pc.iy, fx = pc.fx, fy = pc.fy;
         const float wx1 = (fx + 1.0f) - ix, wx0 = ix - fx, wy1 = (fy + 1.0f) - iy, wy0 = iy - fy;
         float R[3];
+#if EOT_PACKED_MATH
+        blend3_packed(v00, v01, v10, v11, wx1, wx0, wy1, wy0, one, R);
+#else
         blend3(v00, v01, v10, v11, wx1, wx0, wy1, wy0, R);
+#endif
         const bool p0 = !(R[0] < -1.0f), p1 = !(R[1] < -1.0f), p2 = !(R[2] < -1.0f);   // attacker.py:440
         if (p0 || p1 || p2) {
           pasted = (unsigned)p0 | ((unsigned)p1 << 1) | ((unsigned)p2 << 2);
@@ -350,7 +354,7 @@ template <bool kMask>
 __global__ void __launch_bounds__(kThreads, EOT_COMP_MINB) k_composite3(EotShape s, Layout L, char* ws,
                                                                        const float* __restrict__ images, float* out, float* mask,
                                                                        const int32_t* __restrict__ offsets, int b0, int b1,
-                                                                       int group, int ngroups) {
+                                                                       int group, int ngroups, float one) {
   const int lane = threadIdx.x & 31;
   const BoxPlan* plans = reinterpret_cast<const BoxPlan*>(ws + L.off_plans);
   const float* ubuf = reinterpret_cast<const float*>(ws + L.off_u);
@@ -391,11 +395,11 @@ __global__ void __launch_bounds__(kThreads, EOT_COMP_MINB) k_composite3(EotShape
         if (me.t6 != 0.0f || me.t7 != 0.0f)
           composite_row_main<kMask, true>(me, plans, rowtab, routes + (size_t)j * L.rslot, lfull, W, j, wy, cand, others, first, last,
                                           images + img_off, out + img_off, kMask ? mask + img_off : nullptr, open_count, open_list,
-                                          open_cap, lane);
+                                          open_cap, one, lane);
         else
           composite_row_main<kMask, false>(me, plans, rowtab, routes + (size_t)j * L.rslot, lfull, W, j, wy, cand, others, first, last,
                                            images + img_off, out + img_off, kMask ? mask + img_off : nullptr, open_count, open_list,
-                                           open_cap, lane);
+                                           open_cap, one, lane);
       }
     }
     it = lo + tk.item(nxt);
@@ -482,10 +486,10 @@ int launch_composite3(const EotShape& s, const Layout& L, char* ws, const int32_
                       float* mask, int b0, int b1, int group, int ngroups, cudaStream_t st) {
   const int nsm = sm_count();
   if (mask) {
-    k_composite3<true><<<nsm * EOT_COMP_MINB, kThreads, 0, st>>>(s, L, ws, images, out, mask, offsets, b0, b1, group, ngroups);
+    k_composite3<true><<<nsm * EOT_COMP_MINB, kThreads, 0, st>>>(s, L, ws, images, out, mask, offsets, b0, b1, group, ngroups, 1.0f);
     k_composite_rest<true><<<nsm * 2, kThreads, 0, st>>>(s, L, ws, images, out, mask, offsets, b0, b1, group, ngroups);
   } else {
-    k_composite3<false><<<nsm * EOT_COMP_MINB, kThreads, 0, st>>>(s, L, ws, images, out, mask, offsets, b0, b1, group, ngroups);
+    k_composite3<false><<<nsm * EOT_COMP_MINB, kThreads, 0, st>>>(s, L, ws, images, out, mask, offsets, b0, b1, group, ngroups, 1.0f);
     k_composite_rest<false><<<nsm * 2, kThreads, 0, st>>>(s, L, ws, images, out, mask, offsets, b0, b1, group, ngroups);
   }
   count_launches(2);

@@ -341,7 +341,20 @@ __device__ void patch_stats_block(const EotShape& s, int b, int chunk, int nchun
 // sum of Y over the image (brightness_matcher.py:55,59,62,64) in float64.
 // ------------------------------------------------------------------------------------------------
 #ifndef EOT_PASS_PIX
-#define EOT_PASS_PIX 16
+#define EOT_PASS_PIX 8
+#endif
+#ifndef EOT_PASS_STREAM
+#define EOT_PASS_STREAM 0
+#endif
+#if EOT_PASS_STREAM >= 1
+#define EOT_PASS_LD(p) __ldcs(p)
+#else
+#define EOT_PASS_LD(p) __ldg(p)
+#endif
+#if EOT_PASS_STREAM >= 2
+#define EOT_PASS_ST(p, v) __stcs(p, v)
+#else
+#define EOT_PASS_ST(p, v) (*(p) = (v))
 #endif
 constexpr int kPassPixPerThread = EOT_PASS_PIX;   // batches of 2 x 4 pixels
 constexpr int kPassPixPerBlock = kThreads * kPassPixPerThread;
@@ -374,9 +387,9 @@ __device__ __forceinline__ void image_pass_block(int HW, int b, int chunk, const
         const int pix = pix0 + ((half * 2 + k) * kThreads + threadIdx.x) * 4;
         if (pix < HW) {
           const int q = (pix >> 2) * 3;
-          v[k][0] = __ldg(in4 + q);
-          v[k][1] = __ldg(in4 + q + 1);
-          v[k][2] = __ldg(in4 + q + 2);
+          v[k][0] = EOT_PASS_LD(in4 + q);
+          v[k][1] = EOT_PASS_LD(in4 + q + 1);
+          v[k][2] = EOT_PASS_LD(in4 + q + 2);
         }
       }
 #pragma unroll
@@ -385,7 +398,7 @@ __device__ __forceinline__ void image_pass_block(int HW, int b, int chunk, const
         if (pix < HW) {
           const int q = (pix >> 2) * 3;
           const float4 a = v[k][0], bb = v[k][1], c = v[k][2];
-          if (o) { o4[q] = a; o4[q + 1] = bb; o4[q + 2] = c; }
+          if (o) { EOT_PASS_ST(o4 + q, a); EOT_PASS_ST(o4 + q + 1, bb); EOT_PASS_ST(o4 + q + 2, c); }
           if (mk) { const float4 z = make_float4(0.f, 0.f, 0.f, 0.f); m4[q] = z; m4[q + 1] = z; m4[q + 2] = z; }
           acc += (double)luma_of(a.x, a.y, a.z);
           acc += (double)luma_of(a.w, bb.x, bb.y);

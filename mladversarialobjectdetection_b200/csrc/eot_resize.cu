@@ -7,10 +7,10 @@
 // shared-memory scratch and consumes it itself -- no CTA barrier, no strip staging, no cross-warp traffic.
 //   rows pass     lane = source column (128-bit loads of the RGBX matched patch, coalesced); the row's span start and
 //                 tap weights are warp-uniform registers
-//   columns pass  lane = output texel of the item's flat texel range (rows may be shorter than a warp: the item is swept
-//                 in 32-texel segments across its rows); per-texel tap table read coalesced; taps from the warp's scratch
-//   noise         Philox4x32-10 words of a segment (96 elements = 24-25 counter values) are produced by the first 25
-//                 lanes into the scratch and picked up by the texel lanes (stride 3 words: conflict-free)
+//   columns pass  lane = output column; the column's taps are fetched once and used for every row of the item; taps from
+//                 the warp's scratch
+//   noise         Philox4x32-10 words of 128 columns of a row (384 elements = 96 counter values: three rounds of the
+//                 full warp) are produced into the scratch and picked up by the texel lanes (stride 3 words: conflict-free)
 // Items are handed out by an atomic ticket per warp (fetched one item ahead, together with its (box, block) record
 // from the item table the geometry role wrote).
 //
@@ -20,14 +20,19 @@
 
 namespace eot {
 
+constexpr int kNoiseChunk = 128;                                   // texels per Philox round trip: 96 counters = 3 full warps
+constexpr int kNoiseWords = (kNoiseChunk * 3 / 4 + 1) * 4;          // words of one chunk (+ one counter when it starts unaligned)
+
 __host__ __device__ inline size_t resize_warp_smem(const EotShape& s, const Layout& L) {
-  return (size_t)L.rb * s.patch_size * 16 + 32 * 16;     // intermediate rows + Philox words (25 x uint4, padded)
+  // intermediate rows + the Philox words of one chunk per row of the item
+  return (size_t)L.rb * s.patch_size * 16 + (size_t)L.rb * kNoiseWords * 4;
 }
 
 // SPAN == 2: two-tap table; SPAN > 2: compile-time span from the tap-major weight table; SPAN == 0: run-time span.
 template <int SPAN>
 __device__ __forceinline__ void resize_item(const EotShape& s, const Layout& L, char* ws, const BoxPlan* __restrict__ pl, int j,
-                                            int blk, float4* inter, uint32_t* words, int lane) {
+                                            int blk, float4* inter, uint32_t* words, float one, int lane) {
+  constexpr int NS = SPAN > 2 ? SPAN : 1;
   const int P = s.patch_size;
   const int ps = pl->ps;
   const int span = SPAN > 2 ? SPAN : pl->span;
@@ -53,22 +58,27 @@ __device__ __forceinline__ void resize_item(const EotShape& s, const Layout& L, 
       for (int x = lane; x < P; x += 64) {
         const int x2 = min(x + 32, P - 1);                        // tail: recomputes the last column (same value)
         const float4 a0 = ra[x], b0 = rb[x], a1 = ra[x2], b1 = rb[x2];
+#if EOT_PACKED_MATH
+        irow[x] = lerp2_texel(a0, b0, wa, wb, one);
+        irow[x2] = lerp2_texel(a1, b1, wa, wb, one);
+#else
         irow[x] = make_float4(wa * a0.x + wb * b0.x, wa * a0.y + wb * b0.y, wa * a0.z + wb * b0.z, 0.0f);
         irow[x2] = make_float4(wa * a1.x + wb * b1.x, wa * a1.y + wb * b1.y, wa * a1.z + wb * b1.z, 0.0f);
+#endif
       }
     } else if (SPAN > 2) {
       const int st = __ldg(starts + oy);
-      float w[SPAN > 2 ? SPAN : 1];
-      int ro[SPAN > 2 ? SPAN : 1];
+      float w[NS];
+      int ro[NS];
 #pragma unroll
-      for (int k = 0; k < SPAN; ++k) { w[k] = __ldg(wts + k * ps + oy); ro[k] = min(st + k, P - 1) * P; }
+      for (int k = 0; k < NS; ++k) { w[k] = __ldg(wts + k * ps + oy); ro[k] = min(st + k, P - 1) * P; }
       for (int x = lane; x < P; x += 32) {
-        float4 v[SPAN > 2 ? SPAN : 1];
+        float4 v[NS];
 #pragma unroll
-        for (int k = 0; k < SPAN; ++k) v[k] = m4[ro[k] + x];
+        for (int k = 0; k < NS; ++k) v[k] = m4[ro[k] + x];
         float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
 #pragma unroll
-        for (int k = 0; k < SPAN; ++k) { a0 = a0 + w[k] * v[k].x; a1 = a1 + w[k] * v[k].y; a2 = a2 + w[k] * v[k].z; }
+        for (int k = 0; k < NS; ++k) { a0 = a0 + w[k] * v[k].x; a1 = a1 + w[k] * v[k].y; a2 = a2 + w[k] * v[k].z; }
         irow[x] = make_float4(a0, a1, a2, 0.0f);
       }
     } else {
@@ -85,62 +95,79 @@ __device__ __forceinline__ void resize_item(const EotShape& s, const Layout& L, 
     }
   }
   __syncwarp();
-  // ---- columns pass + noise + delta + clip over the item's flat texel range ----
-  const int ntex = nrows * ps;
-  const uint32_t e_base = (uint32_t)(r0 * ps) * 3u;              // noise element index of the item's first texel
+  // ---- columns pass + noise + delta + clip, chunks of kNoiseChunk output columns over all rows of the item ----
   const float amp = s.noise_amp;
-  const int rb = L.rb;
-  for (int seg = 0; seg < ntex; seg += 32) {
-    const uint32_t e0 = e_base + 3u * (uint32_t)seg;
-    const uint32_t g0 = e0 >> 2;
-    const int nel = 3 * min(32, ntex - seg);
-    const int ngroups = (int)(((e0 + (uint32_t)nel - 1u) >> 2) - g0) + 1;
-    if (lane < ngroups) reinterpret_cast<uint4*>(words)[lane] = philox4x32_10(g0 + (uint32_t)lane, key0, key1);
+  const float nlo = -amp, nrng = amp - nlo;                         // TF random_uniform range map: u * (hi - lo) + lo
+  for (int c0 = 0; c0 < ps; c0 += kNoiseChunk) {
+    const int cn = min(kNoiseChunk, ps - c0);                       // columns of this chunk
+    // Philox words of the chunk's elements, per row: element e = (row * ps + column) * 3 + channel sits in word e & 3 of
+    // counter e >> 2; 96 counters (3 rounds of the full warp) serve 128 texels
+    for (int r = 0; r < nrows; ++r) {
+      const uint32_t e0 = (uint32_t)((r0 + r) * ps + c0) * 3u;
+      const uint32_t g0 = e0 >> 2;
+      const int nctr = (int)(((e0 + (uint32_t)cn * 3u - 1u) >> 2) - g0) + 1;
+      uint4* wr = reinterpret_cast<uint4*>(words + r * kNoiseWords);
+      for (int c = lane; c < nctr; c += 32) wr[c] = philox4x32_10(g0 + (uint32_t)c, key0, key1);
+    }
     __syncwarp();
-    const int t = seg + lane;
-    if (t < ntex) {
-      int r = 0, ox = t;
-      if (ox >= ps) { ox -= ps; r = 1; }
-      if (rb > 2) {
-        if (ox >= ps) { ox -= ps; r = 2; }
-        if (ox >= ps) { ox -= ps; r = 3; }
-      }
-      const float4* irow = inter + r * P;
-      float a0, a1, a2;
-      if (SPAN == 2) {
-        const float4 tt = __ldg(tab2 + ox);
-        const float4 va = irow[__float_as_int(tt.x)], vb = irow[__float_as_int(tt.y)];
-        a0 = tt.z * va.x + tt.w * vb.x;
-        a1 = tt.z * va.y + tt.w * vb.y;
-        a2 = tt.z * va.z + tt.w * vb.z;
-      } else if (SPAN > 2) {
-        const int st = __ldg(starts + ox);
-        float w[SPAN > 2 ? SPAN : 1];
+    for (int seg = 0; seg < cn; seg += 32) {
+      const int oc = seg + lane;                                    // column inside the chunk
+      if (oc < cn) {
+        const int ox = c0 + oc;
+        // the column's taps are shared by the rows of the item
+        float4 tt;
+        int st = 0;
+        float w[NS];
+        if (SPAN == 2) {
+          tt = __ldg(tab2 + ox);
+        } else {
+          st = __ldg(starts + ox);
+          if (SPAN > 2) {
 #pragma unroll
-        for (int k = 0; k < SPAN; ++k) w[k] = __ldg(wts + k * ps + ox);
-        a0 = 0.0f; a1 = 0.0f; a2 = 0.0f;
-#pragma unroll
-        for (int k = 0; k < SPAN; ++k) {
-          const float4 v = irow[min(st + k, P - 1)];
-          a0 = a0 + w[k] * v.x; a1 = a1 + w[k] * v.y; a2 = a2 + w[k] * v.z;
+            for (int k = 0; k < NS; ++k) w[k] = __ldg(wts + k * ps + ox);
+          }
         }
-      } else {
-        const int st = __ldg(starts + ox);
-        a0 = 0.0f; a1 = 0.0f; a2 = 0.0f;
-        for (int k = 0; k < span; ++k) {
-          const float wk = __ldg(wts + k * ps + ox);
-          const float4 v = irow[min(st + k, P - 1)];
-          a0 = a0 + wk * v.x; a1 = a1 + wk * v.y; a2 = a2 + wk * v.z;
+        for (int r = 0; r < nrows; ++r) {
+          const float4* irow = inter + r * P;
+          float a0, a1, a2;
+          if (SPAN == 2) {
+            const float4 va = irow[__float_as_int(tt.x)], vb = irow[__float_as_int(tt.y)];
+#if EOT_PACKED_MATH
+            const float4 ab = lerp2_texel(va, vb, tt.z, tt.w, one);
+            a0 = ab.x; a1 = ab.y; a2 = ab.z;
+#else
+            a0 = tt.z * va.x + tt.w * vb.x;
+            a1 = tt.z * va.y + tt.w * vb.y;
+            a2 = tt.z * va.z + tt.w * vb.z;
+#endif
+          } else if (SPAN > 2) {
+            a0 = 0.0f; a1 = 0.0f; a2 = 0.0f;
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+              const float4 v = irow[min(st + k, P - 1)];
+              a0 = a0 + w[k] * v.x; a1 = a1 + w[k] * v.y; a2 = a2 + w[k] * v.z;
+            }
+          } else {
+            a0 = 0.0f; a1 = 0.0f; a2 = 0.0f;
+            for (int k = 0; k < span; ++k) {
+              const float wk = __ldg(wts + k * ps + ox);
+              const float4 v = irow[min(st + k, P - 1)];
+              a0 = a0 + wk * v.x; a1 = a1 + wk * v.y; a2 = a2 + wk * v.z;
+            }
+          }
+          const uint32_t e0 = (uint32_t)((r0 + r) * ps + c0) * 3u;
+          const uint32_t* wp = words + r * kNoiseWords + ((e0 & 3u) + 3u * (uint32_t)oc);
+          // TF Uint32ToFloat: mantissa bits -> [1,2) - 1
+          const float n0 = (__uint_as_float((wp[0] & 0x7FFFFFu) | 0x3F800000u) - 1.0f) * nrng + nlo;
+          const float n1 = (__uint_as_float((wp[1] & 0x7FFFFFu) | 0x3F800000u) - 1.0f) * nrng + nlo;
+          const float n2 = (__uint_as_float((wp[2] & 0x7FFFFFu) | 0x3F800000u) - 1.0f) * nrng + nlo;
+          const float v0 = (a0 + n0) + delta, v1 = (a1 + n1) + delta, v2 = (a2 + n2) + delta;
+          const unsigned bits = (unsigned)(fabsf(v0) <= 1.0f) | ((unsigned)(fabsf(v1) <= 1.0f) << 1) |
+                                ((unsigned)(fabsf(v2) <= 1.0f) << 2);
+          u4[(r0 + r + 2) * S + ox + 2] =
+              make_float4(clampf(v0, -1.0f, 1.0f), clampf(v1, -1.0f, 1.0f), clampf(v2, -1.0f, 1.0f), __uint_as_float(bits));
         }
       }
-      const uint32_t* wp = words + ((e0 & 3u) + 3u * (uint32_t)lane);
-      const float v0 = (a0 + noise_from_word(wp[0], amp)) + delta;
-      const float v1 = (a1 + noise_from_word(wp[1], amp)) + delta;
-      const float v2 = (a2 + noise_from_word(wp[2], amp)) + delta;
-      const unsigned bits = (unsigned)(fabsf(v0) <= 1.0f) | ((unsigned)(fabsf(v1) <= 1.0f) << 1) |
-                            ((unsigned)(fabsf(v2) <= 1.0f) << 2);
-      u4[(r0 + r + 2) * S + ox + 2] =
-          make_float4(clampf(v0, -1.0f, 1.0f), clampf(v1, -1.0f, 1.0f), clampf(v2, -1.0f, 1.0f), __uint_as_float(bits));
     }
     __syncwarp();
   }
@@ -151,7 +178,7 @@ __device__ __forceinline__ void resize_item(const EotShape& s, const Layout& L, 
 #endif
 __global__ void __launch_bounds__(kThreads, EOT_RESIZE_MINB) k_resize2(EotShape s, Layout L, char* ws,
                                                                       const int32_t* __restrict__ offsets, int b0, int b1,
-                                                                      int ticket_slot) {
+                                                                      int ticket_slot, float one) {
   extern __shared__ __align__(16) unsigned char resize_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t per_warp = resize_warp_smem(s, L);
@@ -169,12 +196,12 @@ __global__ void __launch_bounds__(kThreads, EOT_RESIZE_MINB) k_resize2(EotShape 
     const int nxt = tk.draw(lane);                    // next item's ticket travels while this one computes
     const BoxPlan* pl = plans + item.x;
     const int mode = pl->two_tap ? 2 : pl->span;
-    if (mode == 2) resize_item<2>(s, L, ws, pl, item.x, item.y, inter, words, lane);
-    else if (mode == 5) resize_item<5>(s, L, ws, pl, item.x, item.y, inter, words, lane);
-    else if (mode == 7) resize_item<7>(s, L, ws, pl, item.x, item.y, inter, words, lane);
-    else if (mode == 3) resize_item<3>(s, L, ws, pl, item.x, item.y, inter, words, lane);
-    else if (mode == 9) resize_item<9>(s, L, ws, pl, item.x, item.y, inter, words, lane);
-    else resize_item<0>(s, L, ws, pl, item.x, item.y, inter, words, lane);
+    if (mode == 2) resize_item<2>(s, L, ws, pl, item.x, item.y, inter, words, one, lane);
+    else if (mode == 5) resize_item<5>(s, L, ws, pl, item.x, item.y, inter, words, one, lane);
+    else if (mode == 7) resize_item<7>(s, L, ws, pl, item.x, item.y, inter, words, one, lane);
+    else if (mode == 3) resize_item<3>(s, L, ws, pl, item.x, item.y, inter, words, one, lane);
+    else if (mode == 9) resize_item<9>(s, L, ws, pl, item.x, item.y, inter, words, one, lane);
+    else resize_item<0>(s, L, ws, pl, item.x, item.y, inter, words, one, lane);
     it = lo + tk.item(nxt);
     if (it < hi) item = __ldcg(items + it);
   }
@@ -192,7 +219,7 @@ int launch_resize2(const EotShape& s, const Layout& L, char* ws, const int32_t* 
   int per_sm = EOT_RESIZE_MINB;
   const size_t budget = 220 * 1024;
   while (per_sm > 1 && (smem + 1024) * per_sm > budget) --per_sm;
-  k_resize2<<<sm_count() * per_sm, kThreads, smem, st>>>(s, L, ws, offsets, b0, b1, ticket_slot);
+  k_resize2<<<sm_count() * per_sm, kThreads, smem, st>>>(s, L, ws, offsets, b0, b1, ticket_slot, 1.0f);
   count_launches(1);
   return EOT_OK;
 }
