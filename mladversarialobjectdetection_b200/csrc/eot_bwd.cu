@@ -56,12 +56,15 @@ __device__ __forceinline__ void window_grad_texel(const BoxPlan& me, const Windo
     ix = ix / proj;
     iy = iy / proj;
   }
-  const float x0f = floorf(ix), y0f = floorf(iy);
+  // floorf for |v| < 2^22 as two full-rate additions (v + 1.5 * 2^23 rounded down; the integer sits in the mantissa);
+  // anything further out (or NaN) lands outside the window in the tests below, as it must
+  const float mx = __fadd_rd(ix, 12582912.0f), my = __fadd_rd(iy, 12582912.0f);
+  const float x0f = mx - 12582912.0f, y0f = my - 12582912.0f;
   const float wx0 = ix - x0f, wx1 = (x0f + 1.0f) - ix, wy0 = iy - y0f, wy1 = (y0f + 1.0f) - iy;
   const int D = wc.D, W = wc.W;
   float v00[3], v01[3], v10[3], v11[3];
   if (x0f >= 0.0f && x0f < wc.Dm1 && y0f >= 0.0f && y0f < wc.Dm1) {            // all four taps inside the window
-    const int xi0 = (int)x0f, yi0 = (int)y0f;
+    const int xi0 = __float_as_int(mx) - 0x4B400000, yi0 = __float_as_int(my) - 0x4B400000;
     const int rt = yi0 * D + xi0, px = yi0 * W + xi0;
     // the four route bytes first, then all (predicated) gradient loads: one round trip each, not two per row
     const unsigned r00 = wc.route[rt], r01 = wc.route[rt + 1], r10 = wc.route[rt + D], r11 = wc.route[rt + D + 1];
@@ -76,7 +79,7 @@ __device__ __forceinline__ void window_grad_texel(const BoxPlan& me, const Windo
 #pragma unroll
     for (int c = 0; c < 3; ++c) v00[c] = v01[c] = v10[c] = v11[c] = 0.0f;
     if (!((bx0 || bx1) && (by0 || by1))) return;
-    const int xi0 = (int)x0f, yi0 = (int)y0f;
+    const int xi0 = __float_as_int(mx) - 0x4B400000, yi0 = __float_as_int(my) - 0x4B400000;
     const int rt = yi0 * D + xi0, px = yi0 * W + xi0;
     if (by0 && bx0) routed_grad3(wc.route, wc.Gwin, rt, px, v00);
     if (by0 && bx1) routed_grad3(wc.route, wc.Gwin, rt + 1, px + 1, v01);
@@ -93,6 +96,7 @@ __device__ __forceinline__ void window_grad_texel(const BoxPlan& me, const Windo
 //   columns pass  acc[r][px]  += sum_{k: ox0 <= st(px) + k < ox0 + cw} wT[px][k] * inter[r][st(px) + k - ox0]
 template <int TK>
 __device__ __forceinline__ void adjoint_passes(int P, int oy_last, int tstride, int py0, int rows, int oy_lo, int ox0, int cw,
+                                               int ncols_total,
                                                const float4* tile, float4* inter, const float* s_wt, const int2* s_st,
                                                float* acc) {
   const float inv_cw = 1.0f / (float)cw;
@@ -121,18 +125,32 @@ __device__ __forceinline__ void adjoint_passes(int P, int oy_last, int tstride, 
   }
   __syncthreads();
   const int P3 = P * 3;
+  const float inv_P = 1.0f / (float)P;
+  const bool whole = TK > 0 && ox0 == 0 && ncols_total == cw;     // the chunk is the whole box width
   for (int idx = threadIdx.x; idx < rows * P; idx += blockDim.x) {
-    const int r = idx / P, px = idx - r * P;
+    int r = (int)(((float)idx + 0.5f) * inv_P);
+    int px = idx - r * P;
+    if (px < 0) { --r; px += P; } else if (px >= P) { ++r; px -= P; }
     const int2 sc = s_st[px];
-    const int k0 = max(0, ox0 - sc.x), k1 = min(sc.y, ox0 + cw - sc.x);      // this chunk's share of the taps of px
-    if (k0 >= k1) continue;
     const float* w = s_wt + px * tstride;
-    const float4* irow = inter + r * cw - ox0;
     float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
-    for (int k = k0; k < k1; ++k) {
-      const float4 v = irow[sc.x + k];
-      const float wk = w[k];
-      a0 += wk * v.x; a1 += wk * v.y; a2 += wk * v.z;
+    if (whole) {                                                  // fixed tap count: zero-weight padded taps at a clamped column
+      const float4* irow = inter + r * cw;
+#pragma unroll
+      for (int k = 0; k < (TK > 0 ? TK : 1); ++k) {
+        const float4 v = irow[min(sc.x + k, cw - 1)];
+        const float wk = w[k];
+        a0 += wk * v.x; a1 += wk * v.y; a2 += wk * v.z;
+      }
+    } else {
+      const int k0 = max(0, ox0 - sc.x), k1 = min(sc.y, ox0 + cw - sc.x);    // this chunk's share of the taps of px
+      if (k0 >= k1) continue;
+      const float4* irow = inter + r * cw - ox0;
+      for (int k = k0; k < k1; ++k) {
+        const float4 v = irow[sc.x + k];
+        const float wk = w[k];
+        a0 += wk * v.x; a1 += wk * v.y; a2 += wk * v.z;
+      }
     }
     float* o = acc + r * P3 + px * 3;
     o[0] += a0; o[1] += a1; o[2] += a2;
@@ -256,11 +274,11 @@ __global__ void __launch_bounds__(kThreads, EOT_BWD_MINB) k_bwd_image(EotShape s
         }
         __syncthreads();
         // B + C
-        if (tstride == 3) adjoint_passes<3>(P, oy_hi - 1, tstride, py0, rows, oy_lo, ox0, cw, tile, inter, s_wt, s_st, acc);
-        else if (tstride == 4) adjoint_passes<4>(P, oy_hi - 1, tstride, py0, rows, oy_lo, ox0, cw, tile, inter, s_wt, s_st, acc);
-        else if (tstride == 5) adjoint_passes<5>(P, oy_hi - 1, tstride, py0, rows, oy_lo, ox0, cw, tile, inter, s_wt, s_st, acc);
-        else if (tstride == 6) adjoint_passes<6>(P, oy_hi - 1, tstride, py0, rows, oy_lo, ox0, cw, tile, inter, s_wt, s_st, acc);
-        else adjoint_passes<0>(P, oy_hi - 1, tstride, py0, rows, oy_lo, ox0, cw, tile, inter, s_wt, s_st, acc);
+        if (tstride == 3) adjoint_passes<3>(P, oy_hi - 1, tstride, py0, rows, oy_lo, ox0, cw, ps, tile, inter, s_wt, s_st, acc);
+        else if (tstride == 4) adjoint_passes<4>(P, oy_hi - 1, tstride, py0, rows, oy_lo, ox0, cw, ps, tile, inter, s_wt, s_st, acc);
+        else if (tstride == 5) adjoint_passes<5>(P, oy_hi - 1, tstride, py0, rows, oy_lo, ox0, cw, ps, tile, inter, s_wt, s_st, acc);
+        else if (tstride == 6) adjoint_passes<6>(P, oy_hi - 1, tstride, py0, rows, oy_lo, ox0, cw, ps, tile, inter, s_wt, s_st, acc);
+        else adjoint_passes<0>(P, oy_hi - 1, tstride, py0, rows, oy_lo, ox0, cw, ps, tile, inter, s_wt, s_st, acc);
       }
     }
     __syncthreads();

@@ -410,8 +410,11 @@ __global__ void __launch_bounds__(kThreads, EOT_COMP_MINB) k_composite3(EotShape
 // The rest: (1) the open pixels k_composite3 listed, one lane each: the older boxes of the image whose range covers the
 // pixel are sampled newest first for the channels still open; (2) whole rows of the items k_composite3 skipped (and of
 // every item, should the list have overflowed) through composite_row_general.
+#ifndef EOT_REST_MINB
+#define EOT_REST_MINB 2
+#endif
 template <bool kMask>
-__global__ void __launch_bounds__(kThreads) k_composite_rest(EotShape s, Layout L, char* ws, const float* __restrict__ images,
+__global__ void __launch_bounds__(kThreads, EOT_REST_MINB) k_composite_rest(EotShape s, Layout L, char* ws, const float* __restrict__ images,
                                                              float* out, float* mask, const int32_t* __restrict__ offsets, int b0,
                                                              int b1, int group, int ngroups) {
   const int lane = threadIdx.x & 31;
@@ -487,10 +490,10 @@ int launch_composite3(const EotShape& s, const Layout& L, char* ws, const int32_
   const int nsm = sm_count();
   if (mask) {
     k_composite3<true><<<nsm * EOT_COMP_MINB, kThreads, 0, st>>>(s, L, ws, images, out, mask, offsets, b0, b1, group, ngroups, 1.0f);
-    k_composite_rest<true><<<nsm * 2, kThreads, 0, st>>>(s, L, ws, images, out, mask, offsets, b0, b1, group, ngroups);
+    k_composite_rest<true><<<nsm * EOT_REST_MINB, kThreads, 0, st>>>(s, L, ws, images, out, mask, offsets, b0, b1, group, ngroups);
   } else {
     k_composite3<false><<<nsm * EOT_COMP_MINB, kThreads, 0, st>>>(s, L, ws, images, out, mask, offsets, b0, b1, group, ngroups, 1.0f);
-    k_composite_rest<false><<<nsm * 2, kThreads, 0, st>>>(s, L, ws, images, out, mask, offsets, b0, b1, group, ngroups);
+    k_composite_rest<false><<<nsm * EOT_REST_MINB, kThreads, 0, st>>>(s, L, ws, images, out, mask, offsets, b0, b1, group, ngroups);
   }
   count_launches(2);
   return EOT_OK;

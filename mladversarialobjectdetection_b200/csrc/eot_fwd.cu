@@ -436,8 +436,11 @@ __device__ __forceinline__ void image_pass_block(int HW, int b, int chunk, const
 //   [0, n_geom)                         geometry of box j                   (n_geom = N or 0)
 //   [.., + n_stat_imgs*pchunks)         patch luma statistics               (n_stat_imgs = B or 0)
 //   [.., + (b1-b0)*cpi)                 image pass (copy + luma sum) of images [b0,b1), the HBM-bound bulk
+#ifndef EOT_PREPASS_MINB
+#define EOT_PREPASS_MINB 6
+#endif
 template <bool kVec>
-__global__ void __launch_bounds__(kThreads) k_prepass(EotShape s, Layout L, const float* __restrict__ patch,
+__global__ void __launch_bounds__(kThreads, EOT_PREPASS_MINB) k_prepass(EotShape s, Layout L, const float* __restrict__ patch,
                                                       const float* __restrict__ print_wb, const float* __restrict__ boxes,
                                                       const int32_t* __restrict__ offsets,
                                                       const EotBoxParams* __restrict__ params,
