@@ -107,3 +107,19 @@ def make_batch(B: int, H: int, W: int, *, first_image: int = 0, seed: int = 1234
                  np.asarray(offs, dtype=np.int32),
                  np.concatenate(params) if params else np.zeros(0, dtype=BOX_PARAMS),
                  np.stack(wbs).astype(F))
+
+
+def objective_inputs(seed: int = 8, B: int = 2, H: int = 64):
+    """Seeded victim outputs for the objective / first-pass checks (the inputs of tests/golden/objective_ref.npz): class logits
+    with ~5 % of the anchors pushed towards `person`, box regressions ~N(0, .3).  Returns (cls levels, box levels) as lists of
+    float32 [B,h,w,810] / [B,h,w,36] arrays for an EfficientDet-D0-shaped head (levels 3..7, 9 anchors, 90 classes)."""
+    from .anchors import feature_sizes
+    rng = np.random.default_rng(seed)
+    fs = feature_sizes((H, H), 7)[3:]
+    cls = [rng.normal(-3, 2.5, (B, h, w, 810)).astype(np.float32) for h, w in fs]
+    for c in cls:
+        v = c.reshape(B, -1, 90)
+        pick = rng.random(v.shape[:2]) < 0.05
+        v[pick, 0] += 8.0
+    box = [rng.normal(0, 0.3, (B, h, w, 36)).astype(np.float32) for h, w in fs]
+    return cls, box

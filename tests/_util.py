@@ -26,15 +26,6 @@ def run_forward(patch_np, scale, bt, geom=None, want_mask=False, patch_t=None):
 
 
 def objective_fixture_inputs(seed=8, B=2, H=64):
-    """Seeded victim outputs of the objective fixtures (tests/golden/objective_ref.npz): class logits with ~5 % of the
-    anchors pushed towards `person`, box regressions ~N(0, .3)."""
-    from mladversarialobjectdetection_b200.anchors import feature_sizes
-    rng = np.random.default_rng(seed)
-    fs = feature_sizes((H, H), 7)[3:]
-    cls = [rng.normal(-3, 2.5, (B, h, w, 810)).astype(np.float32) for h, w in fs]
-    for c in cls:
-        v = c.reshape(B, -1, 90)
-        pick = rng.random(v.shape[:2]) < 0.05
-        v[pick, 0] += 8.0
-    box = [rng.normal(0, 0.3, (B, h, w, 36)).astype(np.float32) for h, w in fs]
-    return cls, box
+    """Seeded victim outputs of the objective fixtures (tests/golden/objective_ref.npz); lives in the package
+    (synth.objective_inputs) because __graft_entry__.smoke() uses it too."""
+    return synth.objective_inputs(seed, B, H)

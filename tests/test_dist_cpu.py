@@ -28,6 +28,8 @@ def _worker(rank, world, port, out_dir):
     bt = synth.make_batch(B, 64, 64, seed=5, max_boxes=3)
     full = RaggedBoxes(torch.from_numpy(bt.boxes), torch.from_numpy(bt.offsets))
     mine = full.slice_rows(rank * per, (rank + 1) * per)
+    from mladversarialobjectdetection_b200.attacker import resolve_first_image
+    assert resolve_first_image(None, per) == rank * per and resolve_first_image(7, per) == 7   # the layers shard by rank on their own
     smp = TransformSampler(seed=3)
     params = smp.box_params(4, rank * per, mine.row_splits, mine.values.shape[0])
     wb = smp.print_wb(4, rank * per, per, "cpu")
