@@ -283,6 +283,7 @@ __device__ int geometry_block(const EotShape& s, const Layout& L, int j, const f
 }
 
 constexpr int kMaxOrderedImages = 2048;   // batches beyond this keep the identity order (the ranking is quadratic in one CTA)
+constexpr int kSmallRolesScratch = kThreads * 16 + kMaxOrderedImages * 4;   // prefix-sum partials + image costs
 
 // Exclusive prefix sums of the per-box work-item counts (one CTA; N is a few hundred to a few thousand).
 __device__ __forceinline__ int4 add4(int4 a, int4 b) { return make_int4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
@@ -432,26 +433,18 @@ __device__ __forceinline__ void image_pass_block(int HW, int b, int chunk, const
   }
 }
 
-// One launch, three independent roles selected by the block index (they only meet at k_match):
-//   [0, n_geom)                         geometry of box j                   (n_geom = N or 0)
-//   [.., + n_stat_imgs*pchunks)         patch luma statistics               (n_stat_imgs = B or 0)
-//   [.., + (b1-b0)*cpi)                 image pass (copy + luma sum) of images [b0,b1), the HBM-bound bulk
-#ifndef EOT_PREPASS_MINB
-#define EOT_PREPASS_MINB 6
-#endif
-template <bool kVec>
-__global__ void __launch_bounds__(kThreads, EOT_PREPASS_MINB) k_prepass(EotShape s, Layout L, const float* __restrict__ patch,
-                                                      const float* __restrict__ print_wb, const float* __restrict__ boxes,
-                                                      const int32_t* __restrict__ offsets,
-                                                      const EotBoxParams* __restrict__ params,
-                                                      const float* __restrict__ scale, const float* __restrict__ images,
-                                                      float* out, float* mask, char* ws, int n_geom, int n_stat_imgs,
-                                                      int pchunks, int cpi, int b0) {
-  __shared__ double red[32];
-  int blk = blockIdx.x;
+// The two small roles of the pre-pass (by block index): [0, n_geom) geometry of box j (the last one to finish also
+// builds the prefix sums, the item lists and the image order), then n_stat_imgs * pchunks blocks of patch luma
+// statistics.  true: this block had one of them.
+__device__ bool small_roles(const EotShape& s, const Layout& L, int blk, const float* __restrict__ patch,
+                            const float* __restrict__ print_wb, const float* __restrict__ boxes,
+                            const int32_t* __restrict__ offsets, const EotBoxParams* __restrict__ params,
+                            const float* __restrict__ scale, char* ws, int n_geom, int n_stat_imgs, int pchunks, double* red,
+                            void* scratch /* kSmallRolesScratch bytes of shared memory, 16-byte aligned */) {
   if (blk < n_geom) {
     __shared__ int s_last;
-    __shared__ int4 s_part[kThreads];
+    int4* s_part = reinterpret_cast<int4*>(scratch);               // [kThreads]
+    unsigned* s_cost = reinterpret_cast<unsigned*>(s_part + kThreads);   // [kMaxOrderedImages]
     geometry_block(s, L, blk, boxes, offsets, params, scale, ws, nullptr);
     __threadfence();
     __syncthreads();
@@ -469,7 +462,6 @@ __global__ void __launch_bounds__(kThreads, EOT_PREPASS_MINB) k_prepass(EotShape
         const BoxPlan* pls = reinterpret_cast<const BoxPlan*>(ws + L.off_plans);
         int* order = reinterpret_cast<int*>(ws + L.off_order);
         const int B = s.batch;
-        __shared__ unsigned s_cost[kMaxOrderedImages];
         if (B <= kMaxOrderedImages) {
           for (int b = threadIdx.x; b < B; b += blockDim.x) {
             unsigned c = 0;
@@ -496,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, EOT_PREPASS_MINB) k_prepass(EotShape
         for (int i = 0; i < n.w; ++i) citems[at.w + i] = make_int2(j, i);
       }
     }
-    return;
+    return true;
   }
   blk -= n_geom;
   if (blk < n_stat_imgs * pchunks) {
@@ -506,12 +498,158 @@ __global__ void __launch_bounds__(kThreads, EOT_PREPASS_MINB) k_prepass(EotShape
       int32_t* off_copy = reinterpret_cast<int32_t*>(ws + L.off_offsets);
       for (int i = 0; i <= s.batch; ++i) off_copy[i] = min(offsets[i], s.total_boxes);
     }
-    return;
+    return true;
   }
+  return false;
+}
+
+// One launch, three independent roles selected by the block index (they only meet at k_match):
+//   [0, n_geom)                         geometry of box j                   (n_geom = N or 0)
+//   [.., + n_stat_imgs*pchunks)         patch luma statistics               (n_stat_imgs = B or 0)
+//   [.., + (b1-b0)*cpi)                 image pass (copy + luma sum) of images [b0,b1), the HBM-bound bulk
+#ifndef EOT_PREPASS_MINB
+#define EOT_PREPASS_MINB 6
+#endif
+template <bool kVec>
+__global__ void __launch_bounds__(kThreads, EOT_PREPASS_MINB) k_prepass(EotShape s, Layout L, const float* __restrict__ patch,
+                                                      const float* __restrict__ print_wb, const float* __restrict__ boxes,
+                                                      const int32_t* __restrict__ offsets,
+                                                      const EotBoxParams* __restrict__ params,
+                                                      const float* __restrict__ scale, const float* __restrict__ images,
+                                                      float* out, float* mask, char* ws, int n_geom, int n_stat_imgs,
+                                                      int pchunks, int cpi, int b0) {
+  __shared__ double red[32];
+  __shared__ __align__(16) unsigned char s_scratch[kSmallRolesScratch];
+  int blk = blockIdx.x;
+  if (small_roles(s, L, blk, patch, print_wb, boxes, offsets, params, scale, ws, n_geom, n_stat_imgs, pchunks, red, s_scratch)) return;
+  blk -= n_geom;
   blk -= n_stat_imgs * pchunks;
   const int b = b0 + blk / cpi, chunk = blk % cpi;
   image_pass_block<kVec>(s.height * s.width, b, chunk, images, out, mask, reinterpret_cast<double*>(ws + L.off_ysum_img),
                          reinterpret_cast<int*>(ws + L.off_oor), red);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Image pass as a bulk-copy pipeline (cp.async.bulk + mbarrier: the TMA engine moves the bytes, the threads only read
+// the staged tile for the luma sum).  Persistent CTAs over contiguous ranges of 1024-pixel tiles (12 KB; 48 bytes per
+// thread), kBulkStages buffers per CTA:
+//   thread 0   posts the byte count on the stage's mbarrier and issues the global -> shared copy of a tile kBulkStages - 1
+//              tiles ahead; after the CTA has read a tile it issues the shared -> global copy of the same buffer
+//              (bulk group) and, before it refills a buffer, waits until the copy that last read it has done reading
+//   all        wait on the stage's mbarrier, read their four pixels (3 x LDS.128), accumulate luma in float64 and the
+//              out-of-range flag; per image one block tree reduction + one atomicAdd
+// Used when out != images, no mask is written and the rows are 16-byte aligned; every other case takes k_prepass.
+// ------------------------------------------------------------------------------------------------
+#ifndef EOT_PREPASS_BULK
+#define EOT_PREPASS_BULK 1
+#endif
+constexpr int kBulkTilePix = 4 * kThreads;                         // 1024 pixels = 12288 bytes
+#ifndef EOT_BULK_STAGES
+#define EOT_BULK_STAGES 2
+#endif
+#ifndef EOT_BULK_CTAS
+#define EOT_BULK_CTAS 6
+#endif
+constexpr int kBulkStages = EOT_BULK_STAGES;
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_addr(src)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_parity(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "EOT_BULK_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra EOT_BULK_WAIT_%=;\n"
+      "}\n" ::"r"(smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, EOT_BULK_CTAS) k_prepass_bulk(EotShape s, Layout L, const float* __restrict__ patch,
+                                                              const float* __restrict__ print_wb, const float* __restrict__ boxes,
+                                                              const int32_t* __restrict__ offsets,
+                                                              const EotBoxParams* __restrict__ params,
+                                                              const float* __restrict__ scale, const float* __restrict__ images,
+                                                              float* out, char* ws, int n_geom, int n_stat_imgs, int pchunks,
+                                                              int n_copy_ctas, int b0, int b1) {
+  extern __shared__ __align__(128) unsigned char stage_mem[];     // kBulkStages x 12288 bytes
+  __shared__ double red[32];
+  __shared__ __align__(8) uint64_t s_full[kBulkStages];
+  static_assert((size_t)EOT_BULK_STAGES * kBulkTilePix * 12 >= (size_t)kSmallRolesScratch, "the stage buffers double as the small roles' scratch");
+  int blk = blockIdx.x;
+  if (small_roles(s, L, blk, patch, print_wb, boxes, offsets, params, scale, ws, n_geom, n_stat_imgs, pchunks, red, stage_mem)) return;
+  blk -= n_geom + n_stat_imgs * pchunks;
+  const int HW = s.height * s.width;
+  const int tpi = (HW + kBulkTilePix - 1) / kBulkTilePix;         // tiles per image
+  // CTA (image slot, part): `parts` CTAs sweep one image together, tile k of the image going to part k % parts, so an
+  // image is read and written as one linear stream and every CTA sums the luma of ONE image at a time (block reduction
+  // + one atomic per image, no contention); with more images than CTAs a CTA takes images slot, slot + slots, ...
+  const int n_img = b1 - b0;
+  const int parts = max(1, n_copy_ctas / n_img);
+  const int slots = n_copy_ctas / parts;                          // image slots served concurrently
+  const int slot = blk / parts, part = blk - slot * parts;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kBulkStages; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&s_full[i])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int tiles_mine = part < tpi ? (tpi - part + parts - 1) / parts : 0;      // per image
+  const int imgs_mine = slot < slots ? (n_img - slot + slots - 1) / slots : 0;
+  const int my_tiles = tiles_mine * imgs_mine;
+  auto tile_img = [&](int it) { return b0 + slot + (it / tiles_mine) * slots; };
+  auto tile_k = [&](int it) { return part + (it % tiles_mine) * parts; };
+  auto tile_bytes = [&](int it) { return (uint32_t)(min(kBulkTilePix, HW - tile_k(it) * kBulkTilePix) * 12); };
+  auto tile_off = [&](int it) { return ((size_t)tile_img(it) * HW + (size_t)tile_k(it) * kBulkTilePix) * 3; };
+  if (threadIdx.x == 0)                                           // prologue: the first kBulkStages - 1 tiles
+    for (int it = 0; it < my_tiles && it < kBulkStages - 1; ++it)
+      bulk_load(stage_mem + (size_t)(it % kBulkStages) * kBulkTilePix * 12, images + tile_off(it), tile_bytes(it), &s_full[it % kBulkStages]);
+  double* ysum_img = reinterpret_cast<double*>(ws + L.off_ysum_img);
+  int* oor_flags = reinterpret_cast<int*>(ws + L.off_oor);
+  double acc = 0.0;
+  bool oor = false;
+  for (int it = 0; it < my_tiles; ++it) {
+    const int stg = it % kBulkStages;
+    bulk_wait_parity(&s_full[stg], (uint32_t)((it / kBulkStages) & 1));
+    const float4* tp = reinterpret_cast<const float4*>(stage_mem + (size_t)stg * kBulkTilePix * 12) + threadIdx.x * 3;
+    if ((int)(threadIdx.x * 4) < (int)(tile_bytes(it) / 12)) {
+      const float4 a = tp[0], bb = tp[1], c = tp[2];
+      acc += (double)luma_of(a.x, a.y, a.z);
+      acc += (double)luma_of(a.w, bb.x, bb.y);
+      acc += (double)luma_of(bb.z, bb.w, c.x);
+      acc += (double)luma_of(c.y, c.z, c.w);
+      const float m0 = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w)));
+      const float m1 = fmaxf(fmaxf(fabsf(bb.x), fabsf(bb.y)), fmaxf(fabsf(bb.z), fabsf(bb.w)));
+      const float m2 = fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fmaxf(fabsf(c.z), fabsf(c.w)));
+      const float sum = (a.x + a.y + a.z + a.w) + (bb.x + bb.y + bb.z + bb.w) + (c.x + c.y + c.z + c.w);
+      oor = oor || !(fmaxf(fmaxf(m0, m1), m2) <= 1.0f) || (sum != sum);        // fmaxf drops NaN: test the sum too
+    }
+    __syncthreads();                                              // every thread has read the tile
+    if (threadIdx.x == 0) {
+      bulk_store(out + tile_off(it), stage_mem + (size_t)stg * kBulkTilePix * 12, tile_bytes(it));
+      const int itn = it + kBulkStages - 1;                       // refill the buffer of the previous tile
+      if (itn < my_tiles) {
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // ... once its outgoing copy has done reading it
+        const int sn = itn % kBulkStages;
+        bulk_load(stage_mem + (size_t)sn * kBulkTilePix * 12, images + tile_off(itn), tile_bytes(itn), &s_full[sn]);
+      }
+    }
+    if ((it + 1) % tiles_mine == 0) {                             // (uniform) last tile of this image for this CTA
+      const int any = __syncthreads_or(oor ? 1 : 0);
+      acc = block_sum(acc, red);
+      if (threadIdx.x == 0) { atomicAdd(ysum_img + tile_img(it), acc); if (any) atomicOr(oor_flags + tile_img(it), 1); }
+      acc = 0.0; oor = false;
+    }
+  }
+  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -702,7 +840,20 @@ static int launch_forward(const EotShape& s, const Layout& L, const float* patch
     const int n_geom = g == 0 ? N : 0, n_stat = g == 0 ? B : 0;
     const long long nblocks = (long long)n_geom + (long long)n_stat * pchunks + (long long)(b1 - b0) * cpi;
     if (nblocks >= (1ll << 31)) { set_error("eot_apply_fwd: grid too large"); return EOT_ERR_BAD_SHAPE; }
-    if (vec)
+    // bulk-copy pipeline when the pass really copies (out of place, no mask) and tiles / rows are 16-byte aligned
+    const bool bulk = EOT_PREPASS_BULK && vec && !mask && out_images != images;
+    if (bulk) {
+      const size_t smem = (size_t)kBulkStages * kBulkTilePix * 12;
+      static thread_local bool attr_set = false;
+      if (!attr_set) {
+        EOT_CHECK_CUDA(cudaFuncSetAttribute(k_prepass_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+      }
+      const long long tiles = (long long)(b1 - b0) * ((HW + kBulkTilePix - 1) / kBulkTilePix);
+      const int copy_ctas = (int)(tiles < (long long)EOT_BULK_CTAS * sm_count() ? tiles : (long long)EOT_BULK_CTAS * sm_count());
+      k_prepass_bulk<<<(unsigned)(n_geom + n_stat * pchunks + copy_ctas), kThreads, smem, st>>>(
+          s, L, patch, print_wb, boxes, box_offsets, params, scale, images, out_images, ws, n_geom, n_stat, pchunks, copy_ctas, b0, b1);
+    } else if (vec)
       k_prepass<true><<<(unsigned)nblocks, kThreads, 0, st>>>(s, L, patch, print_wb, boxes, box_offsets, params, scale, images,
                                                               out_images, mask, ws, n_geom, n_stat, pchunks, cpi, b0);
     else
