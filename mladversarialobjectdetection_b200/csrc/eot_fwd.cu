@@ -543,7 +543,10 @@ __global__ void __launch_bounds__(kThreads, EOT_PREPASS_MINB) k_prepass(EotShape
 #ifndef EOT_PREPASS_BULK
 #define EOT_PREPASS_BULK 1
 #endif
-constexpr int kBulkTilePix = 4 * kThreads;                         // 1024 pixels = 12288 bytes
+#ifndef EOT_BULK_QUADS
+#define EOT_BULK_QUADS 1
+#endif
+constexpr int kBulkTilePix = 4 * EOT_BULK_QUADS * kThreads;        // 1024 pixels = 12288 bytes per quad
 #ifndef EOT_BULK_STAGES
 #define EOT_BULK_STAGES 2
 #endif
@@ -619,18 +622,22 @@ __global__ void __launch_bounds__(kThreads, EOT_BULK_CTAS) k_prepass_bulk(EotSha
   for (int it = 0; it < my_tiles; ++it) {
     const int stg = it % kBulkStages;
     bulk_wait_parity(&s_full[stg], (uint32_t)((it / kBulkStages) & 1));
-    const float4* tp = reinterpret_cast<const float4*>(stage_mem + (size_t)stg * kBulkTilePix * 12) + threadIdx.x * 3;
-    if ((int)(threadIdx.x * 4) < (int)(tile_bytes(it) / 12)) {
-      const float4 a = tp[0], bb = tp[1], c = tp[2];
-      acc += (double)luma_of(a.x, a.y, a.z);
-      acc += (double)luma_of(a.w, bb.x, bb.y);
-      acc += (double)luma_of(bb.z, bb.w, c.x);
-      acc += (double)luma_of(c.y, c.z, c.w);
-      const float m0 = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w)));
-      const float m1 = fmaxf(fmaxf(fabsf(bb.x), fabsf(bb.y)), fmaxf(fabsf(bb.z), fabsf(bb.w)));
-      const float m2 = fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fmaxf(fabsf(c.z), fabsf(c.w)));
-      const float sum = (a.x + a.y + a.z + a.w) + (bb.x + bb.y + bb.z + bb.w) + (c.x + c.y + c.z + c.w);
-      oor = oor || !(fmaxf(fmaxf(m0, m1), m2) <= 1.0f) || (sum != sum);        // fmaxf drops NaN: test the sum too
+#pragma unroll
+    for (int qd = 0; qd < EOT_BULK_QUADS; ++qd) {
+      const int px = (qd * kThreads + threadIdx.x) * 4;           // first of this thread's four pixels inside the tile
+      const float4* tp = reinterpret_cast<const float4*>(stage_mem + (size_t)stg * kBulkTilePix * 12) + (px >> 2) * 3;
+      if (px < (int)(tile_bytes(it) / 12)) {
+        const float4 a = tp[0], bb = tp[1], c = tp[2];
+        acc += (double)luma_of(a.x, a.y, a.z);
+        acc += (double)luma_of(a.w, bb.x, bb.y);
+        acc += (double)luma_of(bb.z, bb.w, c.x);
+        acc += (double)luma_of(c.y, c.z, c.w);
+        const float m0 = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w)));
+        const float m1 = fmaxf(fmaxf(fabsf(bb.x), fabsf(bb.y)), fmaxf(fabsf(bb.z), fabsf(bb.w)));
+        const float m2 = fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fmaxf(fabsf(c.z), fabsf(c.w)));
+        const float sum = (a.x + a.y + a.z + a.w) + (bb.x + bb.y + bb.z + bb.w) + (c.x + c.y + c.z + c.w);
+        oor = oor || !(fmaxf(fmaxf(m0, m1), m2) <= 1.0f) || (sum != sum);      // fmaxf drops NaN: test the sum too
+      }
     }
     __syncthreads();                                              // every thread has read the tile
     if (threadIdx.x == 0) {
