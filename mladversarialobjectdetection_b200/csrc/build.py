@@ -18,7 +18,7 @@ LIB = os.path.join(PKG, "libeotpatch.so")
 OBJ_DIR = os.path.join(HERE, "_build")
 SOURCES = {"capi.cu": [], "eot_fwd.cu": ["-fmad=false"], "eot_resize.cu": ["-fmad=false"], "eot_composite.cu": ["-fmad=false"], "eot_bwd.cu": [], "eot_draw.cu": ["-fmad=false"], "score_max.cu": ["-fmad=false"], "nms.cu": ["-fmad=false"], "input_pipeline.cu": ["-fmad=false"], "adv_u8.cu": ["-fmad=false"], "victim_ops.cu": [],
            "patch_opt.cu": []}
-HEADERS = ["eot_common.cuh", os.path.join("..", "..", "include", "eotpatch.h")]
+HEADERS = ["eot_common.cuh", "eot_resize.cuh", "eot_composite.cuh", os.path.join("..", "..", "include", "eotpatch.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2", "--expt-relaxed-constexpr"]
 

@@ -83,6 +83,8 @@ struct Layout {
                            //            of image group g
   size_t off_tickets;      // int32[kTicketSlots][kTicketLanes][64]  work tickets: slot = kernel (x image group), lane = one of
                            //            the interleaved sub-queues (own 256-byte line each: same-address atomics serialise)
+  size_t off_fused;        // int32[...] fused forward kernel: readiness flag, task total, per-image progress counters, step table
+                           //            (fused_ints(); zeroed with the accumulators by the call's memset)
   size_t off_plans;        // BoxPlan[N]
   size_t off_starts;       // int32[N][Lmin]
   size_t off_weights;      // float[N][wcap]  tap-major: weight of tap k of output index o at [k * ps + o]
@@ -128,6 +130,15 @@ struct Layout {
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Control block of the fused forward kernel (eot_fwd.cu: k_forward_fused), int32 units:
+//   [0] tables ready   [1] tasks in the queue   [2] finished patch-statistics blocks   [3] images whose composite is done
+//   [64 + 8 b + i]     image b: 0 tiles read (luma summed), 1 tiles stored, 2 match parts, 3 resize items, 4 composite items done
+//   step_start[steps + 1], step_info int4[steps]   with steps = B + 2 * skew (skew <= kMaxSkew)
+constexpr int kMaxSkew = 48;
+__host__ __device__ inline size_t fused_steps_cap(int B) { return (size_t)B + 2 * kMaxSkew; }
+__host__ __device__ inline size_t fused_start_ints(int B) { return (fused_steps_cap(B) + 1 + 3) / 4 * 4; }
+__host__ __device__ inline size_t fused_ints(int B) { return 64 + 8 * (size_t)B + fused_start_ints(B) + 4 * fused_steps_cap(B); }
+
 __host__ __device__ inline Layout make_layout(const EotShape& s) {
   Layout L;
   const size_t B = (size_t)s.batch, N = (size_t)(s.total_boxes > 0 ? s.total_boxes : 0);
@@ -155,6 +166,7 @@ __host__ __device__ inline Layout make_layout(const EotShape& s) {
   L.off_oor = o;          o = align_up(o + B * sizeof(int32_t), 256);
   L.off_counters = o;     o = align_up(o + 32 * sizeof(int32_t), 256);
   L.off_tickets = o;      o = align_up(o + (size_t)kTicketSlots * kTicketLanes * 256, 256);
+  L.off_fused = o;        o = align_up(o + fused_ints((int)B) * sizeof(int32_t), 256);
   L.off_plans = o;        o = align_up(o + N * sizeof(BoxPlan), 256);
   L.off_starts = o;       o = align_up(o + N * (size_t)lmin * sizeof(int32_t), 256);
   L.off_weights = o;      o = align_up(o + N * (size_t)L.wcap * sizeof(float), 256);

@@ -13,8 +13,11 @@
 //   k_composite3      (eot_composite.cu) projective bilinear sample of the ring-padded u_j, `< -1` mask,
 //                     sequential-paste resolution, clip, store, route bytes
 #include "eot_common.cuh"
+#include "eot_composite.cuh"
+#include "eot_resize.cuh"
 
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 namespace eot {
@@ -435,8 +438,8 @@ __device__ __forceinline__ void image_pass_block(int HW, int b, int chunk, const
 
 // The two small roles of the pre-pass (by block index): [0, n_geom) geometry of box j (the last one to finish also
 // builds the prefix sums, the item lists and the image order), then n_stat_imgs * pchunks blocks of patch luma
-// statistics.  true: this block had one of them.
-__device__ bool small_roles(const EotShape& s, const Layout& L, int blk, const float* __restrict__ patch,
+// statistics.  0: neither; 1: this block had one of them; 2: ... and was the geometry block that built the tables.
+__device__ int small_roles(const EotShape& s, const Layout& L, int blk, const float* __restrict__ patch,
                             const float* __restrict__ print_wb, const float* __restrict__ boxes,
                             const int32_t* __restrict__ offsets, const EotBoxParams* __restrict__ params,
                             const float* __restrict__ scale, char* ws, int n_geom, int n_stat_imgs, int pchunks, double* red,
@@ -488,7 +491,7 @@ __device__ bool small_roles(const EotShape& s, const Layout& L, int blk, const f
         for (int i = 0; i < n.w; ++i) citems[at.w + i] = make_int2(j, i);
       }
     }
-    return true;
+    return s_last ? 2 : 1;
   }
   blk -= n_geom;
   if (blk < n_stat_imgs * pchunks) {
@@ -498,9 +501,9 @@ __device__ bool small_roles(const EotShape& s, const Layout& L, int blk, const f
       int32_t* off_copy = reinterpret_cast<int32_t*>(ws + L.off_offsets);
       for (int i = 0; i <= s.batch; ++i) off_copy[i] = min(offsets[i], s.total_boxes);
     }
-    return true;
+    return 1;
   }
-  return false;
+  return 0;
 }
 
 // One launch, three independent roles selected by the block index (they only meet at k_match):
@@ -641,10 +644,10 @@ __global__ void __launch_bounds__(kThreads, EOT_BULK_CTAS) k_prepass_bulk(EotSha
     }
     __syncthreads();                                              // every thread has read the tile
     if (threadIdx.x == 0) {
-      bulk_store(out + tile_off(it), stage_mem + (size_t)stg * kBulkTilePix * 12, tile_bytes(it));
+      if (out) bulk_store(out + tile_off(it), stage_mem + (size_t)stg * kBulkTilePix * 12, tile_bytes(it));
       const int itn = it + kBulkStages - 1;                       // refill the buffer of the previous tile
       if (itn < my_tiles) {
-        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // ... once its outgoing copy has done reading it
+        if (out) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // ... once its outgoing copy has done reading it
         const int sn = itn % kBulkStages;
         bulk_load(stage_mem + (size_t)sn * kBulkTilePix * 12, images + tile_off(itn), tile_bytes(itn), &s_full[sn]);
       }
@@ -662,8 +665,8 @@ __global__ void __launch_bounds__(kThreads, EOT_BULK_CTAS) k_prepass_bulk(EotSha
 // ------------------------------------------------------------------------------------------------
 // print adjust + brightness match of the patch for image b (attacker.py:372; brightness_matcher.py:43-73)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void match_block(const EotShape& s, const Layout& L, const float* __restrict__ patch,
-                                            const float* __restrict__ print_wb, char* ws, int b, int part, int nparts);
+__device__ __forceinline__ void match_range(const EotShape& s, const Layout& L, const float* __restrict__ patch,
+                                            const float* __restrict__ print_wb, char* ws, int b, int t0, int tstride);
 
 // blocks [0, nb * pchunks): match the patch to image b0 + blk / pchunks (needs the finished pre-pass: mean luma)
 __global__ void __launch_bounds__(kThreads) k_match(EotShape s, Layout L, const float* __restrict__ patch,
@@ -675,11 +678,12 @@ __global__ void __launch_bounds__(kThreads) k_match(EotShape s, Layout L, const 
   if (blk % pchunks == 0 && threadIdx.x == 0 &&
       (reinterpret_cast<const int*>(ws + L.off_oor)[b] != 0 || offsets[b + 1] - offsets[b] > 32))
     atomicOr(reinterpret_cast<int*>(ws + L.off_counters) + 6, 1);
-  match_block(s, L, patch, print_wb, ws, b, blk % pchunks, pchunks);
+  match_range(s, L, patch, print_wb, ws, b, (blk % pchunks) * blockDim.x + threadIdx.x, pchunks * blockDim.x);
 }
 
-__device__ __forceinline__ void match_block(const EotShape& s, const Layout& L, const float* __restrict__ patch,
-                                            const float* __restrict__ print_wb, char* ws, int b, int part, int nparts) {
+// texels t0, t0 + tstride, ... of the matched patch of image b
+__device__ __forceinline__ void match_range(const EotShape& s, const Layout& L, const float* __restrict__ patch,
+                                            const float* __restrict__ print_wb, char* ws, int b, int t0, int tstride) {
   const int P = s.patch_size;
   const double* ysum_img = reinterpret_cast<const double*>(ws + L.off_ysum_img);
   const double* ysum_patch = reinterpret_cast<const double*>(ws + L.off_ysum_patch);
@@ -688,7 +692,7 @@ __device__ __forceinline__ void match_block(const EotShape& s, const Layout& L, 
   const float* wb = print_wb + (size_t)b * 6;
   const float* base = patch + (s.num_patches > 1 ? (int64_t)b * s.patch_stride_n : 0);
   float4* m = reinterpret_cast<float4*>(ws + L.off_match) + (size_t)b * P * P;
-  for (int t = part * blockDim.x + threadIdx.x; t < P * P; t += nparts * blockDim.x) {
+  for (int t = t0; t < P * P; t += tstride) {
     const int py = t / P, px = t - py * P;
     const float* p = base + (int64_t)py * s.patch_stride_y + (int64_t)px * s.patch_stride_x;
     const TexelYuv y = texel_yuv(__ldg(p), __ldg(p + 1), __ldg(p + 2), wb);
@@ -732,6 +736,347 @@ __global__ void __launch_bounds__(kThreads) k_bm_apply(const float* __restrict__
     out[i * 3 + 1] = clampf(g, 0.0f, 1.0f) * EOT_C255_127 - 1.0f;
     out[i * 3 + 2] = clampf(b, 0.0f, 1.0f) * EOT_C255_127 - 1.0f;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The whole forward as ONE persistent kernel (cooperative launch: every CTA resident).  The image pass is bandwidth
+// bound and the window work (match, resize, composite) instruction bound; as separate kernels they run back to back
+// (the window kernels hold every register of an SM, nothing co-resides) and pay five kernel boundaries.  Here
+//   CTAs [0, n_copy)   stream the images through shared memory with the bulk-copy engine (as k_prepass_bulk, `slots`
+//                      images at a time, in image order), then join the window work;
+//   the other CTAs     first run the geometry / patch-statistics roles, the last geometry block also lays out the task
+//                      queue, then every WARP draws tasks from one ordered queue.
+// Task queue, by step k:  match parts of image k,  resize items of image k - skew,  composite items of image k - 2 skew.
+// A task waits (acquire spin on a per-image counter) only for tasks EARLIER in the queue or for the copy CTAs, which
+// wait for nobody: with every CTA resident and tickets drawn in order, the lowest unfinished task can always run.
+//   match(b)      needs the image's luma sum (all tiles of b read) and the patch statistics
+//   resize(b)     needs every match part of b
+//   composite(b)  needs every resize item of b and the stored copy of image b (it overwrites pixels of it)
+// Tail: once every image's composite items are done, all threads share the open-pixel list / general rows
+// (composite_rest_body).
+// ------------------------------------------------------------------------------------------------
+#ifndef EOT_FUSED_STAGES
+#define EOT_FUSED_STAGES 4
+#endif
+#ifndef EOT_FUSED_MINB
+#define EOT_FUSED_MINB 4
+#endif
+constexpr int kFusedStages = EOT_FUSED_STAGES;
+constexpr int kFusedTilePix = 4 * kThreads;                        // 1024 pixels = 12288 bytes
+constexpr int kMatchTexels = 512;                                  // texels per match task (one warp)
+
+struct FusedView {
+  int* ctl;
+  int* img;
+  int* step_start;
+  int4* step_info;
+};
+__device__ __forceinline__ FusedView fused_view(char* ws, const Layout& L, int B) {
+  FusedView v;
+  v.ctl = reinterpret_cast<int*>(ws + L.off_fused);
+  v.img = v.ctl + 64;
+  v.step_start = v.img + 8 * (size_t)B;
+  v.step_info = reinterpret_cast<int4*>(v.step_start + fused_start_ints(B));
+  return v;
+}
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Warp-wide wait until *p >= v: lane 0 polls (acquire) with exponential back-off -- thousands of warps polling a handful of
+// L2 lines at full rate starve the very atomics they wait for.  A wait that outlasts ~2 s (a lost signal: a bug, never
+// load) raises error flag 16 and goes on, so that a fault shows as a failed call instead of a hung device.
+__device__ __forceinline__ void wait_ge(const int* p, int v, int* err, int* spins) {
+  if ((threadIdx.x & 31) == 0 && ld_acquire(p) < v) {
+    unsigned ns = 128, n = 0;
+    while (ld_acquire(p) < v) {
+      __nanosleep(ns);
+      if (ns < 2048) ns *= 2;
+      if (++n > (1u << 20)) { atomicOr(err, 16); break; }
+    }
+    if (spins) atomicAdd(spins, (int)n);
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned long long global_ns();
+// Completion of one task of a per-image counter; with the debug timeline on, the task that completes the image's stage
+// (count `full`) stamps the time into `stamp`.
+__device__ __forceinline__ void warp_signal(int* p, int lane, int full = 0, int* stamp = nullptr, unsigned long long t_base = 0) {
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence();
+    const int old = atomicAdd(p, 1);
+    if (stamp && old == full - 1) *stamp = (int)(global_ns() - t_base);
+  }
+}
+
+// Task queue layout, by the geometry block that finished last (all its threads).
+__device__ void build_steps(const EotShape& s, const Layout& L, char* ws, const int32_t* __restrict__ offsets, int N, int skew,
+                            int nM, int* scratch /* >= B + 2 skew ints of shared memory */) {
+  const int B = s.batch, steps = B + 2 * skew;
+  const FusedView fv = fused_view(ws, L, B);
+  const int4* base = reinterpret_cast<const int4*>(ws + L.off_base);
+  __syncthreads();
+  for (int k = threadIdx.x; k < steps; k += blockDim.x) {
+    const int m = k < B ? nM : 0;
+    int nR = 0, rbase = 0, nC = 0, cbase = 0;
+    const int bR = k - skew, bC = k - 2 * skew;
+    if (bR >= 0 && bR < B) { rbase = base[min(offsets[bR], N)].z; nR = base[min(offsets[bR + 1], N)].z - rbase; }
+    if (bC >= 0 && bC < B) { cbase = base[min(offsets[bC], N)].w; nC = base[min(offsets[bC + 1], N)].w - cbase; }
+    fv.step_info[k] = make_int4(m, nR, rbase, cbase);
+    scratch[k] = m + nR + nC;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0, empty = 0;
+    for (int k = 0; k < steps; ++k) {
+      fv.step_start[k] = run;
+      run += scratch[k];
+      if (k >= 2 * skew && scratch[k] - fv.step_info[k].x - fv.step_info[k].y == 0) ++empty;   // image without composite items
+    }
+    fv.step_start[steps] = run;
+    fv.ctl[1] = run;
+    if (empty) atomicAdd(fv.ctl + 3, empty);
+    __threadfence();
+    atomicExch(fv.ctl, 1);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, EOT_FUSED_MINB) k_forward_fused(
+    EotShape s, Layout L, const float* __restrict__ patch, const float* __restrict__ print_wb, const float* __restrict__ boxes,
+    const int32_t* __restrict__ offsets, const EotBoxParams* __restrict__ params, const float* __restrict__ scale,
+    const float* __restrict__ images, float* out, char* ws, int n_geom, int pchunks, int n_copy, int slots, int skew, int nM,
+    float one, int prefetch, int dbg) {
+  extern __shared__ __align__(128) unsigned char fsmem[];         // copy role: stage buffers; window work: per-warp scratch
+  __shared__ double red[32];
+  __shared__ __align__(8) uint64_t s_full[kFusedStages];
+  const int B = s.batch, HW = s.height * s.width;
+  const FusedView fv = fused_view(ws, L, B);
+  int* counters = reinterpret_cast<int*>(ws + L.off_counters);
+  int* err = counters + 2;
+  unsigned long long t_base = 0;
+  if (dbg && threadIdx.x == 0) {                                   // debug timeline (EOT_KERNEL_TIMES=1): ns since the first CTA started
+    const unsigned long long now = global_ns();
+    const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(fv.ctl + 8), 0ull, now);
+    t_base = old ? old : now;
+  }
+  if (dbg) {                                                       // (every lane 0 stamps)
+    __shared__ unsigned long long s_base;
+    if (threadIdx.x == 0) s_base = t_base;
+    __syncthreads();
+    t_base = s_base;
+  }
+  const int tpi = (HW + kFusedTilePix - 1) / kFusedTilePix;       // tiles per image
+  const int parts = n_copy / slots;                               // CTAs sweeping one image together
+  const int pass_expected = min(parts, tpi);                      // CTAs that own tiles of an image
+
+  if ((int)blockIdx.x < n_copy) {
+    // ---- copy role --------------------------------------------------------------------------------------------------
+    const int blk = blockIdx.x;
+    const int slot = blk / parts, part = blk - slot * parts;
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < kFusedStages; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&s_full[i])));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int tiles_mine = part < tpi ? (tpi - part + parts - 1) / parts : 0;      // per image
+    const int imgs_mine = (B - slot + slots - 1) / slots;
+    const int my_tiles = tiles_mine * imgs_mine;
+    auto tile_img = [&](int it) { return slot + (it / tiles_mine) * slots; };
+    auto tile_k = [&](int it) { return part + (it % tiles_mine) * parts; };
+    auto tile_bytes = [&](int it) { return (uint32_t)(min(kFusedTilePix, HW - tile_k(it) * kFusedTilePix) * 12); };
+    auto tile_off = [&](int it) { return ((size_t)tile_img(it) * HW + (size_t)tile_k(it) * kFusedTilePix) * 3; };
+    auto stage_ptr = [&](int stg) { return fsmem + (size_t)stg * kFusedTilePix * 12; };
+    if (threadIdx.x == 0)
+      for (int it = 0; it < my_tiles && it < kFusedStages - 1; ++it)
+        bulk_load(stage_ptr(it % kFusedStages), images + tile_off(it), tile_bytes(it), &s_full[it % kFusedStages]);
+    double* ysum_img = reinterpret_cast<double*>(ws + L.off_ysum_img);
+    int* oor_flags = reinterpret_cast<int*>(ws + L.off_oor);
+    double acc = 0.0;
+    bool oor = false;
+    int sig_it = tiles_mine - 1;                                  // (thread 0) last tile of the next image to report as stored
+    for (int it = 0; it < my_tiles; ++it) {
+      const int stg = it % kFusedStages;
+      bulk_wait_parity(&s_full[stg], (uint32_t)((it / kFusedStages) & 1));
+      const int px = threadIdx.x * 4;                             // this thread's four pixels inside the tile
+      const float4* tp = reinterpret_cast<const float4*>(stage_ptr(stg)) + threadIdx.x * 3;
+      if (px < (int)(tile_bytes(it) / 12)) {
+        const float4 a = tp[0], bb = tp[1], c = tp[2];
+        acc += (double)luma_of(a.x, a.y, a.z);
+        acc += (double)luma_of(a.w, bb.x, bb.y);
+        acc += (double)luma_of(bb.z, bb.w, c.x);
+        acc += (double)luma_of(c.y, c.z, c.w);
+        const float m0 = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w)));
+        const float m1 = fmaxf(fmaxf(fabsf(bb.x), fabsf(bb.y)), fmaxf(fabsf(bb.z), fabsf(bb.w)));
+        const float m2 = fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fmaxf(fabsf(c.z), fabsf(c.w)));
+        const float sum = (a.x + a.y + a.z + a.w) + (bb.x + bb.y + bb.z + bb.w) + (c.x + c.y + c.z + c.w);
+        oor = oor || !(fmaxf(fmaxf(m0, m1), m2) <= 1.0f) || (sum != sum);        // fmaxf drops NaN: test the sum too
+      }
+      __syncthreads();                                            // every thread has read the tile
+      if (threadIdx.x == 0) {
+        bulk_store(out + tile_off(it), stage_ptr(stg), tile_bytes(it));
+        const int itn = it + kFusedStages - 1;                    // refill the buffer of the previous tile
+        if (itn < my_tiles) {
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // ... once its outgoing copy has done reading it
+          bulk_load(stage_ptr(itn % kFusedStages), images + tile_off(itn), tile_bytes(itn), &s_full[itn % kFusedStages]);
+        }
+        if (sig_it <= it - 2) {                                   // stores up to tile it - 2 complete: report finished images
+          asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
+          __threadfence();
+          while (sig_it <= it - 2) { atomicAdd(fv.img + 8 * tile_img(sig_it) + 1, 1); sig_it += tiles_mine; }
+        }
+      }
+      if ((it + 1) % tiles_mine == 0) {                           // (uniform) last tile of this image for this CTA
+        const int any = __syncthreads_or(oor ? 1 : 0);
+        acc = block_sum(acc, red);
+        if (threadIdx.x == 0) {
+          const int b = tile_img(it);
+          atomicAdd(ysum_img + b, acc);
+          if (any) atomicOr(oor_flags + b, 1);
+          __threadfence();
+          const int oldc = atomicAdd(fv.img + 8 * b, 1);
+          if (dbg && oldc == pass_expected - 1 && (b == 0 || b == 4 || b == 16 || b == 32)) fv.ctl[28 + (b == 0 ? 0 : b == 4 ? 1 : b == 16 ? 2 : 3)] = (int)(global_ns() - t_base);
+        }
+        acc = 0.0; oor = false;
+      }
+    }
+    if (threadIdx.x == 0) {
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      __threadfence();
+      while (sig_it < my_tiles) { atomicAdd(fv.img + 8 * tile_img(sig_it) + 1, 1); sig_it += tiles_mine; }
+    }
+    if (dbg && threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned long long*>(fv.ctl + 10), global_ns() - t_base);
+    __syncthreads();                                              // the stage buffers become the warps' scratch
+  } else {
+    // ---- geometry and patch statistics ------------------------------------------------------------------------------
+    const int n_small = n_geom + B * pchunks, nwin = gridDim.x - n_copy;
+    for (int blk = blockIdx.x - n_copy; blk < n_small; blk += nwin) {
+      const int r = small_roles(s, L, blk, patch, print_wb, boxes, offsets, params, scale, ws, n_geom, B, pchunks, red, fsmem);
+      if (blk >= n_geom && threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(fv.ctl + 2, 1) == B * pchunks - 1 && dbg) fv.ctl[25] = (int)(global_ns() - t_base);
+      }
+      if (r == 2) {
+        if (dbg && threadIdx.x == 0) fv.ctl[27] = (int)(global_ns() - t_base);
+        build_steps(s, L, ws, offsets, n_geom, skew, nM, reinterpret_cast<int*>(fsmem));
+        if (dbg && threadIdx.x == 0) fv.ctl[24] = (int)(global_ns() - t_base);
+      }
+      __syncthreads();
+    }
+    if (dbg && threadIdx.x == 0) atomicMax(fv.ctl + 26, (int)(global_ns() - t_base));
+  }
+
+  // ---- window work: one ordered task queue, one task per warp at a time ------------------------------------------------
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  wait_ge(fv.ctl, 1, err, nullptr);
+  const int total = __ldcg(fv.ctl + 1), steps = B + 2 * skew;
+  const int P = s.patch_size;
+  const size_t per_warp = resize_warp_smem(s, L);
+  float4* inter = reinterpret_cast<float4*>(fsmem + (size_t)warp * per_warp);
+  uint32_t* words = reinterpret_cast<uint32_t*>(fsmem + (size_t)warp * per_warp + (size_t)L.rb * P * 16);
+  const BoxPlan* plans = reinterpret_cast<const BoxPlan*>(ws + L.off_plans);
+  const int2* items = reinterpret_cast<const int2*>(ws + L.off_items);
+  const int2* citems = reinterpret_cast<const int2*>(ws + L.off_citems);
+  const float* ubuf = reinterpret_cast<const float*>(ws + L.off_u);
+  uint8_t* routes = reinterpret_cast<uint8_t*>(ws + L.off_route);
+  const int2* rowtab = reinterpret_cast<const int2*>(ws + L.off_rowtab);
+  const int open_cap = (int)L.open_cap;
+  int* open_count = counters + 8;
+  int2* open_list = reinterpret_cast<int2*>(ws + L.off_open);
+  const int W = s.width, lfull = s.height < s.width ? s.height : s.width;
+  const size_t img_elems = (size_t)HW * 3;
+  const int n_stat_blocks = B * pchunks;
+  WarpTickets tk;
+  tk.init(ws, L.off_tickets, 0);
+  int t = tk.item(tk.draw(lane));
+  while (t < total) {
+    const int nxt = prefetch ? tk.draw(lane) : 0;                 // next task's ticket travels while this one computes
+    int lo = 0, hi = steps;                                       // step of task t: last k with step_start[k] <= t
+    while (hi - lo > 1) { const int m = (lo + hi) >> 1; if (fv.step_start[m] <= t) lo = m; else hi = m; }
+    const int k = lo;
+    int r = t - fv.step_start[k];
+    const int4 info = fv.step_info[k];
+    if (r < info.x) {
+      // match part r of image k
+      const int b = k;
+      wait_ge(fv.ctl + 2, n_stat_blocks, err, dbg ? fv.ctl + 20 : nullptr);
+      wait_ge(fv.img + 8 * b, pass_expected, err, dbg ? fv.ctl + 20 : nullptr);
+      if (r == 0 && lane == 0 && (reinterpret_cast<const int*>(ws + L.off_oor)[b] != 0 || offsets[b + 1] - offsets[b] > 32))
+        atomicOr(counters + 6, 1);                                // the tail has whole rows to redo
+      match_range(s, L, patch, print_wb, ws, b, r * 32 + lane, info.x * 32);
+      warp_signal(fv.img + 8 * b + 2, lane, nM, dbg ? fv.img + 8 * b + 5 : nullptr, t_base);
+    } else if ((r -= info.x) < info.y) {
+      // resize item of image k - skew
+      const int b = k - skew;
+      const int2 item = __ldcg(items + info.z + r);
+      wait_ge(fv.img + 8 * b + 2, nM, err, dbg ? fv.ctl + 21 : nullptr);
+      const BoxPlan* pl = plans + item.x;
+      const int mode = pl->two_tap ? 2 : pl->span;
+      if (mode == 2) resize_item<2>(s, L, ws, pl, item.x, item.y, inter, words, one, lane);
+      else if (mode == 5) resize_item<5>(s, L, ws, pl, item.x, item.y, inter, words, one, lane);
+      else if (mode == 7) resize_item<7>(s, L, ws, pl, item.x, item.y, inter, words, one, lane);
+      else if (mode == 3) resize_item<3>(s, L, ws, pl, item.x, item.y, inter, words, one, lane);
+      else if (mode == 9) resize_item<9>(s, L, ws, pl, item.x, item.y, inter, words, one, lane);
+      else resize_item<0>(s, L, ws, pl, item.x, item.y, inter, words, one, lane);
+      warp_signal(fv.img + 8 * b + 3, lane, info.y, dbg ? fv.img + 8 * b + 6 : nullptr, t_base);
+    } else {
+      // composite item of image k - 2 skew
+      r -= info.y;
+      const int b = k - 2 * skew;
+      const int2 item = __ldcg(citems + info.w + r);
+      const int n_resize = fv.step_info[b + skew].y;
+      const int n_comp = fv.step_start[k + 1] - fv.step_start[k] - info.x - info.y;
+      wait_ge(fv.img + 8 * b + 3, n_resize, err, dbg ? fv.ctl + 22 : nullptr);
+      wait_ge(fv.img + 8 * b + 1, pass_expected, err, dbg ? fv.ctl + 23 : nullptr);
+      const int j = item.x, r0 = item.y * kCompRows;
+      const SegBox me = load_segbox(plans + j, ubuf);
+      const int r1 = min(r0 + kCompRows, me.d);
+      const int first = plans[j].first_box, last = plans[j].last_box;
+      if (!item_is_general(reinterpret_cast<const int*>(ws + L.off_oor)[me.image], first, last)) {   // else: the tail
+        bool cand = false;                                        // lane l looks after box first + l of the image
+        {
+          const int q = first + lane;
+          if (q < last && q != j) {
+            const BoxPlan* o = plans + q;
+            const int4 g = *reinterpret_cast<const int4*>(&o->y0);   // y0, x0, ps, d
+            cand = o->valid && g.x < me.y0 + r1 && g.x + g.w > me.y0 + r0 && g.y < me.x0 + me.d && g.y + g.w > me.x0;
+          }
+        }
+        const bool others = __any_sync(0xffffffffu, cand);
+        const size_t img_off = (size_t)me.image * img_elems;
+        for (int wy = r0; wy < r1; ++wy) {
+          if (me.t6 != 0.0f || me.t7 != 0.0f)
+            composite_row_main<false, true>(me, plans, rowtab, routes + (size_t)j * L.rslot, lfull, W, j, wy, cand, others, first,
+                                            last, images + img_off, out + img_off, nullptr, open_count, open_list, open_cap, one, lane);
+          else
+            composite_row_main<false, false>(me, plans, rowtab, routes + (size_t)j * L.rslot, lfull, W, j, wy, cand, others, first,
+                                             last, images + img_off, out + img_off, nullptr, open_count, open_list, open_cap, one, lane);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence();
+        if (atomicAdd(fv.img + 8 * b + 4, 1) == n_comp - 1) {
+          atomicAdd(fv.ctl + 3, 1);
+          if (dbg) fv.img[8 * b + 7] = (int)(global_ns() - t_base);
+        }
+      }
+    }
+    t = tk.item(prefetch ? nxt : tk.draw(lane));
+  }
+  // ---- tail: open pixels and general rows, shared by every thread of the grid -------------------------------------------
+  if (dbg && threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned long long*>(fv.ctl + 12), global_ns() - t_base);
+  wait_ge(fv.ctl + 3, B, err, nullptr);
+  if (dbg && threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned long long*>(fv.ctl + 14), global_ns() - t_base);
+  composite_rest_body<false>(s, L, ws, images, out, nullptr, offsets, 0, B, 0, 1, blockIdx.x * blockDim.x + threadIdx.x,
+                             gridDim.x * blockDim.x);
+  if (dbg && threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned long long*>(fv.ctl + 16), global_ns() - t_base);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -825,6 +1170,81 @@ static int forward_groups(int B, int N) {
   return g < 1 ? 1 : (g > kMaxGroups ? kMaxGroups : (g > B ? B : g));
 }
 
+// The fused forward (k_forward_fused): memset of the accumulators + ONE cooperative launch.  Shapes it does not take
+// (mask output, in-place, unaligned rows, no boxes, image groups) stay on the kernel sequence of launch_forward.
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e && *e ? atoi(e) : dflt;
+}
+static int launch_forward_fused(const EotShape& s, const Layout& L, const float* patch, const float* scale, const float* images,
+                                const float* boxes, const int32_t* box_offsets, const EotBoxParams* params,
+                                const float* print_wb, float* out_images, char* ws, cudaStream_t st, bool* taken) {
+  *taken = false;
+  const int B = s.batch, P = s.patch_size, N = s.total_boxes;
+  const size_t smem_win = resize_warp_smem(s, L) * (kThreads / 32);
+  const size_t smem_copy = (size_t)kFusedStages * kFusedTilePix * 12;
+  const size_t smem = smem_win > smem_copy ? smem_win : smem_copy;
+  if (smem > 200 * 1024 || (size_t)(B + 2 * kMaxSkew) * 4 > smem) return EOT_OK;   // (launch_forward reports the patch side)
+  struct Cfg { size_t smem; int per_sm; int dev; };
+  static thread_local Cfg cfg = {0, 0, -1};
+  int dev = 0;
+  EOT_CHECK_CUDA(cudaGetDevice(&dev));
+  if (cfg.smem != smem || cfg.dev != dev) {
+    EOT_CHECK_CUDA(cudaFuncSetAttribute(k_forward_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    EOT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_forward_fused, kThreads, smem));
+    cfg = {smem, occ, dev};
+  }
+  if (cfg.per_sm < 2) return EOT_OK;
+  static const int copy_per_sm = env_int("EOT_FUSED_COPY", 0), slots_env = env_int("EOT_FUSED_SLOTS", 4),
+                   skew_env = env_int("EOT_FUSED_SKEW", 16), prefetch_env = env_int("EOT_FUSED_PREFETCH", 1),
+                   dbg_env = env_int("EOT_KERNEL_TIMES", 0);
+  const int nsm = sm_count();
+  const int grid = nsm * cfg.per_sm;
+  int slots = slots_env < 1 ? 1 : (slots_env > B ? B : slots_env);
+  int cps = copy_per_sm > 0 ? copy_per_sm : cfg.per_sm / 2;
+  if (cps > cfg.per_sm - 1) cps = cfg.per_sm - 1;
+  int n_copy = nsm * cps / slots * slots;                         // `slots` images at a time, n_copy / slots CTAs each
+  if (n_copy < slots) return EOT_OK;
+  const int skew = skew_env < 1 ? 1 : (skew_env > kMaxSkew ? kMaxSkew : skew_env);
+  int nM = (P * P + kMatchTexels - 1) / kMatchTexels;
+  int pchunks = max(1, min((P * P + kThreads * 4 - 1) / (kThreads * 4), 64));
+  int n_geom = N;
+  float one = 1.0f;
+  int prefetch = prefetch_env, dbg = dbg_env;
+  EotShape sv = s;
+  Layout Lv = L;
+  EOT_CHECK_CUDA(cudaMemsetAsync(ws + L.off_ysum_img, 0, L.off_plans - L.off_ysum_img, st));
+  void* args[] = {&sv, &Lv, &patch, &print_wb, &boxes, &box_offsets, &params, &scale, &images, &out_images, &ws,
+                  &n_geom, &pchunks, &n_copy, &slots, const_cast<int*>(&skew), &nM, &one, &prefetch, &dbg};
+  EOT_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)k_forward_fused, dim3(grid), dim3(kThreads), args, smem, st));
+  count_launches(1);
+  EOT_CHECK_CUDA(cudaPeekAtLastError());
+  if (dbg) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone) {
+      int ctl[32];
+      EOT_CHECK_CUDA(cudaMemcpyAsync(ctl, ws + L.off_fused, sizeof(ctl), cudaMemcpyDeviceToHost, st));
+      EOT_CHECK_CUDA(cudaStreamSynchronize(st));
+      const unsigned long long* tt = reinterpret_cast<const unsigned long long*>(ctl + 8);
+      if (dbg > 1) {
+        static int img[8 * 4096];
+        const int nb = B < 4096 ? B : 4096;
+        EOT_CHECK_CUDA(cudaMemcpy(img, ws + L.off_fused + 256, (size_t)nb * 32, cudaMemcpyDeviceToHost));
+        for (int b = 0; b < nb; b += (nb > 32 ? nb / 32 : 1))
+          fprintf(stderr, "[eot]   image %3d: match %6.1f resize %6.1f composite %6.1f us (items %d %d)\n", b, img[8 * b + 5] * 1e-3,
+                  img[8 * b + 6] * 1e-3, img[8 * b + 7] * 1e-3, img[8 * b + 3], img[8 * b + 4]);
+      }
+      fprintf(stderr, "[eot] fused: last geometry block starts tables %.1f us, tables ready %.1f, statistics done %.1f, small roles end (max) %.1f; pass of image 0 / 4 / 16 / 32 done %.1f %.1f %.1f %.1f\n",
+              ctl[27] * 1e-3, ctl[24] * 1e-3, ctl[25] * 1e-3, ctl[26] * 1e-3, ctl[28] * 1e-3, ctl[29] * 1e-3, ctl[30] * 1e-3, ctl[31] * 1e-3);
+      fprintf(stderr, "[eot] fused: tasks %d, copy done %.1f us, queue done %.1f us, composites done %.1f us, end %.1f us; polls M %d R %d C %d store %d (grid %d, copy CTAs %d, slots %d, skew %d)\n",
+              ctl[1], tt[1] * 1e-3, tt[2] * 1e-3, tt[3] * 1e-3, tt[4] * 1e-3, ctl[20], ctl[21], ctl[22], ctl[23], grid, n_copy, slots, skew);
+    }
+  }
+  *taken = true;
+  return EOT_OK;
+}
+
 // Enqueues the whole forward: memset of the small accumulators, then per image group the pre-pass (image pass; the
 // first one also carries the geometry and patch-statistics roles) on the caller's stream and match -> resize ->
 // composite on the auxiliary stream, so that the HBM-bound image pass of group g + 1 overlaps the L2-resident,
@@ -833,6 +1253,17 @@ static int launch_forward(const EotShape& s, const Layout& L, const float* patch
                           const float* boxes, const int32_t* box_offsets, const EotBoxParams* params,
                           const float* print_wb, float* out_images, float* mask, char* ws, cudaStream_t st) {
   const int B = s.batch, P = s.patch_size, HW = s.height * s.width, N = s.total_boxes;
+  {
+    static const int fused_on = env_int("EOT_FWD_FUSED", 0);
+    const bool vec0 = (HW % 4 == 0) && (((uintptr_t)images | (uintptr_t)out_images) & 15) == 0;
+    if (fused_on && N > 0 && vec0 && !mask && out_images != images && forward_groups(B, N) == 1) {
+      bool taken = false;
+      StageTimer ftimer(st, "eot_apply_fwd (fused)");
+      if (int rc = launch_forward_fused(s, L, patch, scale, images, boxes, box_offsets, params, print_wb, out_images, ws, st, &taken))
+        return rc;
+      if (taken) { ftimer.mark("all"); return EOT_OK; }
+    }
+  }
   StageTimer timer(st, "eot_apply_fwd");
   EOT_CHECK_CUDA(cudaMemsetAsync(ws + L.off_ysum_img, 0, L.off_plans - L.off_ysum_img, st));
   const int pchunks = max(1, min((P * P + kThreads * 4 - 1) / (kThreads * 4), 64));
@@ -842,13 +1273,15 @@ static int launch_forward(const EotShape& s, const Layout& L, const float* patch
   AuxStream* aux = nullptr;
   if (G > 1)
     if (int rc = aux_stream(&aux)) return rc;
+  float* pass_out = out_images;
   for (int g = 0; g < G; ++g) {
     const int b0 = (int)((long long)B * g / G), b1 = (int)((long long)B * (g + 1) / G);
     const int n_geom = g == 0 ? N : 0, n_stat = g == 0 ? B : 0;
     const long long nblocks = (long long)n_geom + (long long)n_stat * pchunks + (long long)(b1 - b0) * cpi;
     if (nblocks >= (1ll << 31)) { set_error("eot_apply_fwd: grid too large"); return EOT_ERR_BAD_SHAPE; }
     // bulk-copy pipeline when the pass really copies (out of place, no mask) and tiles / rows are 16-byte aligned
-    const bool bulk = EOT_PREPASS_BULK && vec && !mask && out_images != images;
+    static const int bulk_env = env_int("EOT_PREPASS_BULK_ON", 1);
+    const bool bulk = EOT_PREPASS_BULK && bulk_env && vec && !mask && out_images != images;
     if (bulk) {
       const size_t smem = (size_t)kBulkStages * kBulkTilePix * 12;
       static thread_local bool attr_set = false;
@@ -859,13 +1292,13 @@ static int launch_forward(const EotShape& s, const Layout& L, const float* patch
       const long long tiles = (long long)(b1 - b0) * ((HW + kBulkTilePix - 1) / kBulkTilePix);
       const int copy_ctas = (int)(tiles < (long long)EOT_BULK_CTAS * sm_count() ? tiles : (long long)EOT_BULK_CTAS * sm_count());
       k_prepass_bulk<<<(unsigned)(n_geom + n_stat * pchunks + copy_ctas), kThreads, smem, st>>>(
-          s, L, patch, print_wb, boxes, box_offsets, params, scale, images, out_images, ws, n_geom, n_stat, pchunks, copy_ctas, b0, b1);
+          s, L, patch, print_wb, boxes, box_offsets, params, scale, images, pass_out, ws, n_geom, n_stat, pchunks, copy_ctas, b0, b1);
     } else if (vec)
       k_prepass<true><<<(unsigned)nblocks, kThreads, 0, st>>>(s, L, patch, print_wb, boxes, box_offsets, params, scale, images,
-                                                              out_images, mask, ws, n_geom, n_stat, pchunks, cpi, b0);
+                                                              pass_out, mask, ws, n_geom, n_stat, pchunks, cpi, b0);
     else
       k_prepass<false><<<(unsigned)nblocks, kThreads, 0, st>>>(s, L, patch, print_wb, boxes, box_offsets, params, scale, images,
-                                                               out_images, mask, ws, n_geom, n_stat, pchunks, cpi, b0);
+                                                               pass_out, mask, ws, n_geom, n_stat, pchunks, cpi, b0);
     count_launches(1);
     if (G == 1) timer.mark("prepass");
     if (N == 0) continue;
