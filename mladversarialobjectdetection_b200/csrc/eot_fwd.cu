@@ -158,30 +158,41 @@ __device__ __forceinline__ int2 inverse_span_search(const int* starts, int n_out
 }
 
 // One CTA per box: plan, span table, inverse-span table, work-item counts.
+// Under a saturated memory system every dependent global round trip of this role costs ~1.5 us and the image pass cannot
+// end before the role does, so the chain is kept short: the image of the box is found by all threads at once (no binary
+// search over the CSR), and the span starts / tap weights the later steps read back live in shared memory (`scratch`,
+// `scratch_bytes`; boxes whose tables do not fit read them back from global memory).
 __device__ int geometry_block(const EotShape& s, const Layout& L, int j, const float* __restrict__ boxes,
                                const int32_t* __restrict__ offsets, const EotBoxParams* __restrict__ params,
-                               const float* __restrict__ scale, char* ws, EotBoxGeometry* geom_out) {
+                               const float* __restrict__ scale, char* ws, EotBoxGeometry* geom_out, void* scratch,
+                               int scratch_bytes) {
   __shared__ BoxPlan spl;
   __shared__ int s_maxcnt;
+  __shared__ int s_img[3];                                        // image of box j, its CSR range
   int* counters = ws ? reinterpret_cast<int*>(ws + L.off_counters) : nullptr;
+  if (threadIdx.x == 0) { s_maxcnt = 0; s_img[0] = -1; s_img[1] = 0; s_img[2] = 0; }
+  __syncthreads();
+  for (int b = threadIdx.x; b < s.batch; b += blockDim.x) {       // image of box j: offsets[b] <= j < offsets[b + 1]
+    const int lo = offsets[b], hi = offsets[b + 1];
+    if (lo <= j && j < hi) { s_img[0] = b; s_img[1] = lo; s_img[2] = hi; }
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
-    s_maxcnt = 0;
     // total_boxes is a CAPACITY: the boxes in use are [0, box_offsets[B]) (read here, on the device, so that a caller
     // whose box count comes out of a kernel -- the first pass' NMS -- needs no host read); the slots past them are
     // invalid boxes without work.  More boxes than the capacity: flagged (eot_check_workspace), the surplus is dropped.
     const int n_used = offsets[s.batch];
     if (n_used > s.total_boxes && counters) atomicOr(counters + 2, 8);
-    int a = 0, b = s.batch;                       // image of box j: last b with offsets[b] <= j
-    while (a < b) { const int m = (a + b) >> 1; if (offsets[m + 1] <= j) a = m + 1; else b = m; }
-    const bool used = j < n_used && a < s.batch;
-    if (!used) a = s.batch - 1;
+    const bool used = j < n_used && s_img[0] >= 0;
+    const int a = used ? s_img[0] : s.batch - 1;
+    const int first = used ? s_img[1] : offsets[a], last = used ? s_img[2] : offsets[a + 1];
     EotBoxParams prm = {};
     float bx[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     if (used) {
       prm = params[j];
       for (int k = 0; k < 4; ++k) bx[k] = boxes[(size_t)j * 4 + k];
     }
-    BoxPlan pl = make_plan(bx, *scale, prm, s, a, offsets[a], min(offsets[a + 1], s.total_boxes), (int64_t)j * L.slot,
+    BoxPlan pl = make_plan(bx, *scale, prm, s, a, first, min(last, s.total_boxes), (int64_t)j * L.slot,
                            used && counters ? counters + 2 : nullptr);
     if (!used) pl.valid = 0;
     if (pl.valid) pl.span = span_cfg(pl.ps, s.patch_size).span;
@@ -204,16 +215,29 @@ __device__ int geometry_block(const EotShape& s, const Layout& L, int j, const f
   int* starts = reinterpret_cast<int*>(ws + L.off_starts) + (size_t)j * L.lmin;
   float* weights = reinterpret_cast<float*>(ws + L.off_weights) + (size_t)j * L.wcap;
   const SpanCfg cfg = span_cfg(ps, P);
+  // shared-memory copies of the starts and of the tap-major weights, when they fit
+  const bool staged = scratch && (size_t)ps * (cfg.span + 1) * 4 <= (size_t)scratch_bytes;
+  int* s_starts = reinterpret_cast<int*>(scratch);
+  float* s_w = reinterpret_cast<float*>(scratch) + ps;
   // Two-tap form: with span 3 (up-sampling / unit scale) the triangle kernel has at most two adjacent non-zero taps per
   // output index; when that holds for every index of the box (checked, not assumed) the resize reads (a, b, wa, wb).
   // Dropping a tap of weight 0 drops an addition of +-0: the sums are the oracle's.
   float4* tab2 = reinterpret_cast<float4*>(ws + L.off_tab2) + (size_t)j * L.lmin;
   bool two = cfg.span == 3;
   for (int o = threadIdx.x; o < ps; o += blockDim.x) {
-    span_row(o, cfg, P, starts + o, weights + o, ps);
+    int st;
+    if (staged) {
+      span_row(o, cfg, P, &st, s_w + o, ps);
+      s_starts[o] = st;
+      starts[o] = st;
+      for (int k = 0; k < cfg.span; ++k) weights[(size_t)k * ps + o] = s_w[(size_t)k * ps + o];
+    } else {
+      span_row(o, cfg, P, &st, weights + o, ps);
+      starts[o] = st;
+    }
     if (cfg.span == 3) {
-      const float w0 = weights[o], w1 = weights[ps + o], w2 = weights[2 * ps + o];
-      const int st = starts[o];
+      const float* wsrc = staged ? s_w : weights;
+      const float w0 = wsrc[o], w1 = wsrc[ps + o], w2 = wsrc[2 * ps + o];
       int ia; float wa, wb;
       if (w2 == 0.0f) { ia = st; wa = w0; wb = w1; }
       else if (w0 == 0.0f) { ia = st + 1; wa = w1; wb = w2; }
@@ -225,11 +249,13 @@ __device__ int geometry_block(const EotShape& s, const Layout& L, int j, const f
   }
   const int all_two = __syncthreads_and(two ? 1 : 0);   // (also: starts[] of this box are complete)
   if (threadIdx.x == 0) reinterpret_cast<BoxPlan*>(ws + L.off_plans)[j].two_tap = all_two;
+  const int* st_src = staged ? s_starts : starts;
+  const float* w_src = staged ? s_w : weights;
   int2* inv = reinterpret_cast<int2*>(ws + L.off_inv) + (size_t)j * P;
   float* wt = reinterpret_cast<float*>(ws + L.off_wt) + (size_t)j * P * L.tcap;
   int2* stt = reinterpret_cast<int2*>(ws + L.off_stt) + (size_t)j * (P + 1);
   for (int i = threadIdx.x; i < P; i += blockDim.x) {
-    const int2 rng = inverse_span_search(starts, ps, cfg.span, i);
+    const int2 rng = inverse_span_search(st_src, ps, cfg.span, i);
     inv[i] = rng;
     int cnt = rng.y - rng.x + 1;
     if (cnt < 0) cnt = 0;
@@ -242,16 +268,23 @@ __device__ int geometry_block(const EotShape& s, const Layout& L, int j, const f
   // stride = the largest tap count of this box
   const int tstride = max(s_maxcnt, 1);
   for (int i = threadIdx.x; i < P; i += blockDim.x) {
-    const int2 rng = inv[i];
-    const int cnt = stt[i].y;
-    for (int k = 0; k < tstride; ++k) {
-      const int o = rng.x + k;
-      float w = 0.0f;
-      if (k < cnt) {
-        const int kk = i - starts[o];
-        if (kk >= 0 && kk < cfg.span) w = weights[(size_t)kk * ps + o];
+    const int2 rng = inverse_span_search(st_src, ps, cfg.span, i);    // (recomputed: cheaper than the global read-back)
+    int cnt = rng.y - rng.x + 1;
+    cnt = cnt < 0 ? 0 : (cnt > L.tcap ? L.tcap : cnt);
+    for (int k0 = 0; k0 < tstride; k0 += 4) {                     // the loads of four taps travel together
+      float w[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int k = k0 + q, o = rng.x + k;
+        w[q] = 0.0f;
+        if (k < cnt) {
+          const int kk = i - st_src[o];
+          if (kk >= 0 && kk < cfg.span) w[q] = w_src[(size_t)kk * ps + o];
+        }
       }
-      wt[(size_t)i * tstride + k] = w;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (k0 + q < tstride) wt[(size_t)i * tstride + k0 + q] = w[q];
     }
   }
   if (threadIdx.x == 0) {
@@ -318,7 +351,7 @@ __global__ void __launch_bounds__(kThreads) k_geometry_only(EotShape s, Layout L
                                                             const int32_t* __restrict__ offsets,
                                                             const EotBoxParams* __restrict__ params,
                                                             const float* __restrict__ scale, EotBoxGeometry* geom_out) {
-  geometry_block(s, L, blockIdx.x, boxes, offsets, params, scale, nullptr, geom_out);
+  geometry_block(s, L, blockIdx.x, boxes, offsets, params, scale, nullptr, geom_out, nullptr, 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -448,7 +481,7 @@ __device__ int small_roles(const EotShape& s, const Layout& L, int blk, const fl
     __shared__ int s_last;
     int4* s_part = reinterpret_cast<int4*>(scratch);               // [kThreads]
     unsigned* s_cost = reinterpret_cast<unsigned*>(s_part + kThreads);   // [kMaxOrderedImages]
-    geometry_block(s, L, blk, boxes, offsets, params, scale, ws, nullptr);
+    geometry_block(s, L, blk, boxes, offsets, params, scale, ws, nullptr, scratch, kSmallRolesScratch);
     __threadfence();
     __syncthreads();
     int* counters = reinterpret_cast<int*>(ws + L.off_counters);
@@ -497,6 +530,10 @@ __device__ int small_roles(const EotShape& s, const Layout& L, int blk, const fl
   if (blk < n_stat_imgs * pchunks) {
     const int b = blk / pchunks;
     patch_stats_block(s, b, blk - b * pchunks, pchunks, patch, print_wb, reinterpret_cast<double*>(ws + L.off_ysum_patch), red);
+    if (threadIdx.x == 0) {                              // (thread 0 added the block's sum) finished statistics blocks
+      __threadfence();
+      atomicAdd(reinterpret_cast<int*>(ws + L.off_fused) + 2, 1);
+    }
     if (blk == 0 && threadIdx.x == 0) {                  // CSR copy for the backward
       int32_t* off_copy = reinterpret_cast<int32_t*>(ws + L.off_offsets);
       for (int i = 0; i <= s.batch; ++i) off_copy[i] = min(offsets[i], s.total_boxes);
@@ -531,6 +568,44 @@ __global__ void __launch_bounds__(kThreads, EOT_PREPASS_MINB) k_prepass(EotShape
   image_pass_block<kVec>(s.height * s.width, b, chunk, images, out, mask, reinterpret_cast<double*>(ws + L.off_ysum_img),
                          reinterpret_cast<int*>(ws + L.off_oor), red);
 }
+
+// ---- acquire / release plumbing between CTAs of one launch ----
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Warp-wide wait until *p >= v: lane 0 polls (acquire) with exponential back-off -- thousands of warps polling a handful of
+// L2 lines at full rate starve the very atomics they wait for.  A wait that outlasts ~2 s (a lost signal: a bug, never
+// load) raises error flag 16 and goes on, so that a fault shows as a failed call instead of a hung device.
+__device__ __forceinline__ void wait_ge(const int* p, int v, int* err, int* spins, bool one_thread = false) {
+  if (one_thread) {                                               // called by a single thread (no warp convergence)
+    unsigned ns = 64, n = 0;
+    while (ld_acquire(p) < v) {
+      __nanosleep(ns);
+      if (ns < 2048) ns *= 2;
+      if (++n > (1u << 20)) { atomicOr(err, 16); break; }
+    }
+    return;
+  }
+  if ((threadIdx.x & 31) == 0 && ld_acquire(p) < v) {
+    unsigned ns = 128, n = 0;
+    while (ld_acquire(p) < v) {
+      __nanosleep(ns);
+      if (ns < 2048) ns *= 2;
+      if (++n > (1u << 20)) { atomicOr(err, 16); break; }
+    }
+    if (spins) atomicAdd(spins, (int)n);
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void match_range(const EotShape& s, const Layout& L, const float* __restrict__ patch,
+                                            const float* __restrict__ print_wb, char* ws, int b, int t0, int tstride);
 
 // ------------------------------------------------------------------------------------------------
 // Image pass as a bulk-copy pipeline (cp.async.bulk + mbarrier: the TMA engine moves the bytes, the threads only read
@@ -655,7 +730,11 @@ __global__ void __launch_bounds__(kThreads, EOT_BULK_CTAS) k_prepass_bulk(EotSha
     if ((it + 1) % tiles_mine == 0) {                             // (uniform) last tile of this image for this CTA
       const int any = __syncthreads_or(oor ? 1 : 0);
       acc = block_sum(acc, red);
-      if (threadIdx.x == 0) { atomicAdd(ysum_img + tile_img(it), acc); if (any) atomicOr(oor_flags + tile_img(it), 1); }
+      const int b = tile_img(it);
+      if (threadIdx.x == 0) {
+        atomicAdd(ysum_img + b, acc);
+        if (any) atomicOr(oor_flags + b, 1);
+      }
       acc = 0.0; oor = false;
     }
   }
@@ -665,9 +744,6 @@ __global__ void __launch_bounds__(kThreads, EOT_BULK_CTAS) k_prepass_bulk(EotSha
 // ------------------------------------------------------------------------------------------------
 // print adjust + brightness match of the patch for image b (attacker.py:372; brightness_matcher.py:43-73)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void match_range(const EotShape& s, const Layout& L, const float* __restrict__ patch,
-                                            const float* __restrict__ print_wb, char* ws, int b, int t0, int tstride);
-
 // blocks [0, nb * pchunks): match the patch to image b0 + blk / pchunks (needs the finished pre-pass: mean luma)
 __global__ void __launch_bounds__(kThreads) k_match(EotShape s, Layout L, const float* __restrict__ patch,
                                                     const float* __restrict__ print_wb, const int32_t* __restrict__ offsets,
@@ -687,8 +763,8 @@ __device__ __forceinline__ void match_range(const EotShape& s, const Layout& L, 
   const int P = s.patch_size;
   const double* ysum_img = reinterpret_cast<const double*>(ws + L.off_ysum_img);
   const double* ysum_patch = reinterpret_cast<const double*>(ws + L.off_ysum_patch);
-  const float mu_t = (float)(ysum_img[b] / (double)((size_t)s.height * s.width));
-  const float mu_s = (float)(ysum_patch[b] / (double)((size_t)P * P));
+  const float mu_t = (float)(__ldcg(ysum_img + b) / (double)((size_t)s.height * s.width));
+  const float mu_s = (float)(__ldcg(ysum_patch + b) / (double)((size_t)P * P));
   const float* wb = print_wb + (size_t)b * 6;
   const float* base = patch + (s.num_patches > 1 ? (int64_t)b * s.patch_stride_n : 0);
   float4* m = reinterpret_cast<float4*>(ws + L.off_match) + (size_t)b * P * P;
@@ -779,32 +855,6 @@ __device__ __forceinline__ FusedView fused_view(char* ws, const Layout& L, int B
   v.step_info = reinterpret_cast<int4*>(v.step_start + fused_start_ints(B));
   return v;
 }
-__device__ __forceinline__ int ld_acquire(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-// Warp-wide wait until *p >= v: lane 0 polls (acquire) with exponential back-off -- thousands of warps polling a handful of
-// L2 lines at full rate starve the very atomics they wait for.  A wait that outlasts ~2 s (a lost signal: a bug, never
-// load) raises error flag 16 and goes on, so that a fault shows as a failed call instead of a hung device.
-__device__ __forceinline__ void wait_ge(const int* p, int v, int* err, int* spins) {
-  if ((threadIdx.x & 31) == 0 && ld_acquire(p) < v) {
-    unsigned ns = 128, n = 0;
-    while (ld_acquire(p) < v) {
-      __nanosleep(ns);
-      if (ns < 2048) ns *= 2;
-      if (++n > (1u << 20)) { atomicOr(err, 16); break; }
-    }
-    if (spins) atomicAdd(spins, (int)n);
-  }
-  __syncwarp();
-}
-__device__ __forceinline__ unsigned long long global_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-__device__ __forceinline__ unsigned long long global_ns();
 // Completion of one task of a per-image counter; with the debug timeline on, the task that completes the image's stage
 // (count `full`) stamps the time into `stamp`.
 __device__ __forceinline__ void warp_signal(int* p, int lane, int full = 0, int* stamp = nullptr, unsigned long long t_base = 0) {
@@ -958,10 +1008,6 @@ __global__ void __launch_bounds__(kThreads, EOT_FUSED_MINB) k_forward_fused(
     const int n_small = n_geom + B * pchunks, nwin = gridDim.x - n_copy;
     for (int blk = blockIdx.x - n_copy; blk < n_small; blk += nwin) {
       const int r = small_roles(s, L, blk, patch, print_wb, boxes, offsets, params, scale, ws, n_geom, B, pchunks, red, fsmem);
-      if (blk >= n_geom && threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(fv.ctl + 2, 1) == B * pchunks - 1 && dbg) fv.ctl[25] = (int)(global_ns() - t_base);
-      }
       if (r == 2) {
         if (dbg && threadIdx.x == 0) fv.ctl[27] = (int)(global_ns() - t_base);
         build_steps(s, L, ws, offsets, n_geom, skew, nM, reinterpret_cast<int*>(fsmem));
