@@ -351,7 +351,7 @@ def run_ours(args):
         return d
     kernels = [
         entry("eot_apply_fwd (k_prepass + k_match + k_resize2 + k_composite3 + k_composite_rest)", 24.0 * H * H * B + 12.0 * P * P, t_fwd),
-        entry("eot_apply_bwd (k_bwd_window + k_bwd_resize + ...)", win_bytes + 12.0 * P * P, t_bwd,
+        entry("eot_apply_bwd (k_bwd_image + k_bwd_texel)", win_bytes + 12.0 * P * P, t_bwd,
               "expected latency/shared-memory bound: touches only the patch windows"),
         entry("score_max_fwd (k_score_fwd)", 376.0 * A * B + 16.0 * A, t_sf),
         entry("score_max_bwd (k_score_zero + scatter)", 360.0 * A * B, t_sb),

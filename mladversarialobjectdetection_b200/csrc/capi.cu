@@ -32,6 +32,11 @@ int sm_count() {
   return n;
 }
 
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("EOT_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 static bool stage_times_enabled() {
   static const bool on = [] { const char* e = getenv("EOT_KERNEL_TIMES"); return e && e[0] == '1'; }();
   return on;

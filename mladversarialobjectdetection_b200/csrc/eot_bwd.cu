@@ -199,6 +199,7 @@ __global__ void __launch_bounds__(kThreads, EOT_BWD_MINB) k_bwd_image(EotShape s
   extern __shared__ __align__(16) unsigned char bsm[];
   __shared__ double red[32];
   __shared__ int s_item;
+  pdl_trigger();
   const BwdSmem m = bwd_smem_plan(s, L);
   float* acc = reinterpret_cast<float*>(bsm);
   int2* s_st = reinterpret_cast<int2*>(bsm + m.off_st);
@@ -323,6 +324,7 @@ __global__ void __launch_bounds__(kThreads) k_bwd_texel(EotShape s, Layout L, ch
                                                         const float* __restrict__ print_wb, int groups, float* grad_patch,
                                                         int accumulate) {
   __shared__ int s_last;
+  pdl_wait();
   const int P = s.patch_size, PP = P * P;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int g = blockIdx.y;
@@ -408,8 +410,8 @@ extern "C" int eot_apply_bwd(const EotShape* shape, const float* patch, const fl
   k_bwd_image<<<grid, kThreads, m.total, st>>>(s, L, ws, grad_images, patch, print_wb);
   timer.mark("image");
   const int groups = B < kBwdGroups ? B : kBwdGroups;
-  k_bwd_texel<<<dim3((PP + kThreads - 1) / kThreads, groups), kThreads, 0, st>>>(s, L, ws, patch, print_wb, groups, grad_patch,
-                                                                                  accumulate);
+  EOT_CHECK_CUDA(launch_pdl(k_bwd_texel, dim3((PP + kThreads - 1) / kThreads, groups), dim3(kThreads), 0, st, s, L, ws, patch, print_wb,
+                            groups, grad_patch, accumulate));
   timer.mark("texel");
   count_launches(2);
   EOT_CHECK_CUDA(cudaPeekAtLastError());

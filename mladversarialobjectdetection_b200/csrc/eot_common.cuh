@@ -46,6 +46,9 @@ namespace eot {
 #define EOT_BWD_ROWS_CAP 32
 #endif
 constexpr int kCompRows = EOT_COMP_ROWS;  // window rows per composite work item (one warp)
+// forward resize: texels per Philox round trip (96 counters = 3 full warps) and the words of one such chunk of a row
+constexpr int kNoiseChunk = 128;
+constexpr int kNoiseWords = (kNoiseChunk * 3 / 4 + 1) * 4;          // (+ one counter when the chunk starts unaligned)
 constexpr int kThreads = 256;
 // Work tickets.  One atomic counter handing out every item of a kernel is the bottleneck of warp-granular items (a
 // same-address atomic completes every ~2.3 ns on B200: 27 k items = 60 us).  Each kernel therefore owns kTicketLanes
@@ -153,8 +156,10 @@ __host__ __device__ inline Layout make_layout(const EotShape& s) {
   L.tcap = 3 * ((lmin + s.patch_size - 1) / s.patch_size) + 3;
   int rr = 2560 / s.patch_size;              // <= 40 KB of RGBX float32 intermediate rows
   L.resize_rows = rr > EOT_RESIZE_ROWS_CAP ? EOT_RESIZE_ROWS_CAP : (rr < 1 ? 1 : rr);
+  // rows per forward resize item: two when four CTAs of eight such warps still fit an SM's shared memory (P <= 110),
+  // else one -- measured at P = 300: 4 CTAs per SM with one row per item beat 2 CTAs with two rows (137 -> 131 us)
   L.rb = EOT_RESIZE_RB;
-  while (L.rb > 1 && (size_t)L.rb * s.patch_size * 16 > 12 * 1024) --L.rb;   // <= 12 KB of intermediate rows per warp
+  while (L.rb > 1 && 8 * (size_t)L.rb * ((size_t)s.patch_size * 16 + kNoiseWords * 4) > 53 * 1024) --L.rb;
   L.cr = EOT_COMP_ROWS;
   L.p3_magic = (uint32_t)((((uint64_t)1 << 32) + (uint64_t)(s.patch_size * 3) - 1) / (uint64_t)(s.patch_size * 3));
   const size_t PP3 = (size_t)s.patch_size * s.patch_size * 3;
@@ -243,6 +248,29 @@ struct StageTimer {
   const char* names[16];
 };
 
+// Programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream drains (launch latency
+// and block ramp-up overlap the predecessor's tail); it calls pdl_wait() before touching anything an earlier kernel
+// wrote.  Every kernel of a chain waits, so completion stays transitive.  EOT_PDL=0 launches plainly.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  // measured on B200 (profiles/r02_fused_forward.md): eager launches gain (config 4: 135 -> 125 us, config 2 unchanged), replays of
+  // a captured graph lose (config 2: 191 -> 199 us) -- graph edges are cheap already -- so captures launch plainly
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  const bool capturing = cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone;
+  cfg.numAttrs = (pdl_enabled() && !capturing) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 #define EOT_CHECK_CUDA(expr)                                   \
   do {                                                         \
     cudaError_t _e = (expr);                                   \
@@ -251,6 +279,12 @@ struct StageTimer {
 
 #ifdef __CUDACC__
 // ---- small device helpers ---------------------------------------------------------------------------
+// (no-op for a plain launch)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Lets the next kernel of the stream (if launched with launch_pdl) become resident as this grid's CTAs retire; it still
+// waits in pdl_wait() for this grid to complete.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // Makes a pointer opaque to the optimiser: under register pressure ptxas otherwise re-derives per-row base pointers
 // from the kernel parameters (a dozen 64-bit instructions) at every use inside the pixel loops.
 template <typename T>

@@ -27,6 +27,8 @@ __global__ void __launch_bounds__(kThreads, EOT_COMP_MINB) k_composite3(EotShape
                                                                        const float* __restrict__ images, float* out, float* mask,
                                                                        const int32_t* __restrict__ offsets, int b0, int b1,
                                                                        int group, int ngroups, float one) {
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const BoxPlan* plans = reinterpret_cast<const BoxPlan*>(ws + L.off_plans);
   const float* ubuf = reinterpret_cast<const float*>(ws + L.off_u);
@@ -86,6 +88,7 @@ template <bool kMask>
 __global__ void __launch_bounds__(kThreads, EOT_REST_MINB) k_composite_rest(EotShape s, Layout L, char* ws, const float* __restrict__ images,
                                                              float* out, float* mask, const int32_t* __restrict__ offsets, int b0,
                                                              int b1, int group, int ngroups) {
+  pdl_wait();
   composite_rest_body<kMask>(s, L, ws, images, out, mask, offsets, b0, b1, group, ngroups, blockIdx.x * blockDim.x + threadIdx.x,
                              gridDim.x * blockDim.x);
 }
@@ -94,11 +97,11 @@ int launch_composite3(const EotShape& s, const Layout& L, char* ws, const int32_
                       float* mask, int b0, int b1, int group, int ngroups, cudaStream_t st) {
   const int nsm = sm_count();
   if (mask) {
-    k_composite3<true><<<nsm * EOT_COMP_MINB, kThreads, 0, st>>>(s, L, ws, images, out, mask, offsets, b0, b1, group, ngroups, 1.0f);
-    k_composite_rest<true><<<nsm * EOT_REST_MINB, kThreads, 0, st>>>(s, L, ws, images, out, mask, offsets, b0, b1, group, ngroups);
+    EOT_CHECK_CUDA(launch_pdl(k_composite3<true>, dim3(nsm * EOT_COMP_MINB), dim3(kThreads), 0, st, s, L, ws, images, out, mask, offsets, b0, b1, group, ngroups, 1.0f));
+    EOT_CHECK_CUDA(launch_pdl(k_composite_rest<true>, dim3(nsm * EOT_REST_MINB), dim3(kThreads), 0, st, s, L, ws, images, out, mask, offsets, b0, b1, group, ngroups));
   } else {
-    k_composite3<false><<<nsm * EOT_COMP_MINB, kThreads, 0, st>>>(s, L, ws, images, out, mask, offsets, b0, b1, group, ngroups, 1.0f);
-    k_composite_rest<false><<<nsm * EOT_REST_MINB, kThreads, 0, st>>>(s, L, ws, images, out, mask, offsets, b0, b1, group, ngroups);
+    EOT_CHECK_CUDA(launch_pdl(k_composite3<false>, dim3(nsm * EOT_COMP_MINB), dim3(kThreads), 0, st, s, L, ws, images, out, mask, offsets, b0, b1, group, ngroups, 1.0f));
+    EOT_CHECK_CUDA(launch_pdl(k_composite_rest<false>, dim3(nsm * EOT_REST_MINB), dim3(kThreads), 0, st, s, L, ws, images, out, mask, offsets, b0, b1, group, ngroups));
   }
   count_launches(2);
   return EOT_OK;

@@ -560,6 +560,7 @@ __global__ void __launch_bounds__(kThreads, EOT_PREPASS_MINB) k_prepass(EotShape
                                                       int pchunks, int cpi, int b0) {
   __shared__ double red[32];
   __shared__ __align__(16) unsigned char s_scratch[kSmallRolesScratch];
+  pdl_trigger();
   int blk = blockIdx.x;
   if (small_roles(s, L, blk, patch, print_wb, boxes, offsets, params, scale, ws, n_geom, n_stat_imgs, pchunks, red, s_scratch)) return;
   blk -= n_geom;
@@ -666,6 +667,7 @@ __global__ void __launch_bounds__(kThreads, EOT_BULK_CTAS) k_prepass_bulk(EotSha
   __shared__ double red[32];
   __shared__ __align__(8) uint64_t s_full[kBulkStages];
   static_assert((size_t)EOT_BULK_STAGES * kBulkTilePix * 12 >= (size_t)kSmallRolesScratch, "the stage buffers double as the small roles' scratch");
+  pdl_trigger();
   int blk = blockIdx.x;
   if (small_roles(s, L, blk, patch, print_wb, boxes, offsets, params, scale, ws, n_geom, n_stat_imgs, pchunks, red, stage_mem)) return;
   blk -= n_geom + n_stat_imgs * pchunks;
@@ -748,6 +750,8 @@ __global__ void __launch_bounds__(kThreads, EOT_BULK_CTAS) k_prepass_bulk(EotSha
 __global__ void __launch_bounds__(kThreads) k_match(EotShape s, Layout L, const float* __restrict__ patch,
                                                     const float* __restrict__ print_wb, const int32_t* __restrict__ offsets,
                                                     char* ws, int b0, int pchunks) {
+  pdl_wait();
+  pdl_trigger();
   const int blk = blockIdx.x;
   const int b = b0 + blk / pchunks;
   // images the composite's common path does not take (values outside [-1,1], more than 32 boxes): tell its second kernel
@@ -1354,7 +1358,7 @@ static int launch_forward(const EotShape& s, const Layout& L, const float* patch
       EOT_CHECK_CUDA(cudaStreamWaitEvent(aux->stream, aux->pre[g], 0));
       sw = aux->stream;
     }
-    k_match<<<(b1 - b0) * pchunks, kThreads, 0, sw>>>(s, L, patch, print_wb, box_offsets, ws, b0, pchunks);
+    EOT_CHECK_CUDA(launch_pdl(k_match, dim3((b1 - b0) * pchunks), dim3(kThreads), 0, sw, s, L, patch, print_wb, box_offsets, ws, b0, pchunks));
     count_launches(1);
     if (G == 1) timer.mark("match");
     if (int rc = launch_resize2(s, L, ws, box_offsets, b0, b1, 2 * g, sw)) return rc;

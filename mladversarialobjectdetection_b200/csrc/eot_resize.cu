@@ -27,6 +27,8 @@ __global__ void __launch_bounds__(kThreads, EOT_RESIZE_MINB) k_resize2(EotShape 
                                                                       const int32_t* __restrict__ offsets, int b0, int b1,
                                                                       int ticket_slot, float one) {
   extern __shared__ __align__(16) unsigned char resize_smem[];
+  pdl_wait();
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t per_warp = resize_warp_smem(s, L);
   float4* inter = reinterpret_cast<float4*>(resize_smem + (size_t)warp * per_warp);
@@ -66,7 +68,7 @@ int launch_resize2(const EotShape& s, const Layout& L, char* ws, const int32_t* 
   int per_sm = EOT_RESIZE_MINB;
   const size_t budget = 220 * 1024;
   while (per_sm > 1 && (smem + 1024) * per_sm > budget) --per_sm;
-  k_resize2<<<sm_count() * per_sm, kThreads, smem, st>>>(s, L, ws, offsets, b0, b1, ticket_slot, 1.0f);
+  EOT_CHECK_CUDA(launch_pdl(k_resize2, dim3(sm_count() * per_sm), dim3(kThreads), smem, st, s, L, ws, offsets, b0, b1, ticket_slot, 1.0f));
   count_launches(1);
   return EOT_OK;
 }

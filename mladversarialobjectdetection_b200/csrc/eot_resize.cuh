@@ -4,8 +4,6 @@
 
 namespace eot {
 
-constexpr int kNoiseChunk = 128;                                   // texels per Philox round trip: 96 counters = 3 full warps
-constexpr int kNoiseWords = (kNoiseChunk * 3 / 4 + 1) * 4;          // words of one chunk (+ one counter when it starts unaligned)
 
 __host__ __device__ inline size_t resize_warp_smem(const EotShape& s, const Layout& L) {
   // intermediate rows + the Philox words of one chunk per row of the item
