@@ -39,8 +39,6 @@ __global__ void __launch_bounds__(kThreads, EOT_COMP_MINB) k_composite3(EotShape
   const int open_cap = (int)(L.open_cap / ngroups);               // the group's share of the open-pixel list
   int* open_count = reinterpret_cast<int*>(ws + L.off_counters) + 8 + group;
   int2* open_list = reinterpret_cast<int2*>(ws + L.off_open) + (size_t)group * open_cap;
-  const int W = s.width, lfull = s.height < s.width ? s.height : s.width;
-  const size_t img_elems = (size_t)s.height * s.width * 3;
   const int lo = base[min(offsets[b0], s.total_boxes)].w, hi = base[min(offsets[b1], s.total_boxes)].w;
   WarpTickets tk;
   tk.init(ws, L.off_tickets, 2 * group + 1);
@@ -48,34 +46,8 @@ __global__ void __launch_bounds__(kThreads, EOT_COMP_MINB) k_composite3(EotShape
   int2 item = it < hi ? __ldcg(citems + it) : make_int2(0, 0);
   while (it < hi) {
     const int nxt = tk.draw(lane);                                // next item's ticket travels while this one computes
-    const int j = item.x, r0 = item.y * kCompRows;
-    const SegBox me = load_segbox(plans + j, ubuf);
-    const int r1 = min(r0 + kCompRows, me.d);
-    const int first = plans[j].first_box, last = plans[j].last_box;
-    if (!item_is_general(reinterpret_cast<const int*>(ws + L.off_oor)[me.image], first, last)) {   // else: k_composite_rest
-      // lane l looks after box first + l of the image: does its window meet the item's rows at all?
-      bool cand = false;
-      {
-        const int q = first + lane;
-        if (q < last && q != j) {
-          const BoxPlan* o = plans + q;
-          const int4 g = *reinterpret_cast<const int4*>(&o->y0);   // y0, x0, ps, d
-          cand = o->valid && g.x < me.y0 + r1 && g.x + g.w > me.y0 + r0 && g.y < me.x0 + me.d && g.y + g.w > me.x0;
-        }
-      }
-      const bool others = __any_sync(0xffffffffu, cand);
-      const size_t img_off = (size_t)me.image * img_elems;
-      for (int wy = r0; wy < r1; ++wy) {
-        if (me.t6 != 0.0f || me.t7 != 0.0f)
-          composite_row_main<kMask, true>(me, plans, rowtab, routes + (size_t)j * L.rslot, lfull, W, j, wy, cand, others, first, last,
-                                          images + img_off, out + img_off, kMask ? mask + img_off : nullptr, open_count, open_list,
-                                          open_cap, one, lane);
-        else
-          composite_row_main<kMask, false>(me, plans, rowtab, routes + (size_t)j * L.rslot, lfull, W, j, wy, cand, others, first, last,
-                                           images + img_off, out + img_off, kMask ? mask + img_off : nullptr, open_count, open_list,
-                                           open_cap, one, lane);
-      }
-    }
+    composite_item_main<kMask>(s, L, ws, plans, ubuf, rowtab, routes, images, out, mask, item.x, item.y, open_count, open_list, open_cap,
+                               one, lane);
     it = lo + tk.item(nxt);
     if (it < hi) item = __ldcg(citems + it);
   }

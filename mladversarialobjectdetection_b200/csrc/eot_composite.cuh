@@ -243,10 +243,9 @@ __device__ __forceinline__ PixCoord pix_coord(const SegBox& me, float xf, float 
 template <bool kMask, bool kProj>
 __device__ __forceinline__ void composite_row_main(const SegBox& me, const BoxPlan* __restrict__ plans,
                                                    const int2* __restrict__ rowtab, uint8_t* route_j, int lfull, int W, int j,
-                                                   int wy, bool cand, bool others, int first, int last,
+                                                   int wy, const int2 sp, const ColRange mine, bool others, int first, int last,
                                                    const float* __restrict__ img, float* o_img, float* m_img, int* open_count,
                                                    int2* open_list, int open_cap, float one, int lane) {
-  const int2 sp = __ldg(rowtab + (size_t)j * lfull + wy);
   if (sp.x > sp.y) return;
   const int S = me.S;
   // texel (yi, xi) of the padded window sits at u[(yi - org) * S + (xi - org)]; with the floor coordinates taken
@@ -254,8 +253,6 @@ __device__ __forceinline__ void composite_row_main(const SegBox& me, const BoxPl
   // small)
   const int fold = (int)(0u - (0x4B400000u + (unsigned)me.org) * (unsigned)(S + 1));
   const int gy = me.y0 + wy;
-  ColRange mine = {1, 0};
-  if (cand) mine = candidate_range(plans, rowtab, lfull, first + lane, j, last, gy, false);
   const bool newer = first + lane > j && mine.a <= mine.b;
   // hull of the older boxes' ranges in this image row, in window columns (empty: [1, 0])
   int oa = 1, ob = 0;
@@ -330,6 +327,59 @@ __device__ __forceinline__ void composite_row_main(const SegBox& me, const BoxPl
       }
     }
     cur = e + 1;
+  }
+}
+
+// One work item of the common case: window rows [item_block * kCompRows, ...) of box j.  Lane l looks after box first + l
+// of the image (its geometry stays in registers for the item); the row-table entries of every row of the item -- the box's own
+// and lane l's candidate's -- are loaded up front, together: one round trip per item instead of two dependent ones per row.
+template <bool kMask>
+__device__ __forceinline__ void composite_item_main(const EotShape& s, const Layout& L, char* ws, const BoxPlan* __restrict__ plans,
+                                                    const float* ubuf, const int2* __restrict__ rowtab, uint8_t* routes,
+                                                    const float* __restrict__ images, float* out, float* mask, int j,
+                                                    int item_block, int* open_count, int2* open_list, int open_cap, float one,
+                                                    int lane) {
+  const int W = s.width, lfull = s.height < s.width ? s.height : s.width;
+  const size_t img_elems = (size_t)s.height * s.width * 3;
+  const int r0 = item_block * kCompRows;
+  const SegBox me = load_segbox(plans + j, ubuf);
+  const int r1 = min(r0 + kCompRows, me.d);
+  const int first = plans[j].first_box, last = plans[j].last_box;
+  if (item_is_general(reinterpret_cast<const int*>(ws + L.off_oor)[me.image], first, last)) return;   // k_composite_rest's
+  // does the window of box first + lane meet the item's rows at all?
+  bool cand = false;
+  int4 g = make_int4(0, 0, 0, 0);                                 // y0, x0, ps, d of the lane's box
+  const int q = first + lane;
+  if (q < last && q != j) {
+    const BoxPlan* o = plans + q;
+    g = *reinterpret_cast<const int4*>(&o->y0);
+    cand = o->valid && g.x < me.y0 + r1 && g.x + g.w > me.y0 + r0 && g.y < me.x0 + me.d && g.y + g.w > me.x0;
+  }
+  const bool others = __any_sync(0xffffffffu, cand);
+  // (loading the box's own ranges earlier, beside its plan, was measured slower: +3.5 us of register pressure)
+  int2 sp[kCompRows], csp[kCompRows];
+#pragma unroll
+  for (int r = 0; r < kCompRows; ++r) {
+    const int wy = min(r0 + r, me.d - 1), gy = me.y0 + wy;
+    sp[r] = __ldg(rowtab + (size_t)j * lfull + wy);
+    csp[r] = make_int2(1, 0);
+    if (cand && gy >= g.x && gy < g.x + g.w) csp[r] = __ldg(rowtab + (size_t)q * lfull + (gy - g.x));
+  }
+  const size_t img_off = (size_t)me.image * img_elems;
+#pragma unroll
+  for (int r = 0; r < kCompRows; ++r) {
+    const int wy = r0 + r;
+    if (wy >= r1) break;
+    ColRange mine = {1, 0};
+    if (csp[r].x <= csp[r].y) { mine.a = g.y + csp[r].x; mine.b = g.y + csp[r].y; }
+    if (me.t6 != 0.0f || me.t7 != 0.0f)
+      composite_row_main<kMask, true>(me, plans, rowtab, routes + (size_t)j * L.rslot, lfull, W, j, wy, sp[r], mine, others, first, last,
+                                      images + img_off, out + img_off, kMask ? mask + img_off : nullptr, open_count, open_list,
+                                      open_cap, one, lane);
+    else
+      composite_row_main<kMask, false>(me, plans, rowtab, routes + (size_t)j * L.rslot, lfull, W, j, wy, sp[r], mine, others, first, last,
+                                       images + img_off, out + img_off, kMask ? mask + img_off : nullptr, open_count, open_list,
+                                       open_cap, one, lane);
   }
 }
 

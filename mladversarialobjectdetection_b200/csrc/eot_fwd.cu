@@ -1039,8 +1039,6 @@ __global__ void __launch_bounds__(kThreads, EOT_FUSED_MINB) k_forward_fused(
   const int open_cap = (int)L.open_cap;
   int* open_count = counters + 8;
   int2* open_list = reinterpret_cast<int2*>(ws + L.off_open);
-  const int W = s.width, lfull = s.height < s.width ? s.height : s.width;
-  const size_t img_elems = (size_t)HW * 3;
   const int n_stat_blocks = B * pchunks;
   WarpTickets tk;
   tk.init(ws, L.off_tickets, 0);
@@ -1084,31 +1082,8 @@ __global__ void __launch_bounds__(kThreads, EOT_FUSED_MINB) k_forward_fused(
       const int n_comp = fv.step_start[k + 1] - fv.step_start[k] - info.x - info.y;
       wait_ge(fv.img + 8 * b + 3, n_resize, err, dbg ? fv.ctl + 22 : nullptr);
       wait_ge(fv.img + 8 * b + 1, pass_expected, err, dbg ? fv.ctl + 23 : nullptr);
-      const int j = item.x, r0 = item.y * kCompRows;
-      const SegBox me = load_segbox(plans + j, ubuf);
-      const int r1 = min(r0 + kCompRows, me.d);
-      const int first = plans[j].first_box, last = plans[j].last_box;
-      if (!item_is_general(reinterpret_cast<const int*>(ws + L.off_oor)[me.image], first, last)) {   // else: the tail
-        bool cand = false;                                        // lane l looks after box first + l of the image
-        {
-          const int q = first + lane;
-          if (q < last && q != j) {
-            const BoxPlan* o = plans + q;
-            const int4 g = *reinterpret_cast<const int4*>(&o->y0);   // y0, x0, ps, d
-            cand = o->valid && g.x < me.y0 + r1 && g.x + g.w > me.y0 + r0 && g.y < me.x0 + me.d && g.y + g.w > me.x0;
-          }
-        }
-        const bool others = __any_sync(0xffffffffu, cand);
-        const size_t img_off = (size_t)me.image * img_elems;
-        for (int wy = r0; wy < r1; ++wy) {
-          if (me.t6 != 0.0f || me.t7 != 0.0f)
-            composite_row_main<false, true>(me, plans, rowtab, routes + (size_t)j * L.rslot, lfull, W, j, wy, cand, others, first,
-                                            last, images + img_off, out + img_off, nullptr, open_count, open_list, open_cap, one, lane);
-          else
-            composite_row_main<false, false>(me, plans, rowtab, routes + (size_t)j * L.rslot, lfull, W, j, wy, cand, others, first,
-                                             last, images + img_off, out + img_off, nullptr, open_count, open_list, open_cap, one, lane);
-        }
-      }
+      composite_item_main<false>(s, L, ws, plans, ubuf, rowtab, routes, images, out, nullptr, item.x, item.y, open_count, open_list,
+                                 open_cap, one, lane);
       __syncwarp();
       if (lane == 0) {
         __threadfence();
