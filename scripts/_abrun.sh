@@ -1,6 +1,5 @@
-timeout 900 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; echo bench rc=$?
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'^k_|^eot' --csv --log-file gpurun_out/r02_launches_bench.csv python bench.py --steps 2 --warmup 1 --launch-list --no-graphs > gpurun_out/ncu_bench.log 2>&1; echo ncu-bench rc=$?; tail -2 gpurun_out/ncu_bench.log
-python scripts/launch_summary.py gpurun_out/r02_launches_bench.csv 2>&1 | tail -40
-timeout 600 ncu --set full --import-source on --clock-control none -k regex:'k_prepass|k_match|k_resize2|k_composite|k_bwd' -c 7 -o gpurun_out/prof_r02_s3_final -f python scripts/kernel_loop.py --iters 1 --warmup 0 --what fwd,bwd > gpurun_out/ncu_s3_final.log 2>&1; echo ncu-full rc=$?
-timeout 300 python scripts/step_launch_list.py > gpurun_out/r02_step_launches.txt 2>&1; echo steplist rc=$?
-bash scripts/fwd_times.sh fwd,bwd 2>&1 | tail -9
+nvidia-smi --query-gpu=index,name --format=csv,noheader
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_c2_2gpu.json 2> gpurun_out/bench_c2_2gpu.err; echo c2x2 rc=$?
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus 2 --workload c3 --steps 5 --warmup 3 > gpurun_out/bench_c3_2gpu.json 2> gpurun_out/bench_c3_2gpu.err; echo c3x2 rc=$?
+timeout 600 python bench.py --workload c4 --steps 5 --warmup 3 > gpurun_out/bench_c4_1gpu.json 2> gpurun_out/bench_c4_1gpu.err; echo c4 rc=$?
