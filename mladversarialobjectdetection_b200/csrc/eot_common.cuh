@@ -88,6 +88,7 @@ struct Layout {
                            //            the interleaved sub-queues (own 256-byte line each: same-address atomics serialise)
   size_t off_fused;        // int32[...] fused forward kernel: readiness flag, task total, per-image progress counters, step table
                            //            (fused_ints(); zeroed with the accumulators by the call's memset)
+  size_t off_cost;         // uint32[B] window work of image b (sum of ps^2 over its valid boxes), added up by the geometry blocks
   size_t off_plans;        // BoxPlan[N]
   size_t off_starts;       // int32[N][Lmin]
   size_t off_weights;      // float[N][wcap]  tap-major: weight of tap k of output index o at [k * ps + o]
@@ -172,6 +173,7 @@ __host__ __device__ inline Layout make_layout(const EotShape& s) {
   L.off_counters = o;     o = align_up(o + 32 * sizeof(int32_t), 256);
   L.off_tickets = o;      o = align_up(o + (size_t)kTicketSlots * kTicketLanes * 256, 256);
   L.off_fused = o;        o = align_up(o + fused_ints((int)B) * sizeof(int32_t), 256);
+  L.off_cost = o;         o = align_up(o + B * sizeof(uint32_t), 256);
   L.off_plans = o;        o = align_up(o + N * sizeof(BoxPlan), 256);
   L.off_starts = o;       o = align_up(o + N * (size_t)lmin * sizeof(int32_t), 256);
   L.off_weights = o;      o = align_up(o + N * (size_t)L.wcap * sizeof(float), 256);

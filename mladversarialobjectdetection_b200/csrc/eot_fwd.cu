@@ -198,6 +198,8 @@ __device__ int geometry_block(const EotShape& s, const Layout& L, int j, const f
     if (pl.valid) pl.span = span_cfg(pl.ps, s.patch_size).span;
     spl = pl;
     if (ws) {
+      if (pl.valid)   // window work of the image (the backward hands out the heaviest images first)
+        atomicAdd(reinterpret_cast<unsigned*>(ws + L.off_cost) + pl.image, min((unsigned)pl.ps * (unsigned)pl.ps, 1u << 22));
       reinterpret_cast<BoxPlan*>(ws + L.off_plans)[j] = pl;
       reinterpret_cast<int4*>(ws + L.off_cnt)[j] =
           pl.valid ? make_int4(fwd_strips(pl.ps, L.resize_rows), 0, (pl.ps + L.rb - 1) / L.rb, (pl.d + L.cr - 1) / L.cr)
@@ -320,15 +322,34 @@ __device__ int geometry_block(const EotShape& s, const Layout& L, int j, const f
 
 constexpr int kMaxOrderedImages = 2048;   // batches beyond this keep the identity order (the ranking is quadratic in one CTA)
 constexpr int kSmallRolesScratch = kThreads * 16 + kMaxOrderedImages * 4;   // prefix-sum partials + image costs
+constexpr int kMaxSortedBoxes = 1024;                              // key and two counts per box in the same scratch (12 KB)
+static_assert(kMaxSortedBoxes * 12 <= kSmallRolesScratch && kMaxSortedBoxes % kThreads == 0, "sorted item lists: scratch");
 
 // Exclusive prefix sums of the per-box work-item counts (one CTA; N is a few hundred to a few thousand).
 __device__ __forceinline__ int4 add4(int4 a, int4 b) { return make_int4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
-__device__ void scan_block(int N, const int4* cnt, int4* base, int4* part /* [blockDim.x] shared */) {
+// Every count is loaded once, all loads of a thread together (the block runs while the image pass saturates the memory
+// system: each dependent round trip costs ~1.5 us); with `items` / `citems` the forward's item lists are written in box
+// order from the registers that hold counts and positions.
+constexpr int kScanPer = 4;                                        // boxes per thread held in registers (N <= 1024)
+constexpr int kMaxListedBoxes = 1024;                              // boxes whose list positions fit the shared-memory scratch
+__device__ __forceinline__ int pack_counts(int nz, int nw) { return (nz & 0xffff) | (nw << 16); }
+// s_pos / s_n (may alias `part`): per box, where its resize / composite items start in the lists and how many there are
+// (box order), for write_item_lists; only filled when N <= kMaxListedBoxes.
+__device__ void scan_block(int N, const int4* cnt, int4* base, int4* part /* [blockDim.x] shared */, int2* s_pos, int* s_n) {
   const int T = blockDim.x;
   const int per = (N + T - 1) / T;
   const int j0 = threadIdx.x * per, j1 = min(N, j0 + per);
+  const bool regs = per <= kScanPer;
+  int4 c[kScanPer];
   int4 sum = make_int4(0, 0, 0, 0);
-  for (int j = j0; j < j1; ++j) sum = add4(sum, __ldcg(cnt + j));
+  if (regs) {
+#pragma unroll
+    for (int q = 0; q < kScanPer; ++q) c[q] = (j0 + q < j1) ? __ldcg(cnt + j0 + q) : make_int4(0, 0, 0, 0);
+#pragma unroll
+    for (int q = 0; q < kScanPer; ++q) sum = add4(sum, c[q]);
+  } else {
+    for (int j = j0; j < j1; ++j) sum = add4(sum, __ldcg(cnt + j));
+  }
   part[threadIdx.x] = sum;
   __syncthreads();
   for (int d = 1; d < T; d <<= 1) {
@@ -339,12 +360,38 @@ __device__ void scan_block(int N, const int4* cnt, int4* base, int4* part /* [bl
     __syncthreads();
   }
   int4 run = threadIdx.x ? part[threadIdx.x - 1] : make_int4(0, 0, 0, 0);
-  for (int j = j0; j < j1; ++j) {
-    base[j] = run;
-    run = add4(run, __ldcg(cnt + j));
+  const int4 total = part[T - 1];
+  __syncthreads();                                                // (s_pos / s_n may overlay the partial sums)
+  if (regs) {
+#pragma unroll
+    for (int q = 0; q < kScanPer; ++q) {
+      const int j = j0 + q;
+      if (j < j1) {
+        base[j] = run;
+        if (s_pos) { s_pos[j] = make_int2(run.z, run.w); s_n[j] = pack_counts(c[q].z, c[q].w); }
+        run = add4(run, c[q]);
+      }
+    }
+  } else {
+    for (int j = j0; j < j1; ++j) {
+      base[j] = run;
+      run = add4(run, __ldcg(cnt + j));
+    }
   }
-  if ((int)threadIdx.x == T - 1) base[N] = part[T - 1];
+  if ((int)threadIdx.x == T - 1) base[N] = total;
   __syncthreads();
+}
+
+// The forward's item lists from the per-box positions: one warp per box, lanes write consecutive items (one thread per
+// box would issue ~40 k scattered 8-byte stores from a single SM: ~20 us of its store pipe while the image pass waits).
+__device__ void write_item_lists(int N, const int2* s_pos, const int* s_n, int2* items, int2* citems) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int j = warp; j < N; j += nwarps) {
+    const int2 at = s_pos[j];
+    const int n = s_n[j], nz = n & 0xffff, nw = (unsigned)n >> 16;
+    for (int i = lane; i < nz; i += 32) items[at.x + i] = make_int2(j, i);
+    for (int i = lane; i < nw; i += 32) citems[at.y + i] = make_int2(j, i);
+  }
 }
 
 __global__ void __launch_bounds__(kThreads) k_geometry_only(EotShape s, Layout L, const float* __restrict__ boxes,
@@ -476,7 +523,7 @@ __device__ int small_roles(const EotShape& s, const Layout& L, int blk, const fl
                             const float* __restrict__ print_wb, const float* __restrict__ boxes,
                             const int32_t* __restrict__ offsets, const EotBoxParams* __restrict__ params,
                             const float* __restrict__ scale, char* ws, int n_geom, int n_stat_imgs, int pchunks, double* red,
-                            void* scratch /* kSmallRolesScratch bytes of shared memory, 16-byte aligned */) {
+                            void* scratch /* kSmallRolesScratch bytes of shared memory, 16-byte aligned */, int sort_items) {
   if (blk < n_geom) {
     __shared__ int s_last;
     int4* s_part = reinterpret_cast<int4*>(scratch);               // [kThreads]
@@ -487,41 +534,118 @@ __device__ int small_roles(const EotShape& s, const Layout& L, int blk, const fl
     int* counters = reinterpret_cast<int*>(ws + L.off_counters);
     if (threadIdx.x == 0) s_last = (atomicAdd(counters + 5, 1) == n_geom - 1);
     __syncthreads();
+
     if (s_last) {                                        // last geometry block: prefix sums of the work-item counts
       __threadfence();
       const int4* cnt = reinterpret_cast<const int4*>(ws + L.off_cnt);
       int4* base = reinterpret_cast<int4*>(ws + L.off_base);
-      scan_block(n_geom, cnt, base, s_part);
-      // images by decreasing window work (sum of ps^2 over their valid boxes; ties by index): the backward's per-image
-      // items are handed out heaviest first
-      {
-        const BoxPlan* pls = reinterpret_cast<const BoxPlan*>(ws + L.off_plans);
-        int* order = reinterpret_cast<int*>(ws + L.off_order);
-        const int B = s.batch;
-        if (B <= kMaxOrderedImages) {
-          for (int b = threadIdx.x; b < B; b += blockDim.x) {
-            unsigned c = 0;
-            for (int j = min(offsets[b], n_geom); j < min(offsets[b + 1], n_geom); ++j)
-              c += pls[j].valid ? min((unsigned)pls[j].ps * (unsigned)pls[j].ps, 1u << 22) : 0u;
-            s_cost[b] = c;
-          }
-          __syncthreads();
-          for (int b = threadIdx.x; b < B; b += blockDim.x) {
-            const unsigned mine = s_cost[b];
-            int rank = 0;
-            for (int o2 = 0; o2 < B; ++o2) rank += (s_cost[o2] > mine || (s_cost[o2] == mine && o2 < b)) ? 1 : 0;
-            order[rank] = b;
-          }
-        } else {
-          for (int b = threadIdx.x; b < B; b += blockDim.x) order[b] = b;
-        }
-      }
       int2* items = reinterpret_cast<int2*>(ws + L.off_items);    // forward resize / composite items in ticket order
       int2* citems = reinterpret_cast<int2*>(ws + L.off_citems);
-      for (int j = threadIdx.x; j < n_geom; j += blockDim.x) {
-        const int4 n = __ldcg(cnt + j), at = base[j];
-        for (int i = 0; i < n.z; ++i) items[at.z + i] = make_int2(j, i);
-        for (int i = 0; i < n.w; ++i) citems[at.w + i] = make_int2(j, i);
+      const bool sorted = sort_items && n_geom <= kMaxSortedBoxes && n_geom <= kMaxListedBoxes;
+      // images by decreasing window work (ties by index): the backward's per-image items are handed out heaviest first.
+      // The costs were added up by the geometry blocks; their loads travel with the scan's.
+      const int B = s.batch;
+      int* order = reinterpret_cast<int*>(ws + L.off_order);
+      const unsigned* cost = reinterpret_cast<const unsigned*>(ws + L.off_cost);
+      const bool listed = n_geom <= kMaxListedBoxes;              // positions and counts of every box fit the scratch
+      int2* s_pos = reinterpret_cast<int2*>(scratch);
+      int* s_n = reinterpret_cast<int*>(s_pos + kMaxListedBoxes);
+      unsigned my_cost[kMaxOrderedImages / kThreads];             // (the scan's scratch overlays s_cost)
+#pragma unroll
+      for (int q = 0; q < kMaxOrderedImages / kThreads; ++q) {
+        const int b = threadIdx.x + q * kThreads;
+        my_cost[q] = (b < B && B <= kMaxOrderedImages) ? __ldcg(cost + b) : 0u;
+      }
+      scan_block(n_geom, cnt, base, s_part, listed && !sorted ? s_pos : nullptr, s_n);
+      if (listed && !sorted) {
+        write_item_lists(n_geom, s_pos, s_n, items, citems);
+        __syncthreads();
+      } else if (!listed) {                                       // very many boxes: one thread per box, box order
+        for (int j = threadIdx.x; j < n_geom; j += blockDim.x) {
+          const int4 n = __ldcg(cnt + j), at = base[j];
+          for (int i = 0; i < n.z; ++i) items[at.z + i] = make_int2(j, i);
+          for (int i = 0; i < n.w; ++i) citems[at.w + i] = make_int2(j, i);
+        }
+        __syncthreads();
+      }
+#pragma unroll
+      for (int q = 0; q < kMaxOrderedImages / kThreads; ++q) {
+        const int b = threadIdx.x + q * kThreads;
+        if (b < B && B <= kMaxOrderedImages) s_cost[b] = my_cost[q];
+      }
+      __syncthreads();
+      if (B <= kMaxOrderedImages) {
+        for (int b = threadIdx.x; b < B; b += blockDim.x) {
+          const unsigned mine = s_cost[b];
+          int rank = 0;
+          for (int o2 = 0; o2 < B; ++o2) rank += (s_cost[o2] > mine || (s_cost[o2] == mine && o2 < b)) ? 1 : 0;
+          order[rank] = b;
+        }
+      } else {
+        for (int b = threadIdx.x; b < B; b += blockDim.x) order[b] = b;
+      }
+      if (sorted) {
+        // Largest boxes first (item cost grows with the patch side): the persistent kernels end on the cheapest items, so
+        // the tail in which warps run dry is as short as an item can be.  Only valid when one call takes the whole list
+        // (image groups and the fused kernel address the list by image and keep box order).
+        int* s_key = reinterpret_cast<int*>(scratch);              // [N] resize items of box j (proportional to its side)
+        int2* s_cnt = reinterpret_cast<int2*>(s_key + ((n_geom + 1) & ~1));   // [N] (resize, composite) counts in rank order -> prefix
+        constexpr int kPer = kMaxSortedBoxes / kThreads;           // boxes per thread, counts and ranks in registers
+        int4 nq[kPer];
+        int rq[kPer];
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) {
+          const int j = threadIdx.x + q * kThreads;
+          nq[q] = j < n_geom ? __ldcg(cnt + j) : make_int4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) {
+          const int j = threadIdx.x + q * kThreads;
+          if (j < n_geom) s_key[j] = nq[q].z;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) {
+          const int j = threadIdx.x + q * kThreads;
+          rq[q] = 0;
+          if (j < n_geom) {
+            const int mine = nq[q].z;
+            int rank = 0;
+            for (int k = 0; k < n_geom; ++k) rank += (s_key[k] > mine || (s_key[k] == mine && k < j)) ? 1 : 0;
+            rq[q] = rank;
+            s_cnt[rank] = make_int2(nq[q].z, nq[q].w);
+          }
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {                                    // exclusive prefix over the ranks, one warp
+          int2 run = make_int2(0, 0);
+          for (int r0 = 0; r0 < n_geom; r0 += 32) {
+            const int r = r0 + threadIdx.x;
+            const int2 v = r < n_geom ? s_cnt[r] : make_int2(0, 0);
+            int2 inc = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+              const int ax = __shfl_up_sync(0xffffffffu, inc.x, d), ay = __shfl_up_sync(0xffffffffu, inc.y, d);
+              if ((int)threadIdx.x >= d) { inc.x += ax; inc.y += ay; }
+            }
+            if (r < n_geom) s_cnt[r] = make_int2(run.x + inc.x - v.x, run.y + inc.y - v.y);
+            run.x += __shfl_sync(0xffffffffu, inc.x, 31);
+            run.y += __shfl_sync(0xffffffffu, inc.y, 31);
+          }
+        }
+        __syncthreads();
+        int2 at[kPer];
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) at[q] = (threadIdx.x + q * kThreads < n_geom) ? s_cnt[rq[q]] : make_int2(0, 0);
+        __syncthreads();                                          // (s_pos / s_n overlay the keys and the prefix)
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) {
+          const int j = threadIdx.x + q * kThreads;
+          if (j < n_geom) { s_pos[j] = at[q]; s_n[j] = pack_counts(nq[q].z, nq[q].w); }
+        }
+        __syncthreads();
+        write_item_lists(n_geom, s_pos, s_n, items, citems);
       }
     }
     return s_last ? 2 : 1;
@@ -557,12 +681,12 @@ __global__ void __launch_bounds__(kThreads, EOT_PREPASS_MINB) k_prepass(EotShape
                                                       const EotBoxParams* __restrict__ params,
                                                       const float* __restrict__ scale, const float* __restrict__ images,
                                                       float* out, float* mask, char* ws, int n_geom, int n_stat_imgs,
-                                                      int pchunks, int cpi, int b0) {
+                                                      int pchunks, int cpi, int b0, int sort_items) {
   __shared__ double red[32];
   __shared__ __align__(16) unsigned char s_scratch[kSmallRolesScratch];
   pdl_trigger();
   int blk = blockIdx.x;
-  if (small_roles(s, L, blk, patch, print_wb, boxes, offsets, params, scale, ws, n_geom, n_stat_imgs, pchunks, red, s_scratch)) return;
+  if (small_roles(s, L, blk, patch, print_wb, boxes, offsets, params, scale, ws, n_geom, n_stat_imgs, pchunks, red, s_scratch, sort_items)) return;
   blk -= n_geom;
   blk -= n_stat_imgs * pchunks;
   const int b = b0 + blk / cpi, chunk = blk % cpi;
@@ -662,14 +786,14 @@ __global__ void __launch_bounds__(kThreads, EOT_BULK_CTAS) k_prepass_bulk(EotSha
                                                               const EotBoxParams* __restrict__ params,
                                                               const float* __restrict__ scale, const float* __restrict__ images,
                                                               float* out, char* ws, int n_geom, int n_stat_imgs, int pchunks,
-                                                              int n_copy_ctas, int b0, int b1) {
+                                                              int n_copy_ctas, int b0, int b1, int sort_items) {
   extern __shared__ __align__(128) unsigned char stage_mem[];     // kBulkStages x 12288 bytes
   __shared__ double red[32];
   __shared__ __align__(8) uint64_t s_full[kBulkStages];
   static_assert((size_t)EOT_BULK_STAGES * kBulkTilePix * 12 >= (size_t)kSmallRolesScratch, "the stage buffers double as the small roles' scratch");
   pdl_trigger();
   int blk = blockIdx.x;
-  if (small_roles(s, L, blk, patch, print_wb, boxes, offsets, params, scale, ws, n_geom, n_stat_imgs, pchunks, red, stage_mem)) return;
+  if (small_roles(s, L, blk, patch, print_wb, boxes, offsets, params, scale, ws, n_geom, n_stat_imgs, pchunks, red, stage_mem, sort_items)) return;
   blk -= n_geom + n_stat_imgs * pchunks;
   const int HW = s.height * s.width;
   const int tpi = (HW + kBulkTilePix - 1) / kBulkTilePix;         // tiles per image
@@ -1011,7 +1135,7 @@ __global__ void __launch_bounds__(kThreads, EOT_FUSED_MINB) k_forward_fused(
     // ---- geometry and patch statistics ------------------------------------------------------------------------------
     const int n_small = n_geom + B * pchunks, nwin = gridDim.x - n_copy;
     for (int blk = blockIdx.x - n_copy; blk < n_small; blk += nwin) {
-      const int r = small_roles(s, L, blk, patch, print_wb, boxes, offsets, params, scale, ws, n_geom, B, pchunks, red, fsmem);
+      const int r = small_roles(s, L, blk, patch, print_wb, boxes, offsets, params, scale, ws, n_geom, B, pchunks, red, fsmem, 0);
       if (r == 2) {
         if (dbg && threadIdx.x == 0) fv.ctl[27] = (int)(global_ns() - t_base);
         build_steps(s, L, ws, offsets, n_geom, skew, nM, reinterpret_cast<int*>(fsmem));
@@ -1295,6 +1419,8 @@ static int launch_forward(const EotShape& s, const Layout& L, const float* patch
   const int cpi = (HW + kPassPixPerBlock - 1) / kPassPixPerBlock;
   const bool vec = (HW % 4 == 0) && (((uintptr_t)images | (uintptr_t)out_images | (uintptr_t)(mask ? mask : out_images)) & 15) == 0;
   const int G = forward_groups(B, N);
+  static const int sort_env = env_int("EOT_SORT_ITEMS", 1);
+  const int sort_items = (G == 1 && sort_env) ? 1 : 0;               // one call takes the whole item list: largest boxes first
   AuxStream* aux = nullptr;
   if (G > 1)
     if (int rc = aux_stream(&aux)) return rc;
@@ -1317,13 +1443,13 @@ static int launch_forward(const EotShape& s, const Layout& L, const float* patch
       const long long tiles = (long long)(b1 - b0) * ((HW + kBulkTilePix - 1) / kBulkTilePix);
       const int copy_ctas = (int)(tiles < (long long)EOT_BULK_CTAS * sm_count() ? tiles : (long long)EOT_BULK_CTAS * sm_count());
       k_prepass_bulk<<<(unsigned)(n_geom + n_stat * pchunks + copy_ctas), kThreads, smem, st>>>(
-          s, L, patch, print_wb, boxes, box_offsets, params, scale, images, pass_out, ws, n_geom, n_stat, pchunks, copy_ctas, b0, b1);
+          s, L, patch, print_wb, boxes, box_offsets, params, scale, images, pass_out, ws, n_geom, n_stat, pchunks, copy_ctas, b0, b1, sort_items);
     } else if (vec)
       k_prepass<true><<<(unsigned)nblocks, kThreads, 0, st>>>(s, L, patch, print_wb, boxes, box_offsets, params, scale, images,
-                                                              pass_out, mask, ws, n_geom, n_stat, pchunks, cpi, b0);
+                                                              pass_out, mask, ws, n_geom, n_stat, pchunks, cpi, b0, sort_items);
     else
       k_prepass<false><<<(unsigned)nblocks, kThreads, 0, st>>>(s, L, patch, print_wb, boxes, box_offsets, params, scale, images,
-                                                               pass_out, mask, ws, n_geom, n_stat, pchunks, cpi, b0);
+                                                               pass_out, mask, ws, n_geom, n_stat, pchunks, cpi, b0, sort_items);
     count_launches(1);
     if (G == 1) timer.mark("prepass");
     if (N == 0) continue;

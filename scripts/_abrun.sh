@@ -1,5 +1,9 @@
-nvidia-smi --query-gpu=index,name --format=csv,noheader
-timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_c2_2gpu.json 2> gpurun_out/bench_c2_2gpu.err; echo c2x2 rc=$?
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus 2 --workload c3 --steps 5 --warmup 3 > gpurun_out/bench_c3_2gpu.json 2> gpurun_out/bench_c3_2gpu.err; echo c3x2 rc=$?
-timeout 600 python bench.py --workload c4 --steps 5 --warmup 3 > gpurun_out/bench_c4_1gpu.json 2> gpurun_out/bench_c4_1gpu.err; echo c4 rc=$?
+timeout 900 python -m pytest tests/test_gpu_forward.py tests/test_gpu_crowd_and_sizes.py tests/test_gpu_fullsize.py tests/test_gpu_backward.py tests/test_gpu_variants.py -x -q 2>&1 | tail -3
+EOTPATCH_LIB=_ab/geomdbg.so EOT_FWD_FUSED=1 EOT_FUSED_SKEW=32 EOT_KERNEL_TIMES=1 timeout 120 python scripts/kernel_loop.py --iters 1 --warmup 1 --what fwd 2>&1 | grep "slowest\|last geometry" | tail -2
+t() { echo -n "$*: "; env "$@" timeout 120 python scripts/kernel_loop.py --time --iters 40 --warmup 3 --what fwd,bwd $SH 2>&1 | grep -E "us per call|rror" | tr '\n' ' '; echo; }
+SH=""
+for i in 1 2 3; do
+t EOT_SORT_ITEMS=0
+t EOT_SORT_ITEMS=1
+done
+bash scripts/fwd_times.sh fwd 2>&1 | tail -6
