@@ -416,12 +416,12 @@ __device__ __forceinline__ void composite_rest_body(const EotShape& s, const Lay
       const int e = (gy * W + gx) * 3;
       for (int k = j - 1; k >= pj->first_box && missing; --k) {   // older boxes, newest first
         const BoxPlan* o = plans + k;
-        const int4 g = *reinterpret_cast<const int4*>(&o->y0);     // y0, x0, ps, d
+        const SegBox ob = load_segbox(o, ubuf);                     // (all of the plan's fields in one round trip)
+        const int4 g = make_int4(ob.y0, ob.x0, 0, ob.d);            // y0, x0, -, d
         if (!o->valid || gy < g.x || gy >= g.x + g.w) continue;
         const int2 sp = __ldg(rowtab + (size_t)k * lfull + (gy - g.x));
         const int xk = gx - g.y, yk = gy - g.x;
         if (xk < sp.x || xk > sp.y) continue;
-        const SegBox ob = load_segbox(o, ubuf);
         const float ykf = (float)yk;
         float R[3];
         if (!sample_row_px(ob, padded_base(ob), (float)xk, ob.t1 * ykf, ob.t4 * ykf, ob.t7 * ykf, ob.t6 != 0.0f || ob.t7 != 0.0f, R))

@@ -896,17 +896,33 @@ __device__ __forceinline__ void match_range(const EotShape& s, const Layout& L, 
   const float* wb = print_wb + (size_t)b * 6;
   const float* base = patch + (s.num_patches > 1 ? (int64_t)b * s.patch_stride_n : 0);
   float4* m = reinterpret_cast<float4*>(ws + L.off_match) + (size_t)b * P * P;
-  for (int t = t0; t < P * P; t += tstride) {
-    const int py = t / P, px = t - py * P;
-    const float* p = base + (int64_t)py * s.patch_stride_y + (int64_t)px * s.patch_stride_x;
-    const TexelYuv y = texel_yuv(__ldg(p), __ldg(p + 1), __ldg(p + 2), wb);
-    const float yp = clampf((y.y - mu_s) + mu_t, 0.0f, 1.0f);
-    // rgb = [Y',U,V] . K'  as ((Y'*K'0c + U*K'1c) + V*K'2c)
-    const float r = (yp * 1.0f + y.u * EOT_I10) + y.v * EOT_I20;
-    const float g = (yp * 1.0f + y.u * EOT_I11) + y.v * EOT_I21;
-    const float bl = (yp * 1.0f + y.u * EOT_I12) + y.v * EOT_I22;
-    m[t] = make_float4(clampf(r, 0.0f, 1.0f) * EOT_C255_127 - 1.0f, clampf(g, 0.0f, 1.0f) * EOT_C255_127 - 1.0f,
-                       clampf(bl, 0.0f, 1.0f) * EOT_C255_127 - 1.0f, 0.0f);
+  float w6[6];                                                    // the image's print-adjust coefficients: loaded once
+#pragma unroll
+  for (int k = 0; k < 6; ++k) w6[k] = __ldg(wb + k);
+  // four texels per round: their patch values are fetched together (the kernel is a chain of L2 round trips otherwise)
+  for (int t4 = t0; t4 < P * P; t4 += 4 * tstride) {
+    float v[4][3];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int t = min(t4 + q * tstride, P * P - 1);
+      const int py = t / P, px = t - py * P;
+      const float* p = base + (int64_t)py * s.patch_stride_y + (int64_t)px * s.patch_stride_x;
+      v[q][0] = __ldg(p); v[q][1] = __ldg(p + 1); v[q][2] = __ldg(p + 2);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int t = t4 + q * tstride;
+      if (t < P * P) {
+        const TexelYuv y = texel_yuv(v[q][0], v[q][1], v[q][2], w6);
+        const float yp = clampf((y.y - mu_s) + mu_t, 0.0f, 1.0f);
+        // rgb = [Y',U,V] . K'  as ((Y'*K'0c + U*K'1c) + V*K'2c)
+        const float r = (yp * 1.0f + y.u * EOT_I10) + y.v * EOT_I20;
+        const float g = (yp * 1.0f + y.u * EOT_I11) + y.v * EOT_I21;
+        const float bl = (yp * 1.0f + y.u * EOT_I12) + y.v * EOT_I22;
+        m[t] = make_float4(clampf(r, 0.0f, 1.0f) * EOT_C255_127 - 1.0f, clampf(g, 0.0f, 1.0f) * EOT_C255_127 - 1.0f,
+                           clampf(bl, 0.0f, 1.0f) * EOT_C255_127 - 1.0f, 0.0f);
+      }
+    }
   }
 }
 
