@@ -151,6 +151,11 @@ typedef struct ScoreShape {
 } ScoreShape;
 
 int score_workspace_bytes(const ScoreShape* shape, size_t* bytes);
+/* Byte offset, inside the score workspace, of the dense candidate scores score_max_fwd leaves there:
+ * float [B, A], the person score of a valid candidate anchor or -1 (the reference's ragged `scores` of
+ * attacker.py:134-139 in dense form).  It is what person_nms takes as `cand_score`; callers ask for the
+ * offset instead of restating the workspace layout.  Host-only, no launch. */
+int score_candidate_offset(const ScoreShape* shape, size_t* offset);
 
 /* cls_levels / box_levels: HOST arrays of num_levels device pointers, level l is
  * [B, H_l, W_l, 9*num_classes] / [B, H_l, W_l, 9*4].  anchors: [A,4].

@@ -16,7 +16,7 @@ SCORE_MAX_LEVELS = 8
 
 # every symbol include/eotpatch.h declares (tests check the export list against the header)
 SYMBOLS = ["eot_last_error", "eot_version", "eot_launch_count", "eot_workspace_bytes", "eot_box_geometry", "eot_apply_fwd",
-           "eot_apply_bwd", "eot_draw_transforms", "eot_brightness_match", "eot_check_workspace", "score_workspace_bytes", "score_max_fwd", "score_max_bwd",
+           "eot_apply_bwd", "eot_draw_transforms", "eot_brightness_match", "eot_check_workspace", "score_workspace_bytes", "score_candidate_offset", "score_max_fwd", "score_max_bwd",
            "person_nms_workspace_bytes", "person_nms", "eot_letterbox_normalize", "eot_channel_sums",
            "eot_augment_batch", "adv_u8_box_geometry", "adv_u8_print_patch", "adv_u8_workspace_bytes", "adv_u8_add_patches",
            "patch_tv_grad", "adam_clip_update", "attack_pack_scalars", "attack_step_metrics", "nhwc_bias_act_fwd", "nhwc_bias_silu_bwd",
@@ -72,6 +72,7 @@ def _declare(lib):
     lib.eot_brightness_match.argtypes = [vp, i64, vp, i64, vp, vp, sz, vp]
     lib.eot_check_workspace.argtypes = [ctypes.POINTER(EotShape), vp, vp]
     lib.score_workspace_bytes.argtypes = [ctypes.POINTER(ScoreShape), ctypes.POINTER(sz)]
+    lib.score_candidate_offset.argtypes = [ctypes.POINTER(ScoreShape), ctypes.POINTER(sz)]
     lib.score_max_fwd.argtypes = [ctypes.POINTER(ScoreShape), ctypes.POINTER(vp), ctypes.POINTER(vp), vp, vp, vp,
                                   vp, vp, sz, vp]
     lib.score_max_bwd.argtypes = [ctypes.POINTER(ScoreShape), ctypes.POINTER(vp), vp, vp, ctypes.POINTER(vp), vp,

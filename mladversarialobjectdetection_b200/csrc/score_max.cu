@@ -297,6 +297,13 @@ extern "C" int score_workspace_bytes(const ScoreShape* shape, size_t* bytes) {
   return EOT_OK;
 }
 
+extern "C" int score_candidate_offset(const ScoreShape* shape, size_t* offset) {
+  if (int rc = check_score_shape(shape)) return rc;
+  if (!offset) { set_error("offset is NULL"); return EOT_ERR_NULL_POINTER; }
+  *offset = score_layout(*shape).off_cand;
+  return EOT_OK;
+}
+
 extern "C" int score_max_fwd(const ScoreShape* shape, const float* const* cls_levels, const float* const* box_levels,
                              const float* anchors, float* max_scores, int32_t* argmax_anchor, int32_t* num_candidates,
                              void* workspace, size_t workspace_bytes, void* stream) {

@@ -273,16 +273,14 @@ def score_max_forward(cls_levels: Sequence[torch.Tensor], box_levels: Sequence[t
     return max_scores, argmax, ncand, ScoreContext(shape, ws, cls_levels, max_scores)
 
 
-def _align(x: int, a: int = 256) -> int:
-    return (x + a - 1) // a * a
-
-
 def score_candidate_view(ctx: ScoreContext) -> torch.Tensor:
     """[B,A] float32 view of the candidate scores score_max_fwd left in its workspace (score, or -1 where the
     anchor is not a person / not a valid box): the reference's ragged `scores` of attacker.py:134-139 in dense
-    form.  Layout mirrors `score_layout` in csrc/score_max.cu."""
+    form; the library says where they sit (`score_candidate_offset`)."""
     B, A = ctx.shape.batch, ctx.shape.total_anchors
-    off = _align(_align(B * 8) + 2 * B * 4)
+    o = ctypes.c_size_t(0)
+    _lib.check(_lib.load().score_candidate_offset(ctypes.byref(ctx.shape), ctypes.byref(o)))
+    off = int(o.value)
     return ctx.workspace[off: off + B * A * 4].view(torch.float32).view(B, A)
 
 

@@ -315,9 +315,10 @@ class EotFirstPassBoxesOp : public tf::OpKernel {
     void* st = StreamOf(ctx);
     EOT_OP_OK(ctx, score_max_fwd(&s, cls, box, anchors.flat<float>().data(), M.flat<float>().data(),
                                  am.flat<tf::int32>().data(), nc.flat<tf::int32>().data(), sws.flat<tf::uint8>().data(), sbytes, st));
-    // the dense candidate scores sit in the score workspace behind the keys and the counters (ScoreLayout, csrc/score_max.cu)
-    auto align = [](size_t x) { return (x + 255) / 256 * 256; };
-    const float* cand = reinterpret_cast<const float*>(sws.flat<tf::uint8>().data() + align(align((size_t)s.batch * 8) + 2 * (size_t)s.batch * 4));
+    // the dense candidate scores score_max_fwd left in its workspace
+    size_t cand_off = 0;
+    EOT_OP_OK(ctx, score_candidate_offset(&s, &cand_off));
+    const float* cand = reinterpret_cast<const float*>(sws.flat<tf::uint8>().data() + cand_off);
     EOT_OP_OK(ctx, person_nms(&n, cand, box, anchors.flat<float>().data(), boxes->flat<float>().data(),
                               scores->flat<float>().data(), vlen->flat<tf::int32>().data(), splits->flat<tf::int32>().data(),
                               rboxes->flat<float>().data(), rscores->flat<float>().data(), nws.flat<tf::uint8>().data(), nbytes, st));
