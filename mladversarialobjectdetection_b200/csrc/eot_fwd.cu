@@ -749,7 +749,11 @@ __device__ __forceinline__ void match_range(const EotShape& s, const Layout& L, 
 #ifndef EOT_BULK_QUADS
 #define EOT_BULK_QUADS 1
 #endif
-constexpr int kBulkTilePix = 4 * EOT_BULK_QUADS * kThreads;        // 1024 pixels = 12288 bytes per quad
+#ifndef EOT_BULK_TILE_PIX
+#define EOT_BULK_TILE_PIX (4 * EOT_BULK_QUADS * kThreads)          // 1024 pixels = 12288 bytes per quad
+#endif
+constexpr int kBulkTilePix = EOT_BULK_TILE_PIX;                    // a smaller tile leaves the last threads of a quad idle
+static_assert(kBulkTilePix % 32 == 0 && kBulkTilePix <= 4 * EOT_BULK_QUADS * kThreads, "tile: 128-byte multiple, covered by the quads");
 #ifndef EOT_BULK_STAGES
 #define EOT_BULK_STAGES 2
 #endif

@@ -158,3 +158,29 @@ def test_patch_tiff_is_read_back_by_an_independent_codec(tmp_path):
     p2, s2 = patch_io.load_weights(str(tmp_path / "w"))
     np.testing.assert_array_equal(p2, patch)
     assert abs(s2 - 0.4) < 1e-7
+
+
+def test_score_candidate_offset_is_where_the_layout_puts_the_candidates():
+    """Host-only entry point: keys uint64[B] and the two int32[B] counters, each padded to 256 bytes, precede the dense
+    candidate scores (csrc/score_max.cu score_layout); the offset stays inside the workspace and leaves room for [B,A]."""
+    import __graft_entry__
+    __graft_entry__.build()
+    lib = _lib.load()
+
+    def up(x):
+        return (x + 255) // 256 * 256
+
+    for B, locs in [(1, [16, 4, 1]), (8, [4096, 1024, 256, 64, 16]), (64, [4096, 1024, 256, 64, 16]), (33, [16384, 4096, 1024, 256, 64])]:
+        s = _lib.ScoreShape()
+        s.batch, s.num_levels, s.num_classes, s.anchors_per_loc = B, len(locs), 90, 9
+        for i, n in enumerate(locs):
+            s.level_locs[i] = n
+        s.total_anchors = 9 * sum(locs)
+        s.image_height = s.image_width = 512.0
+        s.min_area = 100.0
+        off, tot = ctypes.c_size_t(0), ctypes.c_size_t(0)
+        assert lib.score_candidate_offset(ctypes.byref(s), ctypes.byref(off)) == 0
+        assert lib.score_workspace_bytes(ctypes.byref(s), ctypes.byref(tot)) == 0
+        assert off.value == up(up(B * 8) + 2 * B * 4)
+        assert off.value + B * s.total_anchors * 4 <= tot.value
+    assert lib.score_candidate_offset(ctypes.byref(s), None) != 0
