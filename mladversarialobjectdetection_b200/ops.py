@@ -279,7 +279,7 @@ def score_candidate_view(ctx: ScoreContext) -> torch.Tensor:
     form; the library says where they sit (`score_candidate_offset`)."""
     B, A = ctx.shape.batch, ctx.shape.total_anchors
     o = ctypes.c_size_t(0)
-    _lib.check(_lib.load().score_candidate_offset(ctypes.byref(ctx.shape), ctypes.byref(o)))
+    _lib.check(_lib.load().score_candidate_offset(ctypes.byref(ctx.shape), ctypes.byref(o)), "score_candidate_offset")
     off = int(o.value)
     return ctx.workspace[off: off + B * A * 4].view(torch.float32).view(B, A)
 

@@ -184,3 +184,25 @@ def test_score_candidate_offset_is_where_the_layout_puts_the_candidates():
         assert off.value == up(up(B * 8) + 2 * B * 4)
         assert off.value + B * s.total_anchors * 4 <= tot.value
     assert lib.score_candidate_offset(ctypes.byref(s), None) != 0
+
+
+def test_candidate_view_slices_the_workspace_at_the_library_offset():
+    """ops.score_candidate_view on a host tensor standing in for the workspace (slicing only, no launch)."""
+    import __graft_entry__
+    __graft_entry__.build()
+    import torch
+    from mladversarialobjectdetection_b200 import ops
+    lib = _lib.load()
+    s = _lib.ScoreShape()
+    s.batch, s.num_levels, s.num_classes, s.anchors_per_loc = 3, 2, 90, 9
+    s.level_locs[0], s.level_locs[1] = 16, 4
+    s.total_anchors = 9 * 20
+    s.image_height = s.image_width = 64.0
+    s.min_area = 100.0
+    tot, off = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    assert lib.score_workspace_bytes(ctypes.byref(s), ctypes.byref(tot)) == 0
+    assert lib.score_candidate_offset(ctypes.byref(s), ctypes.byref(off)) == 0
+    ws = torch.zeros(tot.value, dtype=torch.uint8)
+    ws[off.value: off.value + 3 * 180 * 4].view(torch.float32).copy_(torch.arange(3 * 180, dtype=torch.float32))
+    view = ops.score_candidate_view(ops.ScoreContext(s, ws, [], torch.zeros(3)))
+    assert view.shape == (3, 180) and torch.equal(view.flatten(), torch.arange(3 * 180, dtype=torch.float32))
