@@ -181,3 +181,41 @@ def test_patcher_chain_gradient_against_finite_differences_without_rotation():
         num = (loss(patch + F(eps) * d) - loss(patch - F(eps) * d)) / (2 * eps)
         ana = float((g * d).sum())
         assert abs(num - ana) <= 2e-2 * max(1.0, abs(ana)), (num, ana)
+
+
+@pytest.mark.parametrize("deg,pa,pb", [(15.0, 0.0, 0.0), (-20.0, 0.0, 0.0), (7.0, 2e-4, -1.5e-4)])
+def test_projective_matches_scipy_grid_constant_interpolation(deg, pa, pb):
+    """Independent implementation of the same sampling rule: scipy.ndimage.map_coordinates(order=1, mode='grid-constant',
+    cval=fill) is bilinear interpolation over an image extended by the constant on every side, i.e. taps outside the
+    image READ AS THE FILL and are blended (ImageProjectiveTransformV3 BILINEAR + CONSTANT) -- the
+    edge behaviour attacker.py:440's `< -1` test depends on.  Same float32 coordinates, float64 blend: agreement at
+    float32 rounding level, and the set of elements below -1 is the same away from rounding ties."""
+    from scipy import ndimage
+    D = 97
+    img = np.random.default_rng(5).uniform(-1, 1, (D, D, 3)).astype(F)
+    th = deg * np.pi / 180
+    T = tfops.rotation_transform(F(np.cos(th)), F(np.sin(th)), D, F(pa), F(pb))
+    R = tfops.projective_bilinear(img, T, -2.0)
+    ix, iy, _ = tfops.projective_coords(T, D, D)
+    coords = np.stack([np.asarray(iy, dtype=np.float64), np.asarray(ix, dtype=np.float64)])
+    S = np.stack([ndimage.map_coordinates(img[..., c].astype(np.float64), coords, order=1, mode="grid-constant", cval=-2.0)
+                  for c in range(3)], -1)
+    assert np.abs(R - S).max() < 2e-6
+    clear = np.abs(S + 1.0) > 1e-5                      # away from the threshold the two roundings agree on the mask
+    assert np.array_equal((R < -1)[clear], (S < -1)[clear])
+    assert 0.03 < (R < -1).mean() < 0.25
+
+
+@pytest.mark.parametrize("P,ps", [(100, 37), (100, 64), (100, 160), (30, 97), (64, 64)])
+def test_aa_resize_matches_pillow_float_bilinear(P, ps):
+    """Second independent implementation of the antialiased triangle resize: Pillow's Image.resize(BILINEAR) on a float
+    ('F' mode) image widens the triangle by the down-sampling factor and normalises the taps exactly like
+    ScaleAndTranslate(kernel 'triangle', antialias=True) (tf.image.resize's documentation names Pillow as its model).
+    Pillow runs the horizontal pass first and keeps float64 taps and a float64 scale, TF a float32 scale and its float32
+    reciprocal: agreement at the level of float32 rounding of the sample positions (measured: 0 ... 4.3e-6)."""
+    PIL = pytest.importorskip("PIL.Image")
+    x = np.random.default_rng(P * 1000 + ps).uniform(-1, 1, (P, P, 3)).astype(F)
+    y = tfops.aa_resize(x, ps, ps)
+    z = np.stack([np.asarray(PIL.fromarray(x[..., c], mode="F").resize((ps, ps), resample=PIL.BILINEAR)) for c in range(3)], -1)
+    assert z.shape == y.shape
+    assert np.abs(y - z).max() < 1e-5
