@@ -86,6 +86,9 @@ def workload_config(args, n_gpus):
                                     "into the convs; cuDNN convs at the framework's default TF32 setting, as TF 2.8; per-channel "
                                     "bias + SiLU and the squeeze-excite gate applied by one-pass libeotpatch epilogue kernels)",
             "parallelism": f"dp{n_gpus}", "first_pass_included": not args.no_first_pass,
+            "first_pass_note": "clean victim pass + score kernel + device NMS run every step, but the random-init victim (cls bias "
+                               "-log 99) puts no score above 0.5, so the NMS sees no candidate and the synthetic boxes are pasted; "
+                               "the NMS under load (240 candidates / image) is timed under neighbours",
             "cuda_graphs": "victim passes (clean forward+score; attacked forward+score+objective grad+backward)" if not args.no_graphs else "off",
             "l2": "inputs larger than L2 (images %.0f MB/GPU > 126 MB)" % (args.batch * args.image ** 2 * 12 / 1e6)}
 
